@@ -1,0 +1,216 @@
+"""Training step builder (reference: `graph.Manager`, `graph.py:204-315`).
+
+The reference assembles one TF graph: per-worker loss/gradient subgraphs pinned to the workers' devices, the GAR
+and `apply_gradients` pinned to the PS, an evaluator replica, and `train_tn = total_loss` gated on the update op.
+`Manager` keeps that surface (`step`, `rate`, `optimizer`, `total_loss`, `train()`≈`sess.run(train_tn)`,
+`evaluate()`≈`sess.run(eval_tns)`) on an SPMD runtime: every rank hosts `w = n / R` logical workers and owns 1/R
+of the parameter server (see `parallel/aggregation.py`).
+
+One synchronous step on a rank:
+  1. for each local worker: next batch (already prefetched to the device), forward, loss, backward — gradients are
+     written by the layer kernels directly into that worker's row of the peer-mapped `[w, d]` gradient matrix;
+  2. optional l1 / l2 regularisation gradient (same formulas as `graph.py:125-139`);
+  3. real Byzantine workers overwrite their row with the selected attack;
+  4. the aggregation engine runs (fused kernel: gather + GAR + optimizer + parameter broadcast);
+  5. the bf16 compute copy of the parameters is refreshed (unless the fused kernel already wrote it).
+"""
+
+import time
+
+import torch
+import torch.distributed as dist
+
+from .. import attacks as attacks_pkg
+from .. import tools
+from ..models import Context
+from ..ops import gar as gar_ops
+from ..parallel.aggregation import make_aggregation
+from .flat import FlatLayout, regularization
+from .optimizers import optimizers
+from .schedules import build, learning_rates
+
+
+def _default_device():
+  if torch.cuda.is_available():
+    return torch.device("cuda", torch.cuda.current_device())
+  return torch.device("cpu")
+
+
+class Manager:
+  """Full training + evaluation state of one rank."""
+
+  def __init__(self, experiment, aggregator, nbworkers, optimizer="sgd", optimizer_args=None, learning_rate="fixed", learning_rate_args=None,
+               regularizations=(-1., -1.), trace=False, *, attack=None, nb_real_byz=0, device=None, group=None, engine="auto", backend="auto",
+               dtype=None, seed=0, placement=None, debug_checksum=False, engine_args=None):
+    self.device = torch.device(device) if device is not None else _default_device()
+    self.group = group
+    self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+    self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+    self.experiment, self.aggregator, self.n = experiment, aggregator, nbworkers
+    self.l1, self.l2 = regularizations
+    self.tracer = tools.Tracer(enabled=trace, cuda=self.device.type == "cuda")
+    self.debug_checksum = debug_checksum
+    cuda = self.device.type == "cuda"
+    self.dtype = dtype if dtype is not None else (torch.bfloat16 if cuda else torch.float32)
+    if backend == "auto":
+      backend = "native" if cuda else "torch"
+    self.backend = backend
+    # -- learning rate, optimizer ------------------------------------------------- #
+    self.rate = build(learning_rates, "learning rate decay", learning_rate, learning_rate_args)
+    self.optimizer = build(optimizers, "optimizer", optimizer, optimizer_args)
+    # -- model, layout -------------------------------------------------------------- #
+    self.model = experiment.model()
+    self.layout = FlatLayout()
+    state_shapes = {}
+    self.model.declare(self.layout, state_shapes)
+    self.layout.freeze()
+    # -- aggregation engine (owns params + gradient rows) -------------------------- #
+    self.aggregation = make_aggregation(engine, aggregator, self.layout, nbworkers, self.optimizer, group, self.device, **(engine_args or {}))
+    self.w = self.aggregation.w
+    self.params = self.aggregation.params
+    self.grads = self.aggregation.grads
+    self.states = {name: torch.zeros(shape, dtype=torch.float32, device=self.device) for name, shape in state_shapes.items()}
+    # identical initial parameters on every rank: same seed, CPU generator, then copy
+    generator = torch.Generator().manual_seed(seed)
+    init = torch.zeros(self.layout.padded_size, dtype=torch.float32)
+    init_states = {name: torch.zeros(shape, dtype=torch.float32) for name, shape in state_shapes.items()}
+    self.model.initialize(self.layout.views(init), init_states, generator)
+    self.params.copy_(init)
+    for name, value in init_states.items():
+      self.states[name].copy_(value)
+    self.master_views = self.layout.views(self.params)
+    if self.dtype != torch.float32:
+      fused_copy = getattr(self.aggregation, "params_bf16", None)
+      self._weights_flat = fused_copy if fused_copy is not None else torch.zeros(self.layout.padded_size, dtype=self.dtype, device=self.device)
+      self._weights_by_kernel = fused_copy is not None
+      self.weight_views = self.layout.views(self._weights_flat)
+    else:
+      self._weights_flat, self._weights_by_kernel, self.weight_views = None, True, self.master_views
+    self._refresh_weights(force=True)
+    # -- workers -------------------------------------------------------------------- #
+    if placement is None:
+      placement = [(i // self.w, i % self.w) for i in range(nbworkers)]
+    self.placement = placement
+    self.local_workers = [i for i, (rank, _) in enumerate(placement) if rank == self.rank]
+    self.contexts = []
+    self._dropout_gen = torch.Generator(device=self.device).manual_seed(seed * 977 + self.rank + 1)
+    for i in self.local_workers:
+      ctx = Context(self.backend, True, self.dtype, self.device)
+      ctx.weights, ctx.master, ctx.state = self.weight_views, self.master_views, self.states
+      ctx.grads = self.layout.views(self.grads[placement[i][1]])
+      ctx.generator = self._dropout_gen
+      ctx.worker_id, ctx.nbworkers = i, nbworkers
+      self.contexts.append(ctx)
+    self.eval_ctx = Context(self.backend, False, self.dtype, self.device)
+    self.eval_ctx.weights, self.eval_ctx.master, self.eval_ctx.state = self.weight_views, self.master_views, self.states
+    self.eval_ctx.generator = self._dropout_gen
+    self.streams = [experiment.train_stream(i, nbworkers, self.device) for i in self.local_workers]
+    # -- attack --------------------------------------------------------------------- #
+    self.nb_real_byz = nb_real_byz
+    self.attack = attack
+    self.byzantine = set(range(nbworkers - nb_real_byz, nbworkers)) if (attack is not None and nb_real_byz > 0) else set()
+    self._attack_state = {i: {} for i in self.byzantine}
+    # -- counters ------------------------------------------------------------------- #
+    self.step = 0
+    self.total_loss = None
+    self._loss_buf = torch.zeros(1, dtype=torch.float32, device=self.device)
+    self.h2d_bytes_per_step = sum(getattr(s, "h2d_bytes", 0) for s in self.streams)
+    tools.info("Model %r: %d variables, d = %d (padded %d); %d worker(s) on this rank; compute dtype %s; nn backend %r; engine %r" % (
+      self.model.name, len(self.layout.names), self.layout.size, self.layout.padded_size, len(self.local_workers), str(self.dtype).replace("torch.", ""),
+      self.backend, self.aggregation.name), context="graph")
+
+  # ---------------------------------------------------------------------------- #
+  def _refresh_weights(self, force=False):
+    if self._weights_flat is None:
+      return
+    if self._weights_by_kernel and not force:
+      return
+    if self.device.type == "cuda" and self.dtype == torch.bfloat16:
+      gar_ops.cast_bf16_(self.params, self._weights_flat)
+    else:
+      self._weights_flat.copy_(self.params)
+
+  def compute_gradients(self):
+    """Phase 1-3 of a step: local workers' losses and gradients (+ regularisation, + attacks). Returns the list of losses."""
+    batches = [next(stream) for stream in self.streams]
+    trace = self.tracer if (self.tracer.enabled or self.tracer.cuda) else None
+    losses = self.experiment.losses(self.model, batches, self.contexts, trace)
+    if (self.l1 is not None and self.l1 > 0.) or (self.l2 is not None and self.l2 > 0.):
+      reg_loss, reg_grad = regularization(self.params, self.l1, self.l2)
+      for j in range(len(self.local_workers)):
+        self.grads[self.placement[self.local_workers[j]][1]].add_(reg_grad)
+        losses[j] = losses[j] + reg_loss
+    for j, i in enumerate(self.local_workers):
+      if i in self.byzantine:
+        self.attack.apply(self.grads[self.placement[i][1]], i, self.step, self._attack_state[i])
+    return losses
+
+  def train(self):
+    """One synchronous training step (the reference's `sess.run(train_tn)`); returns the total loss as a 0-d device tensor."""
+    rate = self.rate(self.step)
+    with self.tracer.span("Workers: loss and gradient computation"):
+      losses = self.compute_gradients()
+    with self.tracer.span("Master: aggregated gradient computation and application"):
+      self.aggregation.step(rate)
+    self._refresh_weights()
+    self.step += 1
+    total = torch.stack([l.float().reshape(()) for l in losses]).sum() if losses else self._loss_buf.new_zeros(())
+    if self.world > 1:
+      self._loss_buf[0] = total
+      dist.all_reduce(self._loss_buf, group=self.group)
+      total = self._loss_buf[0]
+    self.total_loss = total
+    if self.debug_checksum:
+      self.check_replicas()
+    return total
+
+  def evaluate(self):
+    """`{"top1-X-acc": float}` on one evaluation batch, with the live parameters."""
+    batch = self.experiment.eval_batch(self.device)
+    metrics = self.experiment.accuracy(self.model, batch, self.eval_ctx)
+    return {key: float(val) for key, val in metrics.items()}
+
+  def check_replicas(self):
+    """Debug mode: every rank must hold bit-identical parameters after a step."""
+    if self.device.type == "cuda":
+      digest = gar_ops.checksum(self.params)
+    else:
+      digest = torch.tensor([hash(self.params.numpy().tobytes()) & (2 ** 62 - 1)], dtype=torch.int64)
+    if self.world > 1:
+      gathered = [torch.zeros_like(digest) for _ in range(self.world)]
+      dist.all_gather(gathered, digest, group=self.group)
+      values = [int(g.item()) for g in gathered]
+      if len(set(values)) != 1:
+        raise RuntimeError("Replica divergence at step %d: parameter checksums %r" % (self.step, values))
+    return int(digest.item())
+
+  # ---------------------------------------------------------------------------- #
+  def state_dict(self):
+    agg = self.aggregation.state_dict()
+    return {"global_step": self.step, "params": self.params.detach().to("cpu", copy=True), "optimizer": self.optimizer.name,
+            "aggregation": agg, "states": {k: v.detach().to("cpu", copy=True) for k, v in self.states.items()},
+            "layout": self.layout.describe(), "time": time.time()}
+
+  def load_state_dict(self, state):
+    if state["params"].numel() != self.params.numel():
+      raise tools.UserException("Checkpoint holds %d parameters, the model needs %d" % (state["params"].numel(), self.params.numel()))
+    self.params.copy_(state["params"].to(self.device))
+    for name, value in state.get("states", {}).items():
+      if name in self.states:
+        self.states[name].copy_(value.to(self.device))
+    if state.get("optimizer") == self.optimizer.name:
+      self.aggregation.load_state_dict(state["aggregation"])
+    else:
+      tools.warning("Checkpoint was written with optimizer %r, now using %r: slots are reset" % (state.get("optimizer"), self.optimizer.name))
+    self.step = int(state["global_step"])
+    self._refresh_weights(force=True)
+    if self.device.type == "cuda":
+      torch.cuda.synchronize(self.device)
+    if self.world > 1:
+      dist.barrier(group=self.group)
+
+  def close(self):
+    for stream in self.streams:
+      close = getattr(stream, "close", None)
+      if close is not None:
+        close()

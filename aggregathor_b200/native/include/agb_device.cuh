@@ -1,0 +1,96 @@
+// Device-side helpers shared by the sm_100a kernel libraries: error macro, system-scope
+// synchronisation primitives for peer-mapped memory, streaming vector loads/stores, NVLS
+// (multimem) wrappers, warp/block reductions.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+
+#define AGB_CUDA_OK(expr) do { cudaError_t err__ = (expr); if (err__ != cudaSuccess) { \
+    std::fprintf(stderr, "[agb] CUDA error %s at %s:%d: %s\n", cudaGetErrorName(err__), __FILE__, __LINE__, cudaGetErrorString(err__)); \
+    return static_cast<int>(err__) ? static_cast<int>(err__) : 1; } } while (0)
+
+namespace agb {
+
+// ---- system-scope flags (cross-GPU) -------------------------------------- //
+__device__ __forceinline__ void st_release_sys(uint32_t* addr, uint32_t value) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(addr), "r"(value) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(uint32_t const* addr) {
+    uint32_t value;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(value) : "l"(addr) : "memory");
+    return value;
+}
+__device__ __forceinline__ void fence_sys() {
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
+}
+// Spin until *addr reaches `target` (monotonic epochs, wrap-safe signed difference). The
+// iteration bound turns a protocol bug into a trap instead of a hung GPU.
+__device__ __forceinline__ void wait_flag_sys(uint32_t const* addr, uint32_t target) {
+    unsigned long long spins = 0;
+    while (static_cast<int32_t>(ld_acquire_sys(addr) - target) < 0) {
+        __nanosleep(64);
+        if (++spins > (1ull << 26)) { // several seconds
+            printf("[agb] wait_flag_sys timeout: flag %p = %u, expected >= %u (block %d)\n", (void const*) addr, ld_acquire_sys(addr), target, (int) blockIdx.x);
+            __trap();
+        }
+    }
+}
+
+// ---- streaming 128-bit accesses ------------------------------------------ //
+// Peer gradient tiles are read exactly once: do not allocate them in L1.
+__device__ __forceinline__ float4 ld_stream_f4(float const* addr) {
+    float4 v;
+    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(addr));
+    return v;
+}
+__device__ __forceinline__ float4 ld_volatile_f4(float const* addr) {
+    float4 v;
+    asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(addr));
+    return v;
+}
+__device__ __forceinline__ float ld_volatile_f(float const* addr) {
+    float v;
+    asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(addr));
+    return v;
+}
+__device__ __forceinline__ void st_stream_f4(float* addr, float4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// ---- NVLS (multicast-mapped memory) -------------------------------------- //
+// One store lands in every GPU bound to the multicast object.
+__device__ __forceinline__ void multimem_st_f4(float* mc_addr, float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(mc_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// In-switch reduction: returns the sum over all bound GPUs of the 4 floats at mc_addr.
+__device__ __forceinline__ float4 multimem_ld_reduce_add_f4(float const* mc_addr) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc_addr) : "memory");
+    return v;
+}
+
+// ---- reductions ------------------------------------------------------------ //
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int offset = 16; offset > 0; offset >>= 1)
+        v += __shfl_xor_sync(0xffffffffu, v, offset);
+    return v;
+}
+
+__device__ __forceinline__ bool is_finite(float v) {
+    return (__float_as_uint(v) & 0x7f800000u) != 0x7f800000u;
+}
+
+// Total order used by every aggregation rule: finite ascending, then non-finite, ties -> lower index.
+__device__ __forceinline__ bool before(float a, int ia, float b, int ib) {
+    bool fa = is_finite(a), fb = is_finite(b);
+    if (fa != fb)
+        return fa;
+    if (fa && a != b)
+        return a < b;
+    return ia < ib;
+}
+
+} // namespace agb

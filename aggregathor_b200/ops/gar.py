@@ -1,0 +1,170 @@
+"""Python front-end of the sm_100a aggregation kernels (`native/op_gar`).
+
+`aggregate(spec, G)` is the stand-alone `[n, d] -> [d]` custom op (the `-co` flavour of
+the reference, which only ever had a CPU kernel: `native/op_krum/op.cpp:98-107`).
+`FusedLauncher` drives the full gather + rule + optimizer + broadcast kernel for one rank
+(see `parallel/fused.py` for the multi-GPU wiring).
+"""
+
+import ctypes
+
+import torch
+
+from .. import tools
+from ..aggregators import FusedSpec
+
+MAX_WORKERS = 16
+MAX_RANKS = 16
+MAX_PAIRS = MAX_WORKERS * (MAX_WORKERS - 1) // 2
+OPTIMIZERS = {"none": 0, "sgd": 1, "adam": 2, "rmsprop": 3, "adagrad": 4, "adadelta": 5}
+
+_ERRORS = {
+  100: "unsupported number of workers/ranks (n <= 16, R <= 16)", 101: "slice bounds must be multiples of 4 elements",
+  102: "unknown rule", 103: "invalid Krum parameters", 104: "invalid Bulyan parameters", 105: "invalid beta",
+  106: "optimizer requested without parameter buffers", 107: "optimizer slots missing", 108: "scratch buffers missing",
+  109: "signal pads missing"}
+
+
+def _lib():
+  from .. import native
+  return native.library("op_gar")
+
+
+def _stream_ptr(stream=None):
+  stream = torch.cuda.current_stream() if stream is None else stream
+  return ctypes.c_void_p(stream.cuda_stream)
+
+
+def _check(status, what):
+  if status != 0:
+    raise RuntimeError("native op " + what + " failed with status " + str(status) + (" (" + _ERRORS[status] + ")" if status in _ERRORS else " (CUDA error)"))
+
+
+def max_ctas():
+  return int(_lib().agb_gar_max_ctas())
+
+
+class FusedLauncher:
+  """Holds the scratch buffers and argument arrays of one rank's fused aggregation kernel."""
+
+  def __init__(self, device, n):
+    if n > MAX_WORKERS:
+      raise tools.UserException("The sm_100a aggregation kernels hold one value per worker in registers and support n <= %d workers (got %d)" % (MAX_WORKERS, n))
+    self.device = torch.device(device)
+    self.n = n
+    with torch.cuda.device(self.device):
+      ctas = max(1, max_ctas())
+    self.cta_partials = torch.zeros(ctas * MAX_PAIRS, dtype=torch.float32, device=self.device)
+    self.local_mailbox = torch.zeros(MAX_RANKS * MAX_PAIRS, dtype=torch.float32, device=self.device)
+    self.dist_out = torch.zeros(n * n, dtype=torch.float32, device=self.device)
+    self.info = torch.zeros(64, dtype=torch.int32, device=self.device)
+    self._ptrs = (ctypes.c_ulonglong * 96)()
+    self._ints = (ctypes.c_int * 10)()
+    self._longs = (ctypes.c_longlong * 2)()
+    self._floats = (ctypes.c_float * 4)()
+    self._func = _lib().agb_gar_fused
+    self._func.restype = ctypes.c_int
+
+  def launch(self, spec, rows, lo, hi, *, agg_out=None, opt="none", lr=0.0, hyper=(0.0, 0.0, 0.0), param=None,
+             slot0=None, slot1=None, param_dst=None, param_mc=0, param_bf16_dst=None, rank=0, R=1, signals=None, mailboxes=None,
+             epoch=1, staging=None, max_ctas_limit=0, stream=None):
+    """`rows`: n device addresses of the workers' gradient rows; pointers are raw ints (local or peer-mapped)."""
+    ptrs = self._ptrs
+    for i in range(96):
+      ptrs[i] = 0
+    if len(rows) != spec.n:
+      raise tools.UserException("Expected %d gradient rows, got %d" % (spec.n, len(rows)))
+    for i, row in enumerate(rows):
+      ptrs[i] = row
+    addr = lambda t: 0 if t is None else (t if isinstance(t, int) else t.data_ptr())
+    ptrs[16] = addr(agg_out)
+    ptrs[17] = addr(param)
+    ptrs[18] = addr(slot0)
+    ptrs[19] = addr(slot1)
+    ptrs[20] = int(param_mc or 0)
+    ptrs[21] = self.cta_partials.data_ptr()
+    ptrs[22] = addr(staging)
+    ptrs[23] = self.dist_out.data_ptr()
+    ptrs[24] = self.info.data_ptr()
+    for q in range(R):
+      ptrs[32 + q] = addr(param_dst[q]) if param_dst is not None else (addr(param) if q == 0 else 0)
+      ptrs[48 + q] = addr(signals[q]) if signals is not None else 0
+      ptrs[64 + q] = addr(mailboxes[q]) if mailboxes is not None else (self.local_mailbox.data_ptr() if q == 0 else 0)
+      ptrs[80 + q] = addr(param_bf16_dst[q]) if param_bf16_dst is not None else 0
+    ints = self._ints
+    ints[0], ints[1], ints[2], ints[3], ints[4] = spec.n, spec.f, spec.m, spec.beta, spec.rule_id
+    ints[5], ints[6], ints[7], ints[8], ints[9] = R, rank, OPTIMIZERS[opt], epoch & 0x7fffffff, max_ctas_limit
+    self._longs[0], self._longs[1] = lo, hi
+    self._floats[0], self._floats[1], self._floats[2], self._floats[3] = lr, hyper[0], hyper[1], hyper[2]
+    with torch.cuda.device(self.device):
+      _check(self._func(ptrs, ints, self._longs, self._floats, _stream_ptr(stream)), "gar_fused")
+
+
+_launchers = {}
+
+
+def aggregate(spec, G, return_details=False):
+  """Stand-alone aggregation of the CUDA matrix `G` ([n, d], fp32) with rule `spec` -> [d] tensor."""
+  if not G.is_cuda:
+    raise tools.UserException("ops.gar.aggregate expects a CUDA tensor")
+  if G.dtype != torch.float32:
+    out = aggregate(spec, G.float(), return_details)
+    return (out[0].to(G.dtype),) + out[1:] if return_details else out.to(G.dtype)
+  n, d = G.shape
+  if n != spec.n:
+    spec = FusedSpec(spec.rule, n, spec.f, spec.m, spec.beta)
+  if n > MAX_WORKERS:  # beyond the register-resident kernels: torch ops on the same device
+    from ..aggregators import _ops
+    fallback = {"average": _ops.torch_average, "average-nan": _ops.torch_average_nan, "median": _ops.torch_median,
+                "averaged-median": lambda M: _ops.torch_averaged_median(M, spec.beta), "krum": lambda M: _ops.torch_krum(M, spec.f, spec.m),
+                "bulyan": lambda M: _ops.torch_bulyan(M, spec.f, spec.m)}[spec.rule]
+    return fallback(G)
+  G = G.contiguous()
+  pad = (-d) % 4
+  if pad or G.data_ptr() % 16:
+    Gp = torch.zeros((n, d + pad), dtype=G.dtype, device=G.device)
+    Gp[:, :d] = G
+    G = Gp
+  dp = d + pad
+  key = (G.device.index, n)
+  launcher = _launchers.get(key)
+  if launcher is None:
+    launcher = _launchers[key] = FusedLauncher(G.device, n)
+  out = torch.empty(dp, dtype=torch.float32, device=G.device)
+  rows = [G.data_ptr() + i * dp * 4 for i in range(n)]
+  launcher.launch(spec, rows, 0, dp, agg_out=out)
+  out = out[:d]
+  if return_details:
+    return out, launcher.dist_out.view(n, n).clone(), launcher.info.clone()
+  return out
+
+
+def sgd_(param, grad, lr):
+  """In-place `param -= lr * grad` on flat fp32 CUDA buffers (baseline path's separate update kernel)."""
+  func = _lib().agb_sgd
+  _check(func(ctypes.c_void_p(param.data_ptr()), ctypes.c_void_p(grad.data_ptr()), ctypes.c_float(lr), ctypes.c_longlong(param.numel()), _stream_ptr()), "sgd")
+  return param
+
+
+def drop_chunks_(grad, rate, mode="nan", previous=None, chunk_bytes=65000, seed=0):
+  """Lossy-transport emulation on a flat fp32 CUDA gradient: lost 65 000-byte chunks -> NaN / zero / previous bytes."""
+  modes = {"nan": 0, "zero": 1, "clever": 2}
+  func = _lib().agb_drop_chunks
+  _check(func(ctypes.c_void_p(grad.data_ptr()), ctypes.c_void_p(previous.data_ptr() if previous is not None else 0), ctypes.c_longlong(grad.numel()),
+              ctypes.c_longlong(chunk_bytes), ctypes.c_float(rate), ctypes.c_int(modes[mode]), ctypes.c_ulonglong(seed & (2 ** 64 - 1)), _stream_ptr()), "drop_chunks")
+  return grad
+
+
+def checksum(tensor):
+  """64-bit position-dependent checksum of a flat fp32 CUDA buffer (cross-rank equality debug mode)."""
+  out = torch.zeros(1, dtype=torch.int64, device=tensor.device)
+  func = _lib().agb_checksum
+  _check(func(ctypes.c_void_p(tensor.data_ptr()), ctypes.c_longlong(tensor.numel()), ctypes.c_void_p(out.data_ptr()), _stream_ptr()), "checksum")
+  return out
+
+
+def cast_bf16_(src, dst):
+  """fp32 -> bf16 copy of a flat buffer (compute copy of the master parameters)."""
+  func = _lib().agb_cast_bf16
+  _check(func(ctypes.c_void_p(src.data_ptr()), ctypes.c_void_p(dst.data_ptr()), ctypes.c_longlong(src.numel()), _stream_ptr()), "cast_bf16")
+  return dst

@@ -1,0 +1,269 @@
+"""Neural-network ops with two providers.
+
+`backend == "native"`: hand-written sm_100a kernels from `native/op_nn` (tcgen05/TMEM/TMA GEMM and
+implicit-GEMM convolution, fused BN/ReLU/residual, pooling, softmax-CE). `backend == "torch"`: aten
+library calls — the fp32/bf16 numerical reference of every kernel test and the baseline arm.
+A native op that is not available for a given shape falls back to the torch provider *only* when
+`AGB_NATIVE_STRICT` is unset; with `AGB_NATIVE_STRICT=1` it raises, so a silent library fallback
+cannot masquerade as the native path.
+
+Tensor conventions: activations (N, C, H, W) with channels_last strides (NHWC memory); conv weights
+are tensors of shape [Cout, kh, kw, Cin] (OHWI memory); linear weights [out, in].
+"""
+
+import os
+
+import torch
+import torch.nn.functional as F
+
+from .. import tools
+
+_CL = torch.channels_last
+_STRICT = bool(os.environ.get("AGB_NATIVE_STRICT", ""))
+launch_count = 0  # number of native kernel launches issued (bench bookkeeping)
+
+
+def _native():
+  from . import nn_native
+  return nn_native
+
+
+def _fallback(op):
+  if _STRICT:
+    raise tools.UserException("Native op " + repr(op) + " unavailable for these arguments and AGB_NATIVE_STRICT is set")
+
+
+def _pad_input(x, pads, value=0.0):
+  t, b, l, r = pads
+  if t == b and l == r:
+    return x, (t, l)
+  return F.pad(x, (l, r, t, b), value=value), (0, 0)
+
+
+def _relu_mask(dy, y):
+  return dy * (y > 0).to(dy.dtype)
+
+
+# ---------------------------------------------------------------------------- #
+# Convolution
+
+def conv2d_forward(backend, x, weight, bias, stride, pads, relu):
+  if backend == "native" and x.is_cuda:
+    out = _native().conv2d_forward(x, weight, bias, stride, pads, relu)
+    if out is not None:
+      return out
+    _fallback("conv2d_forward")
+  xp, padding = _pad_input(x, pads)
+  y = F.conv2d(xp, weight.permute(0, 3, 1, 2), bias.to(x.dtype) if bias is not None else None, stride=stride, padding=padding)
+  if relu:
+    y = torch.relu_(y)
+  return y.contiguous(memory_format=_CL)
+
+
+def conv2d_backward(backend, dy, x, weight, y, stride, pads, relu, has_bias, need_dx, grad_w, grad_b):
+  """Writes dW into `grad_w` ([Cout, kh, kw, Cin] fp32 view) and db into `grad_b`; returns dx or None."""
+  if backend == "native" and x.is_cuda:
+    out = _native().conv2d_backward(dy, x, weight, y, stride, pads, relu, has_bias, need_dx, grad_w, grad_b)
+    if out is not NotImplemented:
+      return out, None, None
+    _fallback("conv2d_backward")
+  if relu:
+    dy = _relu_mask(dy, y)
+  t, b, l, r = pads
+  xp, padding = _pad_input(x, pads)
+  w = weight.permute(0, 3, 1, 2)
+  dxp, dw, db = torch.ops.aten.convolution_backward(
+    dy, xp, w, [weight.shape[0]] if has_bias else None, [stride, stride], list(padding), [1, 1], False, [0, 0], 1, [need_dx, True, has_bias])
+  grad_w.copy_(dw.permute(0, 2, 3, 1))
+  if has_bias:
+    grad_b.copy_(db)
+  dx = None
+  if need_dx:
+    dx = dxp if padding != (0, 0) or (t == 0 and b == 0 and l == 0 and r == 0) else dxp[:, :, t:dxp.shape[2] - b, l:dxp.shape[3] - r]
+    dx = dx.contiguous(memory_format=_CL)
+  return dx, None, None
+
+
+# ---------------------------------------------------------------------------- #
+# Dense
+
+def linear_forward(backend, x, weight, bias, relu):
+  if backend == "native" and x.is_cuda:
+    out = _native().linear_forward(x, weight, bias, relu)
+    if out is not None:
+      return out
+    _fallback("linear_forward")
+  y = F.linear(x, weight, bias.to(x.dtype) if bias is not None else None)
+  return torch.relu_(y) if relu else y
+
+
+def linear_backward(backend, dy, x, weight, y, relu, need_dx, grad_w, grad_b):
+  if backend == "native" and x.is_cuda:
+    out = _native().linear_backward(dy, x, weight, y, relu, need_dx, grad_w, grad_b)
+    if out is not NotImplemented:
+      return out
+    _fallback("linear_backward")
+  if relu:
+    dy = _relu_mask(dy, y)
+  grad_w.copy_(dy.t() @ x)
+  if grad_b is not None:
+    grad_b.copy_(dy.float().sum(dim=0))
+  return dy @ weight if need_dx else None
+
+
+# ---------------------------------------------------------------------------- #
+# Batch normalisation
+
+def batchnorm_forward(backend, x, gamma, beta, moving_mean, moving_var, decay, eps, relu):
+  if backend == "native" and x.is_cuda:
+    out = _native().batchnorm_forward(x, gamma, beta, moving_mean, moving_var, decay, eps, relu)
+    if out is not None:
+      return out
+    _fallback("batchnorm_forward")
+  y, mean, rstd = torch.native_batch_norm(x, gamma, beta, moving_mean, moving_var, True, 1.0 - decay, eps)
+  if relu:
+    y = torch.relu_(y)
+  return y, mean, rstd
+
+
+def batchnorm_inference(backend, x, gamma, beta, moving_mean, moving_var, eps, relu):
+  y = F.batch_norm(x, moving_mean, moving_var, gamma, beta, False, 0.0, eps)
+  return torch.relu_(y) if relu else y
+
+
+def batchnorm_backward(backend, dy, x, y, gamma, mean, rstd, relu, grad_gamma, grad_beta):
+  if backend == "native" and x.is_cuda:
+    out = _native().batchnorm_backward(dy, x, y, gamma, mean, rstd, relu, grad_gamma, grad_beta)
+    if out is not None:
+      return out
+    _fallback("batchnorm_backward")
+  if relu:
+    dy = _relu_mask(dy, y)
+  dx, dgamma, dbeta = torch.ops.aten.native_batch_norm_backward(dy, x, gamma, None, None, mean, rstd, True, 1e-5, [True, gamma is not None, True])
+  if grad_gamma is not None:
+    grad_gamma.copy_(dgamma)
+  grad_beta.copy_(dbeta)
+  return dx
+
+
+# ---------------------------------------------------------------------------- #
+# Element-wise / pooling
+
+def relu_forward(backend, x):
+  return torch.relu(x)
+
+
+def relu_backward(backend, dy, y):
+  if backend == "native" and dy.is_cuda:
+    out = _native().relu_backward(dy, y)
+    if out is not None:
+      return out
+  return _relu_mask(dy, y)
+
+
+def add_relu_forward(backend, a, b, relu):
+  if backend == "native" and a.is_cuda:
+    out = _native().add_relu_forward(a, b, relu)
+    if out is not None:
+      return out
+  y = a + b
+  return torch.relu_(y) if relu else y
+
+
+def add_forward(backend, a, b):
+  if a is None:
+    return b
+  if b is None:
+    return a
+  return a + b
+
+
+def maxpool_forward(backend, x, k, stride, pads):
+  if backend == "native" and x.is_cuda:
+    out = _native().maxpool_forward(x, k, stride, pads)
+    if out is not None:
+      return out, None
+    _fallback("maxpool_forward")
+  t, b, l, r = pads
+  xp = F.pad(x, (l, r, t, b), value=float("-inf")) if any(pads) else x
+  y, index = F.max_pool2d(xp, k, stride, return_indices=True)
+  return y, index
+
+
+def maxpool_backward(backend, dy, shape, index, k, stride, pads, x, y):
+  if backend == "native" and dy.is_cuda and index is None:
+    return _native().maxpool_backward(dy, x, y, k, stride, pads)
+  t, b, l, r = pads
+  n, c, h, w = shape
+  xp_shape = (n, c, h + t + b, w + l + r)
+  dxp = torch.ops.aten.max_pool2d_with_indices_backward(dy, dy.new_empty(xp_shape).contiguous(memory_format=_CL), [k, k], [stride, stride], [0, 0], [1, 1], False, index)
+  return dxp[:, :, t:t + h, l:l + w].contiguous(memory_format=_CL)
+
+
+def global_avgpool_forward(backend, x):
+  if backend == "native" and x.is_cuda:
+    out = _native().global_avgpool_forward(x)
+    if out is not None:
+      return out
+  return x.float().mean(dim=(2, 3), keepdim=True).to(x.dtype)
+
+
+def global_avgpool_backward(backend, dy, shape):
+  n, c, h, w = shape
+  if backend == "native" and dy.is_cuda:
+    out = _native().global_avgpool_backward(dy, shape)
+    if out is not None:
+      return out
+  return (dy / (h * w)).expand(n, c, h, w).contiguous(memory_format=_CL)
+
+
+def subsample_forward(backend, x, stride):
+  return x[:, :, ::stride, ::stride].contiguous(memory_format=_CL)
+
+
+def subsample_backward(backend, dy, shape, stride):
+  dx = torch.zeros(shape, dtype=dy.dtype, device=dy.device).contiguous(memory_format=_CL)
+  dx[:, :, ::stride, ::stride] = dy
+  return dx
+
+
+# ---------------------------------------------------------------------------- #
+# Loss
+
+def softmax_xent(backend, logits, labels, label_smoothing=0.0):
+  """Mean softmax cross-entropy over the batch -> (loss fp32 0-d, dlogits fp32 [B, K])."""
+  if backend == "native" and logits.is_cuda:
+    out = _native().softmax_xent(logits, labels, label_smoothing)
+    if out is not None:
+      return out
+  z = logits.float()
+  logp = torch.log_softmax(z, dim=1)
+  batch, classes = z.shape
+  target = torch.zeros_like(z).scatter_(1, labels.view(-1, 1).long(), 1.0)
+  if label_smoothing > 0.:
+    target = target * (1.0 - label_smoothing) + label_smoothing / classes
+  loss = -(target * logp).sum(dim=1).mean()
+  return loss, (torch.exp(logp) - target) / batch
+
+
+# ---------------------------------------------------------------------------- #
+# Input pipeline tail
+
+_VGG_MEANS = (123.68, 116.78, 103.94)
+
+
+def image_normalize(backend, images, mode, dtype):
+  """uint8 NHWC host-format batch (already on the device) -> normalised (N, C, H, W) channels_last activations.
+  `vgg`: subtract the per-channel ImageNet means; `inception`: x/127.5 - 1; `lenet`: (x - 128)/128."""
+  if backend == "native" and images.is_cuda:
+    out = _native().image_normalize(images, mode, dtype)
+    if out is not None:
+      return out
+  x = images.to(torch.float32)
+  if mode == "vgg" and x.shape[-1] == 3:
+    x = x - torch.tensor(_VGG_MEANS, device=x.device)
+  elif mode == "inception":
+    x = x / 127.5 - 1.0
+  else:
+    x = (x - 128.0) / 128.0
+  return x.to(dtype).permute(0, 3, 1, 2)  # NHWC memory viewed as (N, C, H, W): already channels_last

@@ -1,0 +1,207 @@
+"""The parameter-server step, SPMD style: gather workers' gradients -> GAR -> optimizer -> parameters.
+
+Three interchangeable engines share one interface (`params`, `grads`, `step()`):
+
+* `FusedAggregation` — the product. Gradients and parameters live in symmetric (peer-mapped)
+  memory; ONE cooperative sm_100a kernel per rank (`native/op_gar`) reads the owned coordinate
+  slice of every worker's gradient directly from the peers over NVLink, applies the rule and the
+  optimizer, and stores the new parameter slice into every rank's buffer. No NCCL call, no
+  separate element-wise kernel. Each rank is a worker host *and* 1/R of the parameter server.
+* `BaselineAggregation` — the "reference-style" path measured against: NCCL all-gather of the
+  full flat gradients -> stand-alone GAR kernel over [n, d] -> separate optimizer kernel.
+  (What `graph.py:276-281` does, with NCCL instead of gRPC.)
+* `HostAggregation` — CPU tensors, gloo all-gather, host C++ GARs: the plumbing config
+  (`mnist` + `average`, 2 workers) and the fallback for user plug-in GARs without a fused spec.
+
+Logical workers: n = R * w; rank r hosts workers [r*w, (r+1)*w). The GAR always sees n rows.
+"""
+
+import torch
+import torch.distributed as dist
+
+from .. import tools
+from ..ops import gar as gar_ops
+from .symm import SymmetricHeap
+
+
+def _world(group=None):
+  if dist.is_available() and dist.is_initialized():
+    return dist.get_rank(group), dist.get_world_size(group)
+  return 0, 1
+
+
+class _AggregationBase:
+  """Common state: layout, optimizer spec and slots, update counter."""
+
+  def __init__(self, gar, layout, nbworkers, optimizer, group=None):
+    self.gar = gar
+    self.layout = layout
+    self.n = nbworkers
+    self.optimizer = optimizer
+    self.group = group
+    self.rank, self.world = _world(group)
+    if nbworkers % self.world != 0:
+      raise tools.UserException("The number of workers (%d) must be a multiple of the number of ranks (%d)" % (nbworkers, self.world))
+    self.w = nbworkers // self.world
+    self.d = layout.padded_size
+    self.updates = 0  # number of optimizer updates applied so far
+    self.slots = []
+
+  @property
+  def first_worker(self):
+    return self.rank * self.w
+
+  def state_dict(self):
+    return {"updates": self.updates, "slots": [s.detach().to("cpu", copy=True) for s in self.full_slots()]}
+
+  def load_state_dict(self, state):
+    self.updates = int(state["updates"])
+    for mine, saved in zip(self.slots, state["slots"]):
+      mine.copy_(saved.to(mine.device))
+
+  def full_slots(self):
+    return self.slots
+
+
+class HostAggregation(_AggregationBase):
+  """CPU/gloo engine (also drives arbitrary `_GAR.aggregate()` plug-ins on any device)."""
+
+  name = "host"
+
+  def __init__(self, gar, layout, nbworkers, optimizer, group=None, device="cpu"):
+    super().__init__(gar, layout, nbworkers, optimizer, group)
+    self.device = torch.device(device)
+    self.params = torch.zeros(self.d, dtype=torch.float32, device=self.device)
+    self.grads = torch.zeros((self.w, self.d), dtype=torch.float32, device=self.device)
+    self.slots = optimizer.make_slots(self.params)
+    self._gathered = torch.zeros((self.n, self.d), dtype=torch.float32, device=self.device) if self.world > 1 else self.grads
+    self.last_aggregate = None
+
+  def step(self, rate):
+    if self.world > 1:
+      dist.all_gather_into_tensor(self._gathered, self.grads, group=self.group)
+    aggregated = self.gar.aggregate(self._gathered)
+    self.updates += 1
+    self.optimizer.apply_torch(self.params, aggregated, self.slots, rate, self.updates)
+    self.last_aggregate = aggregated
+
+
+class BaselineAggregation(_AggregationBase):
+  """NCCL all-gather -> stand-alone GAR kernel -> separate update kernel (the baseline, not the product)."""
+
+  name = "baseline"
+
+  def __init__(self, gar, layout, nbworkers, optimizer, group=None, device="cuda"):
+    super().__init__(gar, layout, nbworkers, optimizer, group)
+    self.device = torch.device(device)
+    self.spec = gar.fused_spec()
+    self.params = torch.zeros(self.d, dtype=torch.float32, device=self.device)
+    self.grads = torch.zeros((self.w, self.d), dtype=torch.float32, device=self.device)
+    self.slots = optimizer.make_slots(self.params)
+    self._gathered = torch.zeros((self.n, self.d), dtype=torch.float32, device=self.device) if self.world > 1 else self.grads
+    self.last_aggregate = None
+
+  def step(self, rate):
+    if self.world > 1:
+      dist.all_gather_into_tensor(self._gathered, self.grads, group=self.group)
+    if self.spec is not None and self.n <= gar_ops.MAX_WORKERS:
+      aggregated = gar_ops.aggregate(self.spec, self._gathered)
+    else:
+      aggregated = self.gar.aggregate(self._gathered)
+    self.updates += 1
+    if self.optimizer.name == "sgd":
+      gar_ops.sgd_(self.params, aggregated, rate)
+    else:
+      self.optimizer.apply_torch(self.params, aggregated, self.slots, rate, self.updates)
+    self.last_aggregate = aggregated
+
+
+class FusedAggregation(_AggregationBase):
+  """Fused P2P gather + rule + optimizer + broadcast kernel over symmetric memory."""
+
+  name = "fused"
+
+  def __init__(self, gar, layout, nbworkers, optimizer, group=None, device="cuda", keep_aggregate=False, bf16_copy=False, max_ctas=0):
+    super().__init__(gar, layout, nbworkers, optimizer, group)
+    self.device = torch.device(device)
+    self.spec = gar.fused_spec()
+    if self.spec is None:
+      raise tools.UserException("GAR " + type(gar).__name__ + " has no fused kernel; use the baseline/host engine")
+    if self.spec.n != nbworkers:
+      raise tools.UserException("GAR built for %d workers used with %d" % (self.spec.n, nbworkers))
+    d, w, R = self.d, self.w, self.world
+    self.lo, self.hi = layout.slice_bounds(self.rank, R)
+    distance_rule = self.spec.rule in ("krum", "bulyan")
+    sizes = {"grads": w * d * 4, "params": d * 4, "signals": 3 * gar_ops.MAX_RANKS * 4, "mailbox": gar_ops.MAX_RANKS * gar_ops.MAX_PAIRS * 4}
+    if bf16_copy:
+      sizes["params_bf16"] = d * 2
+    self.heap = SymmetricHeap(SymmetricHeap.required(*sizes.values()), self.device, group)
+    for name, nbytes in sizes.items():
+      self.heap.region(name, nbytes)
+    self.grads = self.heap.local("grads", torch.float32, (w, d))
+    self.params = self.heap.local("params", torch.float32)
+    self.params_bf16 = self.heap.local("params_bf16", torch.bfloat16) if bf16_copy else None
+    self.slots = optimizer.make_slots(self.params)
+    self.aggregate_out = torch.zeros(d, dtype=torch.float32, device=self.device) if keep_aggregate else None
+    # staging keeps the P2P-loaded slice local so that phase D does not cross NVLink again
+    self.staging = torch.empty((self.n, self.hi - self.lo), dtype=torch.float32, device=self.device) if (distance_rule and R > 1) else None
+    self.launcher = gar_ops.FusedLauncher(self.device, self.n)
+    self.max_ctas = max_ctas
+    self.epoch = 0
+    heap = self.heap
+    self._rows = [heap.peer(i // w, "grads") + (i % w) * d * 4 for i in range(self.n)]
+    self._param_dst = [heap.peer(q, "params") for q in range(R)]
+    self._param_bf16_dst = [heap.peer(q, "params_bf16") for q in range(R)] if bf16_copy else None
+    self._signals = [heap.peer(q, "signals") for q in range(R)]
+    self._mailboxes = [heap.peer(q, "mailbox") for q in range(R)]
+    self._param_mc = heap.multicast("params") if R > 1 else 0
+    tools.info("Fused aggregation: rule %r, n = %d (%d per rank), d = %d, slice [%d, %d), provider %s, NVLS multicast %s" % (
+      self.spec.rule, self.n, w, d, self.lo, self.hi, heap.provider, "on" if self._param_mc else "off"), context="fused")
+
+  @property
+  def last_aggregate(self):
+    return self.aggregate_out
+
+  def step(self, rate, stream=None):
+    self.updates += 1
+    self.epoch += 1
+    lr, hyper = self.optimizer.kernel_args(rate, self.updates)
+    self.launcher.launch(
+      self.spec, self._rows, self.lo, self.hi, agg_out=self.aggregate_out, opt=self.optimizer.name, lr=lr, hyper=hyper,
+      param=self.params, slot0=self.slots[0] if len(self.slots) > 0 else None, slot1=self.slots[1] if len(self.slots) > 1 else None,
+      param_dst=self._param_dst, param_mc=self._param_mc, param_bf16_dst=self._param_bf16_dst, rank=self.rank, R=self.world,
+      signals=self._signals, mailboxes=self._mailboxes, epoch=self.epoch, staging=self.staging, max_ctas_limit=self.max_ctas, stream=stream)
+
+  def full_slots(self):
+    """Optimizer slots are only maintained on the owned slice: assemble the full vectors (checkpoints)."""
+    if self.world == 1 or not self.slots:
+      return self.slots
+    full = []
+    for slot in self.slots:
+      merged = slot.clone()
+      for q in range(self.world):
+        lo, hi = self.layout.slice_bounds(q, self.world)
+        piece = merged[lo:hi].contiguous() if q == self.rank else torch.empty(hi - lo, dtype=slot.dtype, device=slot.device)
+        dist.broadcast(piece, src=dist.get_global_rank(self.group, q) if self.group is not None else q, group=self.group)
+        merged[lo:hi] = piece
+      full.append(merged)
+    return full
+
+
+def make_aggregation(kind, gar, layout, nbworkers, optimizer, group=None, device="cpu", **kwargs):
+  """`kind` in {"auto", "fused", "baseline", "host"}; "auto" = fused on CUDA when the rule has a kernel, host on CPU."""
+  device = torch.device(device)
+  if kind == "auto":
+    if device.type != "cuda":
+      kind = "host"
+    elif gar.fused_spec() is not None and nbworkers <= gar_ops.MAX_WORKERS:
+      kind = "fused"
+    else:
+      kind = "baseline"
+  if kind == "fused":
+    return FusedAggregation(gar, layout, nbworkers, optimizer, group, device, **kwargs)
+  if kind == "baseline":
+    return BaselineAggregation(gar, layout, nbworkers, optimizer, group, device)
+  if kind == "host":
+    return HostAggregation(gar, layout, nbworkers, optimizer, group, device)
+  raise tools.UserException("Unknown aggregation engine " + repr(kind))
