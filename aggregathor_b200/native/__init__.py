@@ -235,6 +235,8 @@ def build_all(quiet=True, load=True, strict=False):
     for libdir in sorted(_HERE.iterdir()):
       if not (libdir.is_dir() and libdir.name[:3] in _PREFIXES):
         continue
+      if not any(_scan(libdir)[2:]):
+        continue  # nothing to compile (yet)
       try:
         so_path = _build(libdir, [], quiet)
         results[libdir.name] = so_path

@@ -12,6 +12,7 @@ import torch
 
 from .. import tools
 from ..aggregators import FusedSpec
+from . import counters
 
 MAX_WORKERS = 16
 MAX_RANKS = 16
@@ -36,6 +37,7 @@ def _stream_ptr(stream=None):
 
 
 def _check(status, what):
+  counters.bump()
   if status != 0:
     raise RuntimeError("native op " + what + " failed with status " + str(status) + (" (" + _ERRORS[status] + ")" if status in _ERRORS else " (CUDA error)"))
 

@@ -20,7 +20,6 @@ from .. import tools
 
 _CL = torch.channels_last
 _STRICT = bool(os.environ.get("AGB_NATIVE_STRICT", ""))
-launch_count = 0  # number of native kernel launches issued (bench bookkeeping)
 
 
 def _native():

@@ -1,0 +1,135 @@
+"""sm_100a aggregation kernels vs the host C++ / torch fp32 oracles (single GPU)."""
+
+import pytest
+import torch
+
+from aggregathor_b200 import aggregators
+from aggregathor_b200.aggregators import FusedSpec, _ops
+from aggregathor_b200.engine.flat import FlatLayout
+from aggregathor_b200.engine.optimizers import optimizers
+from aggregathor_b200.engine.schedules import build
+
+pytestmark = pytest.mark.gpu
+
+
+def _data(n, d, seed=0, outliers=2, nan_rows=0):
+  gen = torch.Generator().manual_seed(seed)
+  G = torch.randn(n, d, generator=gen)
+  for k in range(outliers):
+    G[n - 1 - k] = G[n - 1 - k] * 30 + 5
+  for k in range(nan_rows):
+    G[k, 7::13] = float("nan")
+  return G
+
+
+def _close(a, b, tol=2e-5):
+  a, b = a.float().cpu(), b.float().cpu()
+  same_nan = torch.isnan(a) == torch.isnan(b)
+  assert bool(same_nan.all())
+  a, b = torch.nan_to_num(a), torch.nan_to_num(b)
+  assert float((a - b).abs().max()) <= tol * max(1.0, float(b.abs().max())), float((a - b).abs().max())
+
+
+@pytest.mark.parametrize("n,d", [(8, 4096), (5, 1003), (16, 20000), (11, 333)])
+@pytest.mark.parametrize("rule", ["average", "average-nan", "median", "averaged-median"])
+def test_coordinate_rules(rule, n, d):
+  from aggregathor_b200.ops import gar as gar_ops
+  G = _data(n, d, seed=n * 7 + d, nan_rows=1 if rule in ("average-nan", "median") else 0)
+  beta = n - 2
+  spec = FusedSpec(rule, n, beta=beta)
+  out = gar_ops.aggregate(spec, G.cuda())
+  ref = {"average": _ops.host_average, "average-nan": _ops.host_average_nan, "median": _ops.host_median,
+         "averaged-median": lambda M: _ops.host_averaged_median(M, beta)}[rule](G)
+  _close(out, ref)
+
+
+@pytest.mark.parametrize("n,f,d", [(8, 2, 100000), (5, 1, 1000), (16, 3, 30001), (11, 2, 4097), (16, 6, 555)])
+def test_krum(n, f, d):
+  from aggregathor_b200.ops import gar as gar_ops
+  G = _data(n, d, seed=d, outliers=f)
+  m = n - f - 2
+  out, dist, info = gar_ops.aggregate(FusedSpec("krum", n, f=f, m=m), G.cuda(), return_details=True)
+  ref, selected = _ops.host_krum(G, f, m, return_selected=True)
+  mask = sum(1 << int(i) for i in selected)
+  assert int(info[1].item()) & 0xffff == mask, (bin(int(info[1].item())), bin(mask))
+  _close(dist, _ops.host_pairwise_distances(G), tol=1e-4)
+  _close(out, ref)
+
+
+def test_krum_nan_row_never_selected():
+  from aggregathor_b200.ops import gar as gar_ops
+  G = _data(8, 5000, seed=3, outliers=0)
+  G[2, 100] = float("nan")
+  G[5, :] = float("inf")
+  out, dist, info = gar_ops.aggregate(FusedSpec("krum", 8, f=2, m=4), G.cuda(), return_details=True)
+  mask = int(info[1].item())
+  assert not mask & (1 << 2) and not mask & (1 << 5)
+  assert bool(torch.isfinite(out).all())
+  _close(out, _ops.host_krum(G, 2, 4))
+
+
+@pytest.mark.parametrize("n,f,d", [(7, 1, 2000), (8, 1, 50000), (11, 2, 9999), (16, 3, 12345), (16, 2, 777)])
+def test_bulyan(n, f, d):
+  from aggregathor_b200.ops import gar as gar_ops
+  G = _data(n, d, seed=n + d, outliers=f)
+  m = n - f - 2
+  out, dist, info = gar_ops.aggregate(FusedSpec("bulyan", n, f=f, m=m, beta=n - 4 * f - 2), G.cuda(), return_details=True)
+  ref, weights = _ops.host_bulyan(G, f, m, return_weights=True)
+  theta = n - 2 * f - 2
+  assert int(info[0].item()) == theta
+  for k in range(theta):
+    mask = sum(1 << i for i in range(n) if float(weights[k, i]) != 0.0)
+    assert int(info[1 + k].item()) == mask, (k, bin(int(info[1 + k].item())), bin(mask))
+  _close(out, ref)
+
+
+def test_plugin_dispatch_on_cuda():
+  G = _data(8, 3000, seed=11)
+  for name, f in (("average", 0), ("median", 0), ("krum-co", 2), ("krum-tf", 2), ("krum-py", 2), ("averaged-median", 2), ("average-nan", 0)):
+    gar = aggregators.instantiate(name, 8, f, [])
+    _close(gar.aggregate(list(G.cuda())), gar.aggregate(list(G)))
+
+
+@pytest.mark.parametrize("opt,opt_args", [("sgd", []), ("adam", []), ("rmsprop", []), ("adagrad", []), ("adadelta", [])])
+def test_fused_optimizers_single_rank(opt, opt_args):
+  """Fused kernel (R = 1) with every optimizer vs HostAggregation running the same math in torch."""
+  from aggregathor_b200.parallel.aggregation import FusedAggregation, HostAggregation
+  layout = FlatLayout()
+  layout.add("w", (1000, 37))
+  layout.add("b", (37,))
+  layout.freeze()
+  spec = build(optimizers, "optimizer", opt, opt_args)
+  gar = aggregators.instantiate("krum", 8, 2, [])
+  fused = FusedAggregation(gar, layout, 8, spec, device="cuda", keep_aggregate=True)
+  host = HostAggregation(gar, layout, 8, build(optimizers, "optimizer", opt, opt_args), device="cpu")
+  gen = torch.Generator().manual_seed(5)
+  init = torch.randn(layout.padded_size, generator=gen)
+  fused.params.copy_(init)
+  host.params.copy_(init)
+  for step in range(3):
+    G = torch.randn(8, layout.padded_size, generator=gen) * 0.1
+    G[7] += 3.0
+    fused.grads.copy_(G)
+    host.grads.copy_(G)
+    fused.step(0.05)
+    host.step(0.05)
+    torch.cuda.synchronize()
+    _close(fused.last_aggregate, host.last_aggregate)
+    _close(fused.params, host.params, tol=1e-4)
+
+
+def test_drop_chunks_and_checksum():
+  from aggregathor_b200.ops import gar as gar_ops
+  g = torch.ones(200000, device="cuda")
+  gar_ops.drop_chunks_(g, 0.3, "nan", chunk_bytes=65000, seed=1)
+  lost = torch.isnan(g).float().view(-1)
+  frac = float(lost.mean())
+  assert 0.05 < frac < 0.7
+  chunk = 65000 // 4
+  first = lost[:chunk * 12].view(12, chunk)
+  assert bool(((first.mean(dim=1) == 0) | (first.mean(dim=1) == 1)).all())  # whole chunks are lost
+  a = torch.randn(10000, device="cuda")
+  assert int(gar_ops.checksum(a)) == int(gar_ops.checksum(a.clone()))
+  b = a.clone()
+  b[17] += 1e-3
+  assert int(gar_ops.checksum(a)) != int(gar_ops.checksum(b))
