@@ -126,7 +126,7 @@ class Conv2d(Module):
     n, c, h, w = x.shape
     pads = self._pads(h, w)
     weight = ctx.weights[self.name + "/weights"]
-    bias = ctx.weights[self.name + "/biases"] if self.bias else None
+    bias = ctx.master[self.name + "/biases"] if self.bias else None
     y = nn_ops.conv2d_forward(ctx.backend, x, weight, bias, self.stride, pads, self.relu)
     if ctx.training:
       self._saved_x, self._saved_y, self._saved_pads = x, (y if self.relu else None), pads
@@ -167,7 +167,7 @@ class Dense(Module):
   def forward(self, x, ctx):
     x = x.reshape(x.shape[0], -1)
     weight = ctx.weights[self.name + "/weights"]
-    bias = ctx.weights[self.name + "/biases"] if self.bias else None
+    bias = ctx.master[self.name + "/biases"] if self.bias else None
     y = nn_ops.linear_forward(ctx.backend, x, weight, bias, self.relu)
     if ctx.training:
       self._saved_x, self._saved_y = x, (y if self.relu else None)

@@ -1,0 +1,740 @@
+// Memory-bound layer kernels (sm_100a), NHWC bf16 activations, fp32 parameters/statistics:
+// batch-norm (training) forward/backward fused with ReLU, residual add + ReLU, ReLU backward, 3x3/2-style max-pool
+// forward/backward, global average pool, softmax cross-entropy forward+backward, column sums (bias gradients),
+// uint8 image normalisation, im2col / col2im for the k x k convolutions that run as GEMMs.
+//
+// Every tensor is viewed as rows x channels (rows = N*H*W); channels are the contiguous dimension, so all kernels
+// read/write 128-bit vectors along C. Per-channel reductions (BN statistics, bias gradients) accumulate per-thread
+// fp32 partials over a row strip, combine them per CTA in shared memory and finish with one fp64 atomic per channel and CTA.
+// `groups` splits the rows into equal consecutive groups with independent statistics: one group per logical worker, so that
+// several workers' batches can share one launch while keeping per-worker BatchNorm semantics.
+
+#include <cuda_bf16.h>
+
+#include <agb_device.cuh>
+
+using namespace agb;
+
+namespace {
+
+using bf16 = __nv_bfloat16;
+
+__device__ __forceinline__ void unpack8(uint4 const& raw, float (&v)[8]) {
+    __nv_bfloat162 const* h = reinterpret_cast<__nv_bfloat162 const*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 f = __bfloat1622float2(h[i]);
+        v[2 * i] = f.x;
+        v[2 * i + 1] = f.y;
+    }
+}
+__device__ __forceinline__ uint4 pack8(float const (&v)[8]) {
+    uint4 raw;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    return raw;
+}
+
+constexpr int kThreads = 256;
+
+// ---------------------------------------------------------------------------- //
+// Per-channel (and per-group) sums: out[g][c] += sum_r f(...). MODE 0: (x, x^2); MODE 1: (dy', dy' * xhat) with
+// dy' = dy masked by (y > 0) when y != null; MODE 2: (dy') only (bias gradient).
+// C % 8 == 0. Thread layout: lanes along channel octets, the rest along rows.
+template<int MODE>
+__global__ void channel_sums_kernel(bf16 const* __restrict__ a, bf16 const* __restrict__ b, bf16 const* __restrict__ y, float const* __restrict__ mean,
+                                    float const* __restrict__ rstd, double* __restrict__ out, long long rows_per_group, int C, int rows_per_cta) {
+    extern __shared__ float red[];  // [2][row lanes][octets * 8]
+    int const octets = C >> 3;
+    int const lanes_c = octets < kThreads ? octets : kThreads;
+    int const lanes_r = kThreads / lanes_c;
+    int const tc = threadIdx.x % lanes_c, tr = threadIdx.x / lanes_c;
+    int const group = blockIdx.y;
+    long long const row_begin = static_cast<long long>(blockIdx.x) * rows_per_cta;
+    long long const row_end = min(rows_per_group, row_begin + rows_per_cta);
+    long long const base = static_cast<long long>(group) * rows_per_group;
+    for (int ob = 0; ob < octets; ob += lanes_c) {   // uniform trip count: the loop body contains barriers
+        int const o = ob + tc;
+        bool const active = o < octets && tr < lanes_r;
+        float s0[8], s1[8], mu[8], rs[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            s0[j] = 0.f;
+            s1[j] = 0.f;
+            mu[j] = 0.f;
+            rs[j] = 0.f;
+            if (MODE == 1 && active) {
+                mu[j] = mean[group * C + o * 8 + j];
+                rs[j] = rstd[group * C + o * 8 + j];
+            }
+        }
+        if (active) {
+            for (long long r = row_begin + tr; r < row_end; r += lanes_r) {
+                long long const idx = (base + r) * C + o * 8;
+                float va[8];
+                unpack8(*reinterpret_cast<uint4 const*>(a + idx), va);
+                if (MODE == 0) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        s0[j] += va[j];
+                        s1[j] += va[j] * va[j];
+                    }
+                } else {
+                    if (y) {
+                        float vy[8];
+                        unpack8(*reinterpret_cast<uint4 const*>(y + idx), vy);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            va[j] = vy[j] > 0.f ? va[j] : 0.f;
+                    }
+                    if (MODE == 1) {
+                        float vx[8];
+                        unpack8(*reinterpret_cast<uint4 const*>(b + idx), vx);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            s0[j] += va[j];
+                            s1[j] += va[j] * (vx[j] - mu[j]) * rs[j];
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            s0[j] += va[j];
+                    }
+                }
+            }
+        }
+        // combine the row lanes of this octet
+        float* r0 = red + threadIdx.x * 16;   // == (tr * lanes_c + tc) * 16 for the active threads
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            r0[j] = s0[j];
+            r0[8 + j] = s1[j];
+        }
+        __syncthreads();
+        if (tr == 0 && o < octets) {
+            for (int l = 1; l < lanes_r; ++l) {
+                float const* rl = red + (l * lanes_c + tc) * 16;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    s0[j] += rl[j];
+                    s1[j] += rl[8 + j];
+                }
+            }
+            double* dst = out + (static_cast<long long>(group) * C + o * 8) * 2;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                atomicAdd(dst + 2 * j, static_cast<double>(s0[j]));
+                if (MODE != 2)
+                    atomicAdd(dst + 2 * j + 1, static_cast<double>(s1[j]));
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// BN statistics finalisation: mean / rstd, affine coefficients, moving statistics (first group updates them).
+__global__ void bn_finalize_kernel(double const* __restrict__ sums, float const* __restrict__ gamma, float const* __restrict__ beta, float* __restrict__ save_mean,
+                                   float* __restrict__ save_rstd, float* __restrict__ scale, float* __restrict__ shift, float* moving_mean, float* moving_var,
+                                   int C, int groups, long long rows_per_group, float eps, float decay) {
+    int const i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= C * groups)
+        return;
+    int const c = i % C, g = i / C;
+    double const n = static_cast<double>(rows_per_group);
+    double const mean = sums[2 * i] / n;
+    double var = sums[2 * i + 1] / n - mean * mean;
+    if (var < 0.)
+        var = 0.;
+    float const rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    float const gm = gamma ? gamma[c] : 1.f;
+    save_mean[i] = static_cast<float>(mean);
+    save_rstd[i] = rstd;
+    scale[i] = gm * rstd;
+    shift[i] = beta[c] - static_cast<float>(mean) * gm * rstd;
+    if (moving_mean && g == 0) { // unbiased variance in the moving average, as TF's fused batch norm
+        double const unbiased = n > 1. ? var * n / (n - 1.) : var;
+        moving_mean[c] = decay * moving_mean[c] + (1.f - decay) * static_cast<float>(mean);
+        moving_var[c] = decay * moving_var[c] + (1.f - decay) * static_cast<float>(unbiased);
+    }
+}
+
+// y = relu?(x * scale[g][c] + shift[g][c])
+__global__ void bn_apply_kernel(bf16 const* __restrict__ x, bf16* __restrict__ y, float const* __restrict__ scale, float const* __restrict__ shift,
+                                long long total_octets, int C, long long rows_per_group, int relu) {
+    int const octets = C >> 3;
+    long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    long long const stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (; i < total_octets; i += stride) {
+        long long const row = i / octets;
+        int const o = static_cast<int>(i - row * octets);
+        int const g = static_cast<int>(row / rows_per_group);
+        float v[8];
+        unpack8(*reinterpret_cast<uint4 const*>(x + i * 8), v);
+        float const* sc = scale + g * C + o * 8;
+        float const* sh = shift + g * C + o * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            v[j] = v[j] * sc[j] + sh[j];
+            if (relu)
+                v[j] = fmaxf(v[j], 0.f);
+        }
+        *reinterpret_cast<uint4*>(y + i * 8) = pack8(v);
+    }
+}
+
+// BN backward coefficients per (group, channel): dx = a * dy' + b * x + c0 ; dgamma/dbeta summed over groups.
+__global__ void bn_bwd_finalize_kernel(double const* __restrict__ sums, float const* __restrict__ gamma, float const* __restrict__ mean, float const* __restrict__ rstd,
+                                       float* __restrict__ coef, float* __restrict__ dgamma, float* __restrict__ dbeta, int C, int groups, long long rows_per_group) {
+    int const c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C)
+        return;
+    double total_dbeta = 0., total_dgamma = 0.;
+    for (int g = 0; g < groups; ++g) {
+        int const i = g * C + c;
+        double const sum_dy = sums[2 * i], sum_dy_xhat = sums[2 * i + 1];
+        total_dbeta += sum_dy;
+        total_dgamma += sum_dy_xhat;
+        float const gm = gamma ? gamma[c] : 1.f;
+        float const rs = rstd[i], mu = mean[i];
+        float const inv_n = 1.f / static_cast<float>(rows_per_group);
+        // dx = gm*rs * (dy - sum_dy/n - xhat * sum_dy_xhat/n), xhat = (x - mu) * rs
+        float const a = gm * rs;
+        float const b = -gm * rs * rs * rs * static_cast<float>(sum_dy_xhat) * inv_n;
+        float const c0 = -gm * rs * static_cast<float>(sum_dy) * inv_n - b * mu;
+        coef[3 * i] = a;
+        coef[3 * i + 1] = b;
+        coef[3 * i + 2] = c0;
+    }
+    if (dgamma)
+        dgamma[c] = static_cast<float>(total_dgamma);
+    dbeta[c] = static_cast<float>(total_dbeta);
+}
+
+__global__ void bn_bwd_apply_kernel(bf16 const* __restrict__ dy, bf16 const* __restrict__ x, bf16 const* __restrict__ y, bf16* __restrict__ dx, float const* __restrict__ coef,
+                                    long long total_octets, int C, long long rows_per_group) {
+    int const octets = C >> 3;
+    long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    long long const stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (; i < total_octets; i += stride) {
+        long long const row = i / octets;
+        int const o = static_cast<int>(i - row * octets);
+        int const g = static_cast<int>(row / rows_per_group);
+        float vd[8], vx[8];
+        unpack8(*reinterpret_cast<uint4 const*>(dy + i * 8), vd);
+        unpack8(*reinterpret_cast<uint4 const*>(x + i * 8), vx);
+        if (y) {
+            float vy[8];
+            unpack8(*reinterpret_cast<uint4 const*>(y + i * 8), vy);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                vd[j] = vy[j] > 0.f ? vd[j] : 0.f;
+        }
+        float const* cf = coef + (static_cast<long long>(g) * C + o * 8) * 3;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            vd[j] = cf[3 * j] * vd[j] + cf[3 * j + 1] * vx[j] + cf[3 * j + 2];
+        *reinterpret_cast<uint4*>(dx + i * 8) = pack8(vd);
+    }
+}
+
+// out = relu?(a + b) ; b may be null (plain ReLU)
+__global__ void add_relu_kernel(bf16 const* __restrict__ a, bf16 const* __restrict__ b, bf16* __restrict__ out, long long octets, int relu) {
+    long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    long long const stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (; i < octets; i += stride) {
+        float va[8];
+        unpack8(*reinterpret_cast<uint4 const*>(a + i * 8), va);
+        if (b) {
+            float vb[8];
+            unpack8(*reinterpret_cast<uint4 const*>(b + i * 8), vb);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                va[j] += vb[j];
+        }
+        if (relu) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                va[j] = fmaxf(va[j], 0.f);
+        }
+        *reinterpret_cast<uint4*>(out + i * 8) = pack8(va);
+    }
+}
+
+// dx = dy * (y > 0)
+__global__ void relu_bwd_kernel(bf16 const* __restrict__ dy, bf16 const* __restrict__ y, bf16* __restrict__ dx, long long octets) {
+    long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    long long const stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (; i < octets; i += stride) {
+        float vd[8], vy[8];
+        unpack8(*reinterpret_cast<uint4 const*>(dy + i * 8), vd);
+        unpack8(*reinterpret_cast<uint4 const*>(y + i * 8), vy);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            vd[j] = vy[j] > 0.f ? vd[j] : 0.f;
+        *reinterpret_cast<uint4*>(dx + i * 8) = pack8(vd);
+    }
+}
+
+// ---------------------------------------------------------------------------- //
+// Max pooling (k x k, stride s, explicit pads, -inf padding), NHWC. Forward also records the argmax (window-relative index).
+__global__ void maxpool_fwd_kernel(bf16 const* __restrict__ x, bf16* __restrict__ y, unsigned char* __restrict__ arg, int N, int H, int W, int C, int OH, int OW,
+                                   int k, int s, int pad_t, int pad_l) {
+    int const octets = C >> 3;
+    long long const total = static_cast<long long>(N) * OH * OW * octets;
+    long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    long long const stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (; i < total; i += stride) {
+        int const o = static_cast<int>(i % octets);
+        long long rest = i / octets;
+        int const ow = static_cast<int>(rest % OW);
+        rest /= OW;
+        int const oh = static_cast<int>(rest % OH);
+        int const n = static_cast<int>(rest / OH);
+        float best[8];
+        unsigned char where[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            best[j] = -INFINITY;
+            where[j] = 0;
+        }
+        for (int kh = 0; kh < k; ++kh) {
+            int const h = oh * s - pad_t + kh;
+            if (h < 0 || h >= H)
+                continue;
+            for (int kw = 0; kw < k; ++kw) {
+                int const w = ow * s - pad_l + kw;
+                if (w < 0 || w >= W)
+                    continue;
+                float v[8];
+                unpack8(*reinterpret_cast<uint4 const*>(x + ((static_cast<long long>(n) * H + h) * W + w) * C + o * 8), v);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (v[j] > best[j]) {
+                        best[j] = v[j];
+                        where[j] = static_cast<unsigned char>(kh * k + kw);
+                    }
+            }
+        }
+        *reinterpret_cast<uint4*>(y + i * 8) = pack8(best);
+        uint2 packed;
+        unsigned char* pw = reinterpret_cast<unsigned char*>(&packed);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            pw[j] = where[j];
+        *reinterpret_cast<uint2*>(arg + i * 8) = packed;
+    }
+}
+
+// Gather form: every input element sums the gradients of the windows whose argmax it is (no atomics).
+__global__ void maxpool_bwd_kernel(bf16 const* __restrict__ dy, unsigned char const* __restrict__ arg, bf16* __restrict__ dx, int N, int H, int W, int C, int OH, int OW,
+                                   int k, int s, int pad_t, int pad_l) {
+    int const octets = C >> 3;
+    long long const total = static_cast<long long>(N) * H * W * octets;
+    long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    long long const stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (; i < total; i += stride) {
+        int const o = static_cast<int>(i % octets);
+        long long rest = i / octets;
+        int const w = static_cast<int>(rest % W);
+        rest /= W;
+        int const h = static_cast<int>(rest % H);
+        int const n = static_cast<int>(rest / H);
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            acc[j] = 0.f;
+        for (int kh = 0; kh < k; ++kh) {
+            int const th = h + pad_t - kh;
+            if (th < 0 || th % s)
+                continue;
+            int const oh = th / s;
+            if (oh >= OH)
+                continue;
+            for (int kw = 0; kw < k; ++kw) {
+                int const tw = w + pad_l - kw;
+                if (tw < 0 || tw % s)
+                    continue;
+                int const ow = tw / s;
+                if (ow >= OW)
+                    continue;
+                long long const oidx = (((static_cast<long long>(n) * OH + oh) * OW + ow) * octets + o) * 8;
+                float v[8];
+                unpack8(*reinterpret_cast<uint4 const*>(dy + oidx), v);
+                uint2 const packed = *reinterpret_cast<uint2 const*>(arg + oidx);
+                unsigned char const* pw = reinterpret_cast<unsigned char const*>(&packed);
+                unsigned char const me = static_cast<unsigned char>(kh * k + kw);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (pw[j] == me)
+                        acc[j] += v[j];
+            }
+        }
+        *reinterpret_cast<uint4*>(dx + i * 8) = pack8(acc);
+    }
+}
+
+// Global average pool: x [N, HW, C] -> y [N, C]; backward broadcasts dy / HW.
+__global__ void avgpool_fwd_kernel(bf16 const* __restrict__ x, bf16* __restrict__ y, int N, int HW, int C) {
+    int const octets = C >> 3;
+    int const i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * octets)
+        return;
+    int const n = i / octets, o = i % octets;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        acc[j] = 0.f;
+    for (int p = 0; p < HW; ++p) {
+        float v[8];
+        unpack8(*reinterpret_cast<uint4 const*>(x + (static_cast<long long>(n) * HW + p) * C + o * 8), v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            acc[j] += v[j];
+    }
+    float const inv = 1.f / static_cast<float>(HW);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        acc[j] *= inv;
+    *reinterpret_cast<uint4*>(y + static_cast<long long>(i) * 8) = pack8(acc);
+}
+
+__global__ void avgpool_bwd_kernel(bf16 const* __restrict__ dy, bf16* __restrict__ dx, int N, int HW, int C) {
+    int const octets = C >> 3;
+    long long const total = static_cast<long long>(N) * HW * octets;
+    long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    long long const stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    float const inv = 1.f / static_cast<float>(HW);
+    for (; i < total; i += stride) {
+        int const o = static_cast<int>(i % octets);
+        int const n = static_cast<int>(i / (static_cast<long long>(HW) * octets));
+        float v[8];
+        unpack8(*reinterpret_cast<uint4 const*>(dy + (static_cast<long long>(n) * octets + o) * 8), v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            v[j] *= inv;
+        *reinterpret_cast<uint4*>(dx + i * 8) = pack8(v);
+    }
+}
+
+// ---------------------------------------------------------------------------- //
+// Softmax cross-entropy, one warp per row. logits bf16 [B, ld] (K valid columns), labels int64.
+// loss += mean_b(-sum_k t_k log p_k) ; dlogits = (p - t) / B  (bf16, same leading dimension).
+__global__ void softmax_xent_kernel(bf16 const* __restrict__ logits, long long const* __restrict__ labels, bf16* __restrict__ dlogits, float* __restrict__ loss,
+                                    int B, int K, long long ld, float smoothing) {
+    int const warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= B)
+        return;
+    bf16 const* row = logits + static_cast<long long>(warp) * ld;
+    float mx = -INFINITY;
+    for (int k = lane; k < K; k += 32)
+        mx = fmaxf(mx, __bfloat162float(row[k]));
+    for (int off = 16; off > 0; off >>= 1)
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    float sum = 0.f;
+    for (int k = lane; k < K; k += 32)
+        sum += __expf(__bfloat162float(row[k]) - mx);
+    sum = warp_sum(sum);
+    float const lse = mx + __logf(sum);
+    int const label = static_cast<int>(labels[warp]);
+    float const off_t = smoothing / static_cast<float>(K), on_t = 1.f - smoothing + off_t;
+    float const inv_b = 1.f / static_cast<float>(B);
+    float local = 0.f;
+    bf16* drow = dlogits + static_cast<long long>(warp) * ld;
+    for (int k = lane; k < K; k += 32) {
+        float const z = __bfloat162float(row[k]);
+        float const logp = z - lse;
+        float const t = k == label ? on_t : off_t;
+        local -= t * logp;
+        drow[k] = __float2bfloat16((__expf(logp) - t) * inv_b);
+    }
+    local = warp_sum(local);
+    if (lane == 0)
+        atomicAdd(loss, local * inv_b);
+}
+
+// uint8 NHWC image -> bf16 NHWC activations with C padded to `Cpad`: y = (x - mean[c]) * scale
+__global__ void image_normalize_kernel(unsigned char const* __restrict__ x, bf16* __restrict__ y, long long pixels, int C, int Cpad, float m0, float m1, float m2, float scale) {
+    long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    long long const stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (; i < pixels; i += stride) {
+        for (int c = 0; c < Cpad; ++c) {
+            float v = 0.f;
+            if (c < C) {
+                float const m = c == 0 ? m0 : c == 1 ? m1 : m2;
+                v = (static_cast<float>(x[i * C + c]) - m) * scale;
+            }
+            y[i * Cpad + c] = __float2bfloat16(v);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------- //
+// im2col: x NHWC [N,H,W,C] -> col [N*OH*OW, ldcol] with column order (kh, kw, c); zero padding, zero tail columns.
+// One thread per (output pixel, kh, kw, channel octet) when C % 8 == 0, scalar path otherwise (the 3-channel stem).
+__global__ void im2col_kernel(bf16 const* __restrict__ x, bf16* __restrict__ col, int N, int H, int W, int C, int OH, int OW, int k, int s, int pad_t, int pad_l, long long ldcol) {
+    if ((C & 7) == 0) {
+        int const octets = C >> 3;
+        long long const total = static_cast<long long>(N) * OH * OW * k * k * octets;
+        long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+        long long const stride = static_cast<long long>(gridDim.x) * blockDim.x;
+        for (; i < total; i += stride) {
+            int const o = static_cast<int>(i % octets);
+            long long rest = i / octets;
+            int const kw = static_cast<int>(rest % k);
+            rest /= k;
+            int const kh = static_cast<int>(rest % k);
+            rest /= k;
+            long long const pixel = rest;
+            int const ow = static_cast<int>(rest % OW);
+            rest /= OW;
+            int const oh = static_cast<int>(rest % OH);
+            int const n = static_cast<int>(rest / OH);
+            int const h = oh * s - pad_t + kh, w = ow * s - pad_l + kw;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (h >= 0 && h < H && w >= 0 && w < W)
+                v = *reinterpret_cast<uint4 const*>(x + ((static_cast<long long>(n) * H + h) * W + w) * C + o * 8);
+            *reinterpret_cast<uint4*>(col + pixel * ldcol + (kh * k + kw) * C + o * 8) = v;
+        }
+    } else {
+        long long const total = static_cast<long long>(N) * OH * OW * ldcol;
+        long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+        long long const stride = static_cast<long long>(gridDim.x) * blockDim.x;
+        int const kcol = k * k * C;
+        for (; i < total; i += stride) {
+            int const j = static_cast<int>(i % ldcol);
+            long long rest = i / ldcol;
+            int const ow = static_cast<int>(rest % OW);
+            rest /= OW;
+            int const oh = static_cast<int>(rest % OH);
+            int const n = static_cast<int>(rest / OH);
+            bf16 v = __float2bfloat16(0.f);
+            if (j < kcol) {
+                int const c = j % C, kw = (j / C) % k, kh = j / (C * k);
+                int const h = oh * s - pad_t + kh, w = ow * s - pad_l + kw;
+                if (h >= 0 && h < H && w >= 0 && w < W)
+                    v = x[((static_cast<long long>(n) * H + h) * W + w) * C + c];
+            }
+            col[i] = v;
+        }
+    }
+}
+
+// col2im (gather form): dx[n,h,w,c] = sum over (kh,kw) of dcol[n, oh, ow, (kh,kw,c)] for the windows covering (h,w). C % 8 == 0.
+__global__ void col2im_kernel(bf16 const* __restrict__ dcol, bf16* __restrict__ dx, int N, int H, int W, int C, int OH, int OW, int k, int s, int pad_t, int pad_l, long long ldcol) {
+    int const octets = C >> 3;
+    long long const total = static_cast<long long>(N) * H * W * octets;
+    long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    long long const stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (; i < total; i += stride) {
+        int const o = static_cast<int>(i % octets);
+        long long rest = i / octets;
+        int const w = static_cast<int>(rest % W);
+        rest /= W;
+        int const h = static_cast<int>(rest % H);
+        int const n = static_cast<int>(rest / H);
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            acc[j] = 0.f;
+        for (int kh = 0; kh < k; ++kh) {
+            int const th = h + pad_t - kh;
+            if (th < 0 || th % s)
+                continue;
+            int const oh = th / s;
+            if (oh >= OH)
+                continue;
+            for (int kw = 0; kw < k; ++kw) {
+                int const tw = w + pad_l - kw;
+                if (tw < 0 || tw % s)
+                    continue;
+                int const ow = tw / s;
+                if (ow >= OW)
+                    continue;
+                float v[8];
+                unpack8(*reinterpret_cast<uint4 const*>(dcol + ((static_cast<long long>(n) * OH + oh) * OW + ow) * ldcol + (kh * k + kw) * C + o * 8), v);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    acc[j] += v[j];
+            }
+        }
+        *reinterpret_cast<uint4*>(dx + i * 8) = pack8(acc);
+    }
+}
+
+__global__ void cast_sums_kernel(double const* __restrict__ sums, float* __restrict__ out, int C) {
+    int const c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < C)
+        out[c] = static_cast<float>(sums[2 * c]);
+}
+
+inline int grid_for(long long work, int threads = kThreads, int cap = 148 * 8) {
+    long long blocks = (work + threads - 1) / threads;
+    if (blocks > cap)
+        blocks = cap;
+    return blocks < 1 ? 1 : static_cast<int>(blocks);
+}
+
+struct SumsPlan {
+    int rows_per_cta, ctas;
+    size_t smem;
+};
+inline SumsPlan plan_sums(long long rows_per_group, int C, int groups) {
+    int const octets = C >> 3;
+    int const lanes_c = octets < kThreads ? octets : kThreads;
+    int const lanes_r = kThreads / lanes_c;
+    long long target_ctas = (148 * 4 + groups - 1) / groups;
+    long long rows_per_cta = (rows_per_group + target_ctas - 1) / target_ctas;
+    if (rows_per_cta < lanes_r * 4)
+        rows_per_cta = lanes_r * 4;
+    SumsPlan plan;
+    plan.rows_per_cta = static_cast<int>(rows_per_cta);
+    plan.ctas = static_cast<int>((rows_per_group + rows_per_cta - 1) / rows_per_cta);
+    plan.smem = static_cast<size_t>(kThreads) * 16 * sizeof(float);
+    return plan;
+}
+
+} // namespace
+
+extern "C" {
+
+// Workspace layout for BN (caller provides, zeroed `sums` not required: it is cleared here):
+//   sums  double [groups*C*2] | save_mean, save_rstd, scale, shift float [groups*C] each (forward)
+//   sums  double [groups*C*2] | coef float [groups*C*3]                              (backward)
+int agb_bn_forward(void const* x, void* y, void const* gamma, void const* beta, void* moving_mean, void* moving_var, void* save_mean, void* save_rstd,
+                   void* sums, void* scale, void* shift, long long rows, int C, int groups, float eps, float decay, int relu, void* stream) {
+    if ((C & 7) || groups < 1 || rows % groups)
+        return 301;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    long long const rpg = rows / groups;
+    AGB_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C * groups, s));
+    SumsPlan plan = plan_sums(rpg, C, groups);
+    channel_sums_kernel<0><<<dim3(plan.ctas, groups), kThreads, plan.smem, s>>>(static_cast<bf16 const*>(x), nullptr, nullptr, nullptr, nullptr, static_cast<double*>(sums), rpg, C, plan.rows_per_cta);
+    bn_finalize_kernel<<<(C * groups + 127) / 128, 128, 0, s>>>(static_cast<double const*>(sums), static_cast<float const*>(gamma), static_cast<float const*>(beta),
+        static_cast<float*>(save_mean), static_cast<float*>(save_rstd), static_cast<float*>(scale), static_cast<float*>(shift), static_cast<float*>(moving_mean),
+        static_cast<float*>(moving_var), C, groups, rpg, eps, decay);
+    long long const octets = rows * (C >> 3);
+    bn_apply_kernel<<<grid_for(octets), kThreads, 0, s>>>(static_cast<bf16 const*>(x), static_cast<bf16*>(y), static_cast<float const*>(scale), static_cast<float const*>(shift), octets, C, rpg, relu);
+    AGB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int agb_bn_backward(void const* dy, void const* x, void const* y, void const* gamma, void const* save_mean, void const* save_rstd, void* dx, void* dgamma, void* dbeta,
+                    void* sums, void* coef, long long rows, int C, int groups, void* stream) {
+    if ((C & 7) || groups < 1 || rows % groups)
+        return 301;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    long long const rpg = rows / groups;
+    AGB_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C * groups, s));
+    SumsPlan plan = plan_sums(rpg, C, groups);
+    channel_sums_kernel<1><<<dim3(plan.ctas, groups), kThreads, plan.smem, s>>>(static_cast<bf16 const*>(dy), static_cast<bf16 const*>(x), static_cast<bf16 const*>(y),
+        static_cast<float const*>(save_mean), static_cast<float const*>(save_rstd), static_cast<double*>(sums), rpg, C, plan.rows_per_cta);
+    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(static_cast<double const*>(sums), static_cast<float const*>(gamma), static_cast<float const*>(save_mean),
+        static_cast<float const*>(save_rstd), static_cast<float*>(coef), static_cast<float*>(dgamma), static_cast<float*>(dbeta), C, groups, rpg);
+    long long const octets = rows * (C >> 3);
+    bn_bwd_apply_kernel<<<grid_for(octets), kThreads, 0, s>>>(static_cast<bf16 const*>(dy), static_cast<bf16 const*>(x), static_cast<bf16 const*>(y), static_cast<bf16*>(dx),
+        static_cast<float const*>(coef), octets, C, rpg);
+    AGB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// out[c] = sum over rows of dy[r][c] (masked by y > 0 when y != null); `sums` is a double [2*C] workspace.
+int agb_colsum(void const* dy, void const* y, void* out, void* sums, long long rows, int C, void* stream) {
+    if (C & 7)
+        return 301;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    AGB_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, s));
+    SumsPlan plan = plan_sums(rows, C, 1);
+    channel_sums_kernel<2><<<dim3(plan.ctas, 1), kThreads, plan.smem, s>>>(static_cast<bf16 const*>(dy), nullptr, static_cast<bf16 const*>(y), nullptr, nullptr, static_cast<double*>(sums), rows, C, plan.rows_per_cta);
+    cast_sums_kernel<<<(C + 127) / 128, 128, 0, s>>>(static_cast<double const*>(sums), static_cast<float*>(out), C);
+    AGB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int agb_add_relu(void const* a, void const* b, void* out, long long n, int relu, void* stream) {
+    if (n & 7)
+        return 301;
+    add_relu_kernel<<<grid_for(n / 8), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<bf16 const*>(a), static_cast<bf16 const*>(b), static_cast<bf16*>(out), n / 8, relu);
+    AGB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int agb_relu_backward(void const* dy, void const* y, void* dx, long long n, void* stream) {
+    if (n & 7)
+        return 301;
+    relu_bwd_kernel<<<grid_for(n / 8), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<bf16 const*>(dy), static_cast<bf16 const*>(y), static_cast<bf16*>(dx), n / 8);
+    AGB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int agb_maxpool_forward(void const* x, void* y, void* arg, int N, int H, int W, int C, int OH, int OW, int k, int s, int pad_t, int pad_l, void* stream) {
+    if ((C & 7) || k * k > 255)
+        return 301;
+    long long const work = static_cast<long long>(N) * OH * OW * (C >> 3);
+    maxpool_fwd_kernel<<<grid_for(work), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<bf16 const*>(x), static_cast<bf16*>(y), static_cast<unsigned char*>(arg), N, H, W, C, OH, OW, k, s, pad_t, pad_l);
+    AGB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int agb_maxpool_backward(void const* dy, void const* arg, void* dx, int N, int H, int W, int C, int OH, int OW, int k, int s, int pad_t, int pad_l, void* stream) {
+    if (C & 7)
+        return 301;
+    long long const work = static_cast<long long>(N) * H * W * (C >> 3);
+    maxpool_bwd_kernel<<<grid_for(work), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<bf16 const*>(dy), static_cast<unsigned char const*>(arg), static_cast<bf16*>(dx), N, H, W, C, OH, OW, k, s, pad_t, pad_l);
+    AGB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int agb_avgpool_forward(void const* x, void* y, int N, int HW, int C, void* stream) {
+    if (C & 7)
+        return 301;
+    avgpool_fwd_kernel<<<(N * (C >> 3) + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<bf16 const*>(x), static_cast<bf16*>(y), N, HW, C);
+    AGB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int agb_avgpool_backward(void const* dy, void* dx, int N, int HW, int C, void* stream) {
+    if (C & 7)
+        return 301;
+    long long const work = static_cast<long long>(N) * HW * (C >> 3);
+    avgpool_bwd_kernel<<<grid_for(work), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<bf16 const*>(dy), static_cast<bf16*>(dx), N, HW, C);
+    AGB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int agb_softmax_xent(void const* logits, void const* labels, void* dlogits, void* loss, int B, int K, long long ld, float smoothing, void* stream) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    AGB_CUDA_OK(cudaMemsetAsync(loss, 0, sizeof(float), s));
+    int const warps_per_cta = 4;
+    softmax_xent_kernel<<<(B + warps_per_cta - 1) / warps_per_cta, warps_per_cta * 32, 0, s>>>(static_cast<bf16 const*>(logits), static_cast<long long const*>(labels),
+        static_cast<bf16*>(dlogits), static_cast<float*>(loss), B, K, ld, smoothing);
+    AGB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int agb_image_normalize(void const* x, void* y, long long pixels, int C, int Cpad, float m0, float m1, float m2, float scale, void* stream) {
+    image_normalize_kernel<<<grid_for(pixels), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<unsigned char const*>(x), static_cast<bf16*>(y), pixels, C, Cpad, m0, m1, m2, scale);
+    AGB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int agb_im2col(void const* x, void* col, int N, int H, int W, int C, int OH, int OW, int k, int s, int pad_t, int pad_l, long long ldcol, void* stream) {
+    if (ldcol & 7)
+        return 301;
+    long long const work = (C & 7) == 0 ? static_cast<long long>(N) * OH * OW * k * k * (C >> 3) : static_cast<long long>(N) * OH * OW * ldcol;
+    im2col_kernel<<<grid_for(work, kThreads, 148 * 16), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<bf16 const*>(x), static_cast<bf16*>(col), N, H, W, C, OH, OW, k, s, pad_t, pad_l, ldcol);
+    AGB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int agb_col2im(void const* dcol, void* dx, int N, int H, int W, int C, int OH, int OW, int k, int s, int pad_t, int pad_l, long long ldcol, void* stream) {
+    if ((C & 7) || (ldcol & 7))
+        return 301;
+    long long const work = static_cast<long long>(N) * H * W * (C >> 3);
+    col2im_kernel<<<grid_for(work, kThreads, 148 * 16), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<bf16 const*>(dcol), static_cast<bf16*>(dx), N, H, W, C, OH, OW, k, s, pad_t, pad_l, ldcol);
+    AGB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+} // extern "C"

@@ -178,10 +178,11 @@ def add_forward(backend, a, b):
 
 
 def maxpool_forward(backend, x, k, stride, pads):
+  """Returns (y, index): `index` is the torch int64 argmax (library provider) or a uint8 window-relative argmax (native)."""
   if backend == "native" and x.is_cuda:
     out = _native().maxpool_forward(x, k, stride, pads)
     if out is not None:
-      return out, None
+      return out
     _fallback("maxpool_forward")
   t, b, l, r = pads
   xp = F.pad(x, (l, r, t, b), value=float("-inf")) if any(pads) else x
@@ -190,8 +191,8 @@ def maxpool_forward(backend, x, k, stride, pads):
 
 
 def maxpool_backward(backend, dy, shape, index, k, stride, pads, x, y):
-  if backend == "native" and dy.is_cuda and index is None:
-    return _native().maxpool_backward(dy, x, y, k, stride, pads)
+  if index.dtype == torch.uint8:
+    return _native().maxpool_backward(dy, shape, index, k, stride, pads)
   t, b, l, r = pads
   n, c, h, w = shape
   xp_shape = (n, c, h + t + b, w + l + r)

@@ -1,59 +1,410 @@
-"""sm_100a providers of the nn ops (`native/op_nn`). Every function returns None (or NotImplemented for
-backward ops that return None legitimately) when it does not handle the given arguments, in which case
-`ops/nn.py` decides between falling back and failing (AGB_NATIVE_STRICT)."""
+"""sm_100a providers of the nn ops (`native/op_nn`).
+
+Every function returns None (forward ops) or NotImplemented (backward ops whose legitimate result may be None) when it
+does not handle the given arguments; `ops/nn.py` then either falls back to the torch provider or raises
+(`AGB_NATIVE_STRICT=1`). GEMM-shaped work goes through `agb_gemm_bf16` (tcgen05 + TMEM + TMA, `native/op_nn/gemm.cu`):
+
+    mm_nt(x[M,K], w[N,K])  = x @ w.T      forward of dense / 1x1 conv         (A K-major,  B K-major)
+    mm_nn(x[M,K], w[K,N])  = x @ w        data gradient                       (A K-major,  B MN-major)
+    mm_tn(x[K,M], y[K,N])  = x.T @ y      weight gradient, split-K + fp32 red (A MN-major, B MN-major)
+"""
+
+import ctypes
+import os
+
+import torch
+
+from . import counters
+
+_lib_cache = None
+_DISABLED = set(filter(None, os.environ.get("AGB_NATIVE_DISABLE", "").split(",")))
+SM_COUNT = 148
+
+
+def _lib():
+  global _lib_cache
+  if _lib_cache is None:
+    from .. import native
+    _lib_cache = native.library("op_nn")
+  return _lib_cache
+
+
+def _stream():
+  return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+  return ctypes.c_void_p(t.data_ptr() if t is not None else 0)
+
+
+def _check(status, what):
+  counters.bump()
+  if status != 0:
+    raise RuntimeError("native op " + what + " failed with status " + str(status))
+
+
+def enabled(op):
+  return op not in _DISABLED and "all" not in _DISABLED
+
+
+# ---------------------------------------------------------------------------- #
+# GEMM
+
+def _rows(t):
+  """2-D bf16 operand with unit inner stride, row stride % 8 == 0 and a 16-byte aligned base (copy if needed)."""
+  if t.dtype != torch.bfloat16:
+    t = t.to(torch.bfloat16)
+  if t.dim() != 2:
+    t = t.reshape(t.shape[0], -1)
+  if t.stride(1) == 1 and t.stride(0) % 8 == 0 and t.stride(0) >= t.shape[1] and t.data_ptr() % 16 == 0:
+    return t
+  rows, cols = t.shape
+  ld = (cols + 7) // 8 * 8
+  buf = torch.zeros((rows, ld), dtype=torch.bfloat16, device=t.device)
+  buf[:, :cols] = t
+  return buf[:, :cols]
+
+
+def alloc_out(m, n, dtype, device):
+  """[m, n] view of a buffer whose row stride is a multiple of 8 elements (so it can feed the next GEMM through TMA)."""
+  ld = (n + 7) // 8 * 8
+  return torch.empty((m, ld), dtype=dtype, device=device)[:, :n]
+
+
+def _gemm(a, b, out, M, N, K, a_mn, b_mn, bias, relu, splits, bn):
+  func = _lib().agb_gemm_bf16
+  out_fp32 = 1 if out.dtype == torch.float32 else 0
+  if out.stride(1) != 1:
+    raise RuntimeError("GEMM output must have unit inner stride")
+  status = func(_ptr(a), _ptr(b), _ptr(out), ctypes.c_int(M), ctypes.c_int(N), ctypes.c_int(K), ctypes.c_longlong(a.stride(0)), ctypes.c_longlong(b.stride(0)),
+                ctypes.c_longlong(out.stride(0)), ctypes.c_int(1 if a_mn else 0), ctypes.c_int(1 if b_mn else 0), _ptr(bias), ctypes.c_int(1 if relu else 0),
+                ctypes.c_int(out_fp32), ctypes.c_int(splits), ctypes.c_int(bn), _stream())
+  _check(status, "gemm_bf16")
+  return out
+
+
+def mm_nt(x, w, bias=None, relu=False, out=None, out_dtype=torch.bfloat16, bn=0):
+  """x[M,K] @ w[N,K]^T (+ fp32 bias[N], ReLU)."""
+  x, w = _rows(x), _rows(w)
+  M, K = x.shape
+  N = w.shape[0]
+  if out is None:
+    out = alloc_out(M, N, out_dtype, x.device)
+  if bias is not None and bias.dtype != torch.float32:
+    bias = bias.float()
+  return _gemm(x, w, out, M, N, K, False, False, bias, relu, 1, bn)
+
+
+def mm_nn(x, w, out=None, out_dtype=torch.bfloat16, bn=0):
+  """x[M,K] @ w[K,N]."""
+  x, w = _rows(x), _rows(w)
+  M, K = x.shape
+  N = w.shape[1]
+  if out is None:
+    out = alloc_out(M, N, out_dtype, x.device)
+  return _gemm(x, w, out, M, N, K, False, True, None, False, 1, bn)
+
+
+def pick_splits(m_out, n_out, k, bn=128):
+  tiles = ((m_out + 127) // 128) * ((n_out + bn - 1) // bn)
+  kblocks = (k + 63) // 64
+  want = max(1, (2 * SM_COUNT + tiles - 1) // tiles)
+  return max(1, min(kblocks, want, 128))
+
+
+def mm_tn(x, y, out=None, splits=None, bn=0):
+  """x[K,M]^T @ y[K,N] -> fp32 [M,N]; split-K partial sums are accumulated with fp32 atomics (out is zeroed here)."""
+  x, y = _rows(x), _rows(y)
+  K, M = x.shape
+  N = y.shape[1]
+  if out is None:
+    out = torch.empty((M, N), dtype=torch.float32, device=x.device)
+  if splits is None:
+    splits = pick_splits(M, N, K, 64 if N <= 64 else 128)
+  if splits > 1:
+    out.zero_()
+  return _gemm(x, y, out, M, N, K, True, True, None, False, splits, bn)
+
+
+# ---------------------------------------------------------------------------- #
+# Dense
+
+def _masked(dy, y, relu):
+  if not relu:
+    return dy
+  out = relu_backward(dy, y)
+  return out if out is not None else dy * (y > 0).to(dy.dtype)
+
+
+def linear_forward(x, weight, bias, relu):
+  if not enabled("linear"):
+    return None
+  return mm_nt(x, weight, bias, relu)
+
+
+def linear_backward(dy, x, weight, y, relu, need_dx, grad_w, grad_b):
+  if not enabled("linear"):
+    return NotImplemented
+  dy = _rows(_masked(dy, y, relu))
+  mm_tn(dy, x, out=grad_w)
+  if grad_b is not None:
+    grad_b.copy_(colsum(dy))
+  return mm_nn(dy, weight) if need_dx else None
+
+
+# ---------------------------------------------------------------------------- #
+# Convolution (1x1 stride-1 convolutions are GEMMs on the NHWC view; other shapes: see conv.py when available)
+
+def _as_rows(x):
+  """(N, C, H, W) channels_last -> [N*H*W, C] view."""
+  n, c, h, w = x.shape
+  return x.permute(0, 2, 3, 1).reshape(n * h * w, c)
+
+
+def _from_rows(y2d, n, h, w):
+  return y2d.view(n, h, w, y2d.shape[1]).permute(0, 3, 1, 2)
+
+
+def _is_pointwise(weight, stride, pads):
+  return weight.shape[1] == 1 and weight.shape[2] == 1 and stride == 1 and not any(pads)
 
 
 def conv2d_forward(x, weight, bias, stride, pads, relu):
+  if not enabled("conv"):
+    return None
+  if _is_pointwise(weight, stride, pads) and x.is_contiguous(memory_format=torch.channels_last) and x.shape[1] % 8 == 0:
+    n, c, h, w = x.shape
+    y = mm_nt(_as_rows(x), weight.reshape(weight.shape[0], -1), bias, relu)
+    return _from_rows(y if y.stride(0) == y.shape[1] else y.contiguous(), n, h, w)
+  if enabled("convk") and _general_ok(x, weight):
+    return conv2d_forward_general(x, weight, bias, stride, pads, relu)
   return None
 
 
 def conv2d_backward(dy, x, weight, y, stride, pads, relu, has_bias, need_dx, grad_w, grad_b):
+  if not enabled("conv"):
+    return NotImplemented
+  if _is_pointwise(weight, stride, pads) and x.is_contiguous(memory_format=torch.channels_last) and x.shape[1] % 8 == 0 and weight.shape[0] % 8 == 0:
+    n, c, h, w = x.shape
+    dy = _masked(dy, y, relu)
+    if not dy.is_contiguous(memory_format=torch.channels_last):
+      dy = dy.contiguous(memory_format=torch.channels_last)
+    dy2d = _as_rows(dy)
+    mm_tn(dy2d, _as_rows(x), out=grad_w.view(grad_w.shape[0], -1))
+    if has_bias:
+      grad_b.copy_(colsum(dy2d))
+    if not need_dx:
+      return None
+    return _from_rows(mm_nn(dy2d, weight.reshape(weight.shape[0], -1)), n, h, w)
+  if enabled("convk") and _general_ok(x, weight) and dy.dtype == torch.bfloat16:
+    return conv2d_backward_general(dy, x, weight, y, stride, pads, relu, has_bias, need_dx, grad_w, grad_b)
   return NotImplemented
 
 
-def linear_forward(x, weight, bias, relu):
-  return None
+# ---------------------------------------------------------------------------- #
+# General k x k convolution: im2col (bf16, column order kh, kw, c) + the same three GEMMs
+
+def _im2col(x, k, stride, pads, oh, ow):
+  n, c, h, w = x.shape
+  kcol = k * k * c
+  ld = (kcol + 7) // 8 * 8
+  col = torch.empty((n * oh * ow, ld), dtype=torch.bfloat16, device=x.device)
+  func = _lib().agb_im2col
+  _check(func(_ptr(x), _ptr(col), ctypes.c_int(n), ctypes.c_int(h), ctypes.c_int(w), ctypes.c_int(c), ctypes.c_int(oh), ctypes.c_int(ow), ctypes.c_int(k),
+              ctypes.c_int(stride), ctypes.c_int(pads[0]), ctypes.c_int(pads[2]), ctypes.c_longlong(ld), _stream()), "im2col")
+  return col[:, :kcol]
 
 
-def linear_backward(dy, x, weight, y, relu, need_dx, grad_w, grad_b):
-  return NotImplemented
+def _out_size(size, k, stride, lo, hi):
+  return (size + lo + hi - k) // stride + 1
 
 
-def batchnorm_forward(x, gamma, beta, moving_mean, moving_var, decay, eps, relu):
-  return None
+def _weight_rows(weight):
+  """[Cout, kh, kw, Cin] -> [Cout, kh*kw*Cin] rows with a TMA-compatible stride (copy only for the 3-channel stem)."""
+  return weight.reshape(weight.shape[0], -1)
 
 
-def batchnorm_backward(dy, x, y, gamma, mean, rstd, relu, grad_gamma, grad_beta):
-  return None
+def _general_ok(x, weight):
+  return x.is_contiguous(memory_format=torch.channels_last) and x.dtype == torch.bfloat16 and weight.shape[0] % 8 == 0 and weight.shape[1] == weight.shape[2]
+
+
+def conv2d_forward_general(x, weight, bias, stride, pads, relu):
+  n, c, h, w = x.shape
+  k = weight.shape[1]
+  oh, ow = _out_size(h, k, stride, pads[0], pads[1]), _out_size(w, k, stride, pads[2], pads[3])
+  col = _im2col(x, k, stride, pads, oh, ow)
+  y = mm_nt(col, _weight_rows(weight), bias, relu)
+  return _from_rows(y if y.stride(0) == y.shape[1] else y.contiguous(), n, oh, ow)
+
+
+def conv2d_backward_general(dy, x, weight, y, stride, pads, relu, has_bias, need_dx, grad_w, grad_b):
+  n, c, h, w = x.shape
+  k = weight.shape[1]
+  oh, ow = dy.shape[2], dy.shape[3]
+  dy = _masked(dy, y, relu)
+  if not dy.is_contiguous(memory_format=torch.channels_last):
+    dy = dy.contiguous(memory_format=torch.channels_last)
+  dy2d = _as_rows(dy)
+  col = _im2col(x, k, stride, pads, oh, ow)
+  mm_tn(dy2d, col, out=grad_w.view(grad_w.shape[0], -1))
+  del col
+  if has_bias:
+    grad_b.copy_(colsum(dy2d))
+  if not need_dx:
+    return None
+  if c % 8:
+    return NotImplemented
+  dcol = mm_nn(dy2d, _weight_rows(weight))
+  dx = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=x.device)
+  func = _lib().agb_col2im
+  _check(func(_ptr(dcol), _ptr(dx), ctypes.c_int(n), ctypes.c_int(h), ctypes.c_int(w), ctypes.c_int(c), ctypes.c_int(oh), ctypes.c_int(ow), ctypes.c_int(k),
+              ctypes.c_int(stride), ctypes.c_int(pads[0]), ctypes.c_int(pads[2]), ctypes.c_longlong(dcol.stride(0)), _stream()), "col2im")
+  return dx.permute(0, 3, 1, 2)
+
+
+# ---------------------------------------------------------------------------- #
+# Memory-bound layers (native/op_nn/layers.cu)
+
+_workspaces = {}
+
+
+def _workspace(device, name, numel, dtype):
+  key = (device, name, dtype)
+  buf = _workspaces.get(key)
+  if buf is None or buf.numel() < numel:
+    buf = _workspaces[key] = torch.empty(max(numel, 4096), dtype=dtype, device=device)
+  return buf
+
+
+def _cl_ok(*tensors):
+  return all(t is None or (t.dtype == torch.bfloat16 and (t.dim() != 4 or t.is_contiguous(memory_format=torch.channels_last))) for t in tensors)
+
+
+def colsum(dy2d, y2d=None):
+  """fp32 column sums of a [rows, C] bf16 matrix (optionally masked by y > 0): bias gradients."""
+  rows, c = dy2d.shape
+  if c % 8 or dy2d.stride(0) != c:
+    src = dy2d.float() if y2d is None else dy2d.float() * (y2d > 0)
+    return src.sum(dim=0)
+  out = torch.empty(c, dtype=torch.float32, device=dy2d.device)
+  sums = _workspace(dy2d.device, "colsum", 2 * c, torch.float64)
+  _check(_lib().agb_colsum(_ptr(dy2d), _ptr(y2d), _ptr(out), _ptr(sums), ctypes.c_longlong(rows), ctypes.c_int(c), _stream()), "colsum")
+  return out
+
+
+def batchnorm_forward(x, gamma, beta, moving_mean, moving_var, decay, eps, relu, groups=1):
+  if not enabled("bn") or not _cl_ok(x) or x.shape[1] % 8:
+    return None
+  n, c, h, w = x.shape
+  rows = n * h * w
+  y = torch.empty_like(x, memory_format=torch.channels_last)
+  stats = torch.empty((4, groups * c), dtype=torch.float32, device=x.device)  # save_mean, save_rstd, scale, shift
+  sums = _workspace(x.device, "bn_sums", 2 * groups * c, torch.float64)
+  _check(_lib().agb_bn_forward(_ptr(x), _ptr(y), _ptr(gamma), _ptr(beta), _ptr(moving_mean), _ptr(moving_var), _ptr(stats[0]), _ptr(stats[1]), _ptr(sums),
+                               _ptr(stats[2]), _ptr(stats[3]), ctypes.c_longlong(rows), ctypes.c_int(c), ctypes.c_int(groups), ctypes.c_float(eps),
+                               ctypes.c_float(decay), ctypes.c_int(1 if relu else 0), _stream()), "bn_forward")
+  return y, stats[0], stats[1]
+
+
+def batchnorm_backward(dy, x, y, gamma, mean, rstd, relu, grad_gamma, grad_beta, groups=1):
+  if not enabled("bn") or not _cl_ok(x, dy, y) or x.shape[1] % 8:
+    return None
+  if not dy.is_contiguous(memory_format=torch.channels_last):
+    dy = dy.contiguous(memory_format=torch.channels_last)
+  n, c, h, w = x.shape
+  rows = n * h * w
+  dx = torch.empty_like(x, memory_format=torch.channels_last)
+  sums = _workspace(x.device, "bn_sums", 2 * groups * c, torch.float64)
+  coef = _workspace(x.device, "bn_coef", 3 * groups * c, torch.float32)
+  _check(_lib().agb_bn_backward(_ptr(dy), _ptr(x), _ptr(y if relu else None), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dx), _ptr(grad_gamma), _ptr(grad_beta),
+                                _ptr(sums), _ptr(coef), ctypes.c_longlong(rows), ctypes.c_int(c), ctypes.c_int(groups), _stream()), "bn_backward")
+  return dx
 
 
 def relu_backward(dy, y):
-  return None
+  if not enabled("eltwise") or dy.dtype != torch.bfloat16 or y.dtype != torch.bfloat16 or dy.numel() % 8 or dy.stride() != y.stride() or not (dy.is_contiguous() or dy.is_contiguous(memory_format=torch.channels_last)):
+    return None
+  dx = torch.empty_like(dy)
+  _check(_lib().agb_relu_backward(_ptr(dy), _ptr(y), _ptr(dx), ctypes.c_longlong(dy.numel()), _stream()), "relu_backward")
+  return dx
 
 
 def add_relu_forward(a, b, relu):
-  return None
+  if not enabled("eltwise") or a.dtype != torch.bfloat16 or b.dtype != torch.bfloat16 or a.numel() % 8 or a.stride() != b.stride() or not (a.is_contiguous() or a.is_contiguous(memory_format=torch.channels_last)):
+    return None
+  out = torch.empty_like(a)
+  _check(_lib().agb_add_relu(_ptr(a), _ptr(b), _ptr(out), ctypes.c_longlong(a.numel()), ctypes.c_int(1 if relu else 0), _stream()), "add_relu")
+  return out
 
 
 def maxpool_forward(x, k, stride, pads):
-  return None
+  if not enabled("pool") or not _cl_ok(x) or x.shape[1] % 8:
+    return None
+  n, c, h, w = x.shape
+  oh, ow = _out_size(h, k, stride, pads[0], pads[1]), _out_size(w, k, stride, pads[2], pads[3])
+  y = torch.empty((n, c, oh, ow), dtype=x.dtype, device=x.device).contiguous(memory_format=torch.channels_last)
+  arg = torch.empty((n, oh, ow, c), dtype=torch.uint8, device=x.device)
+  _check(_lib().agb_maxpool_forward(_ptr(x), _ptr(y), _ptr(arg), ctypes.c_int(n), ctypes.c_int(h), ctypes.c_int(w), ctypes.c_int(c), ctypes.c_int(oh), ctypes.c_int(ow),
+                                    ctypes.c_int(k), ctypes.c_int(stride), ctypes.c_int(pads[0]), ctypes.c_int(pads[2]), _stream()), "maxpool_forward")
+  return y, arg
 
 
-def maxpool_backward(dy, x, y, k, stride, pads):
-  raise NotImplementedError
+def maxpool_backward(dy, shape, arg, k, stride, pads):
+  n, c, h, w = shape
+  if not dy.is_contiguous(memory_format=torch.channels_last):
+    dy = dy.contiguous(memory_format=torch.channels_last)
+  oh, ow = dy.shape[2], dy.shape[3]
+  dx = torch.empty((n, c, h, w), dtype=dy.dtype, device=dy.device).contiguous(memory_format=torch.channels_last)
+  _check(_lib().agb_maxpool_backward(_ptr(dy), _ptr(arg), _ptr(dx), ctypes.c_int(n), ctypes.c_int(h), ctypes.c_int(w), ctypes.c_int(c), ctypes.c_int(oh), ctypes.c_int(ow),
+                                     ctypes.c_int(k), ctypes.c_int(stride), ctypes.c_int(pads[0]), ctypes.c_int(pads[2]), _stream()), "maxpool_backward")
+  return dx
 
 
 def global_avgpool_forward(x):
-  return None
+  if not enabled("pool") or not _cl_ok(x) or x.shape[1] % 8:
+    return None
+  n, c, h, w = x.shape
+  y = torch.empty((n, c, 1, 1), dtype=x.dtype, device=x.device).contiguous(memory_format=torch.channels_last)
+  _check(_lib().agb_avgpool_forward(_ptr(x), _ptr(y), ctypes.c_int(n), ctypes.c_int(h * w), ctypes.c_int(c), _stream()), "avgpool_forward")
+  return y
 
 
 def global_avgpool_backward(dy, shape):
-  return None
+  n, c, h, w = shape
+  if not enabled("pool") or dy.dtype != torch.bfloat16 or c % 8:
+    return None
+  dy = dy.reshape(n, c).contiguous()
+  dx = torch.empty((n, c, h, w), dtype=dy.dtype, device=dy.device).contiguous(memory_format=torch.channels_last)
+  _check(_lib().agb_avgpool_backward(_ptr(dy), _ptr(dx), ctypes.c_int(n), ctypes.c_int(h * w), ctypes.c_int(c), _stream()), "avgpool_backward")
+  return dx
 
 
 def softmax_xent(logits, labels, label_smoothing):
-  return None
+  if not enabled("xent") or logits.dtype != torch.bfloat16 or logits.stride(1) != 1:
+    return None
+  batch, classes = logits.shape
+  dlogits = torch.empty_strided(logits.shape, logits.stride(), dtype=torch.bfloat16, device=logits.device)
+  loss = torch.empty((), dtype=torch.float32, device=logits.device)
+  labels = labels if labels.dtype == torch.int64 else labels.long()
+  _check(_lib().agb_softmax_xent(_ptr(logits), _ptr(labels), _ptr(dlogits), _ptr(loss), ctypes.c_int(batch), ctypes.c_int(classes), ctypes.c_longlong(logits.stride(0)),
+                                 ctypes.c_float(label_smoothing), _stream()), "softmax_xent")
+  return loss, dlogits
+
+
+_MEANS = {"vgg": (123.68, 116.78, 103.94, 1.0), "inception": (127.5, 127.5, 127.5, 1.0 / 127.5), "lenet": (128.0, 128.0, 128.0, 1.0 / 128.0)}
 
 
 def image_normalize(images, mode, dtype):
-  return None
+  """uint8 NHWC -> bf16 channels_last (N, Cpad, H, W) with the channel dimension zero-padded to 8 (TMA/im2col friendly)."""
+  if not enabled("image") or images.dtype != torch.uint8 or dtype != torch.bfloat16 or images.dim() != 4 or not images.is_contiguous():
+    return None
+  n, h, w, c = images.shape
+  if c > 3:
+    return None
+  m0, m1, m2, scale = _MEANS.get(mode, _MEANS["lenet"])
+  if mode == "vgg" and c != 3:
+    m0, m1, m2, scale = _MEANS["lenet"]
+  out = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=images.device)
+  _check(_lib().agb_image_normalize(_ptr(images), _ptr(out), ctypes.c_longlong(n * h * w), ctypes.c_int(c), ctypes.c_int(c), ctypes.c_float(m0), ctypes.c_float(m1),
+                                    ctypes.c_float(m2), ctypes.c_float(scale), _stream()), "image_normalize")
+  return out.permute(0, 3, 1, 2)

@@ -1,0 +1,77 @@
+"""tcgen05 GEMM (native/op_nn/gemm.cu) vs fp32 torch matmul on the same bf16-rounded operands."""
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand(shape, seed):
+  gen = torch.Generator(device="cuda").manual_seed(seed)
+  return torch.randn(shape, device="cuda", generator=gen).to(torch.bfloat16)
+
+
+def _check(out, ref, tol=2e-3):
+  err = float((out.float() - ref).abs().max())
+  scale = max(1.0, float(ref.abs().max()))
+  assert err <= tol * scale, (err, scale)
+
+
+SHAPES = [(128, 128, 64), (256, 64, 128), (300, 200, 136), (32, 10, 104), (1000, 192, 4096), (25088, 256, 64), (77, 1000, 2048), (4096, 384, 4096), (130, 70, 8)]
+
+
+@pytest.mark.parametrize("m,n,k", SHAPES)
+def test_mm_nt(m, n, k):
+  from aggregathor_b200.ops import nn_native as nat
+  x, w = _rand((m, k), 1), _rand((n, k), 2)
+  ref = x.float() @ w.float().t()
+  _check(nat.mm_nt(x, w, out_dtype=torch.float32), ref)
+  _check(nat.mm_nt(x, w), ref, tol=1e-2)
+  bias = torch.randn(n, device="cuda")
+  _check(nat.mm_nt(x, w, bias=bias, relu=True, out_dtype=torch.float32), torch.relu(ref + bias))
+  for bn in (64, 128, 256):
+    _check(nat.mm_nt(x, w, out_dtype=torch.float32, bn=bn), ref)
+
+
+@pytest.mark.parametrize("m,n,k", SHAPES)
+def test_mm_nn(m, n, k):
+  from aggregathor_b200.ops import nn_native as nat
+  x, w = _rand((m, k), 3), _rand((k, n), 4)
+  ref = x.float() @ w.float()
+  _check(nat.mm_nn(x, w, out_dtype=torch.float32), ref)
+  _check(nat.mm_nn(x, w, out_dtype=torch.float32, bn=64), ref)
+
+
+@pytest.mark.parametrize("m,n,k", SHAPES + [(64, 64, 100352), (256, 2304, 6272)])
+def test_mm_tn(m, n, k):
+  from aggregathor_b200.ops import nn_native as nat
+  x, y = _rand((k, m), 5), _rand((k, n), 6)
+  ref = x.float().t() @ y.float()
+  _check(nat.mm_tn(x, y, splits=1), ref, tol=3e-3)
+  _check(nat.mm_tn(x, y), ref, tol=3e-3)          # automatic split-K with fp32 atomics
+  out = torch.empty((m, n), device="cuda")
+  _check(nat.mm_tn(x, y, out=out, splits=3), ref, tol=3e-3)
+
+
+def test_strided_operands():
+  from aggregathor_b200.ops import nn_native as nat
+  big = _rand((200, 520), 7)
+  x = big[:, :500]            # row stride 520 (multiple of 8), inner 500
+  w = _rand((96, 500), 8)
+  _check(nat.mm_nt(x, w, out_dtype=torch.float32), x.float() @ w.float().t())
+
+
+def test_linear_and_pointwise_conv_layers():
+  """Module-level check: native vs torch provider through models.core (forward, dgrad, wgrad)."""
+  from aggregathor_b200.ops import nn as nn_ops
+  x = _rand((64, 256, 14, 14), 9).contiguous(memory_format=torch.channels_last)
+  w = (_rand((512, 1, 1, 256), 10).float() * 0.05).to(torch.bfloat16)
+  dy = _rand((64, 512, 14, 14), 11).contiguous(memory_format=torch.channels_last)
+  results = {}
+  for backend in ("torch", "native"):
+    y = nn_ops.conv2d_forward(backend, x, w, None, 1, (0, 0, 0, 0), False)
+    gw = torch.zeros((512, 1, 1, 256), device="cuda")
+    dx, _, _ = nn_ops.conv2d_backward(backend, dy, x, w, None, 1, (0, 0, 0, 0), False, False, True, gw, None)
+    results[backend] = (y.float(), dx.float(), gw)
+  for a, b in zip(results["torch"], results["native"]):
+    _check(b, a, tol=2e-2)

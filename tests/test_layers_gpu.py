@@ -1,0 +1,130 @@
+"""Native sm_100a layer kernels vs the torch provider, op by op and end to end (ResNet-50 / cnnet / mnist gradients)."""
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+CL = torch.channels_last
+
+
+def _rand(shape, seed, scale=1.0):
+  gen = torch.Generator(device="cuda").manual_seed(seed)
+  t = (torch.randn(shape, device="cuda", generator=gen) * scale).to(torch.bfloat16)
+  return t.contiguous(memory_format=CL) if len(shape) == 4 else t
+
+
+def _close(a, b, tol):
+  a, b = a.float(), b.float()
+  err = float((a - b).abs().max())
+  scale = max(1e-3, float(b.abs().max()))
+  assert err <= tol * scale, (err, scale)
+
+
+@pytest.mark.parametrize("shape", [(32, 64, 56, 56), (8, 256, 14, 14), (4, 2048, 7, 7), (16, 192, 5, 5)])
+@pytest.mark.parametrize("relu", [False, True])
+def test_batchnorm(shape, relu):
+  from aggregathor_b200.ops import nn as ops
+  x = _rand(shape, 1) * 2 + 0.5
+  dy = _rand(shape, 2)
+  c = shape[1]
+  gamma = torch.rand(c, device="cuda") + 0.5
+  beta = torch.randn(c, device="cuda") * 0.1
+  out = {}
+  for backend in ("torch", "native"):
+    mm, mv = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+    y, mean, rstd = ops.batchnorm_forward(backend, x, gamma, beta, mm, mv, 0.9, 1e-5, relu)
+    gg, gb = torch.zeros(c, device="cuda"), torch.zeros(c, device="cuda")
+    dx = ops.batchnorm_backward(backend, dy, x, y if relu else None, gamma, mean, rstd, relu, gg, gb)
+    out[backend] = (y, mean, rstd, dx, gg, gb, mm, mv)
+  tols = (2e-2, 1e-3, 1e-3, 3e-2, 2e-2, 2e-2, 1e-3, 1e-3)
+  for a, b, tol in zip(out["native"], out["torch"], tols):
+    _close(a, b, tol)
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,hw,pads", [(64, 64, 3, 1, 56, (1, 1, 1, 1)), (128, 128, 3, 2, 28, (1, 1, 1, 1)), (3, 64, 7, 2, 224, (3, 3, 3, 3)),
+                                                        (3, 64, 5, 1, 32, (2, 2, 2, 2)), (64, 64, 5, 1, 16, (2, 2, 2, 2)), (256, 512, 1, 1, 14, (0, 0, 0, 0))])
+def test_conv(cin, cout, k, stride, hw, pads):
+  from aggregathor_b200.ops import nn as ops
+  n = 4
+  x = _rand((n, cin, hw, hw), 3)
+  w = _rand((cout, k, k, cin), 4, scale=(2.0 / (k * k * cin)) ** 0.5)
+  bias = torch.randn(cout, device="cuda") * 0.1
+  out = {}
+  for backend in ("torch", "native"):
+    y = ops.conv2d_forward(backend, x, w, bias, stride, pads, True)
+    dy = _rand(tuple(y.shape), 5)
+    gw, gb = torch.zeros((cout, k, k, cin), device="cuda"), torch.zeros(cout, device="cuda")
+    dx, _, _ = ops.conv2d_backward(backend, dy, x, w, y, stride, pads, True, True, cin % 8 == 0, gw, gb)
+    out[backend] = (y, gw, gb) + ((dx,) if dx is not None else ())
+  for a, b in zip(out["native"], out["torch"]):
+    _close(a, b, 3e-2)
+
+
+def test_pools_and_eltwise():
+  from aggregathor_b200.ops import nn as ops
+  x = _rand((8, 64, 112, 112), 6)
+  for pads, k, s in (((0, 1, 0, 1), 3, 2), ((0, 0, 0, 0), 2, 2), ((1, 1, 1, 1), 3, 2)):
+    res = {}
+    for backend in ("torch", "native"):
+      y, index = ops.maxpool_forward(backend, x, k, s, pads)
+      dy = _rand(tuple(y.shape), 7)
+      res[backend] = (y, ops.maxpool_backward(backend, dy, x.shape, index, k, s, pads, x, y))
+    _close(res["native"][0], res["torch"][0], 1e-6)
+    _close(res["native"][1], res["torch"][1], 1e-2)
+  z = _rand((8, 2048, 7, 7), 8)
+  _close(ops.global_avgpool_forward("native", z), ops.global_avgpool_forward("torch", z), 1e-2)
+  d = _rand((8, 2048, 1, 1), 9)
+  _close(ops.global_avgpool_backward("native", d, z.shape), ops.global_avgpool_backward("torch", d, z.shape), 1e-2)
+  a, b = _rand((8, 256, 14, 14), 10), _rand((8, 256, 14, 14), 11)
+  _close(ops.add_relu_forward("native", a, b, True), ops.add_relu_forward("torch", a, b, True), 1e-2)
+  _close(ops.relu_backward("native", a, b), ops.relu_backward("torch", a, b), 1e-6)
+
+
+def test_softmax_xent_and_image_normalize():
+  from aggregathor_b200.ops import nn as ops
+  logits = _rand((32, 1000), 12) * 3
+  labels = torch.randint(0, 1000, (32,), device="cuda")
+  for smoothing in (0.0, 0.1):
+    l0, d0 = ops.softmax_xent("torch", logits, labels, smoothing)
+    l1, d1 = ops.softmax_xent("native", logits, labels, smoothing)
+    assert abs(float(l0) - float(l1)) < 2e-3 * max(1.0, abs(float(l0)))
+    _close(d1, d0, 2e-2)
+  images = torch.randint(0, 256, (4, 32, 32, 3), device="cuda", dtype=torch.uint8)
+  for mode in ("vgg", "inception"):
+    _close(ops.image_normalize("native", images, mode, torch.bfloat16), ops.image_normalize("torch", images, mode, torch.bfloat16), 1e-2)
+
+
+@pytest.mark.parametrize("name,classes,batch,image", [("resnet_v1_50", 1000, 4, 64), ("cnnet", 10, 16, 32), ("mlp", 10, 32, None)])
+def test_model_gradients_native_vs_torch(name, classes, batch, image):
+  """Whole-model check: same parameters and batch, flat gradients of the two providers must agree (bf16 noise only)."""
+  from aggregathor_b200.engine.flat import FlatLayout
+  from aggregathor_b200.models import Context, get_network
+  model = get_network(name, classes)
+  layout, shapes = FlatLayout(), {}
+  model.declare(layout, shapes)
+  layout.freeze()
+  gen = torch.Generator().manual_seed(0)
+  init = torch.zeros(layout.padded_size)
+  init_states = {k: torch.zeros(v) for k, v in shapes.items()}
+  model.initialize(layout.views(init), init_states, gen)
+  params = init.cuda()
+  weights = params.to(torch.bfloat16)
+  if image is None:
+    x = _rand((batch, 784), 20).abs()
+  else:
+    x = _rand((batch, model.input_shape[0], image, image), 20)
+  labels = torch.randint(0, classes, (batch,), device="cuda")
+  grads, losses = {}, {}
+  for backend in ("torch", "native"):
+    ctx = Context(backend, True, torch.bfloat16, "cuda")
+    ctx.master, ctx.weights = layout.views(params), layout.views(weights)
+    ctx.state = {k: v.clone().cuda() for k, v in init_states.items()}
+    g = torch.zeros(layout.padded_size, device="cuda")
+    ctx.grads = layout.views(g)
+    losses[backend] = float(model.loss_and_backward(x, labels, ctx))
+    grads[backend] = g
+  assert abs(losses["torch"] - losses["native"]) < 3e-2 * max(1.0, abs(losses["torch"])), losses
+  cos = float(torch.nn.functional.cosine_similarity(grads["torch"], grads["native"], dim=0))
+  assert cos > 0.98, cos
+  ratio = float(grads["native"].norm() / grads["torch"].norm())
+  assert 0.9 < ratio < 1.1, ratio
