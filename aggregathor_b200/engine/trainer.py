@@ -15,6 +15,7 @@ One synchronous step on a rank:
   5. the bf16 compute copy of the parameters is refreshed (unless the fused kernel already wrote it).
 """
 
+import os
 import time
 
 import torch
@@ -41,7 +42,7 @@ class Manager:
 
   def __init__(self, experiment, aggregator, nbworkers, optimizer="sgd", optimizer_args=None, learning_rate="fixed", learning_rate_args=None,
                regularizations=(-1., -1.), trace=False, *, attack=None, nb_real_byz=0, device=None, group=None, engine="auto", backend="auto",
-               dtype=None, seed=0, placement=None, debug_checksum=False, engine_args=None):
+               dtype=None, seed=0, placement=None, debug_checksum=False, engine_args=None, use_graphs=None):
     self.device = torch.device(device) if device is not None else _default_device()
     self.group = group
     self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -115,6 +116,13 @@ class Manager:
     self.total_loss = None
     self._loss_buf = torch.zeros(1, dtype=torch.float32, device=self.device)
     self.h2d_bytes_per_step = sum(getattr(s, "h2d_bytes", 0) for s in self.streams)
+    # -- CUDA graph of the workers' forward/backward ---------------------------------- #
+    if use_graphs is None:
+      use_graphs = cuda and not os.environ.get("AGB_NO_GRAPH") and not self._has_dropout(self.model.root) and type(experiment).losses is type(experiment).__mro__[-2].losses
+    self.use_graphs = bool(use_graphs) and cuda
+    self._graph = None
+    self._graph_warmup = 2       # eager steps before capture (lazy kernel attributes, workspaces, autotuning)
+    self._graph_launches = 0
     tools.info("Model %r: %d variables, d = %d (padded %d); %d worker(s) on this rank; compute dtype %s; nn backend %r; engine %r" % (
       self.model.name, len(self.layout.names), self.layout.size, self.layout.padded_size, len(self.local_workers), str(self.dtype).replace("torch.", ""),
       self.backend, self.aggregation.name), context="graph")
@@ -130,11 +138,53 @@ class Manager:
     else:
       self._weights_flat.copy_(self.params)
 
+  @staticmethod
+  def _has_dropout(module):
+    from ..models.core import Dropout
+    if isinstance(module, Dropout):
+      return True
+    return any(Manager._has_dropout(child) for child in module.children())
+
+  def _capture(self, batches):
+    """Record every local worker's forward + backward into one CUDA graph (static shapes, static buffers)."""
+    from ..ops import counters
+    self._static_batches = [(x.clone(), y.clone()) for x, y in batches]
+    torch.cuda.synchronize(self.device)
+    graph = torch.cuda.CUDAGraph()
+    before = counters.launches
+    try:
+      with torch.cuda.graph(graph):
+        losses = self.experiment.losses(self.model, self._static_batches, self.contexts, None)
+        self._static_losses = torch.stack([l.float().reshape(()) for l in losses])
+    except Exception as err:
+      tools.warning("CUDA graph capture failed (" + str(err).splitlines()[0] + "): staying in eager mode", context="graph")
+      self.use_graphs = False
+      torch.cuda.synchronize(self.device)
+      return False
+    self._graph_launches = counters.launches - before
+    self._graph = graph
+    tools.info("Captured the workers' forward/backward into a CUDA graph (%d native kernel launches per replay)" % self._graph_launches, context="graph")
+    return True
+
+  def _replay(self, batches):
+    from ..ops import counters
+    for (sx, sy), (x, y) in zip(self._static_batches, batches):
+      sx.copy_(x, non_blocking=True)
+      sy.copy_(y, non_blocking=True)
+    self._graph.replay()
+    counters.bump(self._graph_launches)
+    return list(self._static_losses.unbind(0))
+
   def compute_gradients(self):
     """Phase 1-3 of a step: local workers' losses and gradients (+ regularisation, + attacks). Returns the list of losses."""
     batches = [next(stream) for stream in self.streams]
-    trace = self.tracer if (self.tracer.enabled or self.tracer.cuda) else None
-    losses = self.experiment.losses(self.model, batches, self.contexts, trace)
+    trace = self.tracer if self.tracer.enabled else None
+    if self.use_graphs and trace is None and self._graph is None and self.step >= self._graph_warmup:
+      self._capture(batches)
+    if self._graph is not None and trace is None:
+      losses = self._replay(batches)
+    else:
+      losses = self.experiment.losses(self.model, batches, self.contexts, trace)
     if (self.l1 is not None and self.l1 > 0.) or (self.l2 is not None and self.l2 > 0.):
       reg_loss, reg_grad = regularization(self.params, self.l1, self.l2)
       for j in range(len(self.local_workers)):
@@ -175,7 +225,8 @@ class Manager:
     if self.device.type == "cuda":
       digest = gar_ops.checksum(self.params)
     else:
-      digest = torch.tensor([hash(self.params.numpy().tobytes()) & (2 ** 62 - 1)], dtype=torch.int64)
+      import hashlib
+      digest = torch.tensor([int.from_bytes(hashlib.blake2b(self.params.numpy().tobytes(), digest_size=7).digest(), "little")], dtype=torch.int64)
     if self.world > 1:
       gathered = [torch.zeros_like(digest) for _ in range(self.world)]
       dist.all_gather(gathered, digest, group=self.group)

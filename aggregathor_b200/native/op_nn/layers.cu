@@ -199,9 +199,9 @@ __global__ void bn_bwd_finalize_kernel(double const* __restrict__ sums, float co
         float const gm = gamma ? gamma[c] : 1.f;
         float const rs = rstd[i], mu = mean[i];
         float const inv_n = 1.f / static_cast<float>(rows_per_group);
-        // dx = gm*rs * (dy - sum_dy/n - xhat * sum_dy_xhat/n), xhat = (x - mu) * rs
+        // dx = gm*rs * (dy - sum_dy/n - xhat * sum_dy_xhat/n), xhat = (x - mu) * rs; sum_dy_xhat already includes one rs
         float const a = gm * rs;
-        float const b = -gm * rs * rs * rs * static_cast<float>(sum_dy_xhat) * inv_n;
+        float const b = -gm * rs * rs * static_cast<float>(sum_dy_xhat) * inv_n;   // xhat * rs = (x - mu) * rs^2
         float const c0 = -gm * rs * static_cast<float>(sum_dy) * inv_n - b * mu;
         coef[3 * i] = a;
         coef[3 * i + 1] = b;

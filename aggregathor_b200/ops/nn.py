@@ -106,7 +106,7 @@ def linear_backward(backend, dy, x, weight, y, relu, need_dx, grad_w, grad_b):
     dy = _relu_mask(dy, y)
   grad_w.copy_(dy.t() @ x)
   if grad_b is not None:
-    grad_b.copy_(dy.float().sum(dim=0))
+    grad_b.copy_((dy if dy.dtype == torch.float64 else dy.float()).sum(dim=0))
   return dy @ weight if need_dx else None
 
 
@@ -205,7 +205,7 @@ def global_avgpool_forward(backend, x):
     out = _native().global_avgpool_forward(x)
     if out is not None:
       return out
-  return x.float().mean(dim=(2, 3), keepdim=True).to(x.dtype)
+  return (x if x.dtype == torch.float64 else x.float()).mean(dim=(2, 3), keepdim=True).to(x.dtype)
 
 
 def global_avgpool_backward(backend, dy, shape):
@@ -236,7 +236,7 @@ def softmax_xent(backend, logits, labels, label_smoothing=0.0):
     out = _native().softmax_xent(logits, labels, label_smoothing)
     if out is not None:
       return out
-  z = logits.float()
+  z = logits if logits.dtype == torch.float64 else logits.float()
   logp = torch.log_softmax(z, dim=1)
   batch, classes = z.shape
   target = torch.zeros_like(z).scatter_(1, labels.view(-1, 1).long(), 1.0)

@@ -1,0 +1,142 @@
+"""End-to-end CPU runs: runner CLI golden files, resume, attacks, the 2-process gloo plumbing config."""
+
+import os
+import pathlib
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from aggregathor_b200 import aggregators, attacks, experiments, tools
+from aggregathor_b200.engine.trainer import Manager
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+LOCAL = ["--server", '{"local": ["127.0.0.1:7000"]}', "--ps-job-name", "local", "--wk-job-name", "local", "--ev-job-name", "local", "--no-wait"]
+
+
+def _run(args, timeout=300, launcher=None):
+  env = dict(os.environ, AGB_NUM_THREADS="2", OMP_NUM_THREADS="2")
+  cmd = (launcher or [sys.executable]) + [str(ROOT / "runner.py")] + args
+  proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=timeout, env=env, cwd=str(ROOT))
+  return proc.returncode, proc.stdout.decode(errors="replace")
+
+
+def test_runner_mnist_average_golden_outputs(tmp_path):
+  ckpt = tmp_path / "ckpt"
+  args = LOCAL + ["--experiment", "mnist", "--aggregator", "average", "--nb-workers", "4", "--max-step", "12", "--learning-rate-args", "initial-rate:0.05",
+                  "--evaluation-delta", "1000", "--evaluation-period", "-1", "--checkpoint-dir", str(ckpt), "--checkpoint-delta", "1000", "--checkpoint-period", "-1",
+                  "--summary-delta", "1000", "--summary-period", "-1", "--stdout-to", str(tmp_path / "out.txt")]
+  code, out = _run(args)
+  assert code == 0, out
+  losses = [float(x) for x in re.findall(r"Step \d+: total loss = ([0-9.eE+-]+)", out)]
+  assert len(losses) == 12 and losses[-1] < losses[0]
+  assert "step(s)/s (all steps)" in out and "Cluster structure and allocation report" in out
+  lines = (ckpt / "eval").read_text().strip().splitlines()
+  assert len(lines) == 2  # first evaluation before training + final evaluation
+  wall, step, metric = lines[-1].split("\t")
+  assert int(step) == 12 and metric.startswith("top1-X-acc:") and float(wall) > 0
+  names = sorted(p.name for p in ckpt.iterdir())
+  assert "model-12.index" in names and "model-12.data-00000-of-00001" in names and "model-12.meta" in names and any(n.startswith("events.out.tfevents") for n in names)
+  events = tools.read_events(next(p for p in ckpt.iterdir() if p.name.startswith("events")))
+  assert events[1]["session_status"] == 1 and events[-1]["session_status"] == 2 and any("learning_rate" in e.get("scalars", {}) for e in events)
+  plain = (tmp_path / "out.txt").read_text()
+  assert "\033[" not in plain and "[train] Step 0: total loss" in plain
+  # resume: --max-step counts additional steps from the restored global step
+  code, out = _run(args[:args.index("--max-step") + 1] + ["3"] + args[args.index("--max-step") + 2:])
+  assert code == 0, out
+  assert "Loading latest checkpoint" in out and "Step 12: total loss" in out and "Step 14: total loss" in out and "Step 15:" not in out.replace("Step 15: top1", "")
+  assert (ckpt / "model-15.index").exists()
+
+
+def test_runner_argument_errors():
+  code, out = _run(["--experiment", "mnist", "--aggregator", "average", "--nb-workers", "2"])
+  assert code != 0 and "One and only one of '--client' and '--server'" in out
+  code, out = _run(LOCAL + ["--experiment", "mnist", "--aggregator", "nope", "--nb-workers", "2", "--max-step", "1"])
+  assert code != 0 and "Unknown name 'nope'" in out and "Traceback" not in out
+  code, out = _run(LOCAL + ["--experiment", "mnist", "--aggregator", "bulyan", "--nb-workers", "8", "--nb-decl-byz-workers", "2", "--max-step", "1"])
+  assert code != 0 and "Bulyan needs n >= 4 f + 3" in out
+
+
+def test_two_process_gloo_plumbing(tmp_path):
+  """BASELINE.json config 1: mnist + average, nb-workers = 2, CPU / gloo, one worker per rank."""
+  port = 29500 + os.getpid() % 400
+  launcher = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", str(port)]
+  args = ["--server", '{"ps": ["127.0.0.1:7000"], "workers": ["127.0.0.1:7001", "127.0.0.1:7002"], "eval": ["127.0.0.1:7000"]}', "--no-wait",
+          "--experiment", "mnist", "--aggregator", "average", "--nb-workers", "2", "--max-step", "8", "--learning-rate-args", "initial-rate:0.05",
+          "--evaluation-delta", "4", "--evaluation-period", "-1", "--checkpoint-dir", str(tmp_path / "c"), "--checkpoint-delta", "8", "--checkpoint-period", "-1",
+          "--summary-dir", "-", "--debug-checksum"]
+  code, out = _run(args, timeout=600, launcher=launcher)
+  assert code == 0, out
+  assert "Step 7: total loss" in out and "Replica divergence" not in out
+  assert (tmp_path / "c" / "model-8.index").exists()
+  assert len((tmp_path / "c" / "eval").read_text().strip().splitlines()) >= 2
+
+
+_RATES = {"sgd": 0.05, "adam": 0.002, "rmsprop": 0.002, "adagrad": 0.02, "adadelta": 1.0}
+
+
+def _manager(gar_name, n, f, attack=None, real=0, opt="sgd", exp="mnist", exp_args=("batch-size:16",), **kwargs):
+  experiment = experiments.instantiate(exp, list(exp_args))
+  gar = aggregators.instantiate(gar_name, n, f, [])
+  return Manager(experiment, gar, n, opt, [], "fixed", ["initial-rate:" + str(_RATES[opt])], device="cpu", attack=attack, nb_real_byz=real, **kwargs)
+
+
+@pytest.mark.parametrize("attack_name,attack_args", [("flip", ["factor:-50"]), ("nan", []), ("random", ["deviation:100"]), ("drop-chunks", ["rate:0.5", "fill:nan"]), ("replay", [])])
+def test_krum_survives_attacks_average_does_not(attack_name, attack_args):
+  attack = attacks.instantiate(attack_name, 7, 2, attack_args)
+  robust = _manager("krum", 7, 2, attack, 2)
+  first = float(robust.train())
+  for _ in range(25):
+    last = float(robust.train())
+  assert last == last and last < first
+  assert robust.evaluate()["top1-X-acc"] > 0.5
+  if attack_name in ("flip", "nan", "random"):
+    naive = _manager("average", 7, 2, attacks.instantiate(attack_name, 7, 2, attack_args), 2)
+    for _ in range(25):
+      loss = float(naive.train())
+    assert not (loss == loss and naive.evaluate()["top1-X-acc"] > 0.5 and loss < first)
+
+
+def test_average_nan_handles_lossy_transport():
+  attack = attacks.instantiate("drop-chunks", 4, 2, ["rate:0.3", "fill:nan", "chunk-bytes:4000"])
+  mgr = _manager("average-nan", 4, 2, attack, 2)
+  losses = [float(mgr.train()) for _ in range(20)]
+  assert all(l == l for l in losses) and losses[-1] < losses[0]
+
+
+@pytest.mark.parametrize("opt", ["sgd", "adam", "rmsprop", "adagrad", "adadelta"])
+def test_optimizers_decrease_loss_and_checkpoint_roundtrip(opt):
+  mgr = _manager("median", 3, 0, opt=opt)
+  losses = [float(mgr.train()) for _ in range(15)]
+  assert losses[-1] < losses[0]
+  state = mgr.state_dict()
+  clone = _manager("median", 3, 0, opt=opt, seed=99)
+  clone.load_state_dict(state)
+  assert clone.step == 15 and torch.equal(clone.params, mgr.params)
+  for a, b in zip(clone.aggregation.slots, mgr.aggregation.slots):
+    assert torch.equal(a, b)
+
+
+def test_regularization_and_mnist_attack_experiment():
+  mgr = _manager("average", 2, 0, regularizations=(1e-4, 1e-3))
+  assert float(mgr.train()) > 0
+  poisoned = _manager("krum", 7, 2, exp="mnistAttack", exp_args=("batch-size:16", "nb-byz:2"))
+  for _ in range(25):
+    loss = float(poisoned.train())
+  assert loss == loss and poisoned.evaluate()["top1-X-acc"] > 0.5
+
+
+def test_experiment_registry_covers_reference_names():
+  names = set(experiments.itemize())
+  assert {"mnist", "mnistAttack", "cnnet", "slim-resnet_v1_50-imagenet", "slim-resnet_v1_18-cifar10", "slim-vgg_16-imagenet", "slim-inception_v3-imagenet"} <= names
+  with pytest.raises(tools.UserException):
+    experiments.instantiate("slim-inception_v3-imagenet", []).model()
+
+
+def test_cnnet_step_on_cpu():
+  mgr = _manager("median", 3, 0, exp="cnnet", exp_args=("batch-size:4", "eval-batch-size:16"))
+  a = float(mgr.train())
+  b = float(mgr.train())
+  assert a == a and b == b and 0.0 <= mgr.evaluate()["top1-X-acc"] <= 1.0
