@@ -65,6 +65,11 @@ def _rows(t):
   return buf[:, :cols]
 
 
+def set_gemm_persistent(enabled):
+  """Select the persistent (one CTA per SM, double-buffered TMEM) or the one-tile-per-CTA GEMM kernel."""
+  _lib().agb_gemm_set_persistent(ctypes.c_int(1 if enabled else 0))
+
+
 def alloc_out(m, n, dtype, device):
   """[m, n] view of a buffer whose row stride is a multiple of 8 elements (so it can feed the next GEMM through TMA)."""
   ld = (n + 7) // 8 * 8

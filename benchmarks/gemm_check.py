@@ -13,6 +13,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from aggregathor_b200.ops import nn_native as nat  # noqa: E402
 
 variant = sys.argv[1]
+persistent = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+nat.set_gemm_persistent(persistent)
 shapes = [(128, 128, 64), (128, 64, 64), (256, 128, 256), (300, 200, 136), (32, 10, 104), (4096, 4096, 4096), (25088, 64, 256), (25088, 256, 64), (8192, 8192, 8192)]
 if variant == "tn":
   shapes = [(128, 128, 64), (64, 64, 128), (256, 128, 256), (200, 300, 136), (64, 64, 100352), (512, 2048, 1568), (4096, 4096, 4096)]
@@ -56,7 +58,7 @@ for m, n, k in shapes:
   end.record()
   torch.cuda.synchronize()
   lib_ms = begin.elapsed_time(end) / iters
-  line = {"variant": variant, "m": m, "n": n, "k": k, "max_err": err, "ref_scale": scale, "ok": err <= 3e-3 * max(1.0, scale), "ms": ms,
+  line = {"variant": variant, "persistent": persistent, "m": m, "n": n, "k": k, "max_err": err, "ref_scale": scale, "ok": err <= 3e-3 * max(1.0, scale), "ms": ms,
           "tflops": 2.0 * m * n * k / ms / 1e9, "cublas_ms": lib_ms, "cublas_tflops": 2.0 * m * n * k / lib_ms / 1e9}
   print(json.dumps(line), flush=True)
   out.write(json.dumps(line) + "\n")

@@ -20,7 +20,7 @@ parser.add_argument("--workers", type=int, default=1)
 args = parser.parse_args()
 experiment = experiments.instantiate("slim-" + args.model + "-imagenet", ["batch-size:" + str(args.batch_size), "synthetic-samples:128"])
 gar = aggregators.instantiate("average", args.workers, 0, [])
-manager = Manager(experiment, gar, args.workers, "sgd", [], "fixed", ["initial-rate:0.01"], device="cuda", engine="fused", backend=args.nn_backend)
+manager = Manager(experiment, gar, args.workers, "sgd", [], "fixed", ["initial-rate:0.01"], device="cuda:0", engine="fused", backend=args.nn_backend)
 for _ in range(3):
   manager.train()
 torch.cuda.synchronize()

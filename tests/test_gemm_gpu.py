@@ -17,6 +17,14 @@ def _check(out, ref, tol=2e-3):
   assert err <= tol * scale, (err, scale)
 
 
+@pytest.fixture(params=[1, 0], ids=["persistent", "tile-per-cta"], autouse=True)
+def gemm_variant(request):
+  from aggregathor_b200.ops import nn_native as nat
+  nat.set_gemm_persistent(request.param)
+  yield
+  nat.set_gemm_persistent(1)
+
+
 SHAPES = [(128, 128, 64), (256, 64, 128), (300, 200, 136), (32, 10, 104), (1000, 192, 4096), (25088, 256, 64), (77, 1000, 2048), (4096, 384, 4096), (130, 70, 8)]
 
 
