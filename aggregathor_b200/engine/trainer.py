@@ -44,6 +44,8 @@ class Manager:
                regularizations=(-1., -1.), trace=False, *, attack=None, nb_real_byz=0, device=None, group=None, engine="auto", backend="auto",
                dtype=None, seed=0, placement=None, debug_checksum=False, engine_args=None, use_graphs=None):
     self.device = torch.device(device) if device is not None else _default_device()
+    if self.device.type == "cuda" and self.device.index is None:
+      self.device = torch.device("cuda", torch.cuda.current_device())
     self.group = group
     self.rank = dist.get_rank(group) if dist.is_initialized() else 0
     self.world = dist.get_world_size(group) if dist.is_initialized() else 1

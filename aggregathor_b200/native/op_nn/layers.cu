@@ -41,96 +41,110 @@ constexpr int kThreads = 256;
 
 // ---------------------------------------------------------------------------- //
 // Per-channel (and per-group) sums: out[g][c] += sum_r f(...). MODE 0: (x, x^2); MODE 1: (dy', dy' * xhat) with
-// dy' = dy masked by (y > 0) when y != null; MODE 2: (dy') only (bias gradient).
-// C % 8 == 0. Thread layout: lanes along channel octets, the rest along rows.
+// dy' = dy masked by (y > 0) when y != null; MODE 2: (dy') only (bias gradient). C % 8 == 0.
+// 2-D decomposition: blockIdx.x = row chunk, blockIdx.y = strip of 64 channels (8 octets), blockIdx.z = group. Inside a
+// CTA 8 lanes cover the strip's octets (128 contiguous bytes per row) and 32 lanes cover rows, 4 rows in flight per
+// thread; one fp64 atomic per channel and CTA, so an address only sees (#row chunks) atomics.
+constexpr int kStripOctets = 8;
+constexpr int kRowLanes = kThreads / kStripOctets;
+constexpr int kRowUnroll = 4;
+
 template<int MODE>
-__global__ void channel_sums_kernel(bf16 const* __restrict__ a, bf16 const* __restrict__ b, bf16 const* __restrict__ y, float const* __restrict__ mean,
+__global__ void __launch_bounds__(kThreads) channel_sums_kernel(bf16 const* __restrict__ a, bf16 const* __restrict__ b, bf16 const* __restrict__ y, float const* __restrict__ mean,
                                     float const* __restrict__ rstd, double* __restrict__ out, long long rows_per_group, int C, int rows_per_cta) {
-    extern __shared__ float red[];  // [2][row lanes][octets * 8]
+    __shared__ float red[kRowLanes][kStripOctets * 16 + 1];
     int const octets = C >> 3;
-    int const lanes_c = octets < kThreads ? octets : kThreads;
-    int const lanes_r = kThreads / lanes_c;
-    int const tc = threadIdx.x % lanes_c, tr = threadIdx.x / lanes_c;
-    int const group = blockIdx.y;
+    int const tc = threadIdx.x % kStripOctets, tr = threadIdx.x / kStripOctets;
+    int const o = blockIdx.y * kStripOctets + tc;
+    int const group = blockIdx.z;
+    bool const active = o < octets;
     long long const row_begin = static_cast<long long>(blockIdx.x) * rows_per_cta;
     long long const row_end = min(rows_per_group, row_begin + rows_per_cta);
     long long const base = static_cast<long long>(group) * rows_per_group;
-    for (int ob = 0; ob < octets; ob += lanes_c) {   // uniform trip count: the loop body contains barriers
-        int const o = ob + tc;
-        bool const active = o < octets && tr < lanes_r;
-        float s0[8], s1[8], mu[8], rs[8];
+    float s0[8], s1[8], mu[8], rs[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            s0[j] = 0.f;
-            s1[j] = 0.f;
-            mu[j] = 0.f;
-            rs[j] = 0.f;
-            if (MODE == 1 && active) {
-                mu[j] = mean[group * C + o * 8 + j];
-                rs[j] = rstd[group * C + o * 8 + j];
-            }
+    for (int j = 0; j < 8; ++j) {
+        s0[j] = 0.f;
+        s1[j] = 0.f;
+        mu[j] = 0.f;
+        rs[j] = 0.f;
+        if (MODE == 1 && active) {
+            mu[j] = mean[group * C + o * 8 + j];
+            rs[j] = rstd[group * C + o * 8 + j];
         }
-        if (active) {
-            for (long long r = row_begin + tr; r < row_end; r += lanes_r) {
-                long long const idx = (base + r) * C + o * 8;
-                float va[8];
-                unpack8(*reinterpret_cast<uint4 const*>(a + idx), va);
-                if (MODE == 0) {
+    }
+    if (active) {
+        for (long long r0 = row_begin + tr; r0 < row_end; r0 += kRowLanes * kRowUnroll) {
+            uint4 ra[kRowUnroll], rb[kRowUnroll], ry[kRowUnroll];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        s0[j] += va[j];
-                        s1[j] += va[j] * va[j];
-                    }
-                } else {
-                    if (y) {
-                        float vy[8];
-                        unpack8(*reinterpret_cast<uint4 const*>(y + idx), vy);
+            for (int u = 0; u < kRowUnroll; ++u) {   // issue every load of the batch before using any of them
+                long long const r = r0 + u * kRowLanes;
+                if (r < row_end) {
+                    long long const idx = (base + r) * C + o * 8;
+                    ra[u] = *reinterpret_cast<uint4 const*>(a + idx);
+                    if (MODE == 1)
+                        rb[u] = *reinterpret_cast<uint4 const*>(b + idx);
+                    if (MODE != 0 && y)
+                        ry[u] = *reinterpret_cast<uint4 const*>(y + idx);
+                }
+            }
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            va[j] = vy[j] > 0.f ? va[j] : 0.f;
-                    }
-                    if (MODE == 1) {
-                        float vx[8];
-                        unpack8(*reinterpret_cast<uint4 const*>(b + idx), vx);
+            for (int u = 0; u < kRowUnroll; ++u) {
+                long long const r = r0 + u * kRowLanes;
+                if (r < row_end) {
+                    float va[8];
+                    unpack8(ra[u], va);
+                    if (MODE == 0) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             s0[j] += va[j];
-                            s1[j] += va[j] * (vx[j] - mu[j]) * rs[j];
+                            s1[j] += va[j] * va[j];
                         }
                     } else {
+                        if (y) {
+                            float vy[8];
+                            unpack8(ry[u], vy);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            s0[j] += va[j];
+                            for (int j = 0; j < 8; ++j)
+                                va[j] = vy[j] > 0.f ? va[j] : 0.f;
+                        }
+                        if (MODE == 1) {
+                            float vx[8];
+                            unpack8(rb[u], vx);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                s0[j] += va[j];
+                                s1[j] += va[j] * (vx[j] - mu[j]) * rs[j];
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                s0[j] += va[j];
+                        }
                     }
                 }
             }
         }
-        // combine the row lanes of this octet
-        float* r0 = red + threadIdx.x * 16;   // == (tr * lanes_c + tc) * 16 for the active threads
+    }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            r0[j] = s0[j];
-            r0[8 + j] = s1[j];
+    for (int j = 0; j < 8; ++j) {
+        red[tr][tc * 16 + j] = s0[j];
+        red[tr][tc * 16 + 8 + j] = s1[j];
+    }
+    __syncthreads();
+    // 128 (or 64) values per CTA: thread t < 128 folds column t over the 32 row lanes in a fixed order
+    int const t = threadIdx.x;
+    if (t < kStripOctets * 16) {
+        int const oc = t / 16, j = t % 16;
+        int const oo = blockIdx.y * kStripOctets + oc;
+        if (oo < octets && (MODE != 2 || j < 8)) {
+            float total = 0.f;
+#pragma unroll 8
+            for (int l = 0; l < kRowLanes; ++l)
+                total += red[l][t];
+            double* dst = out + (static_cast<long long>(group) * C + oo * 8 + (j & 7)) * 2 + (j >> 3);
+            atomicAdd(dst, static_cast<double>(total));
         }
-        __syncthreads();
-        if (tr == 0 && o < octets) {
-            for (int l = 1; l < lanes_r; ++l) {
-                float const* rl = red + (l * lanes_c + tc) * 16;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    s0[j] += rl[j];
-                    s1[j] += rl[8 + j];
-                }
-            }
-            double* dst = out + (static_cast<long long>(group) * C + o * 8) * 2;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                atomicAdd(dst + 2 * j, static_cast<double>(s0[j]));
-                if (MODE != 2)
-                    atomicAdd(dst + 2 * j + 1, static_cast<double>(s1[j]));
-            }
-        }
-        __syncthreads();
     }
 }
 
@@ -160,20 +174,32 @@ __global__ void bn_finalize_kernel(double const* __restrict__ sums, float const*
     }
 }
 
-// y = relu?(x * scale[g][c] + shift[g][c])
-__global__ void bn_apply_kernel(bf16 const* __restrict__ x, bf16* __restrict__ y, float const* __restrict__ scale, float const* __restrict__ shift,
+// y = relu?(x * scale[g][c] + shift[g][c]). Each thread keeps a fixed channel octet (stride is a multiple of `octets`
+// whenever possible) so the coefficients stay in registers and no division happens in the loop.
+__global__ void __launch_bounds__(kThreads) bn_apply_kernel(bf16 const* __restrict__ x, bf16* __restrict__ y, float const* __restrict__ scale, float const* __restrict__ shift,
                                 long long total_octets, int C, long long rows_per_group, int relu) {
-    int const octets = C >> 3;
+    unsigned const octets = static_cast<unsigned>(C >> 3);
+    long long const nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
+    long long const stride = nthreads - nthreads % octets;   // multiple of `octets`: the octet of a thread never changes
     long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    long long const stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    if (i >= stride)
+        return;
+    unsigned const o = static_cast<unsigned>(i % octets);
+    long long const octets_per_group = rows_per_group * octets;
+    int cached_group = -1;
+    float sc[8], sh[8];
     for (; i < total_octets; i += stride) {
-        long long const row = i / octets;
-        int const o = static_cast<int>(i - row * octets);
-        int const g = static_cast<int>(row / rows_per_group);
+        int const g = rows_per_group > 0 && octets_per_group < total_octets ? static_cast<int>(i / octets_per_group) : 0;
+        if (g != cached_group) {
+            cached_group = g;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                sc[j] = scale[g * C + o * 8 + j];
+                sh[j] = shift[g * C + o * 8 + j];
+            }
+        }
         float v[8];
         unpack8(*reinterpret_cast<uint4 const*>(x + i * 8), v);
-        float const* sc = scale + g * C + o * 8;
-        float const* sh = shift + g * C + o * 8;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             v[j] = v[j] * sc[j] + sh[j];
@@ -212,18 +238,35 @@ __global__ void bn_bwd_finalize_kernel(double const* __restrict__ sums, float co
     dbeta[c] = static_cast<float>(total_dbeta);
 }
 
-__global__ void bn_bwd_apply_kernel(bf16 const* __restrict__ dy, bf16 const* __restrict__ x, bf16 const* __restrict__ y, bf16* __restrict__ dx, float const* __restrict__ coef,
+__global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(bf16 const* __restrict__ dy, bf16 const* __restrict__ x, bf16 const* __restrict__ y, bf16* __restrict__ dx, float const* __restrict__ coef,
                                     long long total_octets, int C, long long rows_per_group) {
-    int const octets = C >> 3;
+    unsigned const octets = static_cast<unsigned>(C >> 3);
+    long long const nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
+    long long const stride = nthreads - nthreads % octets;
     long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    long long const stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    if (i >= stride)
+        return;
+    unsigned const o = static_cast<unsigned>(i % octets);
+    long long const octets_per_group = rows_per_group * octets;
+    int cached_group = -1;
+    float ca[8], cb[8], cc[8];
     for (; i < total_octets; i += stride) {
-        long long const row = i / octets;
-        int const o = static_cast<int>(i - row * octets);
-        int const g = static_cast<int>(row / rows_per_group);
+        int const g = octets_per_group < total_octets ? static_cast<int>(i / octets_per_group) : 0;
+        if (g != cached_group) {
+            cached_group = g;
+            float const* cf = coef + (static_cast<long long>(g) * C + o * 8) * 3;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                ca[j] = cf[3 * j];
+                cb[j] = cf[3 * j + 1];
+                cc[j] = cf[3 * j + 2];
+            }
+        }
+        uint4 const rd = *reinterpret_cast<uint4 const*>(dy + i * 8);
+        uint4 const rx = *reinterpret_cast<uint4 const*>(x + i * 8);
         float vd[8], vx[8];
-        unpack8(*reinterpret_cast<uint4 const*>(dy + i * 8), vd);
-        unpack8(*reinterpret_cast<uint4 const*>(x + i * 8), vx);
+        unpack8(rd, vd);
+        unpack8(rx, vx);
         if (y) {
             float vy[8];
             unpack8(*reinterpret_cast<uint4 const*>(y + i * 8), vy);
@@ -231,10 +274,9 @@ __global__ void bn_bwd_apply_kernel(bf16 const* __restrict__ dy, bf16 const* __r
             for (int j = 0; j < 8; ++j)
                 vd[j] = vy[j] > 0.f ? vd[j] : 0.f;
         }
-        float const* cf = coef + (static_cast<long long>(g) * C + o * 8) * 3;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-            vd[j] = cf[3 * j] * vd[j] + cf[3 * j + 1] * vx[j] + cf[3 * j + 2];
+            vd[j] = ca[j] * vd[j] + cb[j] * vx[j] + cc[j];
         *reinterpret_cast<uint4*>(dx + i * 8) = pack8(vd);
     }
 }
@@ -577,21 +619,21 @@ inline int grid_for(long long work, int threads = kThreads, int cap = 148 * 8) {
 }
 
 struct SumsPlan {
-    int rows_per_cta, ctas;
-    size_t smem;
+    int rows_per_cta;
+    dim3 grid;
 };
 inline SumsPlan plan_sums(long long rows_per_group, int C, int groups) {
-    int const octets = C >> 3;
-    int const lanes_c = octets < kThreads ? octets : kThreads;
-    int const lanes_r = kThreads / lanes_c;
-    long long target_ctas = (148 * 4 + groups - 1) / groups;
-    long long rows_per_cta = (rows_per_group + target_ctas - 1) / target_ctas;
-    if (rows_per_cta < lanes_r * 4)
-        rows_per_cta = lanes_r * 4;
+    int const strips = ((C >> 3) + kStripOctets - 1) / kStripOctets;
+    long long target = (148 * 6 + strips * groups - 1) / (strips * groups);   // ~6 CTAs per SM overall
+    if (target < 1)
+        target = 1;
+    long long rows_per_cta = (rows_per_group + target - 1) / target;
+    long long const min_rows = kRowLanes * kRowUnroll;
+    if (rows_per_cta < min_rows)
+        rows_per_cta = min_rows;
     SumsPlan plan;
     plan.rows_per_cta = static_cast<int>(rows_per_cta);
-    plan.ctas = static_cast<int>((rows_per_group + rows_per_cta - 1) / rows_per_cta);
-    plan.smem = static_cast<size_t>(kThreads) * 16 * sizeof(float);
+    plan.grid = dim3(static_cast<unsigned>((rows_per_group + rows_per_cta - 1) / rows_per_cta), strips, groups);
     return plan;
 }
 
@@ -610,7 +652,7 @@ int agb_bn_forward(void const* x, void* y, void const* gamma, void const* beta, 
     long long const rpg = rows / groups;
     AGB_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C * groups, s));
     SumsPlan plan = plan_sums(rpg, C, groups);
-    channel_sums_kernel<0><<<dim3(plan.ctas, groups), kThreads, plan.smem, s>>>(static_cast<bf16 const*>(x), nullptr, nullptr, nullptr, nullptr, static_cast<double*>(sums), rpg, C, plan.rows_per_cta);
+    channel_sums_kernel<0><<<plan.grid, kThreads, 0, s>>>(static_cast<bf16 const*>(x), nullptr, nullptr, nullptr, nullptr, static_cast<double*>(sums), rpg, C, plan.rows_per_cta);
     bn_finalize_kernel<<<(C * groups + 127) / 128, 128, 0, s>>>(static_cast<double const*>(sums), static_cast<float const*>(gamma), static_cast<float const*>(beta),
         static_cast<float*>(save_mean), static_cast<float*>(save_rstd), static_cast<float*>(scale), static_cast<float*>(shift), static_cast<float*>(moving_mean),
         static_cast<float*>(moving_var), C, groups, rpg, eps, decay);
@@ -628,7 +670,7 @@ int agb_bn_backward(void const* dy, void const* x, void const* y, void const* ga
     long long const rpg = rows / groups;
     AGB_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C * groups, s));
     SumsPlan plan = plan_sums(rpg, C, groups);
-    channel_sums_kernel<1><<<dim3(plan.ctas, groups), kThreads, plan.smem, s>>>(static_cast<bf16 const*>(dy), static_cast<bf16 const*>(x), static_cast<bf16 const*>(y),
+    channel_sums_kernel<1><<<plan.grid, kThreads, 0, s>>>(static_cast<bf16 const*>(dy), static_cast<bf16 const*>(x), static_cast<bf16 const*>(y),
         static_cast<float const*>(save_mean), static_cast<float const*>(save_rstd), static_cast<double*>(sums), rpg, C, plan.rows_per_cta);
     bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(static_cast<double const*>(sums), static_cast<float const*>(gamma), static_cast<float const*>(save_mean),
         static_cast<float const*>(save_rstd), static_cast<float*>(coef), static_cast<float*>(dgamma), static_cast<float*>(dbeta), C, groups, rpg);
@@ -646,7 +688,7 @@ int agb_colsum(void const* dy, void const* y, void* out, void* sums, long long r
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     AGB_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, s));
     SumsPlan plan = plan_sums(rows, C, 1);
-    channel_sums_kernel<2><<<dim3(plan.ctas, 1), kThreads, plan.smem, s>>>(static_cast<bf16 const*>(dy), nullptr, static_cast<bf16 const*>(y), nullptr, nullptr, static_cast<double*>(sums), rows, C, plan.rows_per_cta);
+    channel_sums_kernel<2><<<plan.grid, kThreads, 0, s>>>(static_cast<bf16 const*>(dy), nullptr, static_cast<bf16 const*>(y), nullptr, nullptr, static_cast<double*>(sums), rows, C, plan.rows_per_cta);
     cast_sums_kernel<<<(C + 127) / 128, 128, 0, s>>>(static_cast<double const*>(sums), static_cast<float*>(out), C);
     AGB_CUDA_OK(cudaGetLastError());
     return 0;
