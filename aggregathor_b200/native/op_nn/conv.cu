@@ -1,0 +1,346 @@
+// Implicit-GEMM k x k convolution (stride 1, "same" zero padding) on tcgen05: no im2col buffer.
+//
+// Activations are NHWC, so the A operand of the forward GEMM for filter tap (kh, kw) and a 64-channel slice is simply the
+// activation tensor shifted by (kh - pad, kw - pad). A 4-D TMA tensor map (C, W, H, N) lets one `cp.async.bulk.tensor.4d`
+// fetch a *box of pixels* x 64 channels straight into the 128B-swizzled K-major layout the MMA wants; coordinates that
+// fall outside the image are zero-filled by the TMA unit, which is exactly the convolution's padding. The M tile (128
+// rows) is a pixel box bw x bh x bn chosen so that it tiles the feature map: 8x8x2 (56x56), 4x4x8 (28x28), 2x2x32 (14x14),
+// 7x1x16 (7x7, 112 valid rows) ...
+//
+//   forward  y[p, co]      = sum_{kh,kw,ci} x[p + (kh-pad, kw-pad), ci] * W[co, kh, kw, ci]       A: 4-D box of x,  B: K-major W
+//   dgrad    dx[p, ci]     = sum_{kh,kw,co} dy[p + (pad-kh, pad-kw), co] * W[co, kh, kw, ci]      A: 4-D box of dy, B: MN-major W tap
+//   wgrad    dW[co,kh,kw,ci] = sum_p dy[p, co] * x[p + (kh-pad, kw-pad), ci]                       A, B: 4-D MN-major boxes (K = pixels)
+//
+// Pipeline, TMEM double buffering and epilogue are those of the persistent GEMM (gemm_kernels.cuh); only the producer's
+// coordinates and the epilogue's row -> address mapping differ.
+
+#include "gemm_kernels.cuh"
+
+namespace {
+
+struct ConvParams {
+    int N, H, W;            // pixel grid (stride 1 => input and output share it)
+    int Cin, Cout, k, pad;
+    int bw, bh, bn;         // pixel box of one M tile (fwd/dgrad: product <= 128) or one K block (wgrad: product <= 64)
+    int tiles_w, tiles_h, tiles_n;
+};
+
+enum ConvMode { kFwd = 0, kDgrad = 1, kWgrad = 2 };
+
+inline int make_tmap_4d_bf16(CUtensorMap* map, void const* base, int C, int W, int H, int N, int bw, int bh, int bn) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn)
+        return 201;
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(N)};
+    cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(W) * C * 2, static_cast<cuuint64_t>(H) * W * C * 2};
+    cuuint32_t box[4] = {64, static_cast<cuuint32_t>(bw), static_cast<cuuint32_t>(bh), static_cast<cuuint32_t>(bn)};
+    cuuint32_t elem[4] = {1, 1, 1, 1};
+    CUresult res = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (res != CUDA_SUCCESS) {
+        std::fprintf(stderr, "[agb] cuTensorMapEncodeTiled(4d) failed (%d): C %d W %d H %d N %d box %d %d %d\n", (int) res, C, W, H, N, bw, bh, bn);
+        return 202;
+    }
+    return 0;
+}
+
+// One persistent kernel for the three products. `tmap_a`: 4-D map of the activation that plays A (x for fwd, dy for dgrad and
+// wgrad); `tmap_b`: 2-D weight map (fwd: K-major rows [Cout][k*k*Cin]; dgrad: the same matrix read as MN-major boxes) or
+// the 4-D map of x (wgrad).
+template<int BN, int MODE>
+__global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                                                                    GemmParams const p, ConvParams const cp, int items_mn, int splits) {
+    constexpr bool A_MN = MODE == kWgrad, B_MN = MODE != kFwd;
+    using Cfg = Config<BN>;
+    using PCfg = PersistentConfig<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + PCfg::kStages * Cfg::kStageBytes);
+    uint64_t* empty = full + PCfg::kStages;
+    uint64_t* tmem_full = empty + PCfg::kStages;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int const taps = cp.k * cp.k;
+    int const pixel_tiles = cp.tiles_w * cp.tiles_h * cp.tiles_n;
+    int const box_rows = cp.bw * cp.bh * cp.bn;
+    // number of K blocks of one work item before splitting
+    int const cchunks = (MODE == kFwd ? cp.Cin : cp.Cout) / 64;
+    int const total_kblocks = MODE == kWgrad ? pixel_tiles : taps * cchunks;
+    int const total_items = items_mn * splits;
+
+    // Pixel boxes smaller than the MMA tile (7x7 maps) leave rows that TMA never writes: zero the ring once.
+    if (box_rows < (MODE == kWgrad ? 64 : 128)) {
+        uint4* ring = reinterpret_cast<uint4*>(smem);
+        for (uint32_t i = threadIdx.x; i < PCfg::kStages * Cfg::kStageBytes / 16; i += blockDim.x)
+            ring[i] = make_uint4(0, 0, 0, 0);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy zeros visible to the async (TMA/MMA) proxy
+    }
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+        for (int s = 0; s < PCfg::kStages; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(tmem_full + b, 1);
+            mbar_init(tmem_empty + b, 4);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1)
+        tmem_alloc<PCfg::kTmemCols>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t const tmem_base = *tmem_slot;
+
+    // Bytes that one stage really receives (boxes may be smaller than the tile): A box rows * 128 B per 64-wide chunk.
+    uint32_t const a_bytes = MODE == kWgrad ? 2u * box_rows * 128u : static_cast<uint32_t>(box_rows) * 128u;
+    uint32_t const b_bytes = MODE == kWgrad ? (BN / 64) * box_rows * 128u : Cfg::kBBytes;
+
+    // item -> (m index, n tile, tap for wgrad, k split)
+    struct Item { int pw, ph, pn, n0, tap, kb_begin, nkb, m0; };
+    auto decode = [&](int item) {
+        Item it;
+        int const mn = item % items_mn, split = item / items_mn;
+        it.kb_begin = split * p.kblocks_per_split;
+        int const kb_end = min(total_kblocks, it.kb_begin + p.kblocks_per_split);
+        it.nkb = kb_end - it.kb_begin;
+        if (MODE == kWgrad) {
+            int const m_tiles = (cp.Cout + kBM - 1) / kBM, n_tiles = (cp.Cin + BN - 1) / BN;
+            it.tap = mn / (m_tiles * n_tiles);
+            int const rest = mn % (m_tiles * n_tiles);
+            it.m0 = (rest % m_tiles) * kBM;      // output-channel offset
+            it.n0 = (rest / m_tiles) * BN;       // input-channel offset
+            it.pw = it.ph = it.pn = 0;
+        } else {
+            int const tile = mn % pixel_tiles;
+            it.n0 = (mn / pixel_tiles) * BN;
+            it.pw = (tile % cp.tiles_w) * cp.bw;
+            it.ph = ((tile / cp.tiles_w) % cp.tiles_h) * cp.bh;
+            it.pn = (tile / (cp.tiles_w * cp.tiles_h)) * cp.bn;
+            it.tap = 0;
+            it.m0 = 0;
+        }
+        return it;
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t ring = 0;
+            for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+                Item const it = decode(item);
+                for (int i = 0; i < it.nkb; ++i, ++ring) {
+                    int const s = ring % PCfg::kStages;
+                    mbar_wait(empty + s, ((ring / PCfg::kStages) & 1) ^ 1, 21);
+                    uint8_t* a_dst = smem + s * Cfg::kStageBytes;
+                    uint8_t* b_dst = a_dst + Cfg::kABytes;
+                    int const kb = it.kb_begin + i;
+                    mbar_expect_tx(full + s, a_bytes + b_bytes);
+                    if (MODE == kWgrad) {
+                        // K block = pixel box `kb`; A = dy[box, co chunk], B = x[box shifted by the tap, ci chunk]
+                        int const w0 = (kb % cp.tiles_w) * cp.bw, h0 = ((kb / cp.tiles_w) % cp.tiles_h) * cp.bh, n0p = (kb / (cp.tiles_w * cp.tiles_h)) * cp.bn;
+                        int const kh = it.tap / cp.k, kw = it.tap % cp.k;
+                        tma_load_4d(a_dst, &tmap_a, full + s, it.m0, w0, h0, n0p);
+                        tma_load_4d(a_dst + kBK * 128, &tmap_a, full + s, it.m0 + 64, w0, h0, n0p);
+#pragma unroll
+                        for (int c = 0; c < BN / 64; ++c)
+                            tma_load_4d(b_dst + c * kBK * 128, &tmap_b, full + s, it.n0 + c * 64, w0 + kw - cp.pad, h0 + kh - cp.pad, n0p);
+                    } else {
+                        int const tap = kb / cchunks, c0 = (kb % cchunks) * 64;
+                        int const kh = tap / cp.k, kw = tap % cp.k;
+                        int const dw = MODE == kFwd ? kw - cp.pad : cp.pad - kw, dh = MODE == kFwd ? kh - cp.pad : cp.pad - kh;
+                        tma_load_4d(a_dst, &tmap_a, full + s, c0, it.pw + dw, it.ph + dh, it.pn);
+                        if (MODE == kFwd) {
+                            tma_load_2d(b_dst, &tmap_b, full + s, tap * cp.Cin + c0, it.n0);
+                        } else { // dgrad: B[k = co, n = ci] = W[co][tap][ci]: MN-major boxes of 64 ci x 64 co
+#pragma unroll
+                            for (int c = 0; c < BN / 64; ++c)
+                                tma_load_2d(b_dst + c * kBK * 128, &tmap_b, full + s, tap * cp.Cin + it.n0 + c * 64, c0);
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            uint32_t ring = 0, j = 0;
+            for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++j) {
+                Item const it = decode(item);
+                uint32_t const buf = j & 1;
+                mbar_wait(tmem_empty + buf, ((j >> 1) & 1) ^ 1, 22);
+                tc_fence_after();
+                uint32_t const acc = tmem_base + buf * Cfg::kTmemCols;
+                for (int i = 0; i < it.nkb; ++i, ++ring) {
+                    int const s = ring % PCfg::kStages;
+                    mbar_wait(full + s, (ring / PCfg::kStages) & 1, 23);
+                    tc_fence_after();
+                    consume_stage<BN, A_MN, B_MN>(smem_u32(smem + s * Cfg::kStageBytes), acc, i == 0);
+                    umma_commit(empty + s);
+                }
+                umma_commit(tmem_full + buf);
+            }
+        }
+    } else {
+        uint32_t j = 0;
+        for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++j) {
+            Item const it = decode(item);
+            uint32_t const buf = j & 1;
+            mbar_wait(tmem_full + buf, (j >> 1) & 1, 24);
+            tc_fence_after();
+            int const r = (warp & 3) * 32 + lane;
+            bool valid;
+            long long offset;
+            if (MODE == kWgrad) {   // row = output channel; columns = (tap, ci) inside dW[Cout][k*k*Cin]
+                int const co = it.m0 + r;
+                valid = co < cp.Cout;
+                offset = static_cast<long long>(co) * p.ldc + it.tap * cp.Cin;
+            } else {                // row = pixel of the box, (w fastest, then h, then n)
+                int const bi_w = r % cp.bw, bi_h = (r / cp.bw) % cp.bh, bi_n = r / (cp.bw * cp.bh);
+                int const w = it.pw + bi_w, h = it.ph + bi_h, n = it.pn + bi_n;
+                valid = r < box_rows && w < cp.W && h < cp.H && n < cp.N;
+                offset = ((static_cast<long long>(n) * cp.H + h) * cp.W + w) * p.ldc;
+            }
+            epilogue_rows<BN>(p, tmem_base + buf * Cfg::kTmemCols, warp, valid, offset, it.n0);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0)
+                mbar_arrive(tmem_empty + buf);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1)
+        tmem_dealloc<PCfg::kTmemCols>(tmem_base);
+}
+
+template<int BN, int MODE>
+int launch_conv(CUtensorMap const& ta, CUtensorMap const& tb, GemmParams const& p, ConvParams const& cp, int items_mn, int splits, cudaStream_t stream) {
+    using PCfg = PersistentConfig<BN>;
+    auto kernel = conv_tcgen05_kernel<BN, MODE>;
+    static bool configured = false;
+    static int sms = 0;
+    if (!configured) {
+        AGB_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg::kSmemBytes));
+        int device = 0;
+        AGB_CUDA_OK(cudaGetDevice(&device));
+        AGB_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+        configured = true;
+    }
+    long long const items = static_cast<long long>(items_mn) * splits;
+    int const grid = static_cast<int>(items < sms ? items : sms);
+    kernel<<<grid, kThreads, PCfg::kSmemBytes, stream>>>(ta, tb, p, cp, items_mn, splits);
+    AGB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// Pixel box (bw, bh, bn) with bw*bh*bn <= rows, bw | W-tiles etc. Prefers exact tilings of the feature map.
+bool choose_box(int W, int H, int N, int rows, int& bw, int& bh, int& bn) {
+    long long best = -1;
+    for (int w = 1; w <= W && w <= rows; ++w) {
+        if (W % w)
+            continue;
+        for (int h = 1; h <= H && w * h <= rows; ++h) {
+            if (H % h)
+                continue;
+            int n = rows / (w * h);
+            if (n > N)
+                n = N;
+            while (n > 1 && N % n)
+                --n;
+            // prefer full MMA tiles, then spatially compact boxes (halo reuse in L2), then wide rows (long TMA runs)
+            long long const score = static_cast<long long>(w) * h * n * 1000000 + static_cast<long long>(w) * h * 1000 + w;
+            if (score > best) {
+                best = score;
+                bw = w; bh = h; bn = n;
+            }
+        }
+    }
+    return best >= 0;
+}
+
+} // namespace
+
+extern "C" {
+
+// mode 0: y = conv(x, W) (+bias, ReLU) ; mode 1: dx = conv_transpose(dy, W) ; mode 2: dW (+)= dy^T * x (fp32, atomics; caller zeroes).
+// x / dy / y / dx are NHWC bf16 with N x H x W pixels (stride-1, same padding: pad = (k - 1) / 2, odd k);
+// W is [Cout][k][k][Cin] bf16; dW is [Cout][k][k][Cin] fp32. Cin % 64 == 0 and Cout % 64 == 0.
+int agb_conv_implicit(int mode, void const* act, void const* other, void* out, int N, int H, int W, int Cin, int Cout, int k, void const* bias, int relu,
+                      int out_fp32, int splits, int bn, void* stream) {
+    if ((k & 1) == 0 || Cin % 64 || Cout % 64 || N < 1)
+        return 401;
+    ConvParams cp{};
+    cp.N = N; cp.H = H; cp.W = W; cp.Cin = Cin; cp.Cout = Cout; cp.k = k; cp.pad = (k - 1) / 2;
+    if (!choose_box(W, H, N, mode == 2 ? 64 : 128, cp.bw, cp.bh, cp.bn))
+        return 402;
+    cp.tiles_w = W / cp.bw; cp.tiles_h = H / cp.bh; cp.tiles_n = N / cp.bn;
+    int const pixel_tiles = cp.tiles_w * cp.tiles_h * cp.tiles_n;
+    GemmParams p{};
+    p.C = out;
+    p.bias = static_cast<float const*>(bias);
+    p.relu = relu;
+    p.out_fp32 = out_fp32;
+    CUtensorMap ta, tb;
+    int status, items_mn, total_kblocks;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (mode == 0) {
+        p.M = N * H * W; p.N = Cout; p.K = k * k * Cin; p.ldc = Cout;
+        if (bn == 0)
+            bn = Cout <= 64 ? 64 : 128;
+        if ((status = make_tmap_4d_bf16(&ta, act, Cin, W, H, N, cp.bw, cp.bh, cp.bn)))
+            return status;
+        if ((status = make_tmap_2d_bf16(&tb, other, static_cast<uint64_t>(k) * k * Cin, Cout, static_cast<uint64_t>(k) * k * Cin, kBK, bn)))
+            return status;
+        items_mn = pixel_tiles * ((Cout + bn - 1) / bn);
+        total_kblocks = k * k * (Cin / 64);
+    } else if (mode == 1) {
+        p.M = N * H * W; p.N = Cin; p.K = k * k * Cout; p.ldc = Cin;
+        if (bn == 0)
+            bn = Cin <= 64 ? 64 : 128;
+        if ((status = make_tmap_4d_bf16(&ta, act, Cout, W, H, N, cp.bw, cp.bh, cp.bn)))
+            return status;
+        if ((status = make_tmap_2d_bf16(&tb, other, static_cast<uint64_t>(k) * k * Cin, Cout, static_cast<uint64_t>(k) * k * Cin, 64, kBK)))
+            return status;
+        items_mn = pixel_tiles * ((Cin + bn - 1) / bn);
+        total_kblocks = k * k * (Cout / 64);
+    } else if (mode == 2) {
+        p.M = Cout; p.N = Cin; p.K = N * H * W; p.ldc = static_cast<long long>(k) * k * Cin;
+        if (!out_fp32)
+            return 205;
+        if (bn == 0)
+            bn = Cin <= 64 ? 64 : 128;
+        if ((status = make_tmap_4d_bf16(&ta, act, Cout, W, H, N, cp.bw, cp.bh, cp.bn)))
+            return status;
+        if ((status = make_tmap_4d_bf16(&tb, other, Cin, W, H, N, cp.bw, cp.bh, cp.bn)))
+            return status;
+        items_mn = k * k * ((Cout + kBM - 1) / kBM) * ((Cin + bn - 1) / bn);
+        total_kblocks = pixel_tiles;
+    } else {
+        return 403;
+    }
+    if (splits < 1)
+        splits = 1;
+    if (splits > total_kblocks)
+        splits = total_kblocks;
+    if (splits > 1 && !out_fp32)
+        return 205;
+    p.atomic = splits > 1;
+    p.kblocks_per_split = (total_kblocks + splits - 1) / splits;
+    splits = (total_kblocks + p.kblocks_per_split - 1) / p.kblocks_per_split;
+#define AGB_CONV_DISPATCH(MODE) \
+    switch (bn) { \
+        case 64: return launch_conv<64, MODE>(ta, tb, p, cp, items_mn, splits, s); \
+        case 128: return launch_conv<128, MODE>(ta, tb, p, cp, items_mn, splits, s); \
+    } \
+    return 203;
+    if (mode == 0) { AGB_CONV_DISPATCH(kFwd) }
+    if (mode == 1) { AGB_CONV_DISPATCH(kDgrad) }
+    AGB_CONV_DISPATCH(kWgrad)
+#undef AGB_CONV_DISPATCH
+}
+
+} // extern "C"

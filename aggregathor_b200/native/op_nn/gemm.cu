@@ -1,393 +1,5 @@
-// bf16 GEMM on the 5th-generation tensor cores: C[M,N] = op(A) * op(B) with fp32 accumulation in TMEM.
-//
-// One kernel family covers the three products a layer needs:
-//   forward   Y  = X  * W^T      A K-major   ([M,K] rows)      B K-major  ([N,K] rows)
-//   dgrad     dX = dY * W        A K-major   ([M,K] rows)      B MN-major ([K,N] rows, N contiguous)
-//   wgrad     dW = dY^T * X      A MN-major  ([K,M] rows)      B MN-major ([K,N] rows)   (+ split-K)
-// so activations and weights are consumed in the layout they already have: no transposes.
-//
-// Structure (one 128 x BN output tile per CTA, two CTAs per SM so that one CTA's epilogue overlaps the
-// other's main loop):
-//   warp 0      TMA producer: cp.async.bulk.tensor tiles (128B swizzle) into a kStages-deep smem ring,
-//               completion signalled on `full` mbarriers (complete_tx::bytes)
-//   warp 1      allocates TMEM, one elected lane issues tcgen05.mma (kind::f16, M=128, N=BN, K=16) from the
-//               smem descriptors, tcgen05.commit releases ring slots (`empty`) and finally arms `tmem_full`
-//   warps 2..5  epilogue: tcgen05.ld 32x32b -> registers, + bias, ReLU, convert, store (or red.add for split-K)
-//
-// blockIdx.z = K split; each split handles a contiguous range of 64-wide K blocks and, when splits > 1,
-// accumulates with fp32 atomics into a pre-zeroed C.
-
-#include <cuda_bf16.h>
-#include <cstdlib>
-
-#include <agb_device.cuh>
-#include <agb_tcgen05.cuh>
-
-using namespace agb;
-using namespace agb::sm100;
-
-namespace {
-
-constexpr int kBM = 128;       // UMMA M
-constexpr int kBK = 64;        // K elements per stage = one 128-byte swizzle row
-constexpr int kUmmaK = 16;
-constexpr int kThreads = 192;
-
-template<int BN> struct Config {
-    static constexpr int kStages = BN <= 64 ? 4 : 3;   // <= 97 KB of smem for BN <= 128: two CTAs per SM
-    static constexpr uint32_t kABytes = kBM * kBK * 2;
-    static constexpr uint32_t kBBytes = BN * kBK * 2;
-    static constexpr uint32_t kStageBytes = kABytes + kBBytes;
-    static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /* alignment slack */ + 256 /* barriers */;
-    static constexpr uint32_t kTmemCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
-};
-
-struct GemmParams {
-    int M, N, K;            // logical problem
-    long long ldc;          // row stride of C (elements)
-    void* C;
-    float const* bias;      // per-N fp32 bias or null
-    int relu;
-    int out_fp32;           // C element type: 1 = float, 0 = bf16
-    int atomic;             // accumulate with red.add.f32 (split-K); requires out_fp32
-    int kblocks_per_split;
-};
-
-// Epilogue of one 128 x BN accumulator tile: TMEM -> registers -> (+bias, ReLU, convert) -> global memory.
-template<int BN>
-__device__ __forceinline__ void epilogue_tile(GemmParams const& p, uint32_t tmem_acc, int warp, int lane, int m0, int n0) {
-    int const quarter = warp & 3;                 // TMEM lane quarter this warp may access
-    int const row = m0 + quarter * 32 + lane;
-    uint32_t const taddr = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16);
-#pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-        float v[32];
-        tmem_ld_32x32(taddr + c, v);
-        int const col0 = n0 + c;
-        if (row < p.M && col0 < p.N) {
-            if (p.bias) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (col0 + j < p.N)
-                        v[j] += __ldg(p.bias + col0 + j);
-            }
-            if (p.relu) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    v[j] = fmaxf(v[j], 0.f);
-            }
-            bool const full_span = col0 + 32 <= p.N;
-            if (p.out_fp32) {
-                float* dst = static_cast<float*>(p.C) + static_cast<long long>(row) * p.ldc + col0;
-                if (p.atomic) {
-                    if (full_span && (p.ldc & 3) == 0) {   // 128-bit fp32 reductions (sm_90+)
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            atomicAdd(reinterpret_cast<float4*>(dst + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (col0 + j < p.N)
-                                atomicAdd(dst + j, v[j]);
-                    }
-                } else if (full_span && (p.ldc & 3) == 0) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (col0 + j < p.N)
-                            dst[j] = v[j];
-                }
-            } else {
-                __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.C) + static_cast<long long>(row) * p.ldc + col0;
-                if (full_span && (p.ldc & 7) == 0) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]), h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-                        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-                        uint4 packed = make_uint4(*reinterpret_cast<unsigned*>(&h0), *reinterpret_cast<unsigned*>(&h1), *reinterpret_cast<unsigned*>(&h2), *reinterpret_cast<unsigned*>(&h3));
-                        *reinterpret_cast<uint4*>(dst + j) = packed;
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (col0 + j < p.N)
-                            dst[j] = __float2bfloat16(v[j]);
-                }
-            }
-        }
-    }
-}
-
-// Loads of one pipeline stage (A and B tiles of k-block `k`).
-template<int BN, bool A_MN, bool B_MN>
-__device__ __forceinline__ void produce_stage(CUtensorMap const* tmap_a, CUtensorMap const* tmap_b, uint8_t* a_dst, uint64_t* bar, int m0, int n0, int k) {
-    uint8_t* b_dst = a_dst + Config<BN>::kABytes;
-    mbar_expect_tx(bar, Config<BN>::kStageBytes);
-    if (A_MN) { // rows = K index, 64 M-elements per row; one box per 64-wide M chunk
-        tma_load_2d(a_dst, tmap_a, bar, m0, k);
-        tma_load_2d(a_dst + kBK * 128, tmap_a, bar, m0 + 64, k);
-    } else {
-        tma_load_2d(a_dst, tmap_a, bar, k, m0);
-    }
-    if (B_MN) {
-#pragma unroll
-        for (int c = 0; c < BN / 64; ++c)
-            tma_load_2d(b_dst + c * kBK * 128, tmap_b, bar, n0 + c * 64, k);
-    } else {
-        tma_load_2d(b_dst, tmap_b, bar, k, n0);
-    }
-}
-
-// tcgen05.mma over one staged k-block (4 instructions of K = 16).
-template<int BN, bool A_MN, bool B_MN>
-__device__ __forceinline__ void consume_stage(uint32_t a_addr, uint32_t tmem_acc, bool first) {
-    constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, A_MN, B_MN);
-    uint32_t const b_addr = a_addr + Config<BN>::kABytes;
-#pragma unroll
-    for (int kk = 0; kk < kBK / kUmmaK; ++kk) {
-        // K-major: 16 K-elements = 32 B further inside the 128B swizzled row.
-        // MN-major: 16 K-rows = 16 * 128 B further; chunks of 64 MN-elements are kBK * 128 B apart.
-        uint64_t const da = A_MN ? umma_smem_desc(a_addr + kk * kUmmaK * 128, kBK * 128, 1024) : umma_smem_desc(a_addr + kk * kUmmaK * 2, 16, 1024);
-        uint64_t const db = B_MN ? umma_smem_desc(b_addr + kk * kUmmaK * 128, kBK * 128, 1024) : umma_smem_desc(b_addr + kk * kUmmaK * 2, 16, 1024);
-        umma_f16(tmem_acc, da, db, idesc, !(first && kk == 0));
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------------------- //
-// Persistent variant: one CTA per SM loops over (tile, k-split) work items. The smem ring runs continuously across
-// items, and the accumulator is double-buffered in TMEM (2 x BN columns) so that the epilogue of item j overlaps the
-// main loop of item j + 1; barrier setup and the TMEM allocation are paid once per CTA instead of once per tile.
-template<int BN> struct PersistentConfig {
-    static constexpr int kStages = BN <= 64 ? 8 : BN <= 128 ? 6 : 4;
-    static constexpr uint32_t kSmemBytes = kStages * Config<BN>::kStageBytes + 1024 + 256;
-    static constexpr uint32_t kTmemCols = 2 * Config<BN>::kTmemCols;   // <= 512
-};
-
-template<int BN, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, GemmParams const p, int m_tiles, int n_tiles, int splits) {
-    using Cfg = Config<BN>;
-    using PCfg = PersistentConfig<BN>;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + PCfg::kStages * Cfg::kStageBytes);
-    uint64_t* empty = full + PCfg::kStages;
-    uint64_t* tmem_full = empty + PCfg::kStages;   // [2]
-    uint64_t* tmem_empty = tmem_full + 2;          // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-
-    int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int const total_kblocks = (p.K + kBK - 1) / kBK;
-    int const total_items = m_tiles * n_tiles * splits;
-
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmap_a);
-        tma_prefetch_desc(&tmap_b);
-        for (int s = 0; s < PCfg::kStages; ++s) {
-            mbar_init(full + s, 1);
-            mbar_init(empty + s, 1);
-        }
-        for (int b = 0; b < 2; ++b) {
-            mbar_init(tmem_full + b, 1);
-            mbar_init(tmem_empty + b, 4);          // one arrival per epilogue warp
-        }
-        mbar_fence_init();
-    }
-    if (warp == 1)
-        tmem_alloc<PCfg::kTmemCols>(tmem_slot);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    uint32_t const tmem_base = *tmem_slot;
-
-    // item -> (m tile fastest, then n tile, then k split): consecutive CTAs share the same B (weight) tile
-    auto decode = [&](int item, int& m0, int& n0, int& kb_begin, int& nkb) {
-        int const tile = item % (m_tiles * n_tiles), split = item / (m_tiles * n_tiles);
-        m0 = (tile % m_tiles) * kBM;
-        n0 = (tile / m_tiles) * BN;
-        kb_begin = split * p.kblocks_per_split;
-        int const kb_end = min(total_kblocks, kb_begin + p.kblocks_per_split);
-        nkb = kb_end - kb_begin;
-    };
-
-    if (warp == 0) {
-        if (lane == 0) {
-            uint32_t it = 0;   // running k-block counter => ring slot and phase
-            for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-                int m0, n0, kb_begin, nkb;
-                decode(item, m0, n0, kb_begin, nkb);
-                for (int i = 0; i < nkb; ++i, ++it) {
-                    int const s = it % PCfg::kStages;
-                    mbar_wait(empty + s, ((it / PCfg::kStages) & 1) ^ 1, 11);
-                    produce_stage<BN, A_MN, B_MN>(&tmap_a, &tmap_b, smem + s * Cfg::kStageBytes, full + s, m0, n0, (kb_begin + i) * kBK);
-                }
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            uint32_t it = 0, j = 0;
-            for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++j) {
-                int m0, n0, kb_begin, nkb;
-                decode(item, m0, n0, kb_begin, nkb);
-                uint32_t const buf = j & 1;
-                mbar_wait(tmem_empty + buf, ((j >> 1) & 1) ^ 1, 12);   // epilogue drained this accumulator
-                tc_fence_after();
-                uint32_t const acc = tmem_base + buf * Cfg::kTmemCols;
-                for (int i = 0; i < nkb; ++i, ++it) {
-                    int const s = it % PCfg::kStages;
-                    mbar_wait(full + s, (it / PCfg::kStages) & 1, 13);
-                    tc_fence_after();
-                    consume_stage<BN, A_MN, B_MN>(smem_u32(smem + s * Cfg::kStageBytes), acc, i == 0);
-                    umma_commit(empty + s);
-                }
-                umma_commit(tmem_full + buf);
-            }
-        }
-    } else {
-        uint32_t j = 0;
-        for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++j) {
-            int m0, n0, kb_begin, nkb;
-            decode(item, m0, n0, kb_begin, nkb);
-            uint32_t const buf = j & 1;
-            mbar_wait(tmem_full + buf, (j >> 1) & 1, 14);
-            tc_fence_after();
-            epilogue_tile<BN>(p, tmem_base + buf * Cfg::kTmemCols, warp, lane, m0, n0);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0)
-                mbar_arrive(tmem_empty + buf);
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1)
-        tmem_dealloc<PCfg::kTmemCols>(tmem_base);
-}
-
-template<int BN, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(kThreads, BN <= 128 ? 2 : 1) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, GemmParams const p) {
-    using Cfg = Config<BN>;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
-    uint64_t* empty = full + Cfg::kStages;
-    uint64_t* tmem_full = empty + Cfg::kStages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-
-    int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int const m0 = blockIdx.x * kBM, n0 = blockIdx.y * BN;
-    int const total_kblocks = (p.K + kBK - 1) / kBK;
-    int const kb_begin = blockIdx.z * p.kblocks_per_split;
-    int const kb_end = min(total_kblocks, kb_begin + p.kblocks_per_split);
-    int const nkb = kb_end - kb_begin;
-
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmap_a);
-        tma_prefetch_desc(&tmap_b);
-        for (int s = 0; s < Cfg::kStages; ++s) {
-            mbar_init(full + s, 1);
-            mbar_init(empty + s, 1);
-        }
-        mbar_init(tmem_full, 1);
-        mbar_fence_init();
-    }
-    if (warp == 1)
-        tmem_alloc<Cfg::kTmemCols>(tmem_slot);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    uint32_t const tmem_base = *tmem_slot;
-
-    if (nkb > 0) {
-        if (warp == 0) {
-            // ------------------------------ TMA producer ------------------------------ //
-            if (lane == 0) {
-                for (int i = 0; i < nkb; ++i) {
-                    int const s = i % Cfg::kStages;
-                    uint32_t const phase = (i / Cfg::kStages) & 1;
-                    mbar_wait(empty + s, phase ^ 1, 1);
-                    produce_stage<BN, A_MN, B_MN>(&tmap_a, &tmap_b, smem + s * Cfg::kStageBytes, full + s, m0, n0, (kb_begin + i) * kBK);
-                }
-            }
-        } else if (warp == 1) {
-            // ------------------------------ MMA issuer ------------------------------ //
-            if (lane == 0) {
-                for (int i = 0; i < nkb; ++i) {
-                    int const s = i % Cfg::kStages;
-                    uint32_t const phase = (i / Cfg::kStages) & 1;
-                    mbar_wait(full + s, phase, 2);
-                    tc_fence_after();
-                    consume_stage<BN, A_MN, B_MN>(smem_u32(smem + s * Cfg::kStageBytes), tmem_base, i == 0);
-                    umma_commit(empty + s);      // slot reusable once these MMAs have read it
-                }
-                umma_commit(tmem_full);          // accumulator complete
-            }
-        } else {
-            // ------------------------------ epilogue ------------------------------ //
-            mbar_wait(tmem_full, 0, 3);
-            tc_fence_after();
-            epilogue_tile<BN>(p, tmem_base, warp, lane, m0, n0);
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1)
-        tmem_dealloc<Cfg::kTmemCols>(tmem_base);
-}
-
-static int g_persistent = -1;   // -1: read AGB_GEMM_PERSISTENT at first use
-
-template<int BN, bool A_MN, bool B_MN>
-int launch_gemm(CUtensorMap const& ta, CUtensorMap const& tb, GemmParams const& p, int splits, cudaStream_t stream) {
-    using Cfg = Config<BN>;
-    if (g_persistent < 0) {
-        char const* env = std::getenv("AGB_GEMM_PERSISTENT");
-        g_persistent = env ? std::atoi(env) : 1;
-    }
-    int const m_tiles = (p.M + kBM - 1) / kBM, n_tiles = (p.N + BN - 1) / BN;
-    if (g_persistent) {
-        using PCfg = PersistentConfig<BN>;
-        auto kernel = gemm_tcgen05_persistent_kernel<BN, A_MN, B_MN>;
-        static bool configured = false;
-        static int sms = 0;
-        if (!configured) {
-            AGB_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg::kSmemBytes));
-            int device = 0;
-            AGB_CUDA_OK(cudaGetDevice(&device));
-            AGB_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-            configured = true;
-        }
-        long long const items = static_cast<long long>(m_tiles) * n_tiles * splits;
-        int const grid = static_cast<int>(items < sms ? items : sms);
-        kernel<<<grid, kThreads, PCfg::kSmemBytes, stream>>>(ta, tb, p, m_tiles, n_tiles, splits);
-        AGB_CUDA_OK(cudaGetLastError());
-        return 0;
-    }
-    auto kernel = gemm_tcgen05_kernel<BN, A_MN, B_MN>;
-    static bool configured = false;
-    if (!configured) {
-        AGB_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-        configured = true;
-    }
-    dim3 grid(m_tiles, n_tiles, splits);
-    kernel<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
-    AGB_CUDA_OK(cudaGetLastError());
-    return 0;
-}
-
-template<bool A_MN, bool B_MN>
-int dispatch_bn(int bn, CUtensorMap const& ta, CUtensorMap const& tb, GemmParams const& p, int splits, cudaStream_t stream) {
-    switch (bn) {
-        case 64: return launch_gemm<64, A_MN, B_MN>(ta, tb, p, splits, stream);
-        case 128: return launch_gemm<128, A_MN, B_MN>(ta, tb, p, splits, stream);
-        case 256: return launch_gemm<256, A_MN, B_MN>(ta, tb, p, splits, stream);
-    }
-    return 203;
-}
-
-} // namespace
+// C entry points of the tcgen05 GEMM (kernels: gemm_kernels.cuh).
+#include "gemm_kernels.cuh"
 
 extern "C" {
 

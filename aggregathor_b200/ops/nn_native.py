@@ -181,6 +181,8 @@ def conv2d_forward(x, weight, bias, stride, pads, relu):
     n, c, h, w = x.shape
     y = mm_nt(_as_rows(x), weight.reshape(weight.shape[0], -1), bias, relu)
     return _from_rows(y if y.stride(0) == y.shape[1] else y.contiguous(), n, h, w)
+  if _implicit_ok(x, weight, stride, pads):
+    return conv2d_forward_implicit(x, weight, bias, relu)
   if enabled("convk") and _general_ok(x, weight):
     return conv2d_forward_general(x, weight, bias, stride, pads, relu)
   return None
@@ -201,6 +203,8 @@ def conv2d_backward(dy, x, weight, y, stride, pads, relu, has_bias, need_dx, gra
     if not need_dx:
       return None
     return _from_rows(mm_nn(dy2d, weight.reshape(weight.shape[0], -1)), n, h, w)
+  if _implicit_ok(x, weight, stride, pads) and dy.dtype == torch.bfloat16:
+    return conv2d_backward_implicit(dy, x, weight, y, relu, has_bias, need_dx, grad_w, grad_b)
   if enabled("convk") and _general_ok(x, weight) and dy.dtype == torch.bfloat16:
     return conv2d_backward_general(dy, x, weight, y, stride, pads, relu, has_bias, need_dx, grad_w, grad_b)
   return NotImplemented
@@ -264,6 +268,54 @@ def conv2d_backward_general(dy, x, weight, y, stride, pads, relu, has_bias, need
   func = _lib().agb_col2im
   _check(func(_ptr(dcol), _ptr(dx), ctypes.c_int(n), ctypes.c_int(h), ctypes.c_int(w), ctypes.c_int(c), ctypes.c_int(oh), ctypes.c_int(ow), ctypes.c_int(k),
               ctypes.c_int(stride), ctypes.c_int(pads[0]), ctypes.c_int(pads[2]), ctypes.c_longlong(dcol.stride(0)), _stream()), "col2im")
+  return dx.permute(0, 3, 1, 2)
+
+
+# ---------------------------------------------------------------------------- #
+# Implicit-GEMM convolution (native/op_nn/conv.cu): stride 1, odd k, "same" padding, Cin % 64 == 0, Cout % 64 == 0
+
+def _implicit_ok(x, weight, stride, pads):
+  k = weight.shape[1]
+  pad = (k - 1) // 2
+  return (enabled("implicit") and k > 1 and k % 2 == 1 and weight.shape[2] == k and stride == 1 and tuple(pads) == (pad, pad, pad, pad)
+          and x.shape[1] % 64 == 0 and weight.shape[0] % 64 == 0 and x.dtype == torch.bfloat16 and x.is_contiguous(memory_format=torch.channels_last)
+          and weight.is_contiguous())
+
+
+def _conv_implicit(mode, act, other, out, n, h, w, cin, cout, k, bias=None, relu=False, splits=1, bn=0):
+  _check(_lib().agb_conv_implicit(ctypes.c_int(mode), _ptr(act), _ptr(other), _ptr(out), ctypes.c_int(n), ctypes.c_int(h), ctypes.c_int(w), ctypes.c_int(cin),
+                                  ctypes.c_int(cout), ctypes.c_int(k), _ptr(bias), ctypes.c_int(1 if relu else 0), ctypes.c_int(1 if out.dtype == torch.float32 else 0),
+                                  ctypes.c_int(splits), ctypes.c_int(bn), _stream()), "conv_implicit")
+  return out
+
+
+def conv2d_forward_implicit(x, weight, bias, relu):
+  n, cin, h, w = x.shape
+  cout, k = weight.shape[0], weight.shape[1]
+  y = torch.empty((n, h, w, cout), dtype=torch.bfloat16, device=x.device)
+  if bias is not None and bias.dtype != torch.float32:
+    bias = bias.float()
+  _conv_implicit(0, x, weight, y, n, h, w, cin, cout, k, bias, relu)
+  return y.permute(0, 3, 1, 2)
+
+
+def conv2d_backward_implicit(dy, x, weight, y, relu, has_bias, need_dx, grad_w, grad_b):
+  n, cin, h, w = x.shape
+  cout, k = weight.shape[0], weight.shape[1]
+  dy = _masked(dy, y, relu)
+  if not dy.is_contiguous(memory_format=torch.channels_last):
+    dy = dy.contiguous(memory_format=torch.channels_last)
+  tiles = k * k * ((cout + 127) // 128) * ((cin + 127) // 128)
+  kblocks = max(1, n * h * w // 64)
+  splits = max(1, min(kblocks, (2 * SM_COUNT + tiles - 1) // tiles, 64))
+  grad_w.zero_()
+  _conv_implicit(2, dy, x, grad_w, n, h, w, cin, cout, k, splits=splits)
+  if has_bias:
+    grad_b.copy_(colsum(_as_rows(dy)))
+  if not need_dx:
+    return None
+  dx = torch.empty((n, h, w, cin), dtype=torch.bfloat16, device=x.device)
+  _conv_implicit(1, dy, weight, dx, n, h, w, cin, cout, k)
   return dx.permute(0, 3, 1, 2)
 
 

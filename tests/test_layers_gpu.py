@@ -43,13 +43,17 @@ def test_batchnorm(shape, relu):
 
 @pytest.mark.parametrize("cin,cout,k,stride,hw,pads", [(64, 64, 3, 1, 56, (1, 1, 1, 1)), (128, 128, 3, 2, 28, (1, 1, 1, 1)), (3, 64, 7, 2, 224, (3, 3, 3, 3)),
                                                         (3, 64, 5, 1, 32, (2, 2, 2, 2)), (64, 64, 5, 1, 16, (2, 2, 2, 2)), (256, 512, 1, 1, 14, (0, 0, 0, 0)),
-                                                        (64, 64, 3, 2, 57, (0, 1, 0, 1))])
-def test_conv(cin, cout, k, stride, hw, pads):
+                                                        (64, 64, 3, 2, 57, (0, 1, 0, 1)), (64, 128, 3, 1, 28, (1, 1, 1, 1)), (256, 256, 3, 1, 14, (1, 1, 1, 1)),
+                                                        (512, 512, 3, 1, 7, (1, 1, 1, 1)), (128, 64, 5, 1, 12, (2, 2, 2, 2))])
+@pytest.mark.parametrize("implicit", [True, False])
+def test_conv(cin, cout, k, stride, hw, pads, implicit, monkeypatch):
   """Native convolution (forward, wgrad, bias grad, dgrad) vs fp32 autograd on the same bf16-rounded operands."""
   import torch.nn.functional as F
   from aggregathor_b200.ops import nn as ops
+  from aggregathor_b200.ops import nn_native
+  monkeypatch.setattr(nn_native, "_DISABLED", set() if implicit else {"implicit"})
   torch.backends.cudnn.allow_tf32 = False
-  n = 4
+  n = 4 if hw > 7 else 16
   x = _rand((n, cin, hw, hw), 3)
   w = _rand((cout, k, k, cin), 4, scale=(2.0 / (k * k * cin)) ** 0.5).contiguous()
   bias = torch.randn(cout, device="cuda") * 0.1
