@@ -540,25 +540,40 @@ __global__ void im2col_kernel(bf16 const* __restrict__ x, bf16* __restrict__ col
             *reinterpret_cast<uint4*>(col + pixel * ldcol + (kh * k + kw) * C + o * 8) = v;
         }
     } else {
-        long long const total = static_cast<long long>(N) * OH * OW * ldcol;
+        // Few-channel stem (C = 1 or 3): one thread per (output pixel, group of 8 columns) gathers 8 scalars (L1 hits) and
+        // writes one 16-byte vector; (c, kw, kh) advance incrementally, no division in the inner loop.
+        int const groups8 = static_cast<int>(ldcol >> 3);
+        long long const total = static_cast<long long>(N) * OH * OW * groups8;
         long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
         long long const stride = static_cast<long long>(gridDim.x) * blockDim.x;
         int const kcol = k * k * C;
         for (; i < total; i += stride) {
-            int const j = static_cast<int>(i % ldcol);
-            long long rest = i / ldcol;
+            int const g8 = static_cast<int>(i % groups8);
+            long long rest = i / groups8;
             int const ow = static_cast<int>(rest % OW);
             rest /= OW;
             int const oh = static_cast<int>(rest % OH);
             int const n = static_cast<int>(rest / OH);
-            bf16 v = __float2bfloat16(0.f);
-            if (j < kcol) {
-                int const c = j % C, kw = (j / C) % k, kh = j / (C * k);
-                int const h = oh * s - pad_t + kh, w = ow * s - pad_l + kw;
-                if (h >= 0 && h < H && w >= 0 && w < W)
-                    v = x[((static_cast<long long>(n) * H + h) * W + w) * C + c];
+            int j = g8 * 8;
+            int c = j % C, kw = (j / C) % k, kh = j / (C * k);
+            float v[8];
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj, ++j) {
+                v[jj] = 0.f;
+                if (j < kcol) {
+                    int const h = oh * s - pad_t + kh, w = ow * s - pad_l + kw;
+                    if (h >= 0 && h < H && w >= 0 && w < W)
+                        v[jj] = __bfloat162float(x[((static_cast<long long>(n) * H + h) * W + w) * C + c]);
+                }
+                if (++c == C) {
+                    c = 0;
+                    if (++kw == k) {
+                        kw = 0;
+                        ++kh;
+                    }
+                }
             }
-            col[i] = v;
+            *reinterpret_cast<uint4*>(col + (i / groups8) * ldcol + g8 * 8) = pack8(v);
         }
     }
 }
@@ -764,7 +779,7 @@ int agb_image_normalize(void const* x, void* y, long long pixels, int C, int Cpa
 int agb_im2col(void const* x, void* col, int N, int H, int W, int C, int OH, int OW, int k, int s, int pad_t, int pad_l, long long ldcol, void* stream) {
     if (ldcol & 7)
         return 301;
-    long long const work = (C & 7) == 0 ? static_cast<long long>(N) * OH * OW * k * k * (C >> 3) : static_cast<long long>(N) * OH * OW * ldcol;
+    long long const work = (C & 7) == 0 ? static_cast<long long>(N) * OH * OW * k * k * (C >> 3) : static_cast<long long>(N) * OH * OW * (ldcol >> 3);
     im2col_kernel<<<grid_for(work, kThreads, 148 * 16), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<bf16 const*>(x), static_cast<bf16*>(col), N, H, W, C, OH, OW, k, s, pad_t, pad_l, ldcol);
     AGB_CUDA_OK(cudaGetLastError());
     return 0;
