@@ -148,39 +148,16 @@ __global__ void __launch_bounds__(kThreads) channel_sums_kernel(bf16 const* __re
     }
 }
 
-// BN statistics finalisation: mean / rstd, affine coefficients, moving statistics (first group updates them).
-__global__ void bn_finalize_kernel(double const* __restrict__ sums, float const* __restrict__ gamma, float const* __restrict__ beta, float* __restrict__ save_mean,
-                                   float* __restrict__ save_rstd, float* __restrict__ scale, float* __restrict__ shift, float* moving_mean, float* moving_var,
-                                   int C, int groups, long long rows_per_group, float eps, float decay) {
-    int const i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= C * groups)
-        return;
-    int const c = i % C, g = i / C;
-    double const n = static_cast<double>(rows_per_group);
-    double const mean = sums[2 * i] / n;
-    double var = sums[2 * i + 1] / n - mean * mean;
-    if (var < 0.)
-        var = 0.;
-    float const rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-    float const gm = gamma ? gamma[c] : 1.f;
-    save_mean[i] = static_cast<float>(mean);
-    save_rstd[i] = rstd;
-    scale[i] = gm * rstd;
-    shift[i] = beta[c] - static_cast<float>(mean) * gm * rstd;
-    if (moving_mean && g == 0) { // unbiased variance in the moving average, as TF's fused batch norm
-        double const unbiased = n > 1. ? var * n / (n - 1.) : var;
-        moving_mean[c] = decay * moving_mean[c] + (1.f - decay) * static_cast<float>(mean);
-        moving_var[c] = decay * moving_var[c] + (1.f - decay) * static_cast<float>(unbiased);
-    }
-}
-
-// y = relu?(x * scale[g][c] + shift[g][c]). Each thread keeps a fixed channel octet (stride is a multiple of `octets`
-// whenever possible) so the coefficients stay in registers and no division happens in the loop.
-__global__ void __launch_bounds__(kThreads) bn_apply_kernel(bf16 const* __restrict__ x, bf16* __restrict__ y, float const* __restrict__ scale, float const* __restrict__ shift,
-                                long long total_octets, int C, long long rows_per_group, int relu) {
+// y = relu?((x - mean) * rstd * gamma + beta), statistics finalised in-kernel from the fp64 sums (no separate finalise launch).
+// Each thread keeps a fixed channel octet (the stride is a multiple of `octets`), so its coefficients live in registers and
+// the loop is division-free. The thread that meets row 0 of a group also publishes save_mean / save_rstd for its 8 channels
+// and (group 0) updates the moving statistics with the unbiased variance, as TF's fused batch norm does.
+__global__ void __launch_bounds__(kThreads) bn_apply_kernel(bf16 const* __restrict__ x, bf16* __restrict__ y, double const* __restrict__ sums, float const* __restrict__ gamma,
+                                float const* __restrict__ beta, float* __restrict__ save_mean, float* __restrict__ save_rstd, float* moving_mean, float* moving_var,
+                                long long total_octets, int C, long long rows_per_group, float eps, float decay, int relu) {
     unsigned const octets = static_cast<unsigned>(C >> 3);
     long long const nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
-    long long const stride = nthreads - nthreads % octets;   // multiple of `octets`: the octet of a thread never changes
+    long long const stride = nthreads - nthreads % octets;
     long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= stride)
         return;
@@ -189,13 +166,31 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(bf16 const* __restri
     int cached_group = -1;
     float sc[8], sh[8];
     for (; i < total_octets; i += stride) {
-        int const g = rows_per_group > 0 && octets_per_group < total_octets ? static_cast<int>(i / octets_per_group) : 0;
+        int const g = octets_per_group < total_octets ? static_cast<int>(i / octets_per_group) : 0;
         if (g != cached_group) {
             cached_group = g;
+            bool const publish = i - g * octets_per_group < octets;   // this thread owns row 0 of group g for octet o
+            double const n = static_cast<double>(rows_per_group);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                sc[j] = scale[g * C + o * 8 + j];
-                sh[j] = shift[g * C + o * 8 + j];
+                int const c = o * 8 + j, idx = g * C + c;
+                double const mean = sums[2 * idx] / n;
+                double var = sums[2 * idx + 1] / n - mean * mean;
+                if (var < 0.)
+                    var = 0.;
+                float const rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+                float const gm = gamma ? gamma[c] : 1.f;
+                sc[j] = gm * rstd;
+                sh[j] = beta[c] - static_cast<float>(mean) * gm * rstd;
+                if (publish) {
+                    save_mean[idx] = static_cast<float>(mean);
+                    save_rstd[idx] = rstd;
+                    if (moving_mean && g == 0) {
+                        double const unbiased = n > 1. ? var * n / (n - 1.) : var;
+                        moving_mean[c] = decay * moving_mean[c] + (1.f - decay) * static_cast<float>(mean);
+                        moving_var[c] = decay * moving_var[c] + (1.f - decay) * static_cast<float>(unbiased);
+                    }
+                }
             }
         }
         float v[8];
@@ -210,36 +205,11 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(bf16 const* __restri
     }
 }
 
-// BN backward coefficients per (group, channel): dx = a * dy' + b * x + c0 ; dgamma/dbeta summed over groups.
-__global__ void bn_bwd_finalize_kernel(double const* __restrict__ sums, float const* __restrict__ gamma, float const* __restrict__ mean, float const* __restrict__ rstd,
-                                       float* __restrict__ coef, float* __restrict__ dgamma, float* __restrict__ dbeta, int C, int groups, long long rows_per_group) {
-    int const c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C)
-        return;
-    double total_dbeta = 0., total_dgamma = 0.;
-    for (int g = 0; g < groups; ++g) {
-        int const i = g * C + c;
-        double const sum_dy = sums[2 * i], sum_dy_xhat = sums[2 * i + 1];
-        total_dbeta += sum_dy;
-        total_dgamma += sum_dy_xhat;
-        float const gm = gamma ? gamma[c] : 1.f;
-        float const rs = rstd[i], mu = mean[i];
-        float const inv_n = 1.f / static_cast<float>(rows_per_group);
-        // dx = gm*rs * (dy - sum_dy/n - xhat * sum_dy_xhat/n), xhat = (x - mu) * rs; sum_dy_xhat already includes one rs
-        float const a = gm * rs;
-        float const b = -gm * rs * rs * static_cast<float>(sum_dy_xhat) * inv_n;   // xhat * rs = (x - mu) * rs^2
-        float const c0 = -gm * rs * static_cast<float>(sum_dy) * inv_n - b * mu;
-        coef[3 * i] = a;
-        coef[3 * i + 1] = b;
-        coef[3 * i + 2] = c0;
-    }
-    if (dgamma)
-        dgamma[c] = static_cast<float>(total_dgamma);
-    dbeta[c] = static_cast<float>(total_dbeta);
-}
-
-__global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(bf16 const* __restrict__ dy, bf16 const* __restrict__ x, bf16 const* __restrict__ y, bf16* __restrict__ dx, float const* __restrict__ coef,
-                                    long long total_octets, int C, long long rows_per_group) {
+// dx = gm*rs * (dy' - sum_dy/n - xhat * sum_dy_xhat/n) with xhat = (x - mu) * rs, written as a*dy' + b*x + c0; the coefficients
+// come straight from the fp64 sums. The thread owning row 0 of group 0 writes dgamma / dbeta (summed over the groups).
+__global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(bf16 const* __restrict__ dy, bf16 const* __restrict__ x, bf16 const* __restrict__ y, bf16* __restrict__ dx,
+                                    double const* __restrict__ sums, float const* __restrict__ gamma, float const* __restrict__ mean, float const* __restrict__ rstd,
+                                    float* __restrict__ dgamma, float* __restrict__ dbeta, long long total_octets, int C, int groups, long long rows_per_group) {
     unsigned const octets = static_cast<unsigned>(C >> 3);
     long long const nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
     long long const stride = nthreads - nthreads % octets;
@@ -250,16 +220,33 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(bf16 const* __re
     long long const octets_per_group = rows_per_group * octets;
     int cached_group = -1;
     float ca[8], cb[8], cc[8];
+    float const inv_n = 1.f / static_cast<float>(rows_per_group);
     for (; i < total_octets; i += stride) {
         int const g = octets_per_group < total_octets ? static_cast<int>(i / octets_per_group) : 0;
         if (g != cached_group) {
             cached_group = g;
-            float const* cf = coef + (static_cast<long long>(g) * C + o * 8) * 3;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                ca[j] = cf[3 * j];
-                cb[j] = cf[3 * j + 1];
-                cc[j] = cf[3 * j + 2];
+                int const c = o * 8 + j, idx = g * C + c;
+                float const sum_dy = static_cast<float>(sums[2 * idx]), sum_dy_xhat = static_cast<float>(sums[2 * idx + 1]);
+                float const gm = gamma ? gamma[c] : 1.f, rs = rstd[idx], mu = mean[idx];
+                ca[j] = gm * rs;
+                cb[j] = -gm * rs * rs * sum_dy_xhat * inv_n;
+                cc[j] = -gm * rs * sum_dy * inv_n - cb[j] * mu;
+            }
+            if (g == 0 && i < octets) {   // row 0 of group 0
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    int const c = o * 8 + j;
+                    double total_dbeta = 0., total_dgamma = 0.;
+                    for (int gg = 0; gg < groups; ++gg) {
+                        total_dbeta += sums[2 * (gg * C + c)];
+                        total_dgamma += sums[2 * (gg * C + c) + 1];
+                    }
+                    if (dgamma)
+                        dgamma[c] = static_cast<float>(total_dgamma);
+                    dbeta[c] = static_cast<float>(total_dbeta);
+                }
             }
         }
         uint4 const rd = *reinterpret_cast<uint4 const*>(dy + i * 8);
@@ -668,11 +655,10 @@ int agb_bn_forward(void const* x, void* y, void const* gamma, void const* beta, 
     AGB_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C * groups, s));
     SumsPlan plan = plan_sums(rpg, C, groups);
     channel_sums_kernel<0><<<plan.grid, kThreads, 0, s>>>(static_cast<bf16 const*>(x), nullptr, nullptr, nullptr, nullptr, static_cast<double*>(sums), rpg, C, plan.rows_per_cta);
-    bn_finalize_kernel<<<(C * groups + 127) / 128, 128, 0, s>>>(static_cast<double const*>(sums), static_cast<float const*>(gamma), static_cast<float const*>(beta),
-        static_cast<float*>(save_mean), static_cast<float*>(save_rstd), static_cast<float*>(scale), static_cast<float*>(shift), static_cast<float*>(moving_mean),
-        static_cast<float*>(moving_var), C, groups, rpg, eps, decay);
     long long const octets = rows * (C >> 3);
-    bn_apply_kernel<<<grid_for(octets), kThreads, 0, s>>>(static_cast<bf16 const*>(x), static_cast<bf16*>(y), static_cast<float const*>(scale), static_cast<float const*>(shift), octets, C, rpg, relu);
+    bn_apply_kernel<<<grid_for(octets), kThreads, 0, s>>>(static_cast<bf16 const*>(x), static_cast<bf16*>(y), static_cast<double const*>(sums), static_cast<float const*>(gamma),
+        static_cast<float const*>(beta), static_cast<float*>(save_mean), static_cast<float*>(save_rstd), static_cast<float*>(moving_mean), static_cast<float*>(moving_var),
+        octets, C, rpg, eps, decay, relu);
     AGB_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -687,11 +673,10 @@ int agb_bn_backward(void const* dy, void const* x, void const* y, void const* ga
     SumsPlan plan = plan_sums(rpg, C, groups);
     channel_sums_kernel<1><<<plan.grid, kThreads, 0, s>>>(static_cast<bf16 const*>(dy), static_cast<bf16 const*>(x), static_cast<bf16 const*>(y),
         static_cast<float const*>(save_mean), static_cast<float const*>(save_rstd), static_cast<double*>(sums), rpg, C, plan.rows_per_cta);
-    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(static_cast<double const*>(sums), static_cast<float const*>(gamma), static_cast<float const*>(save_mean),
-        static_cast<float const*>(save_rstd), static_cast<float*>(coef), static_cast<float*>(dgamma), static_cast<float*>(dbeta), C, groups, rpg);
     long long const octets = rows * (C >> 3);
     bn_bwd_apply_kernel<<<grid_for(octets), kThreads, 0, s>>>(static_cast<bf16 const*>(dy), static_cast<bf16 const*>(x), static_cast<bf16 const*>(y), static_cast<bf16*>(dx),
-        static_cast<float const*>(coef), octets, C, rpg);
+        static_cast<double const*>(sums), static_cast<float const*>(gamma), static_cast<float const*>(save_mean), static_cast<float const*>(save_rstd),
+        static_cast<float*>(dgamma), static_cast<float*>(dbeta), octets, C, groups, rpg);
     AGB_CUDA_OK(cudaGetLastError());
     return 0;
 }

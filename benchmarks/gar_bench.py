@@ -28,11 +28,11 @@ from aggregathor_b200.parallel.aggregation import BaselineAggregation, FusedAggr
 
 def main():
   parser = argparse.ArgumentParser()
-  parser.add_argument("--d", type=int, default=25557032)
-  parser.add_argument("--nb-workers", type=int, default=8)
-  parser.add_argument("--iters", type=int, default=10)
-  parser.add_argument("--rules", type=str, default="average,average-nan,median,averaged-median,krum,bulyan")
-  parser.add_argument("--out", type=str, default="gpurun_out")
+  parser.add_argument("--gar-dim", dest="d", type=int, default=25557032)
+  parser.add_argument("--gar-workers", dest="nb_workers", type=int, default=8)
+  parser.add_argument("--gar-iters", dest="iters", type=int, default=10)
+  parser.add_argument("--gar-rules", dest="rules", type=str, default="average,average-nan,median,averaged-median,krum,bulyan")
+  parser.add_argument("--gar-out", dest="out", type=str, default="gpurun_out")
   args = parser.parse_args()
   world = int(os.environ.get("WORLD_SIZE", "1"))
   rank = int(os.environ.get("RANK", "0"))

@@ -29,7 +29,7 @@ def _torchrun(nproc, script_args, timeout=600):
 @pytest.mark.skipif(_gpus() < 2, reason="needs at least 2 GPUs")
 def test_fused_matches_baseline_on_all_ranks(tmp_path):
   nproc = 2 if _gpus() < 4 else 4
-  code, out = _torchrun(nproc, [str(ROOT / "benchmarks" / "gar_bench.py"), "--d", "1000003", "--iters", "3", "--out", str(tmp_path)])
+  code, out = _torchrun(nproc, [str(ROOT / "benchmarks" / "gar_bench.py"), "--gar-dim", "1000003", "--gar-iters", "3", "--gar-out", str(tmp_path)])
   assert code == 0, out[-4000:]
   results = json.loads((tmp_path / ("gar_bench_%d.json" % nproc)).read_text())["results"]
   assert set(results) == {"average", "average-nan", "median", "averaged-median", "krum", "bulyan"}
