@@ -42,6 +42,9 @@ struct GarArgs {
     int R, rank;
     long long lo, hi;                  // owned coordinate slice, multiples of 4
     float const* grad[kMaxWorkers];    // row base pointers (local or peer-mapped)
+    float const* grad_mc;              // multicast address of the [w, d] gradient matrix (NVLS in-switch reduction), or null
+    int workers_per_rank;
+    long long row_stride;              // elements between two rows of a rank's gradient matrix
     float* agg_out;                    // optional [d] (local): aggregated gradient of the slice
     int opt;
     float lr, h0, h1, h2;              // adam: b1,b2,eps | rmsprop: decay,momentum,eps | adadelta: rho,eps
@@ -465,16 +468,22 @@ template<int N> __global__ void __launch_bounds__(N <= 8 ? 512 : 256, 1) gar_fus
         for (long long v = tid; v < len4; v += nthreads) {
             long long const x = a.lo + (v << 2);
             float4 g[N];
+            bool const in_switch = a.rule == kAverage && a.grad_mc != nullptr;
 #pragma unroll
             for (int i = 0; i < N; ++i)
-                g[i] = i < n ? ld_stream_f4(a.grad[i] + x) : f4_zero();
+                g[i] = (i < n && !in_switch) ? ld_stream_f4(a.grad[i] + x) : f4_zero();
             float4 out;
             if (a.rule == kAverage) {
                 float4 sum = f4_zero();
+                if (a.grad_mc) {   // NVLS: the switch adds the same row of every rank; rows of one rank are added here
+                    for (int j = 0; j < a.workers_per_rank; ++j)
+                        sum = f4_add(sum, multimem_ld_reduce_add_f4(a.grad_mc + j * a.row_stride + x));
+                } else {
 #pragma unroll
-                for (int i = 0; i < N; ++i)
-                    if (i < n)
-                        sum = f4_add(sum, g[i]);
+                    for (int i = 0; i < N; ++i)
+                        if (i < n)
+                            sum = f4_add(sum, g[i]);
+                }
                 float const count = static_cast<float>(n);
                 out = make_float4(sum.x / count, sum.y / count, sum.z / count, sum.w / count);
             } else {
@@ -598,9 +607,9 @@ int agb_gar_max_ctas() {
 
 // ptrs layout (all device addresses, 0 = absent):
 //   [0..16) gradient rows | [16] agg_out | [17] param | [18] slot0 | [19] slot1 | [20] param_mc
-//   [21] cta_partials | [22] staging | [23] dist_out | [24] info
+//   [21] cta_partials | [22] staging | [23] dist_out | [24] info | [25] grad_mc (multicast address of the gradient matrix)
 //   [32..48) param_dst | [48..64) signal | [64..80) mailbox | [80..96) param_bf16_dst
-// ints: n f m beta rule R rank opt epoch max_ctas ; longs: lo hi ; floats: lr h0 h1 h2
+// ints: n f m beta rule R rank opt epoch max_ctas workers_per_rank ; longs: lo hi row_stride ; floats: lr h0 h1 h2
 int agb_gar_fused(unsigned long long const* ptrs, int const* ints, long long const* longs, float const* floats, void* stream) {
     GarArgs a{};
     a.n = ints[0]; a.f = ints[1]; a.m = ints[2]; a.beta = ints[3]; a.rule = ints[4];
@@ -631,6 +640,9 @@ int agb_gar_fused(unsigned long long const* ptrs, int const* ints, long long con
     a.staging = reinterpret_cast<float*>(ptrs[22]);
     a.dist_out = reinterpret_cast<float*>(ptrs[23]);
     a.info = reinterpret_cast<int*>(ptrs[24]);
+    a.grad_mc = reinterpret_cast<float const*>(ptrs[25]);
+    a.workers_per_rank = ints[10];
+    a.row_stride = longs[2];
     for (int q = 0; q < a.R; ++q) {
         a.param_dst[q] = reinterpret_cast<float*>(ptrs[32 + q]);
         a.signal[q] = reinterpret_cast<uint32_t*>(ptrs[48 + q]);

@@ -61,15 +61,15 @@ class FusedLauncher:
     self.dist_out = torch.zeros(n * n, dtype=torch.float32, device=self.device)
     self.info = torch.zeros(64, dtype=torch.int32, device=self.device)
     self._ptrs = (ctypes.c_ulonglong * 96)()
-    self._ints = (ctypes.c_int * 10)()
-    self._longs = (ctypes.c_longlong * 2)()
+    self._ints = (ctypes.c_int * 11)()
+    self._longs = (ctypes.c_longlong * 3)()
     self._floats = (ctypes.c_float * 4)()
     self._func = _lib().agb_gar_fused
     self._func.restype = ctypes.c_int
 
   def launch(self, spec, rows, lo, hi, *, agg_out=None, opt="none", lr=0.0, hyper=(0.0, 0.0, 0.0), param=None,
              slot0=None, slot1=None, param_dst=None, param_mc=0, param_bf16_dst=None, rank=0, R=1, signals=None, mailboxes=None,
-             epoch=1, staging=None, max_ctas_limit=0, stream=None):
+             epoch=1, staging=None, max_ctas_limit=0, stream=None, grad_mc=0, workers_per_rank=1, row_stride=0):
     """`rows`: n device addresses of the workers' gradient rows; pointers are raw ints (local or peer-mapped)."""
     ptrs = self._ptrs
     for i in range(96):
@@ -88,6 +88,7 @@ class FusedLauncher:
     ptrs[22] = addr(staging)
     ptrs[23] = self.dist_out.data_ptr()
     ptrs[24] = self.info.data_ptr()
+    ptrs[25] = int(grad_mc or 0)
     for q in range(R):
       ptrs[32 + q] = addr(param_dst[q]) if param_dst is not None else (addr(param) if q == 0 else 0)
       ptrs[48 + q] = addr(signals[q]) if signals is not None else 0
@@ -96,7 +97,8 @@ class FusedLauncher:
     ints = self._ints
     ints[0], ints[1], ints[2], ints[3], ints[4] = spec.n, spec.f, spec.m, spec.beta, spec.rule_id
     ints[5], ints[6], ints[7], ints[8], ints[9] = R, rank, OPTIMIZERS[opt], epoch & 0x7fffffff, max_ctas_limit
-    self._longs[0], self._longs[1] = lo, hi
+    self._longs[0], self._longs[1], self._longs[2] = lo, hi, row_stride
+    ints[10] = workers_per_rank
     self._floats[0], self._floats[1], self._floats[2], self._floats[3] = lr, hyper[0], hyper[1], hyper[2]
     with torch.cuda.device(self.device):
       _check(self._func(ptrs, ints, self._longs, self._floats, _stream_ptr(stream)), "gar_fused")

@@ -16,6 +16,8 @@ Three interchangeable engines share one interface (`params`, `grads`, `step()`):
 Logical workers: n = R * w; rank r hosts workers [r*w, (r+1)*w). The GAR always sees n rows.
 """
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -155,6 +157,8 @@ class FusedAggregation(_AggregationBase):
     self._signals = [heap.peer(q, "signals") for q in range(R)]
     self._mailboxes = [heap.peer(q, "mailbox") for q in range(R)]
     self._param_mc = heap.multicast("params") if R > 1 else 0
+    # opt-in: in-switch (NVLS) reduction of the gradients for the `average` rule instead of P2P loads
+    self._grad_mc = heap.multicast("grads") if (R > 1 and self.spec.rule == "average" and os.environ.get("AGB_NVLS_REDUCE")) else 0
     tools.info("Fused aggregation: rule %r, n = %d (%d per rank), d = %d, slice [%d, %d), provider %s, NVLS multicast %s" % (
       self.spec.rule, self.n, w, d, self.lo, self.hi, heap.provider, "on" if self._param_mc else "off"), context="fused")
 
@@ -170,7 +174,8 @@ class FusedAggregation(_AggregationBase):
       self.spec, self._rows, self.lo, self.hi, agg_out=self.aggregate_out, opt=self.optimizer.name, lr=lr, hyper=hyper,
       param=self.params, slot0=self.slots[0] if len(self.slots) > 0 else None, slot1=self.slots[1] if len(self.slots) > 1 else None,
       param_dst=self._param_dst, param_mc=self._param_mc, param_bf16_dst=self._param_bf16_dst, rank=self.rank, R=self.world,
-      signals=self._signals, mailboxes=self._mailboxes, epoch=self.epoch, staging=self.staging, max_ctas_limit=self.max_ctas, stream=stream)
+      signals=self._signals, mailboxes=self._mailboxes, epoch=self.epoch, staging=self.staging, max_ctas_limit=self.max_ctas, stream=stream,
+      grad_mc=self._grad_mc, workers_per_rank=self.w, row_stride=self.d)
 
   def full_slots(self):
     """Optimizer slots are only maintained on the owned slice: assemble the full vectors (checkpoints)."""
