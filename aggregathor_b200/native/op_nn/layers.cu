@@ -170,15 +170,15 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(bf16 const* __restri
         if (g != cached_group) {
             cached_group = g;
             bool const publish = i - g * octets_per_group < octets;   // this thread owns row 0 of group g for octet o
-            double const n = static_cast<double>(rows_per_group);
+            double const n = static_cast<double>(rows_per_group), inv_n = 1.0 / n;   // one fp64 division per thread; the rest is mul/fma
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 int const c = o * 8 + j, idx = g * C + c;
-                double const mean = sums[2 * idx] / n;
-                double var = sums[2 * idx + 1] / n - mean * mean;
+                double const mean = sums[2 * idx] * inv_n;
+                double var = fma(-mean, mean, sums[2 * idx + 1] * inv_n);   // E[x^2] - mean^2 in fp64 (no cancellation trouble)
                 if (var < 0.)
                     var = 0.;
-                float const rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+                float const rstd = rsqrtf(static_cast<float>(var) + eps);
                 float const gm = gamma ? gamma[c] : 1.f;
                 sc[j] = gm * rstd;
                 sh[j] = beta[c] - static_cast<float>(mean) * gm * rstd;

@@ -174,6 +174,10 @@ def add_forward(backend, a, b):
     return b
   if b is None:
     return a
+  if backend == "native" and a.is_cuda:
+    out = _native().add_relu_forward(a, b, False)
+    if out is not None:
+      return out
   return a + b
 
 
@@ -222,7 +226,8 @@ def subsample_forward(backend, x, stride):
 
 
 def subsample_backward(backend, dy, shape, stride):
-  dx = torch.zeros(shape, dtype=dy.dtype, device=dy.device).contiguous(memory_format=_CL)
+  n, c, h, w = shape
+  dx = torch.zeros((n, h, w, c), dtype=dy.dtype, device=dy.device).permute(0, 3, 1, 2)  # zeros allocated directly in NHWC memory
   dx[:, :, ::stride, ::stride] = dy
   return dx
 
