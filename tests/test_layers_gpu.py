@@ -60,14 +60,16 @@ def test_conv(cin, cout, k, stride, hw, pads, implicit, monkeypatch):
   xp = F.pad(x.float(), (pads[2], pads[3], pads[0], pads[1])).requires_grad_(True)
   wf = w.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
   bf = bias.clone().requires_grad_(True)
-  yf = torch.relu(F.conv2d(xp, wf, bf, stride))
-  dy = _rand(tuple(yf.shape), 5)
-  yf.backward(dy.float())
+  pre = F.conv2d(xp, wf, bf, stride)
   y = ops.conv2d_forward("native", x, w, bias, stride, pads, True)
+  _close(y, torch.relu(pre).detach(), 1e-2)
+  dy = _rand(tuple(pre.shape), 5)
+  # the ReLU mask is taken from the native (bf16) output: where |pre| is below the bf16 accumulation noise the fp32 and bf16
+  # masks legitimately differ, and a single flipped element moves a weight-gradient entry by |dy * x|
+  pre.backward(dy.float() * (y > 0).float())
   gw, gb = torch.zeros((cout, k, k, cin), device="cuda"), torch.zeros(cout, device="cuda")
   dx, _, _ = ops.conv2d_backward("native", dy, x, w, y, stride, pads, True, True, cin % 8 == 0, gw, gb)
-  _close(y, yf.detach(), 1e-2)
-  _close(gw, wf.grad.permute(0, 2, 3, 1), 1e-2)   # relu mask from the bf16 output may differ from fp32 where y ~ 0
+  _close(gw, wf.grad.permute(0, 2, 3, 1), 1e-2)
   _close(gb, bf.grad, 1e-2)
   if dx is not None:
     _close(dx, xp.grad[:, :, pads[0]:pads[0] + hw, pads[2]:pads[2] + hw], 1e-2)
