@@ -49,10 +49,74 @@ constexpr int kStripOctets = 8;
 constexpr int kRowLanes = kThreads / kStripOctets;
 constexpr int kRowUnroll = 4;
 
+// Finalisation performed by the LAST CTA of the statistics kernel (atomic ticket): no separate launch.
+struct SumsFinalize {
+    unsigned* ticket;           // zero-initialised counter, reset by the last CTA
+    float const* gamma;
+    float const* beta;
+    float* save_mean;           // MODE 0 out / MODE 1 in
+    float* save_rstd;
+    float* scale;               // MODE 0: [groups*C] ; MODE 1: coef [groups*C*3]
+    float* shift;
+    float* moving_mean;
+    float* moving_var;
+    float* dgamma;              // MODE 1
+    float* dbeta;               // MODE 1 ; MODE 2: the fp32 column sums
+    int groups;
+    float eps, decay;
+};
+
+template<int MODE>
+__device__ void finalize_sums(double const* sums, SumsFinalize const& f, int C, long long rows_per_group) {
+    double const n = static_cast<double>(rows_per_group), inv_n = 1.0 / n;
+    for (int i = threadIdx.x; i < C * f.groups; i += blockDim.x) {
+        int const c = i % C, g = i / C;
+        double const s0 = __ldcg(sums + 2 * i), s1 = __ldcg(sums + 2 * i + 1);
+        if (MODE == 0) {
+            double const mean = s0 * inv_n;
+            double var = fma(-mean, mean, s1 * inv_n);
+            if (var < 0.)
+                var = 0.;
+            float const rstd = rsqrtf(static_cast<float>(var) + f.eps);
+            float const gm = f.gamma ? f.gamma[c] : 1.f;
+            f.save_mean[i] = static_cast<float>(mean);
+            f.save_rstd[i] = rstd;
+            f.scale[i] = gm * rstd;
+            f.shift[i] = f.beta[c] - static_cast<float>(mean) * gm * rstd;
+            if (f.moving_mean && g == 0) { // unbiased variance in the moving average, as TF's fused batch norm
+                double const unbiased = n > 1. ? var * n / (n - 1.) : var;
+                f.moving_mean[c] = f.decay * f.moving_mean[c] + (1.f - f.decay) * static_cast<float>(mean);
+                f.moving_var[c] = f.decay * f.moving_var[c] + (1.f - f.decay) * static_cast<float>(unbiased);
+            }
+        } else if (MODE == 1) {
+            float const gm = f.gamma ? f.gamma[c] : 1.f, rs = f.save_rstd[i], mu = f.save_mean[i];
+            float const inv = static_cast<float>(inv_n);
+            float const a = gm * rs;
+            float const b = -gm * rs * rs * static_cast<float>(s1) * inv;   // xhat * rs = (x - mu) * rs^2
+            f.scale[3 * i] = a;
+            f.scale[3 * i + 1] = b;
+            f.scale[3 * i + 2] = -gm * rs * static_cast<float>(s0) * inv - b * mu;
+            if (g == 0) {
+                double total_dbeta = 0., total_dgamma = 0.;
+                for (int gg = 0; gg < f.groups; ++gg) {
+                    total_dbeta += __ldcg(sums + 2 * (gg * C + c));
+                    total_dgamma += __ldcg(sums + 2 * (gg * C + c) + 1);
+                }
+                if (f.dgamma)
+                    f.dgamma[c] = static_cast<float>(total_dgamma);
+                f.dbeta[c] = static_cast<float>(total_dbeta);
+            }
+        } else {
+            f.dbeta[i] = static_cast<float>(s0);
+        }
+    }
+}
+
 template<int MODE>
 __global__ void __launch_bounds__(kThreads) channel_sums_kernel(bf16 const* __restrict__ a, bf16 const* __restrict__ b, bf16 const* __restrict__ y, float const* __restrict__ mean,
-                                    float const* __restrict__ rstd, double* __restrict__ out, long long rows_per_group, int C, int rows_per_cta) {
+                                    float const* __restrict__ rstd, double* __restrict__ out, long long rows_per_group, int C, int rows_per_cta, SumsFinalize const fin) {
     __shared__ float red[kRowLanes][kStripOctets * 16 + 1];
+    __shared__ bool is_last;
     int const octets = C >> 3;
     int const tc = threadIdx.x % kStripOctets, tr = threadIdx.x / kStripOctets;
     int const o = blockIdx.y * kStripOctets + tc;
@@ -146,18 +210,30 @@ __global__ void __launch_bounds__(kThreads) channel_sums_kernel(bf16 const* __re
             atomicAdd(dst, static_cast<double>(total));
         }
     }
+    // last CTA to finish turns the sums into what the apply kernel needs
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned const total_ctas = gridDim.x * gridDim.y * gridDim.z;
+        unsigned const ticket = atomicAdd(fin.ticket, 1u);
+        is_last = ticket == total_ctas - 1;
+        if (is_last)
+            *fin.ticket = 0;   // ready for the next launch
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        finalize_sums<MODE>(out, fin, C, rows_per_group);
+    }
 }
 
-// y = relu?((x - mean) * rstd * gamma + beta), statistics finalised in-kernel from the fp64 sums (no separate finalise launch).
-// Each thread keeps a fixed channel octet (the stride is a multiple of `octets`), so its coefficients live in registers and
-// the loop is division-free. The thread that meets row 0 of a group also publishes save_mean / save_rstd for its 8 channels
-// and (group 0) updates the moving statistics with the unbiased variance, as TF's fused batch norm does.
-__global__ void __launch_bounds__(kThreads) bn_apply_kernel(bf16 const* __restrict__ x, bf16* __restrict__ y, double const* __restrict__ sums, float const* __restrict__ gamma,
-                                float const* __restrict__ beta, float* __restrict__ save_mean, float* __restrict__ save_rstd, float* moving_mean, float* moving_var,
-                                long long total_octets, int C, long long rows_per_group, float eps, float decay, int relu) {
+// y = relu?(x * scale[g][c] + shift[g][c]). Each thread keeps a fixed channel octet (stride is a multiple of `octets`
+// whenever possible) so the coefficients stay in registers and no division happens in the loop.
+__global__ void __launch_bounds__(kThreads) bn_apply_kernel(bf16 const* __restrict__ x, bf16* __restrict__ y, float const* __restrict__ scale, float const* __restrict__ shift,
+                                long long total_octets, int C, long long rows_per_group, int relu) {
     unsigned const octets = static_cast<unsigned>(C >> 3);
     long long const nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
-    long long const stride = nthreads - nthreads % octets;
+    long long const stride = nthreads - nthreads % octets;   // multiple of `octets`: the octet of a thread never changes
     long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= stride)
         return;
@@ -166,31 +242,13 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(bf16 const* __restri
     int cached_group = -1;
     float sc[8], sh[8];
     for (; i < total_octets; i += stride) {
-        int const g = octets_per_group < total_octets ? static_cast<int>(i / octets_per_group) : 0;
+        int const g = rows_per_group > 0 && octets_per_group < total_octets ? static_cast<int>(i / octets_per_group) : 0;
         if (g != cached_group) {
             cached_group = g;
-            bool const publish = i - g * octets_per_group < octets;   // this thread owns row 0 of group g for octet o
-            double const n = static_cast<double>(rows_per_group), inv_n = 1.0 / n;   // one fp64 division per thread; the rest is mul/fma
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                int const c = o * 8 + j, idx = g * C + c;
-                double const mean = sums[2 * idx] * inv_n;
-                double var = fma(-mean, mean, sums[2 * idx + 1] * inv_n);   // E[x^2] - mean^2 in fp64 (no cancellation trouble)
-                if (var < 0.)
-                    var = 0.;
-                float const rstd = rsqrtf(static_cast<float>(var) + eps);
-                float const gm = gamma ? gamma[c] : 1.f;
-                sc[j] = gm * rstd;
-                sh[j] = beta[c] - static_cast<float>(mean) * gm * rstd;
-                if (publish) {
-                    save_mean[idx] = static_cast<float>(mean);
-                    save_rstd[idx] = rstd;
-                    if (moving_mean && g == 0) {
-                        double const unbiased = n > 1. ? var * n / (n - 1.) : var;
-                        moving_mean[c] = decay * moving_mean[c] + (1.f - decay) * static_cast<float>(mean);
-                        moving_var[c] = decay * moving_var[c] + (1.f - decay) * static_cast<float>(unbiased);
-                    }
-                }
+                sc[j] = scale[g * C + o * 8 + j];
+                sh[j] = shift[g * C + o * 8 + j];
             }
         }
         float v[8];
@@ -205,11 +263,9 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(bf16 const* __restri
     }
 }
 
-// dx = gm*rs * (dy' - sum_dy/n - xhat * sum_dy_xhat/n) with xhat = (x - mu) * rs, written as a*dy' + b*x + c0; the coefficients
-// come straight from the fp64 sums. The thread owning row 0 of group 0 writes dgamma / dbeta (summed over the groups).
-__global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(bf16 const* __restrict__ dy, bf16 const* __restrict__ x, bf16 const* __restrict__ y, bf16* __restrict__ dx,
-                                    double const* __restrict__ sums, float const* __restrict__ gamma, float const* __restrict__ mean, float const* __restrict__ rstd,
-                                    float* __restrict__ dgamma, float* __restrict__ dbeta, long long total_octets, int C, int groups, long long rows_per_group) {
+// dx = a * dy' + b * x + c0 with per-(group, channel) coefficients prepared by the statistics kernel's last CTA.
+__global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(bf16 const* __restrict__ dy, bf16 const* __restrict__ x, bf16 const* __restrict__ y, bf16* __restrict__ dx, float const* __restrict__ coef,
+                                    long long total_octets, int C, long long rows_per_group) {
     unsigned const octets = static_cast<unsigned>(C >> 3);
     long long const nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
     long long const stride = nthreads - nthreads % octets;
@@ -220,33 +276,16 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(bf16 const* __re
     long long const octets_per_group = rows_per_group * octets;
     int cached_group = -1;
     float ca[8], cb[8], cc[8];
-    float const inv_n = 1.f / static_cast<float>(rows_per_group);
     for (; i < total_octets; i += stride) {
         int const g = octets_per_group < total_octets ? static_cast<int>(i / octets_per_group) : 0;
         if (g != cached_group) {
             cached_group = g;
+            float const* cf = coef + (static_cast<long long>(g) * C + o * 8) * 3;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                int const c = o * 8 + j, idx = g * C + c;
-                float const sum_dy = static_cast<float>(sums[2 * idx]), sum_dy_xhat = static_cast<float>(sums[2 * idx + 1]);
-                float const gm = gamma ? gamma[c] : 1.f, rs = rstd[idx], mu = mean[idx];
-                ca[j] = gm * rs;
-                cb[j] = -gm * rs * rs * sum_dy_xhat * inv_n;
-                cc[j] = -gm * rs * sum_dy * inv_n - cb[j] * mu;
-            }
-            if (g == 0 && i < octets) {   // row 0 of group 0
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    int const c = o * 8 + j;
-                    double total_dbeta = 0., total_dgamma = 0.;
-                    for (int gg = 0; gg < groups; ++gg) {
-                        total_dbeta += sums[2 * (gg * C + c)];
-                        total_dgamma += sums[2 * (gg * C + c) + 1];
-                    }
-                    if (dgamma)
-                        dgamma[c] = static_cast<float>(total_dgamma);
-                    dbeta[c] = static_cast<float>(total_dbeta);
-                }
+                ca[j] = cf[3 * j];
+                cb[j] = cf[3 * j + 1];
+                cc[j] = cf[3 * j + 2];
             }
         }
         uint4 const rd = *reinterpret_cast<uint4 const*>(dy + i * 8);
@@ -607,12 +646,6 @@ __global__ void col2im_kernel(bf16 const* __restrict__ dcol, bf16* __restrict__ 
     }
 }
 
-__global__ void cast_sums_kernel(double const* __restrict__ sums, float* __restrict__ out, int C) {
-    int const c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c < C)
-        out[c] = static_cast<float>(sums[2 * c]);
-}
-
 inline int grid_for(long long work, int threads = kThreads, int cap = 148 * 8) {
     long long blocks = (work + threads - 1) / threads;
     if (blocks > cap)
@@ -652,13 +685,19 @@ int agb_bn_forward(void const* x, void* y, void const* gamma, void const* beta, 
         return 301;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     long long const rpg = rows / groups;
-    AGB_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C * groups, s));
+    // workspace: [groups*C*2] doubles, then one zeroed ticket word (zeroed together with the sums)
+    AGB_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(double) * (2 * C * groups + 1), s));
+    SumsFinalize fin{};
+    fin.ticket = reinterpret_cast<unsigned*>(static_cast<double*>(sums) + 2 * C * groups);
+    fin.gamma = static_cast<float const*>(gamma); fin.beta = static_cast<float const*>(beta);
+    fin.save_mean = static_cast<float*>(save_mean); fin.save_rstd = static_cast<float*>(save_rstd);
+    fin.scale = static_cast<float*>(scale); fin.shift = static_cast<float*>(shift);
+    fin.moving_mean = static_cast<float*>(moving_mean); fin.moving_var = static_cast<float*>(moving_var);
+    fin.groups = groups; fin.eps = eps; fin.decay = decay;
     SumsPlan plan = plan_sums(rpg, C, groups);
-    channel_sums_kernel<0><<<plan.grid, kThreads, 0, s>>>(static_cast<bf16 const*>(x), nullptr, nullptr, nullptr, nullptr, static_cast<double*>(sums), rpg, C, plan.rows_per_cta);
+    channel_sums_kernel<0><<<plan.grid, kThreads, 0, s>>>(static_cast<bf16 const*>(x), nullptr, nullptr, nullptr, nullptr, static_cast<double*>(sums), rpg, C, plan.rows_per_cta, fin);
     long long const octets = rows * (C >> 3);
-    bn_apply_kernel<<<grid_for(octets), kThreads, 0, s>>>(static_cast<bf16 const*>(x), static_cast<bf16*>(y), static_cast<double const*>(sums), static_cast<float const*>(gamma),
-        static_cast<float const*>(beta), static_cast<float*>(save_mean), static_cast<float*>(save_rstd), static_cast<float*>(moving_mean), static_cast<float*>(moving_var),
-        octets, C, rpg, eps, decay, relu);
+    bn_apply_kernel<<<grid_for(octets), kThreads, 0, s>>>(static_cast<bf16 const*>(x), static_cast<bf16*>(y), static_cast<float const*>(scale), static_cast<float const*>(shift), octets, C, rpg, relu);
     AGB_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -669,27 +708,36 @@ int agb_bn_backward(void const* dy, void const* x, void const* y, void const* ga
         return 301;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     long long const rpg = rows / groups;
-    AGB_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C * groups, s));
+    AGB_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(double) * (2 * C * groups + 1), s));
+    SumsFinalize fin{};
+    fin.ticket = reinterpret_cast<unsigned*>(static_cast<double*>(sums) + 2 * C * groups);
+    fin.gamma = static_cast<float const*>(gamma);
+    fin.save_mean = const_cast<float*>(static_cast<float const*>(save_mean)); fin.save_rstd = const_cast<float*>(static_cast<float const*>(save_rstd));
+    fin.scale = static_cast<float*>(coef);
+    fin.dgamma = static_cast<float*>(dgamma); fin.dbeta = static_cast<float*>(dbeta);
+    fin.groups = groups;
     SumsPlan plan = plan_sums(rpg, C, groups);
     channel_sums_kernel<1><<<plan.grid, kThreads, 0, s>>>(static_cast<bf16 const*>(dy), static_cast<bf16 const*>(x), static_cast<bf16 const*>(y),
-        static_cast<float const*>(save_mean), static_cast<float const*>(save_rstd), static_cast<double*>(sums), rpg, C, plan.rows_per_cta);
+        static_cast<float const*>(save_mean), static_cast<float const*>(save_rstd), static_cast<double*>(sums), rpg, C, plan.rows_per_cta, fin);
     long long const octets = rows * (C >> 3);
     bn_bwd_apply_kernel<<<grid_for(octets), kThreads, 0, s>>>(static_cast<bf16 const*>(dy), static_cast<bf16 const*>(x), static_cast<bf16 const*>(y), static_cast<bf16*>(dx),
-        static_cast<double const*>(sums), static_cast<float const*>(gamma), static_cast<float const*>(save_mean), static_cast<float const*>(save_rstd),
-        static_cast<float*>(dgamma), static_cast<float*>(dbeta), octets, C, groups, rpg);
+        static_cast<float const*>(coef), octets, C, rpg);
     AGB_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
-// out[c] = sum over rows of dy[r][c] (masked by y > 0 when y != null); `sums` is a double [2*C] workspace.
+// out[c] = sum over rows of dy[r][c] (masked by y > 0 when y != null); `sums` is a double [2*C + 1] workspace.
 int agb_colsum(void const* dy, void const* y, void* out, void* sums, long long rows, int C, void* stream) {
     if (C & 7)
         return 301;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    AGB_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, s));
+    AGB_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(double) * (2 * C + 1), s));
+    SumsFinalize fin{};
+    fin.ticket = reinterpret_cast<unsigned*>(static_cast<double*>(sums) + 2 * C);
+    fin.dbeta = static_cast<float*>(out);
+    fin.groups = 1;
     SumsPlan plan = plan_sums(rows, C, 1);
-    channel_sums_kernel<2><<<plan.grid, kThreads, 0, s>>>(static_cast<bf16 const*>(dy), nullptr, static_cast<bf16 const*>(y), nullptr, nullptr, static_cast<double*>(sums), rows, C, plan.rows_per_cta);
-    cast_sums_kernel<<<(C + 127) / 128, 128, 0, s>>>(static_cast<double const*>(sums), static_cast<float*>(out), C);
+    channel_sums_kernel<2><<<plan.grid, kThreads, 0, s>>>(static_cast<bf16 const*>(dy), nullptr, static_cast<bf16 const*>(y), nullptr, nullptr, static_cast<double*>(sums), rows, C, plan.rows_per_cta, fin);
     AGB_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -344,7 +344,7 @@ def colsum(dy2d, y2d=None):
     src = dy2d.float() if y2d is None else dy2d.float() * (y2d > 0)
     return src.sum(dim=0)
   out = torch.empty(c, dtype=torch.float32, device=dy2d.device)
-  sums = _workspace(dy2d.device, "colsum", 2 * c, torch.float64)
+  sums = _workspace(dy2d.device, "colsum", 2 * c + 1, torch.float64)
   _check(_lib().agb_colsum(_ptr(dy2d), _ptr(y2d), _ptr(out), _ptr(sums), ctypes.c_longlong(rows), ctypes.c_int(c), _stream()), "colsum")
   return out
 
@@ -356,7 +356,7 @@ def batchnorm_forward(x, gamma, beta, moving_mean, moving_var, decay, eps, relu,
   rows = n * h * w
   y = torch.empty_like(x, memory_format=torch.channels_last)
   stats = torch.empty((4, groups * c), dtype=torch.float32, device=x.device)  # save_mean, save_rstd, scale, shift
-  sums = _workspace(x.device, "bn_sums", 2 * groups * c, torch.float64)
+  sums = _workspace(x.device, "bn_sums", 2 * groups * c + 1, torch.float64)
   _check(_lib().agb_bn_forward(_ptr(x), _ptr(y), _ptr(gamma), _ptr(beta), _ptr(moving_mean), _ptr(moving_var), _ptr(stats[0]), _ptr(stats[1]), _ptr(sums),
                                _ptr(stats[2]), _ptr(stats[3]), ctypes.c_longlong(rows), ctypes.c_int(c), ctypes.c_int(groups), ctypes.c_float(eps),
                                ctypes.c_float(decay), ctypes.c_int(1 if relu else 0), _stream()), "bn_forward")
@@ -371,7 +371,7 @@ def batchnorm_backward(dy, x, y, gamma, mean, rstd, relu, grad_gamma, grad_beta,
   n, c, h, w = x.shape
   rows = n * h * w
   dx = torch.empty_like(x, memory_format=torch.channels_last)
-  sums = _workspace(x.device, "bn_sums", 2 * groups * c, torch.float64)
+  sums = _workspace(x.device, "bn_sums", 2 * groups * c + 1, torch.float64)
   coef = _workspace(x.device, "bn_coef", 3 * groups * c, torch.float32)
   _check(_lib().agb_bn_backward(_ptr(dy), _ptr(x), _ptr(y if relu else None), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dx), _ptr(grad_gamma), _ptr(grad_beta),
                                 _ptr(sums), _ptr(coef), ctypes.c_longlong(rows), ctypes.c_int(c), ctypes.c_int(groups), _stream()), "bn_backward")
