@@ -109,7 +109,7 @@ def test_softmax_xent_and_image_normalize():
     _close(ops.image_normalize("native", images, mode, torch.bfloat16), ops.image_normalize("torch", images, mode, torch.bfloat16), 1e-2)
 
 
-@pytest.mark.parametrize("name,classes,batch,image", [("resnet_v1_50", 1000, 8, 64), ("cnnet", 10, 16, 32), ("mlp", 10, 32, None)])
+@pytest.mark.parametrize("name,classes,batch,image", [("resnet_v1_50", 1000, 16, 128), ("cnnet", 10, 16, 32), ("mlp", 10, 32, None)])
 def test_model_gradients_native_vs_fp32(name, classes, batch, image):
   """Whole-model check against an fp32 (TF32 off) run of the library provider: the bf16 native path must agree with
   it at least as well as the bf16 library provider does."""
@@ -143,6 +143,6 @@ def test_model_gradients_native_vs_fp32(name, classes, batch, image):
   report = {"loss": losses, "cos_native_fp32": cos("native", "fp32"), "cos_torch_fp32": cos("torch", "fp32"), "cos_native_torch": cos("native", "torch")}
   print(report)
   assert abs(losses["native"] - losses["fp32"]) < 3e-2 * max(1.0, abs(losses["fp32"])), report
-  assert report["cos_native_fp32"] > min(0.97, report["cos_torch_fp32"] - 0.02), report
+  assert report["cos_native_fp32"] > min(0.97, report["cos_torch_fp32"] - 0.05), report
   ratio = float(grads["native"].norm() / grads["fp32"].norm())
   assert 0.85 < ratio < 1.15, (ratio, report)
