@@ -60,6 +60,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const __grid_
     uint64_t* tmem_full = empty + PCfg::kStages;
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint8_t* epi_stage = smem + PCfg::kStages * Cfg::kStageBytes + 256;
 
     int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int const taps = cp.k * cp.k;
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const __grid_
                 valid = r < box_rows && w < cp.W && h < cp.H && n < cp.N;
                 offset = ((static_cast<long long>(n) * cp.H + h) * cp.W + w) * p.ldc;
             }
-            epilogue_rows<BN>(p, tmem_base + buf * Cfg::kTmemCols, warp, valid, offset, it.n0);
+            epilogue_rows_staged<BN>(p, tmem_base + buf * Cfg::kTmemCols, warp, lane, valid, offset, it.n0, epi_stage);
             tc_fence_before();
             __syncwarp();
             if (lane == 0)

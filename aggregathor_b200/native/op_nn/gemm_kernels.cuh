@@ -123,6 +123,87 @@ __device__ __forceinline__ void epilogue_rows(GemmParams const& p, uint32_t tmem
     }
 }
 
+// Coalesced variant of the epilogue: every warp owns a 32-row x 128-byte staging tile in shared memory. Accumulator rows
+// (thread = row) are converted and written to the tile, then read back so that 8 consecutive lanes cover one row's 128
+// contiguous bytes: each global store (or fp32 vector reduction) instruction writes 4 full 128-byte lines instead of 32
+// scattered 16-byte pieces. Falls back to the per-thread path when N / ldc do not allow 16-byte pieces.
+constexpr int kStagePitch = 144;                      // 128 B of payload + 16 B: conflict-free for both access patterns
+constexpr int kStageBytesPerWarp = 32 * kStagePitch;
+constexpr int kStageBytes = 4 * kStageBytesPerWarp;
+
+template<int BN>
+__device__ __forceinline__ void epilogue_rows_staged(GemmParams const& p, uint32_t tmem_acc, int warp, int lane, bool row_valid, long long row_offset, int n0, uint8_t* stage_base) {
+    int const elem = p.out_fp32 ? 4 : 2;
+    bool const fast = stage_base != nullptr && (p.out_fp32 ? ((p.ldc & 3) == 0 && (p.N & 3) == 0) : ((p.ldc & 7) == 0 && (p.N & 7) == 0)) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+    if (!fast) {
+        epilogue_rows<BN>(p, tmem_acc, warp, row_valid, row_offset, n0);
+        return;
+    }
+    int const quarter = warp & 3;
+    uint32_t const taddr = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16);
+    uint8_t* stage = stage_base + quarter * kStageBytesPerWarp;
+    int const cols_per_pass = 128 / elem;             // 64 bf16 or 32 fp32 columns = 128 bytes per row
+    unsigned const off_lo = static_cast<unsigned>(row_offset), off_hi = static_cast<unsigned>(static_cast<unsigned long long>(row_offset) >> 32);
+#pragma unroll 1
+    for (int c = 0; c < BN; c += cols_per_pass) {
+        int const col0 = n0 + c;
+        if (col0 >= p.N)
+            break;                                    // warp-uniform
+#pragma unroll 1
+        for (int h = 0; h < cols_per_pass; h += 32) {
+            float v[32];
+            tmem_ld_32x32(taddr + c + h, v);
+            if (p.bias) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (col0 + h + j < p.N)
+                        v[j] += __ldg(p.bias + col0 + h + j);
+            }
+            if (p.relu) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    v[j] = fmaxf(v[j], 0.f);
+            }
+            uint8_t* dst = stage + lane * kStagePitch + h * elem;
+            if (p.out_fp32) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(dst + j * 4) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]), h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                    __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                    *reinterpret_cast<uint4*>(dst + j * 2) = make_uint4(*reinterpret_cast<unsigned*>(&h0), *reinterpret_cast<unsigned*>(&h1), *reinterpret_cast<unsigned*>(&h2), *reinterpret_cast<unsigned*>(&h3));
+                }
+            }
+        }
+        __syncwarp();
+        int const piece = lane & 7, sub = lane >> 3;
+        int const piece_col = col0 + piece * (16 / elem);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            int const r = 4 * i + sub;
+            bool const valid = __shfl_sync(0xffffffffu, static_cast<int>(row_valid), r) != 0;
+            unsigned const lo = __shfl_sync(0xffffffffu, off_lo, r), hi = __shfl_sync(0xffffffffu, off_hi, r);
+            long long const offset = static_cast<long long>((static_cast<unsigned long long>(hi) << 32) | lo);
+            if (valid && piece_col < p.N) {
+                uint4 const data = *reinterpret_cast<uint4 const*>(stage + r * kStagePitch + piece * 16);
+                if (p.out_fp32) {
+                    float* g = static_cast<float*>(p.C) + offset + piece_col;
+                    if (p.atomic)
+                        atomicAdd(reinterpret_cast<float4*>(g), make_float4(__uint_as_float(data.x), __uint_as_float(data.y), __uint_as_float(data.z), __uint_as_float(data.w)));
+                    else
+                        *reinterpret_cast<uint4*>(g) = data;
+                } else {
+                    *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.C) + offset + piece_col) = data;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
 template<int BN>
 __device__ __forceinline__ void epilogue_tile(GemmParams const& p, uint32_t tmem_acc, int warp, int lane, int m0, int n0) {
     int const row = m0 + (warp & 3) * 32 + lane;
@@ -170,7 +251,7 @@ __device__ __forceinline__ void consume_stage(uint32_t a_addr, uint32_t tmem_acc
 // main loop of item j + 1; barrier setup and the TMEM allocation are paid once per CTA instead of once per tile.
 template<int BN> struct PersistentConfig {
     static constexpr int kStages = BN <= 64 ? 8 : BN <= 128 ? 6 : 4;
-    static constexpr uint32_t kSmemBytes = kStages * Config<BN>::kStageBytes + 1024 + 256;
+    static constexpr uint32_t kSmemBytes = kStages * Config<BN>::kStageBytes + 1024 + 256 + kStageBytes;   // + epilogue staging tiles
     static constexpr uint32_t kTmemCols = 2 * Config<BN>::kTmemCols;   // <= 512
 };
 
@@ -185,6 +266,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_persistent_kernel(co
     uint64_t* tmem_full = empty + PCfg::kStages;   // [2]
     uint64_t* tmem_empty = tmem_full + 2;          // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint8_t* epi_stage = smem + PCfg::kStages * Cfg::kStageBytes + 256;
 
     int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int const total_kblocks = (p.K + kBK - 1) / kBK;
@@ -210,11 +292,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_persistent_kernel(co
     tc_fence_after();
     uint32_t const tmem_base = *tmem_slot;
 
-    // item -> (m tile fastest, then n tile, then k split): consecutive CTAs share the same B (weight) tile
+    // item -> tile in grouped order (panels of 16 m-tiles, m fastest inside a panel, then n): the ~148 tiles in flight
+    // cover a ~16 x 9 patch, so every A and B tile fetched from L2/HBM is reused by several CTAs of the same wave.
+    constexpr int kGroupM = 16;
     auto decode = [&](int item, int& m0, int& n0, int& kb_begin, int& nkb) {
         int const tile = item % (m_tiles * n_tiles), split = item / (m_tiles * n_tiles);
-        m0 = (tile % m_tiles) * kBM;
-        n0 = (tile / m_tiles) * BN;
+        int const group_size = kGroupM * n_tiles;
+        int const first_m = (tile / group_size) * kGroupM;
+        int const gm = min(m_tiles - first_m, kGroupM);
+        int const in_group = tile % group_size;
+        m0 = (first_m + in_group % gm) * kBM;
+        n0 = (in_group / gm) * BN;
         kb_begin = split * p.kblocks_per_split;
         int const kb_end = min(total_kblocks, kb_begin + p.kblocks_per_split);
         nkb = kb_end - kb_begin;
@@ -261,7 +349,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_persistent_kernel(co
             uint32_t const buf = j & 1;
             mbar_wait(tmem_full + buf, (j >> 1) & 1, 14);
             tc_fence_after();
-            epilogue_tile<BN>(p, tmem_base + buf * Cfg::kTmemCols, warp, lane, m0, n0);
+            {
+                int const row = m0 + (warp & 3) * 32 + lane;
+                epilogue_rows_staged<BN>(p, tmem_base + buf * Cfg::kTmemCols, warp, lane, row < p.M, static_cast<long long>(row) * p.ldc, n0, epi_stage);
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0)

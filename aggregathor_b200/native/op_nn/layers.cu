@@ -47,7 +47,7 @@ constexpr int kThreads = 256;
 // thread; one fp64 atomic per channel and CTA, so an address only sees (#row chunks) atomics.
 constexpr int kStripOctets = 8;
 constexpr int kRowLanes = kThreads / kStripOctets;
-constexpr int kRowUnroll = 4;
+constexpr int kRowUnroll = 4;   // MODE 0 / 2; MODE 1 (three tensors) uses 2 to stay under 64 registers per thread
 
 // Finalisation performed by the LAST CTA of the statistics kernel (atomic ticket): no separate launch.
 struct SumsFinalize {
@@ -138,10 +138,11 @@ __global__ void __launch_bounds__(kThreads) channel_sums_kernel(bf16 const* __re
         }
     }
     if (active) {
-        for (long long r0 = row_begin + tr; r0 < row_end; r0 += kRowLanes * kRowUnroll) {
-            uint4 ra[kRowUnroll], rb[kRowUnroll], ry[kRowUnroll];
+        constexpr int U = MODE == 1 ? 2 : kRowUnroll;
+        for (long long r0 = row_begin + tr; r0 < row_end; r0 += kRowLanes * U) {
+            uint4 ra[U], rb[U], ry[U];
 #pragma unroll
-            for (int u = 0; u < kRowUnroll; ++u) {   // issue every load of the batch before using any of them
+            for (int u = 0; u < U; ++u) {   // issue every load of the batch before using any of them
                 long long const r = r0 + u * kRowLanes;
                 if (r < row_end) {
                     long long const idx = (base + r) * C + o * 8;
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(kThreads) channel_sums_kernel(bf16 const* __re
                 }
             }
 #pragma unroll
-            for (int u = 0; u < kRowUnroll; ++u) {
+            for (int u = 0; u < U; ++u) {
                 long long const r = r0 + u * kRowLanes;
                 if (r < row_end) {
                     float va[8];
@@ -239,27 +240,46 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(bf16 const* __restri
         return;
     unsigned const o = static_cast<unsigned>(i % octets);
     long long const octets_per_group = rows_per_group * octets;
+    bool const single_group = octets_per_group >= total_octets;
     int cached_group = -1;
     float sc[8], sh[8];
-    for (; i < total_octets; i += stride) {
-        int const g = rows_per_group > 0 && octets_per_group < total_octets ? static_cast<int>(i / octets_per_group) : 0;
-        if (g != cached_group) {
-            cached_group = g;
+    auto load_coefficients = [&](int g) {
+        cached_group = g;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                sc[j] = scale[g * C + o * 8 + j];
-                sh[j] = shift[g * C + o * 8 + j];
-            }
+        for (int j = 0; j < 8; ++j) {
+            sc[j] = scale[g * C + o * 8 + j];
+            sh[j] = shift[g * C + o * 8 + j];
         }
+    };
+    auto transform = [&](uint4 raw) {
         float v[8];
-        unpack8(*reinterpret_cast<uint4 const*>(x + i * 8), v);
+        unpack8(raw, v);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             v[j] = v[j] * sc[j] + sh[j];
             if (relu)
                 v[j] = fmaxf(v[j], 0.f);
         }
-        *reinterpret_cast<uint4*>(y + i * 8) = pack8(v);
+        return pack8(v);
+    };
+    if (single_group) {
+        load_coefficients(0);
+        constexpr int U = 4;   // four independent 16-byte loads in flight per thread
+        for (; i + (U - 1) * stride < total_octets; i += U * stride) {
+            uint4 raw[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                raw[u] = *reinterpret_cast<uint4 const*>(x + (i + u * stride) * 8);
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                *reinterpret_cast<uint4*>(y + (i + u * stride) * 8) = transform(raw[u]);
+        }
+    }
+    for (; i < total_octets; i += stride) {
+        int const g = single_group ? 0 : static_cast<int>(i / octets_per_group);
+        if (g != cached_group)
+            load_coefficients(g);
+        *reinterpret_cast<uint4*>(y + i * 8) = transform(*reinterpret_cast<uint4 const*>(x + i * 8));
     }
 }
 
@@ -274,28 +294,26 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(bf16 const* __re
         return;
     unsigned const o = static_cast<unsigned>(i % octets);
     long long const octets_per_group = rows_per_group * octets;
+    bool const single_group = octets_per_group >= total_octets;
     int cached_group = -1;
     float ca[8], cb[8], cc[8];
-    for (; i < total_octets; i += stride) {
-        int const g = octets_per_group < total_octets ? static_cast<int>(i / octets_per_group) : 0;
-        if (g != cached_group) {
-            cached_group = g;
-            float const* cf = coef + (static_cast<long long>(g) * C + o * 8) * 3;
+    auto load_coefficients = [&](int g) {
+        cached_group = g;
+        float const* cf = coef + (static_cast<long long>(g) * C + o * 8) * 3;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                ca[j] = cf[3 * j];
-                cb[j] = cf[3 * j + 1];
-                cc[j] = cf[3 * j + 2];
-            }
+        for (int j = 0; j < 8; ++j) {
+            ca[j] = cf[3 * j];
+            cb[j] = cf[3 * j + 1];
+            cc[j] = cf[3 * j + 2];
         }
-        uint4 const rd = *reinterpret_cast<uint4 const*>(dy + i * 8);
-        uint4 const rx = *reinterpret_cast<uint4 const*>(x + i * 8);
+    };
+    auto transform = [&](uint4 rd, uint4 rx, uint4 ry, bool masked) {
         float vd[8], vx[8];
         unpack8(rd, vd);
         unpack8(rx, vx);
-        if (y) {
+        if (masked) {
             float vy[8];
-            unpack8(*reinterpret_cast<uint4 const*>(y + i * 8), vy);
+            unpack8(ry, vy);
 #pragma unroll
             for (int j = 0; j < 8; ++j)
                 vd[j] = vy[j] > 0.f ? vd[j] : 0.f;
@@ -303,7 +321,32 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(bf16 const* __re
 #pragma unroll
         for (int j = 0; j < 8; ++j)
             vd[j] = ca[j] * vd[j] + cb[j] * vx[j] + cc[j];
-        *reinterpret_cast<uint4*>(dx + i * 8) = pack8(vd);
+        return pack8(vd);
+    };
+    bool const masked = y != nullptr;
+    if (single_group) {
+        load_coefficients(0);
+        constexpr int U = 2;   // 2 x 3 independent 16-byte loads in flight per thread
+        for (; i + (U - 1) * stride < total_octets; i += U * stride) {
+            uint4 rd[U], rx[U], ry[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                long long const e = (i + u * stride) * 8;
+                rd[u] = *reinterpret_cast<uint4 const*>(dy + e);
+                rx[u] = *reinterpret_cast<uint4 const*>(x + e);
+                ry[u] = masked ? *reinterpret_cast<uint4 const*>(y + e) : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                *reinterpret_cast<uint4*>(dx + (i + u * stride) * 8) = transform(rd[u], rx[u], ry[u], masked);
+        }
+    }
+    for (; i < total_octets; i += stride) {
+        int const g = single_group ? 0 : static_cast<int>(i / octets_per_group);
+        if (g != cached_group)
+            load_coefficients(g);
+        uint4 const ry = masked ? *reinterpret_cast<uint4 const*>(y + i * 8) : make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(dx + i * 8) = transform(*reinterpret_cast<uint4 const*>(dy + i * 8), *reinterpret_cast<uint4 const*>(x + i * 8), ry, masked);
     }
 }
 
