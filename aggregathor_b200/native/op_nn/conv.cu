@@ -48,7 +48,7 @@ inline int make_tmap_4d_bf16(CUtensorMap* map, void const* base, int C, int W, i
 // wgrad); `tmap_b`: 2-D weight map (fwd: K-major rows [Cout][k*k*Cin]; dgrad: the same matrix read as MN-major boxes) or
 // the 4-D map of x (wgrad).
 template<int BN, int MODE>
-__global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+__global__ void __launch_bounds__(kPersistentThreads, 1) conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                                                                     GemmParams const p, ConvParams const cp, int items_mn, int splits) {
     constexpr bool A_MN = MODE == kWgrad, B_MN = MODE != kFwd;
     using Cfg = Config<BN>;
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const __grid_
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(tmem_full + b, 1);
-            mbar_init(tmem_empty + b, 4);
+            mbar_init(tmem_empty + b, kEpilogueWarps);
         }
         mbar_fence_init();
     }
@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const __grid_
                 valid = r < box_rows && w < cp.W && h < cp.H && n < cp.N;
                 offset = ((static_cast<long long>(n) * cp.H + h) * cp.W + w) * p.ldc;
             }
-            epilogue_rows_staged<BN>(p, tmem_base + buf * Cfg::kTmemCols, warp, lane, valid, offset, it.n0, epi_stage);
+            epilogue_rows_staged<BN>(p, tmem_base + buf * Cfg::kTmemCols, (warp & 3) | (((warp - 2) >> 2) << 2), lane, valid, offset, it.n0, epi_stage);
             tc_fence_before();
             __syncwarp();
             if (lane == 0)
@@ -233,7 +233,7 @@ int launch_conv(CUtensorMap const& ta, CUtensorMap const& tb, GemmParams const& 
     }
     long long const items = static_cast<long long>(items_mn) * splits;
     int const grid = static_cast<int>(items < sms ? items : sms);
-    kernel<<<grid, kThreads, PCfg::kSmemBytes, stream>>>(ta, tb, p, cp, items_mn, splits);
+    kernel<<<grid, kPersistentThreads, PCfg::kSmemBytes, stream>>>(ta, tb, p, cp, items_mn, splits);
     AGB_CUDA_OK(cudaGetLastError());
     return 0;
 }

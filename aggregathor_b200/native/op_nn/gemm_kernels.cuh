@@ -123,84 +123,142 @@ __device__ __forceinline__ void epilogue_rows(GemmParams const& p, uint32_t tmem
     }
 }
 
-// Coalesced variant of the epilogue: every warp owns a 32-row x 128-byte staging tile in shared memory. Accumulator rows
-// (thread = row) are converted and written to the tile, then read back so that 8 consecutive lanes cover one row's 128
-// contiguous bytes: each global store (or fp32 vector reduction) instruction writes 4 full 128-byte lines instead of 32
-// scattered 16-byte pieces. Falls back to the per-thread path when N / ldc do not allow 16-byte pieces.
+// Coalesced variant of the epilogue, run by 8 warps: two warps share each TMEM lane quarter and split the tile's columns.
+// Every warp owns a 32-row x 128-byte staging tile in shared memory: accumulator rows (thread = row) are loaded from TMEM
+// (all loads of a pass in flight before one wait), converted and written to the tile, then read back so that consecutive
+// lanes cover contiguous bytes of a row: each global store (or fp32 vector reduction) writes full 64/128-byte row
+// segments instead of 32 scattered 16-byte pieces. Falls back to the per-thread path when N / ldc forbid 16-byte pieces.
 constexpr int kStagePitch = 144;                      // 128 B of payload + 16 B: conflict-free for both access patterns
 constexpr int kStageBytesPerWarp = 32 * kStagePitch;
-constexpr int kStageBytes = 4 * kStageBytesPerWarp;
+constexpr int kEpilogueWarps = 8;
+constexpr int kStageBytes = kEpilogueWarps * kStageBytesPerWarp;
+constexpr int kPersistentThreads = 64 + kEpilogueWarps * 32;   // TMA warp + MMA warp + 8 epilogue warps
 
+// `ewarp` in [0, 8): quarter = ewarp & 3 (must equal the hardware warp id & 3), column half = ewarp >> 2.
 template<int BN>
-__device__ __forceinline__ void epilogue_rows_staged(GemmParams const& p, uint32_t tmem_acc, int warp, int lane, bool row_valid, long long row_offset, int n0, uint8_t* stage_base) {
-    int const elem = p.out_fp32 ? 4 : 2;
-    bool const fast = stage_base != nullptr && (p.out_fp32 ? ((p.ldc & 3) == 0 && (p.N & 3) == 0) : ((p.ldc & 7) == 0 && (p.N & 7) == 0)) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
-    if (!fast) {
-        epilogue_rows<BN>(p, tmem_acc, warp, row_valid, row_offset, n0);
+__device__ __forceinline__ void epilogue_rows_staged(GemmParams const& p, uint32_t tmem_acc, int ewarp, int lane, bool row_valid, long long row_offset, int n0, uint8_t* stage_base) {
+    int const quarter = ewarp & 3, half = ewarp >> 2;
+    constexpr int kHalfCols = BN / 2;
+    bool const fast = (p.out_fp32 ? ((p.ldc & 3) == 0 && (p.N & 3) == 0) : ((p.ldc & 7) == 0 && (p.N & 7) == 0)) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+    uint32_t const taddr = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16) + half * kHalfCols;
+    int const nbase = n0 + half * kHalfCols;
+    if (!fast) {   // per-thread stores, 32 columns at a time
+#pragma unroll 1
+        for (int c = 0; c < kHalfCols; c += 32) {
+            float v[32];
+            tmem_ld_32x32(taddr + c, v);
+            int const col0 = nbase + c;
+            if (row_valid && col0 < p.N) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (col0 + j < p.N) {
+                        float val = v[j] + (p.bias ? __ldg(p.bias + col0 + j) : 0.f);
+                        if (p.relu)
+                            val = fmaxf(val, 0.f);
+                        if (p.out_fp32) {
+                            float* dst = static_cast<float*>(p.C) + row_offset + col0 + j;
+                            if (p.atomic)
+                                atomicAdd(dst, val);
+                            else
+                                *dst = val;
+                        } else {
+                            static_cast<__nv_bfloat16*>(p.C)[row_offset + col0 + j] = __float2bfloat16(val);
+                        }
+                    }
+                }
+            }
+        }
         return;
     }
-    int const quarter = warp & 3;
-    uint32_t const taddr = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16);
-    uint8_t* stage = stage_base + quarter * kStageBytesPerWarp;
-    int const cols_per_pass = 128 / elem;             // 64 bf16 or 32 fp32 columns = 128 bytes per row
+    uint8_t* stage = stage_base + ewarp * kStageBytesPerWarp;
     unsigned const off_lo = static_cast<unsigned>(row_offset), off_hi = static_cast<unsigned>(static_cast<unsigned long long>(row_offset) >> 32);
+    if (p.out_fp32) {
+        // 32 fp32 columns (128 B per row) per pass
 #pragma unroll 1
-    for (int c = 0; c < BN; c += cols_per_pass) {
-        int const col0 = n0 + c;
-        if (col0 >= p.N)
-            break;                                    // warp-uniform
-#pragma unroll 1
-        for (int h = 0; h < cols_per_pass; h += 32) {
+        for (int c = 0; c < kHalfCols; c += 32) {
+            int const col0 = nbase + c;
+            if (col0 >= p.N)
+                break;
             float v[32];
-            tmem_ld_32x32(taddr + c + h, v);
+            tmem_ld_32x32(taddr + c, v);
             if (p.bias) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
-                    if (col0 + h + j < p.N)
-                        v[j] += __ldg(p.bias + col0 + h + j);
+                    if (col0 + j < p.N)
+                        v[j] += __ldg(p.bias + col0 + j);
             }
             if (p.relu) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
                     v[j] = fmaxf(v[j], 0.f);
             }
-            uint8_t* dst = stage + lane * kStagePitch + h * elem;
-            if (p.out_fp32) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4*>(dst + j * 4) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
+            for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(stage + lane * kStagePitch + j * 4) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            __syncwarp();
+            int const piece = lane & 7, sub = lane >> 3;
+            int const piece_col = col0 + piece * 4;
 #pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                    __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]), h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-                    __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-                    *reinterpret_cast<uint4*>(dst + j * 2) = make_uint4(*reinterpret_cast<unsigned*>(&h0), *reinterpret_cast<unsigned*>(&h1), *reinterpret_cast<unsigned*>(&h2), *reinterpret_cast<unsigned*>(&h3));
-                }
-            }
-        }
-        __syncwarp();
-        int const piece = lane & 7, sub = lane >> 3;
-        int const piece_col = col0 + piece * (16 / elem);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            int const r = 4 * i + sub;
-            bool const valid = __shfl_sync(0xffffffffu, static_cast<int>(row_valid), r) != 0;
-            unsigned const lo = __shfl_sync(0xffffffffu, off_lo, r), hi = __shfl_sync(0xffffffffu, off_hi, r);
-            long long const offset = static_cast<long long>((static_cast<unsigned long long>(hi) << 32) | lo);
-            if (valid && piece_col < p.N) {
-                uint4 const data = *reinterpret_cast<uint4 const*>(stage + r * kStagePitch + piece * 16);
-                if (p.out_fp32) {
+            for (int i = 0; i < 8; ++i) {
+                int const r = 4 * i + sub;
+                bool const valid = __shfl_sync(0xffffffffu, static_cast<int>(row_valid), r) != 0;
+                unsigned const lo = __shfl_sync(0xffffffffu, off_lo, r), hi = __shfl_sync(0xffffffffu, off_hi, r);
+                long long const offset = static_cast<long long>((static_cast<unsigned long long>(hi) << 32) | lo);
+                if (valid && piece_col < p.N) {
+                    float4 const data = *reinterpret_cast<float4 const*>(stage + r * kStagePitch + piece * 16);
                     float* g = static_cast<float*>(p.C) + offset + piece_col;
                     if (p.atomic)
-                        atomicAdd(reinterpret_cast<float4*>(g), make_float4(__uint_as_float(data.x), __uint_as_float(data.y), __uint_as_float(data.z), __uint_as_float(data.w)));
+                        atomicAdd(reinterpret_cast<float4*>(g), data);
                     else
-                        *reinterpret_cast<uint4*>(g) = data;
-                } else {
-                    *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.C) + offset + piece_col) = data;
+                        *reinterpret_cast<float4*>(g) = data;
                 }
             }
+            __syncwarp();
         }
-        __syncwarp();
+    } else {
+        // bf16: kPass columns per pass (64 when the half is wide enough: 128 B per row), both TMEM loads in flight together
+        constexpr int kPass = kHalfCols >= 64 ? 64 : 32;
+        constexpr int kPieces = kPass * 2 / 16;          // 16-byte pieces per row: 8 or 4
+        constexpr int kRowsPerInstr = 32 / kPieces;
+#pragma unroll 1
+        for (int c = 0; c < kHalfCols; c += kPass) {
+            int const col0 = nbase + c;
+            if (col0 >= p.N)
+                break;
+            uint32_t raw[kPass];
+            tmem_ld_32x32_async(taddr + c, *reinterpret_cast<uint32_t (*)[32]>(&raw[0]));
+            if (kPass == 64)
+                tmem_ld_32x32_async(taddr + c + 32, *reinterpret_cast<uint32_t (*)[32]>(&raw[kPass == 64 ? 32 : 0]));
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < kPass; j += 8) {
+                float v[8];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    v[t] = __uint_as_float(raw[j + t]);
+                    if (p.bias && col0 + j + t < p.N)
+                        v[t] += __ldg(p.bias + col0 + j + t);
+                    if (p.relu)
+                        v[t] = fmaxf(v[t], 0.f);
+                }
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
+                *reinterpret_cast<uint4*>(stage + lane * kStagePitch + j * 2) = make_uint4(*reinterpret_cast<unsigned*>(&h0), *reinterpret_cast<unsigned*>(&h1), *reinterpret_cast<unsigned*>(&h2), *reinterpret_cast<unsigned*>(&h3));
+            }
+            __syncwarp();
+            int const piece = lane % kPieces, sub = lane / kPieces;
+            int const piece_col = col0 + piece * 8;
+#pragma unroll
+            for (int i = 0; i < kPieces; ++i) {
+                int const r = kRowsPerInstr * i + sub;
+                bool const valid = __shfl_sync(0xffffffffu, static_cast<int>(row_valid), r) != 0;
+                unsigned const lo = __shfl_sync(0xffffffffu, off_lo, r), hi = __shfl_sync(0xffffffffu, off_hi, r);
+                long long const offset = static_cast<long long>((static_cast<unsigned long long>(hi) << 32) | lo);
+                if (valid && piece_col < p.N)
+                    *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.C) + offset + piece_col) = *reinterpret_cast<uint4 const*>(stage + r * kStagePitch + piece * 16);
+            }
+            __syncwarp();
+        }
     }
 }
 
@@ -250,13 +308,13 @@ __device__ __forceinline__ void consume_stage(uint32_t a_addr, uint32_t tmem_acc
 // items, and the accumulator is double-buffered in TMEM (2 x BN columns) so that the epilogue of item j overlaps the
 // main loop of item j + 1; barrier setup and the TMEM allocation are paid once per CTA instead of once per tile.
 template<int BN> struct PersistentConfig {
-    static constexpr int kStages = BN <= 64 ? 8 : BN <= 128 ? 6 : 4;
+    static constexpr int kStages = BN <= 64 ? 7 : BN <= 128 ? 5 : 3;   // ring + 36 KB of epilogue staging <= 227 KB
     static constexpr uint32_t kSmemBytes = kStages * Config<BN>::kStageBytes + 1024 + 256 + kStageBytes;   // + epilogue staging tiles
     static constexpr uint32_t kTmemCols = 2 * Config<BN>::kTmemCols;   // <= 512
 };
 
 template<int BN, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, GemmParams const p, int m_tiles, int n_tiles, int splits) {
+__global__ void __launch_bounds__(kPersistentThreads, 1) gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, GemmParams const p, int m_tiles, int n_tiles, int splits) {
     using Cfg = Config<BN>;
     using PCfg = PersistentConfig<BN>;
     extern __shared__ uint8_t smem_raw[];
@@ -281,7 +339,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_persistent_kernel(co
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(tmem_full + b, 1);
-            mbar_init(tmem_empty + b, 4);          // one arrival per epilogue warp
+            mbar_init(tmem_empty + b, kEpilogueWarps);   // one arrival per epilogue warp
         }
         mbar_fence_init();
     }
@@ -350,8 +408,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_persistent_kernel(co
             mbar_wait(tmem_full + buf, (j >> 1) & 1, 14);
             tc_fence_after();
             {
+                int const ewarp = ((warp & 3)) | (((warp - 2) >> 2) << 2);   // quarter from the hardware warp id, half from the warp's group
                 int const row = m0 + (warp & 3) * 32 + lane;
-                epilogue_rows_staged<BN>(p, tmem_base + buf * Cfg::kTmemCols, warp, lane, row < p.M, static_cast<long long>(row) * p.ldc, n0, epi_stage);
+                epilogue_rows_staged<BN>(p, tmem_base + buf * Cfg::kTmemCols, ewarp, lane, row < p.M, static_cast<long long>(row) * p.ldc, n0, epi_stage);
             }
             tc_fence_before();
             __syncwarp();
@@ -460,7 +519,7 @@ int launch_gemm(CUtensorMap const& ta, CUtensorMap const& tb, GemmParams const& 
         }
         long long const items = static_cast<long long>(m_tiles) * n_tiles * splits;
         int const grid = static_cast<int>(items < sms ? items : sms);
-        kernel<<<grid, kThreads, PCfg::kSmemBytes, stream>>>(ta, tb, p, m_tiles, n_tiles, splits);
+        kernel<<<grid, kPersistentThreads, PCfg::kSmemBytes, stream>>>(ta, tb, p, m_tiles, n_tiles, splits);
         AGB_CUDA_OK(cudaGetLastError());
         return 0;
     }

@@ -10,7 +10,23 @@ import contextlib
 import sys
 import time
 
-__all__ = ["Tracer", "device_from_tuple"]
+__all__ = ["Tracer", "trace_graph", "device_from_tuple"]
+
+
+def trace_graph(optn, what, stream=None):
+  """Wrap the callable `optn` so that every call prints `[TRACE] (begin) what` / `[TRACE] (end)   what` around it
+  (the eager counterpart of the reference's `tools.trace_graph`, which wrapped a graph op with `tf.Print` nodes)."""
+  import functools
+
+  @functools.wraps(optn)
+  def traced(*args, **kwargs):
+    out = stream if stream is not None else sys.stderr
+    print("[TRACE] (begin) " + what, file=out)
+    try:
+      return optn(*args, **kwargs)
+    finally:
+      print("[TRACE] (end)   " + what, file=out)
+  return traced
 
 
 def device_from_tuple(job, taskid, devtype, devid):
