@@ -42,11 +42,10 @@ constexpr int kThreads = 256;
 // ---------------------------------------------------------------------------- //
 // Per-channel (and per-group) sums: out[g][c] += sum_r f(...). MODE 0: (x, x^2); MODE 1: (dy', dy' * xhat) with
 // dy' = dy masked by (y > 0) when y != null; MODE 2: (dy') only (bias gradient). C % 8 == 0.
-// 2-D decomposition: blockIdx.x = row chunk, blockIdx.y = strip of 64 channels (8 octets), blockIdx.z = group. Inside a
-// CTA 8 lanes cover the strip's octets (128 contiguous bytes per row) and 32 lanes cover rows, 4 rows in flight per
-// thread; one fp64 atomic per channel and CTA, so an address only sees (#row chunks) atomics.
-constexpr int kStripOctets = 8;
-constexpr int kRowLanes = kThreads / kStripOctets;
+// 2-D decomposition: blockIdx.x = row chunk, blockIdx.y = strip of STRIP octets (8 * STRIP channels), blockIdx.z = group.
+// Inside a CTA, STRIP lanes cover the strip's octets (up to 512 contiguous bytes per row: whole DRAM bursts instead of
+// 128-byte columns) and 256 / STRIP lanes cover rows, several rows in flight per thread; one fp64 atomic per channel and
+// CTA, so an address only sees (#row chunks) atomics.
 constexpr int kRowUnroll = 4;   // MODE 0 / 2; MODE 1 (three tensors) uses 2 to stay under 64 registers per thread
 
 // Finalisation performed by the LAST CTA of the statistics kernel (atomic ticket): no separate launch.
@@ -112,9 +111,10 @@ __device__ void finalize_sums(double const* sums, SumsFinalize const& f, int C, 
     }
 }
 
-template<int MODE>
+template<int MODE, int STRIP>
 __global__ void __launch_bounds__(kThreads) channel_sums_kernel(bf16 const* __restrict__ a, bf16 const* __restrict__ b, bf16 const* __restrict__ y, float const* __restrict__ mean,
                                     float const* __restrict__ rstd, double* __restrict__ out, long long rows_per_group, int C, int rows_per_cta, SumsFinalize const fin) {
+    constexpr int kStripOctets = STRIP, kRowLanes = kThreads / STRIP;
     __shared__ float red[kRowLanes][kStripOctets * 16 + 1];
     __shared__ bool is_last;
     int const octets = C >> 3;
@@ -197,14 +197,13 @@ __global__ void __launch_bounds__(kThreads) channel_sums_kernel(bf16 const* __re
         red[tr][tc * 16 + 8 + j] = s1[j];
     }
     __syncthreads();
-    // 128 (or 64) values per CTA: thread t < 128 folds column t over the 32 row lanes in a fixed order
-    int const t = threadIdx.x;
-    if (t < kStripOctets * 16) {
+    // STRIP * 16 values per CTA: thread t folds column t over the row lanes in a fixed order
+    for (int t = threadIdx.x; t < kStripOctets * 16; t += kThreads) {
         int const oc = t / 16, j = t % 16;
         int const oo = blockIdx.y * kStripOctets + oc;
         if (oo < octets && (MODE != 2 || j < 8)) {
             float total = 0.f;
-#pragma unroll 8
+#pragma unroll
             for (int l = 0; l < kRowLanes; ++l)
                 total += red[l][t];
             double* dst = out + (static_cast<long long>(group) * C + oo * 8 + (j & 7)) * 2 + (j >> 3);
@@ -697,22 +696,36 @@ inline int grid_for(long long work, int threads = kThreads, int cap = 148 * 8) {
 }
 
 struct SumsPlan {
-    int rows_per_cta;
+    int rows_per_cta, strip;
     dim3 grid;
 };
 inline SumsPlan plan_sums(long long rows_per_group, int C, int groups) {
-    int const strips = ((C >> 3) + kStripOctets - 1) / kStripOctets;
+    int const octets = C >> 3;
+    SumsPlan plan;
+    plan.strip = octets >= 32 ? 32 : octets >= 16 ? 16 : 8;
+    int const row_lanes = kThreads / plan.strip;
+    int const strips = (octets + plan.strip - 1) / plan.strip;
     long long target = (148 * 6 + strips * groups - 1) / (strips * groups);   // ~6 CTAs per SM overall
     if (target < 1)
         target = 1;
     long long rows_per_cta = (rows_per_group + target - 1) / target;
-    long long const min_rows = kRowLanes * kRowUnroll;
+    long long const min_rows = static_cast<long long>(row_lanes) * kRowUnroll;
     if (rows_per_cta < min_rows)
         rows_per_cta = min_rows;
-    SumsPlan plan;
     plan.rows_per_cta = static_cast<int>(rows_per_cta);
     plan.grid = dim3(static_cast<unsigned>((rows_per_group + rows_per_cta - 1) / rows_per_cta), strips, groups);
     return plan;
+}
+
+template<int MODE>
+void launch_sums(SumsPlan const& plan, cudaStream_t s, bf16 const* a, bf16 const* b, bf16 const* y, float const* mean, float const* rstd, double* out,
+                 long long rows_per_group, int C, SumsFinalize const& fin) {
+    if (plan.strip == 32)
+        channel_sums_kernel<MODE, 32><<<plan.grid, kThreads, 0, s>>>(a, b, y, mean, rstd, out, rows_per_group, C, plan.rows_per_cta, fin);
+    else if (plan.strip == 16)
+        channel_sums_kernel<MODE, 16><<<plan.grid, kThreads, 0, s>>>(a, b, y, mean, rstd, out, rows_per_group, C, plan.rows_per_cta, fin);
+    else
+        channel_sums_kernel<MODE, 8><<<plan.grid, kThreads, 0, s>>>(a, b, y, mean, rstd, out, rows_per_group, C, plan.rows_per_cta, fin);
 }
 
 } // namespace
@@ -738,7 +751,7 @@ int agb_bn_forward(void const* x, void* y, void const* gamma, void const* beta, 
     fin.moving_mean = static_cast<float*>(moving_mean); fin.moving_var = static_cast<float*>(moving_var);
     fin.groups = groups; fin.eps = eps; fin.decay = decay;
     SumsPlan plan = plan_sums(rpg, C, groups);
-    channel_sums_kernel<0><<<plan.grid, kThreads, 0, s>>>(static_cast<bf16 const*>(x), nullptr, nullptr, nullptr, nullptr, static_cast<double*>(sums), rpg, C, plan.rows_per_cta, fin);
+    launch_sums<0>(plan, s, static_cast<bf16 const*>(x), nullptr, nullptr, nullptr, nullptr, static_cast<double*>(sums), rpg, C, fin);
     long long const octets = rows * (C >> 3);
     bn_apply_kernel<<<grid_for(octets), kThreads, 0, s>>>(static_cast<bf16 const*>(x), static_cast<bf16*>(y), static_cast<float const*>(scale), static_cast<float const*>(shift), octets, C, rpg, relu);
     AGB_CUDA_OK(cudaGetLastError());
@@ -760,8 +773,8 @@ int agb_bn_backward(void const* dy, void const* x, void const* y, void const* ga
     fin.dgamma = static_cast<float*>(dgamma); fin.dbeta = static_cast<float*>(dbeta);
     fin.groups = groups;
     SumsPlan plan = plan_sums(rpg, C, groups);
-    channel_sums_kernel<1><<<plan.grid, kThreads, 0, s>>>(static_cast<bf16 const*>(dy), static_cast<bf16 const*>(x), static_cast<bf16 const*>(y),
-        static_cast<float const*>(save_mean), static_cast<float const*>(save_rstd), static_cast<double*>(sums), rpg, C, plan.rows_per_cta, fin);
+    launch_sums<1>(plan, s, static_cast<bf16 const*>(dy), static_cast<bf16 const*>(x), static_cast<bf16 const*>(y), static_cast<float const*>(save_mean),
+                   static_cast<float const*>(save_rstd), static_cast<double*>(sums), rpg, C, fin);
     long long const octets = rows * (C >> 3);
     bn_bwd_apply_kernel<<<grid_for(octets), kThreads, 0, s>>>(static_cast<bf16 const*>(dy), static_cast<bf16 const*>(x), static_cast<bf16 const*>(y), static_cast<bf16*>(dx),
         static_cast<float const*>(coef), octets, C, rpg);
@@ -780,7 +793,7 @@ int agb_colsum(void const* dy, void const* y, void* out, void* sums, long long r
     fin.dbeta = static_cast<float*>(out);
     fin.groups = 1;
     SumsPlan plan = plan_sums(rows, C, 1);
-    channel_sums_kernel<2><<<plan.grid, kThreads, 0, s>>>(static_cast<bf16 const*>(dy), nullptr, static_cast<bf16 const*>(y), nullptr, nullptr, static_cast<double*>(sums), rows, C, plan.rows_per_cta, fin);
+    launch_sums<2>(plan, s, static_cast<bf16 const*>(dy), nullptr, static_cast<bf16 const*>(y), nullptr, nullptr, static_cast<double*>(sums), rows, C, fin);
     AGB_CUDA_OK(cudaGetLastError());
     return 0;
 }
