@@ -104,6 +104,21 @@ class Manager:
       ctx.generator = self._dropout_gen
       ctx.worker_id, ctx.nbworkers = i, nbworkers
       self.contexts.append(ctx)
+    # all local workers in one pass (per-worker BN statistics / losses / gradients): needs rows 0..w-1 in worker order
+    base = type(experiment).__mro__[-2]
+    contiguous_rows = [placement[i][1] for i in self.local_workers] == list(range(len(self.local_workers)))
+    want_batched = os.environ.get("AGB_BATCH_WORKERS", "1") != "0"
+    self.batched = (want_batched and cuda and len(self.local_workers) > 1 and contiguous_rows and not self._has_dropout(self.model.root)
+                    and type(experiment).losses is base.losses and type(experiment).losses_batched is base.losses_batched)
+    self.batched_ctx = None
+    if self.batched:
+      bctx = Context(self.backend, True, self.dtype, self.device)
+      bctx.weights, bctx.master, bctx.state = self.weight_views, self.master_views, self.states
+      bctx.grads = self.layout.views(self.grads[0])
+      bctx.generator = self._dropout_gen
+      bctx.groups, bctx.group_stride = len(self.local_workers), self.grads.stride(0)
+      bctx.worker_id, bctx.nbworkers = self.local_workers[0], nbworkers
+      self.batched_ctx = bctx
     self.eval_ctx = Context(self.backend, False, self.dtype, self.device)
     self.eval_ctx.weights, self.eval_ctx.master, self.eval_ctx.state = self.weight_views, self.master_views, self.states
     self.eval_ctx.generator = self._dropout_gen
@@ -125,9 +140,9 @@ class Manager:
     self._graph = None
     self._graph_warmup = 2       # eager steps before capture (lazy kernel attributes, workspaces, autotuning)
     self._graph_launches = 0
-    tools.info("Model %r: %d variables, d = %d (padded %d); %d worker(s) on this rank; compute dtype %s; nn backend %r; engine %r" % (
-      self.model.name, len(self.layout.names), self.layout.size, self.layout.padded_size, len(self.local_workers), str(self.dtype).replace("torch.", ""),
-      self.backend, self.aggregation.name), context="graph")
+    tools.info("Model %r: %d variables, d = %d (padded %d); %d worker(s) on this rank%s; compute dtype %s; nn backend %r; engine %r" % (
+      self.model.name, len(self.layout.names), self.layout.size, self.layout.padded_size, len(self.local_workers), " (batched in one pass)" if self.batched else "",
+      str(self.dtype).replace("torch.", ""), self.backend, self.aggregation.name), context="graph")
 
   # ---------------------------------------------------------------------------- #
   def _refresh_weights(self, force=False):
@@ -156,8 +171,7 @@ class Manager:
     before = counters.launches
     try:
       with torch.cuda.graph(graph):
-        losses = self.experiment.losses(self.model, self._static_batches, self.contexts, None)
-        self._static_losses = torch.stack([l.float().reshape(()) for l in losses])
+        self._static_losses = self._run_workers(self._static_batches, None)
     except Exception as err:
       tools.warning("CUDA graph capture failed (" + str(err).splitlines()[0] + "): staying in eager mode", context="graph")
       self.use_graphs = False
@@ -167,6 +181,13 @@ class Manager:
     self._graph = graph
     tools.info("Captured the workers' forward/backward into a CUDA graph (%d native kernel launches per replay)" % self._graph_launches, context="graph")
     return True
+
+  def _run_workers(self, batches, trace):
+    """Forward + backward of every local worker -> fp32 tensor of per-worker losses."""
+    if self.batched and trace is None:
+      return self.experiment.losses_batched(self.model, batches, self.batched_ctx).float()
+    losses = self.experiment.losses(self.model, batches, self.contexts, trace)
+    return torch.stack([l.float().reshape(()) for l in losses])
 
   def _replay(self, batches):
     from ..ops import counters
@@ -186,7 +207,7 @@ class Manager:
     if self._graph is not None and trace is None:
       losses = self._replay(batches)
     else:
-      losses = self.experiment.losses(self.model, batches, self.contexts, trace)
+      losses = list(self._run_workers(batches, trace).unbind(0))
     if (self.l1 is not None and self.l1 > 0.) or (self.l2 is not None and self.l2 > 0.):
       reg_loss, reg_grad = regularization(self.params, self.l1, self.l2)
       for j in range(len(self.local_workers)):

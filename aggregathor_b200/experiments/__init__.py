@@ -57,6 +57,14 @@ class _Experiment:
         out.append(model.loss_and_backward(self.preprocess(inputs, ctx, True), labels, ctx))
     return out
 
+  def losses_batched(self, model, batches, ctx):
+    """All local workers in ONE pass: their batches are concatenated along dim 0 and `ctx.groups` = number of workers (per-worker
+    batch-norm statistics, per-worker loss means, per-worker parameter gradients `ctx.group_stride` elements apart).
+    Returns a tensor of `len(batches)` losses."""
+    inputs = torch.cat([b[0] for b in batches], dim=0)
+    labels = torch.cat([b[1] for b in batches], dim=0)
+    return model.loss_and_backward(self.preprocess(inputs, ctx, True), labels, ctx).reshape(-1)
+
   def accuracy(self, model, batch, ctx, trace=None):
     inputs, labels = batch
     with torch.no_grad():

@@ -41,6 +41,8 @@ class Context:
     self.state = None           # name -> non-trainable state tensor (BN moving statistics)
     self.generator = None       # torch.Generator for dropout
     self.need_input_grad = False
+    self.groups = 1             # logical workers batched in one pass (their batches are consecutive along dim 0)
+    self.group_stride = 0       # elements between two workers' gradient rows (`grads` are worker 0's views)
 
 
 class Module:
@@ -137,7 +139,7 @@ class Conv2d(Module):
     weight = ctx.weights[self.name + "/weights"]
     need_dx = ctx.need_input_grad or not getattr(self, "is_first", False)
     dx, dw, db = nn_ops.conv2d_backward(ctx.backend, dy, x, weight, self._saved_y, self.stride, pads, self.relu, self.bias, need_dx,
-                                        ctx.grads[self.name + "/weights"], ctx.grads[self.name + "/biases"] if self.bias else None)
+                                        ctx.grads[self.name + "/weights"], ctx.grads[self.name + "/biases"] if self.bias else None, ctx.groups, ctx.group_stride)
     self._saved_x = self._saved_y = None
     return dx
 
@@ -176,7 +178,7 @@ class Dense(Module):
   def backward(self, dy, ctx):
     need_dx = ctx.need_input_grad or not getattr(self, "is_first", False)
     dx = nn_ops.linear_backward(ctx.backend, dy, self._saved_x, ctx.weights[self.name + "/weights"], self._saved_y, self.relu, need_dx,
-                                ctx.grads[self.name + "/weights"], ctx.grads[self.name + "/biases"] if self.bias else None)
+                                ctx.grads[self.name + "/weights"], ctx.grads[self.name + "/biases"] if self.bias else None, ctx.groups, ctx.group_stride)
     self._saved_x = self._saved_y = None
     return dx
 
@@ -209,7 +211,7 @@ class BatchNorm(Module):
     mean, var = ctx.state[self.name + "/moving_mean"], ctx.state[self.name + "/moving_variance"]
     if not ctx.training:
       return nn_ops.batchnorm_inference(ctx.backend, x, gamma, beta, mean, var, self.epsilon, self.relu)
-    y, batch_mean, batch_rstd = nn_ops.batchnorm_forward(ctx.backend, x, gamma, beta, mean, var, self.decay, self.epsilon, self.relu)
+    y, batch_mean, batch_rstd = nn_ops.batchnorm_forward(ctx.backend, x, gamma, beta, mean, var, self.decay, self.epsilon, self.relu, ctx.groups)
     self._saved = (x, y if self.relu else None, batch_mean, batch_rstd)
     return y
 
@@ -217,9 +219,38 @@ class BatchNorm(Module):
     x, y, batch_mean, batch_rstd = self._saved
     gamma = ctx.master[self.name + "/gamma"] if self.scale else None
     dx = nn_ops.batchnorm_backward(ctx.backend, dy, x, y, gamma, batch_mean, batch_rstd, self.relu,
-                                   ctx.grads[self.name + "/gamma"] if self.scale else None, ctx.grads[self.name + "/beta"])
+                                   ctx.grads[self.name + "/gamma"] if self.scale else None, ctx.grads[self.name + "/beta"], ctx.groups, ctx.group_stride)
     self._saved = None
     return dx
+
+
+class LayerNorm(Module):
+  """Layer normalisation over the feature dimension of a [rows, features] activation (trainable gamma / beta)."""
+
+  def __init__(self, name, features, epsilon=1e-5):
+    super().__init__(name)
+    self.features, self.epsilon = features, epsilon
+
+  def declare(self, layout, states):
+    layout.add(self.name + "/gamma", (self.features,))
+    layout.add(self.name + "/beta", (self.features,))
+
+  def initialize(self, master, states, generator):
+    master[self.name + "/gamma"].fill_(1.0)
+    master[self.name + "/beta"].zero_()
+
+  def forward(self, x, ctx):
+    x = x.reshape(x.shape[0], -1)
+    y, mean, rstd = nn_ops.layernorm_forward(ctx.backend, x, ctx.master[self.name + "/gamma"], ctx.master[self.name + "/beta"], self.epsilon)
+    if ctx.training:
+      self._saved = (x, mean, rstd)
+    return y
+
+  def backward(self, dy, ctx):
+    x, mean, rstd = self._saved
+    self._saved = None
+    return nn_ops.layernorm_backward(ctx.backend, dy, x, ctx.master[self.name + "/gamma"], mean, rstd, ctx.grads[self.name + "/gamma"], ctx.grads[self.name + "/beta"],
+                                     ctx.groups, ctx.group_stride)
 
 
 class ReLU(Module):
@@ -471,9 +502,10 @@ class Model:
     return y.reshape(y.shape[0], -1)
 
   def loss_and_backward(self, x, labels, ctx):
-    """Forward, mean softmax cross-entropy, backward. Returns the loss (0-d fp32 tensor)."""
+    """Forward, mean softmax cross-entropy, backward. Returns the loss (0-d fp32 tensor; shape [ctx.groups] when several logical
+    workers are batched: each worker's loss is the mean over its own slice of the batch)."""
     logits = self.logits(x, ctx)
-    loss, dlogits = nn_ops.softmax_xent(ctx.backend, logits, labels, self.label_smoothing)
+    loss, dlogits = nn_ops.softmax_xent(ctx.backend, logits, labels, self.label_smoothing, ctx.groups)
     dlogits = dlogits.to(ctx.dtype).reshape(self._raw_shape)
     if dlogits.dim() == 4:
       dlogits = dlogits.contiguous(memory_format=torch.channels_last)

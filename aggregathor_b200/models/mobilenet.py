@@ -32,8 +32,13 @@ class DepthwiseConv2d(Module):
     xp, (t, b, l, r), (h, w) = self._saved
     self._saved = None
     weight = ctx.weights[self.name + "/depthwise_weights"].permute(0, 3, 1, 2)
-    dxp, dw, _ = torch.ops.aten.convolution_backward(dy, xp, weight, None, [self.stride] * 2, [0, 0], [1, 1], False, [0, 0], self.channels, [True, True, False])
-    ctx.grads[self.name + "/depthwise_weights"].copy_(dw.permute(0, 2, 3, 1))
+    from ..ops.nn import group_view
+    pieces = []
+    for g, (dy_g, xp_g) in enumerate(zip(dy.chunk(ctx.groups, dim=0), xp.chunk(ctx.groups, dim=0))):
+      dxp, dw, _ = torch.ops.aten.convolution_backward(dy_g, xp_g, weight, None, [self.stride] * 2, [0, 0], [1, 1], False, [0, 0], self.channels, [True, True, False])
+      group_view(ctx.grads[self.name + "/depthwise_weights"], g, ctx.group_stride).copy_(dw.permute(0, 2, 3, 1))
+      pieces.append(dxp)
+    dxp = pieces[0] if len(pieces) == 1 else torch.cat(pieces, dim=0)
     return dxp[:, :, t:t + h, l:l + w].contiguous(memory_format=torch.channels_last)
 
 

@@ -67,6 +67,10 @@ __device__ __forceinline__ void tma_load_2d(void* dst, CUtensorMap const* map, u
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(void* dst, CUtensorMap const* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void tma_load_4d(void* dst, CUtensorMap const* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                  :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
@@ -177,6 +181,26 @@ inline int make_tmap_2d_bf16(CUtensorMap* map, void const* base, uint64_t inner,
     if (res != CUDA_SUCCESS) {
         std::fprintf(stderr, "[agb] cuTensorMapEncodeTiled failed (%d): base %p inner %llu rows %llu stride %llu box %ux%u\n", (int) res, base,
                      (unsigned long long) inner, (unsigned long long) rows, (unsigned long long) row_stride, box_inner, box_rows);
+        return 202;
+    }
+    return 0;
+}
+
+// 3-D bf16 tensor map over a row-major [groups][rows][inner] view (row stride `row_stride`, group stride `rows * row_stride`):
+// boxes never straddle a group, rows past the end of a group are zero-filled (grouped weight-gradient GEMMs).
+inline int make_tmap_3d_bf16(CUtensorMap* map, void const* base, uint64_t inner, uint64_t rows, uint64_t groups, uint64_t row_stride, uint32_t box_inner, uint32_t box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn)
+        return 201;
+    cuuint64_t dims[3] = {inner, rows, groups};
+    cuuint64_t strides[2] = {row_stride * 2, rows * row_stride * 2};
+    cuuint32_t box[3] = {box_inner, box_rows, 1};
+    cuuint32_t elem[3] = {1, 1, 1};
+    CUresult res = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (res != CUDA_SUCCESS) {
+        std::fprintf(stderr, "[agb] cuTensorMapEncodeTiled(3d) failed (%d): inner %llu rows %llu groups %llu stride %llu\n", (int) res, (unsigned long long) inner,
+                     (unsigned long long) rows, (unsigned long long) groups, (unsigned long long) row_stride);
         return 202;
     }
     return 0;

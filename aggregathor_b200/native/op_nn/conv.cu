@@ -23,6 +23,7 @@ struct ConvParams {
     int Cin, Cout, k, pad;
     int bw, bh, bn;         // pixel box of one M tile (fwd/dgrad: product <= 128) or one K block (wgrad: product <= 64)
     int tiles_w, tiles_h, tiles_n;
+    int groups, images_per_group;   // wgrad of several logical workers: K ranges = image ranges, one output per group
 };
 
 enum ConvMode { kFwd = 0, kDgrad = 1, kWgrad = 2 };
@@ -68,8 +69,9 @@ __global__ void __launch_bounds__(kPersistentThreads, 1) conv_tcgen05_kernel(con
     int const box_rows = cp.bw * cp.bh * cp.bn;
     // number of K blocks of one work item before splitting
     int const cchunks = (MODE == kFwd ? cp.Cin : cp.Cout) / 64;
-    int const total_kblocks = MODE == kWgrad ? pixel_tiles : taps * cchunks;
-    int const total_items = items_mn * splits;
+    int const groups = (MODE == kWgrad && cp.groups > 1) ? cp.groups : 1;
+    int const total_kblocks = MODE == kWgrad ? pixel_tiles / groups : taps * cchunks;
+    int const total_items = items_mn * splits * groups;
 
     // Pixel boxes smaller than the MMA tile (7x7 maps) leave rows that TMA never writes: zero the ring once.
     if (box_rows < (MODE == kWgrad ? 64 : 128)) {
@@ -103,9 +105,11 @@ __global__ void __launch_bounds__(kPersistentThreads, 1) conv_tcgen05_kernel(con
     uint32_t const b_bytes = MODE == kWgrad ? (BN / 64) * box_rows * 128u : Cfg::kBBytes;
 
     // item -> (m index, n tile, tap for wgrad, k split)
-    struct Item { int pw, ph, pn, n0, tap, kb_begin, nkb, m0; };
+    struct Item { int pw, ph, pn, n0, tap, kb_begin, nkb, m0, group; };
     auto decode = [&](int item) {
         Item it;
+        it.group = item / (items_mn * splits);
+        item -= it.group * items_mn * splits;
         int const mn = item % items_mn, split = item / items_mn;
         it.kb_begin = split * p.kblocks_per_split;
         int const kb_end = min(total_kblocks, it.kb_begin + p.kblocks_per_split);
@@ -143,7 +147,8 @@ __global__ void __launch_bounds__(kPersistentThreads, 1) conv_tcgen05_kernel(con
                     mbar_expect_tx(full + s, a_bytes + b_bytes);
                     if (MODE == kWgrad) {
                         // K block = pixel box `kb`; A = dy[box, co chunk], B = x[box shifted by the tap, ci chunk]
-                        int const w0 = (kb % cp.tiles_w) * cp.bw, h0 = ((kb / cp.tiles_w) % cp.tiles_h) * cp.bh, n0p = (kb / (cp.tiles_w * cp.tiles_h)) * cp.bn;
+                        int const w0 = (kb % cp.tiles_w) * cp.bw, h0 = ((kb / cp.tiles_w) % cp.tiles_h) * cp.bh;
+                        int const n0p = (kb / (cp.tiles_w * cp.tiles_h)) * cp.bn + it.group * cp.images_per_group;
                         int const kh = it.tap / cp.k, kw = it.tap % cp.k;
                         tma_load_4d(a_dst, &tmap_a, full + s, it.m0, w0, h0, n0p);
                         tma_load_4d(a_dst + kBK * 128, &tmap_a, full + s, it.m0 + 64, w0, h0, n0p);
@@ -198,7 +203,7 @@ __global__ void __launch_bounds__(kPersistentThreads, 1) conv_tcgen05_kernel(con
             if (MODE == kWgrad) {   // row = output channel; columns = (tap, ci) inside dW[Cout][k*k*Cin]
                 int const co = it.m0 + r;
                 valid = co < cp.Cout;
-                offset = static_cast<long long>(co) * p.ldc + it.tap * cp.Cin;
+                offset = static_cast<long long>(co) * p.ldc + it.tap * cp.Cin + it.group * p.c_group_stride;
             } else {                // row = pixel of the box, (w fastest, then h, then n)
                 int const bi_w = r % cp.bw, bi_h = (r / cp.bw) % cp.bh, bi_n = r / (cp.bw * cp.bh);
                 int const w = it.pw + bi_w, h = it.ph + bi_h, n = it.pn + bi_n;
@@ -231,7 +236,7 @@ int launch_conv(CUtensorMap const& ta, CUtensorMap const& tb, GemmParams const& 
         AGB_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
         configured = true;
     }
-    long long const items = static_cast<long long>(items_mn) * splits;
+    long long const items = static_cast<long long>(items_mn) * splits * ((MODE == kWgrad && cp.groups > 1) ? cp.groups : 1);
     int const grid = static_cast<int>(items < sms ? items : sms);
     kernel<<<grid, kPersistentThreads, PCfg::kSmemBytes, stream>>>(ta, tb, p, cp, items_mn, splits);
     AGB_CUDA_OK(cudaGetLastError());
@@ -270,13 +275,28 @@ extern "C" {
 // mode 0: y = conv(x, W) (+bias, ReLU) ; mode 1: dx = conv_transpose(dy, W) ; mode 2: dW (+)= dy^T * x (fp32, atomics; caller zeroes).
 // x / dy / y / dx are NHWC bf16 with N x H x W pixels (stride-1, same padding: pad = (k - 1) / 2, odd k);
 // W is [Cout][k][k][Cin] bf16; dW is [Cout][k][k][Cin] fp32. Cin % 64 == 0 and Cout % 64 == 0.
+int agb_conv_implicit_grouped(int mode, void const* act, void const* other, void* out, int N, int H, int W, int Cin, int Cout, int k, void const* bias, int relu,
+                              int out_fp32, int splits, int bn, int groups, long long c_group_stride, void* stream);
+
 int agb_conv_implicit(int mode, void const* act, void const* other, void* out, int N, int H, int W, int Cin, int Cout, int k, void const* bias, int relu,
                       int out_fp32, int splits, int bn, void* stream) {
+    return agb_conv_implicit_grouped(mode, act, other, out, N, H, W, Cin, Cout, k, bias, relu, out_fp32, splits, bn, 1, 0, stream);
+}
+
+// `groups` > 1 (mode 2 only): the N images are `groups` consecutive batches of N / groups images; group g accumulates its weight gradient
+// into out + g * c_group_stride.
+int agb_conv_implicit_grouped(int mode, void const* act, void const* other, void* out, int N, int H, int W, int Cin, int Cout, int k, void const* bias, int relu,
+                              int out_fp32, int splits, int bn, int groups, long long c_group_stride, void* stream) {
     if ((k & 1) == 0 || Cin % 64 || Cout % 64 || N < 1)
         return 401;
+    if (groups < 1)
+        groups = 1;
+    if (groups > 1 && (mode != 2 || N % groups))
+        return 404;
     ConvParams cp{};
     cp.N = N; cp.H = H; cp.W = W; cp.Cin = Cin; cp.Cout = Cout; cp.k = k; cp.pad = (k - 1) / 2;
-    if (!choose_box(W, H, N, mode == 2 ? 64 : 128, cp.bw, cp.bh, cp.bn))
+    cp.groups = groups; cp.images_per_group = N / groups;
+    if (!choose_box(W, H, mode == 2 ? N / groups : N, mode == 2 ? 64 : 128, cp.bw, cp.bh, cp.bn))   // boxes never straddle two workers
         return 402;
     cp.tiles_w = W / cp.bw; cp.tiles_h = H / cp.bh; cp.tiles_n = N / cp.bn;
     int const pixel_tiles = cp.tiles_w * cp.tiles_h * cp.tiles_n;
@@ -319,7 +339,7 @@ int agb_conv_implicit(int mode, void const* act, void const* other, void* out, i
         if ((status = make_tmap_4d_bf16(&tb, other, Cin, W, H, N, cp.bw, cp.bh, cp.bn)))
             return status;
         items_mn = k * k * ((Cout + kBM - 1) / kBM) * ((Cin + bn - 1) / bn);
-        total_kblocks = pixel_tiles;
+        total_kblocks = pixel_tiles / groups;
     } else {
         return 403;
     }
@@ -330,6 +350,7 @@ int agb_conv_implicit(int mode, void const* act, void const* other, void* out, i
     if (splits > 1 && !out_fp32)
         return 205;
     p.atomic = splits > 1;
+    p.groups = groups; p.c_group_stride = c_group_stride;
     p.kblocks_per_split = (total_kblocks + splits - 1) / splits;
     splits = (total_kblocks + p.kblocks_per_split - 1) / p.kblocks_per_split;
 #define AGB_CONV_DISPATCH(MODE) \

@@ -14,12 +14,26 @@ int agb_gemm_set_persistent(int enabled) {
 //   b_mn == 0: B is [N rows][K] with row stride ldb      b_mn == 1: B is [K rows][N] with row stride ldb
 // lda/ldb must be multiples of 8 elements, bases 16-byte aligned. splits > 1 => fp32 atomic accumulation into C
 // (caller zeroes C). bn in {64, 128, 256} or 0 for an automatic choice.
+int agb_gemm_bf16_grouped(void const* A, void const* B, void* C, int M, int N, int K, long long lda, long long ldb, long long ldc,
+                          int a_mn, int b_mn, void const* bias, int relu, int out_fp32, int splits, int bn, int groups, long long c_group_stride, void* stream);
+
 int agb_gemm_bf16(void const* A, void const* B, void* C, int M, int N, int K, long long lda, long long ldb, long long ldc,
                   int a_mn, int b_mn, void const* bias, int relu, int out_fp32, int splits, int bn, void* stream) {
+    return agb_gemm_bf16_grouped(A, B, C, M, N, K, lda, ldb, ldc, a_mn, b_mn, bias, relu, out_fp32, splits, bn, 1, 0, stream);
+}
+
+// Grouped form (weight gradients of several logical workers in one launch): A and B hold `groups` consecutive blocks of K rows
+// (a_mn = b_mn = 1 required when groups > 1), group g accumulates into C + g * c_group_stride. K is the per-group depth.
+int agb_gemm_bf16_grouped(void const* A, void const* B, void* C, int M, int N, int K, long long lda, long long ldb, long long ldc,
+                          int a_mn, int b_mn, void const* bias, int relu, int out_fp32, int splits, int bn, int groups, long long c_group_stride, void* stream) {
     if (M <= 0 || N <= 0 || K <= 0)
         return 0;
     if ((lda & 7) || (ldb & 7) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15))
         return 204;
+    if (groups < 1)
+        groups = 1;
+    if (groups > 1 && !(a_mn && b_mn))
+        return 206;
     if (splits < 1)
         splits = 1;
     if (splits > 1 && !out_fp32)
@@ -33,17 +47,22 @@ int agb_gemm_bf16(void const* A, void const* B, void* C, int M, int N, int K, lo
     p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.C = C;
     p.bias = static_cast<float const*>(bias);
     p.relu = relu; p.out_fp32 = out_fp32; p.atomic = splits > 1;
+    p.groups = groups; p.c_group_stride = c_group_stride;
     p.kblocks_per_split = (total_kblocks + splits - 1) / splits;
     splits = (total_kblocks + p.kblocks_per_split - 1) / p.kblocks_per_split;
     CUtensorMap ta, tb;
     int status;
-    if (a_mn)
+    if (a_mn && b_mn)
+        status = make_tmap_3d_bf16(&ta, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), static_cast<uint64_t>(groups), static_cast<uint64_t>(lda), 64, kBK);
+    else if (a_mn)
         status = make_tmap_2d_bf16(&ta, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), static_cast<uint64_t>(lda), 64, kBK);
     else
         status = make_tmap_2d_bf16(&ta, A, static_cast<uint64_t>(K), static_cast<uint64_t>(M), static_cast<uint64_t>(lda), kBK, kBM);
     if (status)
         return status;
-    if (b_mn)
+    if (a_mn && b_mn)
+        status = make_tmap_3d_bf16(&tb, B, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(groups), static_cast<uint64_t>(ldb), 64, kBK);
+    else if (b_mn)
         status = make_tmap_2d_bf16(&tb, B, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldb), 64, kBK);
     else
         status = make_tmap_2d_bf16(&tb, B, static_cast<uint64_t>(K), static_cast<uint64_t>(N), static_cast<uint64_t>(ldb), kBK, static_cast<uint32_t>(bn));

@@ -52,6 +52,8 @@ struct GemmParams {
     int out_fp32;           // C element type: 1 = float, 0 = bf16
     int atomic;             // accumulate with red.add.f32 (split-K); requires out_fp32
     int kblocks_per_split;
+    int groups;              // grouped weight gradients: independent K ranges (one per logical worker) ...
+    long long c_group_stride; // ... each accumulating into C + group * c_group_stride
 };
 
 // Epilogue of one 128 x BN accumulator tile: TMEM -> registers -> (+bias, ReLU, convert) -> global memory.
@@ -270,9 +272,17 @@ __device__ __forceinline__ void epilogue_tile(GemmParams const& p, uint32_t tmem
 
 // Loads of one pipeline stage (A and B tiles of k-block `k`).
 template<int BN, bool A_MN, bool B_MN>
-__device__ __forceinline__ void produce_stage(CUtensorMap const* tmap_a, CUtensorMap const* tmap_b, uint8_t* a_dst, uint64_t* bar, int m0, int n0, int k) {
+__device__ __forceinline__ void produce_stage(CUtensorMap const* tmap_a, CUtensorMap const* tmap_b, uint8_t* a_dst, uint64_t* bar, int m0, int n0, int k, int group = -1) {
     uint8_t* b_dst = a_dst + Config<BN>::kABytes;
     mbar_expect_tx(bar, Config<BN>::kStageBytes);
+    if (A_MN && B_MN && group >= 0) {   // grouped weight gradient: 3-D maps (inner, row in group, group)
+        tma_load_3d(a_dst, tmap_a, bar, m0, k, group);
+        tma_load_3d(a_dst + kBK * 128, tmap_a, bar, m0 + 64, k, group);
+#pragma unroll
+        for (int c = 0; c < BN / 64; ++c)
+            tma_load_3d(b_dst + c * kBK * 128, tmap_b, bar, n0 + c * 64, k, group);
+        return;
+    }
     if (A_MN) { // rows = K index, 64 M-elements per row; one box per 64-wide M chunk
         tma_load_2d(a_dst, tmap_a, bar, m0, k);
         tma_load_2d(a_dst + kBK * 128, tmap_a, bar, m0 + 64, k);
@@ -328,7 +338,7 @@ __global__ void __launch_bounds__(kPersistentThreads, 1) gemm_tcgen05_persistent
 
     int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int const total_kblocks = (p.K + kBK - 1) / kBK;
-    int const total_items = m_tiles * n_tiles * splits;
+    int const total_items = m_tiles * n_tiles * splits * (p.groups > 1 ? p.groups : 1);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
@@ -353,7 +363,10 @@ __global__ void __launch_bounds__(kPersistentThreads, 1) gemm_tcgen05_persistent
     // item -> tile in grouped order (panels of 16 m-tiles, m fastest inside a panel, then n): the ~148 tiles in flight
     // cover a ~16 x 9 patch, so every A and B tile fetched from L2/HBM is reused by several CTAs of the same wave.
     constexpr int kGroupM = 16;
-    auto decode = [&](int item, int& m0, int& n0, int& kb_begin, int& nkb) {
+    int const items_per_group = m_tiles * n_tiles * splits;
+    auto decode = [&](int item, int& m0, int& n0, int& kb_begin, int& nkb, int& group) {
+        group = item / items_per_group;
+        item -= group * items_per_group;
         int const tile = item % (m_tiles * n_tiles), split = item / (m_tiles * n_tiles);
         int const group_size = kGroupM * n_tiles;
         int const first_m = (tile / group_size) * kGroupM;
@@ -365,17 +378,18 @@ __global__ void __launch_bounds__(kPersistentThreads, 1) gemm_tcgen05_persistent
         int const kb_end = min(total_kblocks, kb_begin + p.kblocks_per_split);
         nkb = kb_end - kb_begin;
     };
+    bool const grouped = p.groups > 1 || (A_MN && B_MN);   // TN products always use the 3-D maps
 
     if (warp == 0) {
         if (lane == 0) {
             uint32_t it = 0;   // running k-block counter => ring slot and phase
             for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-                int m0, n0, kb_begin, nkb;
-                decode(item, m0, n0, kb_begin, nkb);
+                int m0, n0, kb_begin, nkb, group;
+                decode(item, m0, n0, kb_begin, nkb, group);
                 for (int i = 0; i < nkb; ++i, ++it) {
                     int const s = it % PCfg::kStages;
                     mbar_wait(empty + s, ((it / PCfg::kStages) & 1) ^ 1, 11);
-                    produce_stage<BN, A_MN, B_MN>(&tmap_a, &tmap_b, smem + s * Cfg::kStageBytes, full + s, m0, n0, (kb_begin + i) * kBK);
+                    produce_stage<BN, A_MN, B_MN>(&tmap_a, &tmap_b, smem + s * Cfg::kStageBytes, full + s, m0, n0, (kb_begin + i) * kBK, grouped ? group : -1);
                 }
             }
         }
@@ -383,8 +397,8 @@ __global__ void __launch_bounds__(kPersistentThreads, 1) gemm_tcgen05_persistent
         if (lane == 0) {
             uint32_t it = 0, j = 0;
             for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++j) {
-                int m0, n0, kb_begin, nkb;
-                decode(item, m0, n0, kb_begin, nkb);
+                int m0, n0, kb_begin, nkb, group;
+                decode(item, m0, n0, kb_begin, nkb, group);
                 uint32_t const buf = j & 1;
                 mbar_wait(tmem_empty + buf, ((j >> 1) & 1) ^ 1, 12);   // epilogue drained this accumulator
                 tc_fence_after();
@@ -402,15 +416,15 @@ __global__ void __launch_bounds__(kPersistentThreads, 1) gemm_tcgen05_persistent
     } else {
         uint32_t j = 0;
         for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++j) {
-            int m0, n0, kb_begin, nkb;
-            decode(item, m0, n0, kb_begin, nkb);
+            int m0, n0, kb_begin, nkb, group;
+            decode(item, m0, n0, kb_begin, nkb, group);
             uint32_t const buf = j & 1;
             mbar_wait(tmem_full + buf, (j >> 1) & 1, 14);
             tc_fence_after();
             {
                 int const ewarp = ((warp & 3)) | (((warp - 2) >> 2) << 2);   // quarter from the hardware warp id, half from the warp's group
                 int const row = m0 + (warp & 3) * 32 + lane;
-                epilogue_rows_staged<BN>(p, tmem_base + buf * Cfg::kTmemCols, ewarp, lane, row < p.M, static_cast<long long>(row) * p.ldc, n0, epi_stage);
+                epilogue_rows_staged<BN>(p, tmem_base + buf * Cfg::kTmemCols, ewarp, lane, row < p.M, static_cast<long long>(row) * p.ldc + group * p.c_group_stride, n0, epi_stage);
             }
             tc_fence_before();
             __syncwarp();
@@ -466,7 +480,7 @@ __global__ void __launch_bounds__(kThreads, BN <= 128 ? 2 : 1) gemm_tcgen05_kern
                     int const s = i % Cfg::kStages;
                     uint32_t const phase = (i / Cfg::kStages) & 1;
                     mbar_wait(empty + s, phase ^ 1, 1);
-                    produce_stage<BN, A_MN, B_MN>(&tmap_a, &tmap_b, smem + s * Cfg::kStageBytes, full + s, m0, n0, (kb_begin + i) * kBK);
+                    produce_stage<BN, A_MN, B_MN>(&tmap_a, &tmap_b, smem + s * Cfg::kStageBytes, full + s, m0, n0, (kb_begin + i) * kBK, (A_MN && B_MN) ? 0 : -1);
                 }
             }
         } else if (warp == 1) {
@@ -517,12 +531,14 @@ int launch_gemm(CUtensorMap const& ta, CUtensorMap const& tb, GemmParams const& 
             AGB_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
             configured = true;
         }
-        long long const items = static_cast<long long>(m_tiles) * n_tiles * splits;
+        long long const items = static_cast<long long>(m_tiles) * n_tiles * splits * (p.groups > 1 ? p.groups : 1);
         int const grid = static_cast<int>(items < sms ? items : sms);
         kernel<<<grid, kPersistentThreads, PCfg::kSmemBytes, stream>>>(ta, tb, p, m_tiles, n_tiles, splits);
         AGB_CUDA_OK(cudaGetLastError());
         return 0;
     }
+    if (p.groups > 1)
+        return 207;   // grouped products need the persistent kernel
     auto kernel = gemm_tcgen05_kernel<BN, A_MN, B_MN>;
     static bool configured = false;
     if (!configured) {

@@ -62,6 +62,7 @@ struct SumsFinalize {
     float* dgamma;              // MODE 1
     float* dbeta;               // MODE 1 ; MODE 2: the fp32 column sums
     int groups;
+    long long group_stride;     // elements between two groups' parameter gradients (dgamma / dbeta / column sums)
     float eps, decay;
 };
 
@@ -95,18 +96,12 @@ __device__ void finalize_sums(double const* sums, SumsFinalize const& f, int C, 
             f.scale[3 * i] = a;
             f.scale[3 * i + 1] = b;
             f.scale[3 * i + 2] = -gm * rs * static_cast<float>(s0) * inv - b * mu;
-            if (g == 0) {
-                double total_dbeta = 0., total_dgamma = 0.;
-                for (int gg = 0; gg < f.groups; ++gg) {
-                    total_dbeta += __ldcg(sums + 2 * (gg * C + c));
-                    total_dgamma += __ldcg(sums + 2 * (gg * C + c) + 1);
-                }
-                if (f.dgamma)
-                    f.dgamma[c] = static_cast<float>(total_dgamma);
-                f.dbeta[c] = static_cast<float>(total_dbeta);
-            }
+            // one gradient per group: each logical worker owns its own dgamma / dbeta
+            if (f.dgamma)
+                f.dgamma[g * f.group_stride + c] = static_cast<float>(s1);
+            f.dbeta[g * f.group_stride + c] = static_cast<float>(s0);
         } else {
-            f.dbeta[i] = static_cast<float>(s0);
+            f.dbeta[g * f.group_stride + c] = static_cast<float>(s0);
         }
     }
 }
@@ -532,7 +527,7 @@ __global__ void avgpool_bwd_kernel(bf16 const* __restrict__ dy, bf16* __restrict
 // Softmax cross-entropy, one warp per row. logits bf16 [B, ld] (K valid columns), labels int64.
 // loss += mean_b(-sum_k t_k log p_k) ; dlogits = (p - t) / B  (bf16, same leading dimension).
 __global__ void softmax_xent_kernel(bf16 const* __restrict__ logits, long long const* __restrict__ labels, bf16* __restrict__ dlogits, float* __restrict__ loss,
-                                    int B, int K, long long ld, float smoothing) {
+                                    int B, int K, long long ld, float smoothing, int rows_per_group) {
     int const warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= B)
         return;
@@ -549,7 +544,7 @@ __global__ void softmax_xent_kernel(bf16 const* __restrict__ logits, long long c
     float const lse = mx + __logf(sum);
     int const label = static_cast<int>(labels[warp]);
     float const off_t = smoothing / static_cast<float>(K), on_t = 1.f - smoothing + off_t;
-    float const inv_b = 1.f / static_cast<float>(B);
+    float const inv_b = 1.f / static_cast<float>(rows_per_group);   // each group (logical worker) averages over its own batch
     float local = 0.f;
     bf16* drow = dlogits + static_cast<long long>(warp) * ld;
     for (int k = lane; k < K; k += 32) {
@@ -561,7 +556,7 @@ __global__ void softmax_xent_kernel(bf16 const* __restrict__ logits, long long c
     }
     local = warp_sum(local);
     if (lane == 0)
-        atomicAdd(loss, local * inv_b);
+        atomicAdd(loss + warp / rows_per_group, local * inv_b);
 }
 
 // uint8 NHWC image -> bf16 NHWC activations with C padded to `Cpad`: y = (x - mean[c]) * scale
@@ -702,7 +697,7 @@ struct SumsPlan {
 inline SumsPlan plan_sums(long long rows_per_group, int C, int groups) {
     int const octets = C >> 3;
     SumsPlan plan;
-    plan.strip = octets >= 32 ? 32 : octets >= 16 ? 16 : 8;
+    plan.strip = 8;   // 128-byte strips measured faster end to end than 256/512-byte ones (more CTAs per tensor)
     int const row_lanes = kThreads / plan.strip;
     int const strips = (octets + plan.strip - 1) / plan.strip;
     long long target = (148 * 6 + strips * groups - 1) / (strips * groups);   // ~6 CTAs per SM overall
@@ -759,7 +754,7 @@ int agb_bn_forward(void const* x, void* y, void const* gamma, void const* beta, 
 }
 
 int agb_bn_backward(void const* dy, void const* x, void const* y, void const* gamma, void const* save_mean, void const* save_rstd, void* dx, void* dgamma, void* dbeta,
-                    void* sums, void* coef, long long rows, int C, int groups, void* stream) {
+                    void* sums, void* coef, long long rows, int C, int groups, long long group_stride, void* stream) {
     if ((C & 7) || groups < 1 || rows % groups)
         return 301;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -771,7 +766,7 @@ int agb_bn_backward(void const* dy, void const* x, void const* y, void const* ga
     fin.save_mean = const_cast<float*>(static_cast<float const*>(save_mean)); fin.save_rstd = const_cast<float*>(static_cast<float const*>(save_rstd));
     fin.scale = static_cast<float*>(coef);
     fin.dgamma = static_cast<float*>(dgamma); fin.dbeta = static_cast<float*>(dbeta);
-    fin.groups = groups;
+    fin.groups = groups; fin.group_stride = group_stride;
     SumsPlan plan = plan_sums(rpg, C, groups);
     launch_sums<1>(plan, s, static_cast<bf16 const*>(dy), static_cast<bf16 const*>(x), static_cast<bf16 const*>(y), static_cast<float const*>(save_mean),
                    static_cast<float const*>(save_rstd), static_cast<double*>(sums), rpg, C, fin);
@@ -782,18 +777,19 @@ int agb_bn_backward(void const* dy, void const* x, void const* y, void const* ga
     return 0;
 }
 
-// out[c] = sum over rows of dy[r][c] (masked by y > 0 when y != null); `sums` is a double [2*C + 1] workspace.
-int agb_colsum(void const* dy, void const* y, void* out, void* sums, long long rows, int C, void* stream) {
-    if (C & 7)
+// out[g * group_stride + c] = sum over the rows of group g of dy[r][c] (masked by y > 0 when y != null);
+// `sums` is a double [2*C*groups + 1] workspace.
+int agb_colsum(void const* dy, void const* y, void* out, void* sums, long long rows, int C, int groups, long long group_stride, void* stream) {
+    if ((C & 7) || groups < 1 || rows % groups)
         return 301;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    AGB_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(double) * (2 * C + 1), s));
+    AGB_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(double) * (2 * C * groups + 1), s));
     SumsFinalize fin{};
-    fin.ticket = reinterpret_cast<unsigned*>(static_cast<double*>(sums) + 2 * C);
+    fin.ticket = reinterpret_cast<unsigned*>(static_cast<double*>(sums) + 2 * C * groups);
     fin.dbeta = static_cast<float*>(out);
-    fin.groups = 1;
-    SumsPlan plan = plan_sums(rows, C, 1);
-    launch_sums<2>(plan, s, static_cast<bf16 const*>(dy), nullptr, static_cast<bf16 const*>(y), nullptr, nullptr, static_cast<double*>(sums), rows, C, fin);
+    fin.groups = groups; fin.group_stride = group_stride;
+    SumsPlan plan = plan_sums(rows / groups, C, groups);
+    launch_sums<2>(plan, s, static_cast<bf16 const*>(dy), nullptr, static_cast<bf16 const*>(y), nullptr, nullptr, static_cast<double*>(sums), rows / groups, C, fin);
     AGB_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -849,12 +845,14 @@ int agb_avgpool_backward(void const* dy, void* dx, int N, int HW, int C, void* s
     return 0;
 }
 
-int agb_softmax_xent(void const* logits, void const* labels, void* dlogits, void* loss, int B, int K, long long ld, float smoothing, void* stream) {
+int agb_softmax_xent(void const* logits, void const* labels, void* dlogits, void* loss, int B, int K, long long ld, float smoothing, int groups, void* stream) {
+    if (groups < 1 || B % groups)
+        return 301;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    AGB_CUDA_OK(cudaMemsetAsync(loss, 0, sizeof(float), s));
+    AGB_CUDA_OK(cudaMemsetAsync(loss, 0, sizeof(float) * groups, s));
     int const warps_per_cta = 4;
     softmax_xent_kernel<<<(B + warps_per_cta - 1) / warps_per_cta, warps_per_cta * 32, 0, s>>>(static_cast<bf16 const*>(logits), static_cast<long long const*>(labels),
-        static_cast<bf16*>(dlogits), static_cast<float*>(loss), B, K, ld, smoothing);
+        static_cast<bf16*>(dlogits), static_cast<float*>(loss), B, K, ld, smoothing, B / groups);
     AGB_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -43,6 +43,18 @@ def _relu_mask(dy, y):
   return dy * (y > 0).to(dy.dtype)
 
 
+def group_view(tensor, group, stride):
+  """View of the same shape `stride` * `group` elements further in the underlying buffer: the gradient of logical worker
+  `group` when `tensor` is worker 0's view into the [w, d] gradient matrix."""
+  if tensor is None or group == 0:
+    return tensor
+  return tensor.as_strided(tensor.shape, tensor.stride(), tensor.storage_offset() + group * stride)
+
+
+def _chunks(tensor, groups):
+  return tensor.chunk(groups, dim=0) if tensor is not None else [None] * groups
+
+
 # ---------------------------------------------------------------------------- #
 # Convolution
 
@@ -59,13 +71,21 @@ def conv2d_forward(backend, x, weight, bias, stride, pads, relu):
   return y.contiguous(memory_format=_CL)
 
 
-def conv2d_backward(backend, dy, x, weight, y, stride, pads, relu, has_bias, need_dx, grad_w, grad_b):
-  """Writes dW into `grad_w` ([Cout, kh, kw, Cin] fp32 view) and db into `grad_b`; returns dx or None."""
+def conv2d_backward(backend, dy, x, weight, y, stride, pads, relu, has_bias, need_dx, grad_w, grad_b, groups=1, group_stride=0):
+  """Writes dW into `grad_w` ([Cout, kh, kw, Cin] fp32 view) and db into `grad_b`; returns dx or None. With `groups` > 1 the batch
+  is `groups` consecutive per-worker batches and worker g's gradients go `g * group_stride` elements after worker 0's."""
   if backend == "native" and x.is_cuda:
-    out = _native().conv2d_backward(dy, x, weight, y, stride, pads, relu, has_bias, need_dx, grad_w, grad_b)
+    out = _native().conv2d_backward(dy, x, weight, y, stride, pads, relu, has_bias, need_dx, grad_w, grad_b, groups, group_stride)
     if out is not NotImplemented:
       return out, None, None
     _fallback("conv2d_backward")
+  if groups > 1:
+    pieces = []
+    for g, (dy_g, x_g, y_g) in enumerate(zip(_chunks(dy, groups), _chunks(x, groups), _chunks(y, groups))):
+      dx_g, _, _ = conv2d_backward(backend, dy_g.contiguous(memory_format=_CL), x_g.contiguous(memory_format=_CL), weight, y_g, stride, pads, relu, has_bias, need_dx,
+                                   group_view(grad_w, g, group_stride), group_view(grad_b, g, group_stride))
+      pieces.append(dx_g)
+    return (torch.cat(pieces, dim=0).contiguous(memory_format=_CL) if need_dx else None), None, None
   if relu:
     dy = _relu_mask(dy, y)
   t, b, l, r = pads
@@ -96,12 +116,16 @@ def linear_forward(backend, x, weight, bias, relu):
   return torch.relu_(y) if relu else y
 
 
-def linear_backward(backend, dy, x, weight, y, relu, need_dx, grad_w, grad_b):
+def linear_backward(backend, dy, x, weight, y, relu, need_dx, grad_w, grad_b, groups=1, group_stride=0):
   if backend == "native" and x.is_cuda:
-    out = _native().linear_backward(dy, x, weight, y, relu, need_dx, grad_w, grad_b)
+    out = _native().linear_backward(dy, x, weight, y, relu, need_dx, grad_w, grad_b, groups, group_stride)
     if out is not NotImplemented:
       return out
     _fallback("linear_backward")
+  if groups > 1:
+    pieces = [linear_backward(backend, dy_g, x_g, weight, y_g, relu, need_dx, group_view(grad_w, g, group_stride), group_view(grad_b, g, group_stride))
+              for g, (dy_g, x_g, y_g) in enumerate(zip(_chunks(dy, groups), _chunks(x, groups), _chunks(y, groups)))]
+    return torch.cat(pieces, dim=0) if need_dx else None
   if relu:
     dy = _relu_mask(dy, y)
   grad_w.copy_(dy.t() @ x)
@@ -113,12 +137,18 @@ def linear_backward(backend, dy, x, weight, y, relu, need_dx, grad_w, grad_b):
 # ---------------------------------------------------------------------------- #
 # Batch normalisation
 
-def batchnorm_forward(backend, x, gamma, beta, moving_mean, moving_var, decay, eps, relu):
+def batchnorm_forward(backend, x, gamma, beta, moving_mean, moving_var, decay, eps, relu, groups=1):
+  """Training-mode batch norm; with `groups` > 1 every consecutive batch slice (one logical worker) has its own statistics;
+  returns (y, mean [groups * C], rstd [groups * C])."""
   if backend == "native" and x.is_cuda:
-    out = _native().batchnorm_forward(x, gamma, beta, moving_mean, moving_var, decay, eps, relu)
+    out = _native().batchnorm_forward(x, gamma, beta, moving_mean, moving_var, decay, eps, relu, groups)
     if out is not None:
       return out
     _fallback("batchnorm_forward")
+  if groups > 1:
+    outs = [batchnorm_forward(backend, x_g.contiguous(memory_format=_CL), gamma, beta, moving_mean if g == 0 else None, moving_var if g == 0 else None, decay, eps, relu)
+            for g, x_g in enumerate(_chunks(x, groups))]
+    return torch.cat([o[0] for o in outs], dim=0).contiguous(memory_format=_CL), torch.cat([o[1] for o in outs]), torch.cat([o[2] for o in outs])
   y, mean, rstd = torch.native_batch_norm(x, gamma, beta, moving_mean, moving_var, True, 1.0 - decay, eps)
   if relu:
     y = torch.relu_(y)
@@ -130,12 +160,18 @@ def batchnorm_inference(backend, x, gamma, beta, moving_mean, moving_var, eps, r
   return torch.relu_(y) if relu else y
 
 
-def batchnorm_backward(backend, dy, x, y, gamma, mean, rstd, relu, grad_gamma, grad_beta):
+def batchnorm_backward(backend, dy, x, y, gamma, mean, rstd, relu, grad_gamma, grad_beta, groups=1, group_stride=0):
   if backend == "native" and x.is_cuda:
-    out = _native().batchnorm_backward(dy, x, y, gamma, mean, rstd, relu, grad_gamma, grad_beta)
+    out = _native().batchnorm_backward(dy, x, y, gamma, mean, rstd, relu, grad_gamma, grad_beta, groups, group_stride)
     if out is not None:
       return out
     _fallback("batchnorm_backward")
+  if groups > 1:
+    c = x.shape[1]
+    pieces = [batchnorm_backward(backend, dy_g.contiguous(memory_format=_CL), x_g.contiguous(memory_format=_CL), y_g, gamma, mean[g * c:(g + 1) * c], rstd[g * c:(g + 1) * c], relu,
+                                 group_view(grad_gamma, g, group_stride), group_view(grad_beta, g, group_stride))
+              for g, (dy_g, x_g, y_g) in enumerate(zip(_chunks(dy, groups), _chunks(x, groups), _chunks(y, groups)))]
+    return torch.cat(pieces, dim=0).contiguous(memory_format=_CL)
   if relu:
     dy = _relu_mask(dy, y)
   dx, dgamma, dbeta = torch.ops.aten.native_batch_norm_backward(dy, x, gamma, None, None, mean, rstd, True, 1e-5, [True, gamma is not None, True])
@@ -143,6 +179,42 @@ def batchnorm_backward(backend, dy, x, y, gamma, mean, rstd, relu, grad_gamma, g
     grad_gamma.copy_(dgamma)
   grad_beta.copy_(dbeta)
   return dx
+
+
+def layernorm_forward(backend, x, gamma, beta, eps):
+  """LayerNorm over the last dimension of a [rows, C] tensor -> (y, mean[rows], rstd[rows])."""
+  if backend == "native" and x.is_cuda:
+    out = _native().layernorm_forward(x, gamma, beta, eps)
+    if out is not None:
+      return out
+    _fallback("layernorm_forward")
+  xf = x if x.dtype == torch.float64 else x.float()
+  mean = xf.mean(dim=1)
+  var = xf.var(dim=1, unbiased=False)
+  rstd = torch.rsqrt(var + eps)
+  y = (xf - mean[:, None]) * rstd[:, None] * gamma.to(xf.dtype) + beta.to(xf.dtype)
+  return y.to(x.dtype), mean, rstd
+
+
+def layernorm_backward(backend, dy, x, gamma, mean, rstd, grad_gamma, grad_beta, groups=1, group_stride=0):
+  if groups > 1:
+    rows = x.shape[0] // groups
+    pieces = [layernorm_backward(backend, dy[g * rows:(g + 1) * rows], x[g * rows:(g + 1) * rows].contiguous(), gamma, mean[g * rows:(g + 1) * rows], rstd[g * rows:(g + 1) * rows],
+                                 group_view(grad_gamma, g, group_stride), group_view(grad_beta, g, group_stride)) for g in range(groups)]
+    return torch.cat(pieces, dim=0)
+  if backend == "native" and x.is_cuda:
+    out = _native().layernorm_backward(dy, x, gamma, mean, rstd, grad_gamma, grad_beta)
+    if out is not None:
+      return out
+    _fallback("layernorm_backward")
+  kind = x.dtype if x.dtype == torch.float64 else torch.float32
+  xf, df = x.to(kind), dy.to(kind)
+  xhat = (xf - mean.to(kind)[:, None]) * rstd.to(kind)[:, None]
+  g = df * gamma.to(kind)
+  grad_gamma.copy_((df * xhat).sum(dim=0))
+  grad_beta.copy_(df.sum(dim=0))
+  dx = rstd.to(kind)[:, None] * (g - g.mean(dim=1, keepdim=True) - xhat * (g * xhat).mean(dim=1, keepdim=True))
+  return dx.to(x.dtype)
 
 
 # ---------------------------------------------------------------------------- #
@@ -235,12 +307,16 @@ def subsample_backward(backend, dy, shape, stride):
 # ---------------------------------------------------------------------------- #
 # Loss
 
-def softmax_xent(backend, logits, labels, label_smoothing=0.0):
-  """Mean softmax cross-entropy over the batch -> (loss fp32 0-d, dlogits fp32 [B, K])."""
+def softmax_xent(backend, logits, labels, label_smoothing=0.0, groups=1):
+  """Mean softmax cross-entropy -> (loss, dlogits [B, K]). `groups` == 1: 0-d loss over the batch; `groups` > 1: one mean per
+  consecutive batch slice (logical worker), loss of shape [groups], gradients scaled by 1 / (B / groups)."""
   if backend == "native" and logits.is_cuda:
-    out = _native().softmax_xent(logits, labels, label_smoothing)
+    out = _native().softmax_xent(logits, labels, label_smoothing, groups)
     if out is not None:
       return out
+  if groups > 1:
+    outs = [softmax_xent(backend, lg, lb, label_smoothing) for lg, lb in zip(_chunks(logits, groups), _chunks(labels, groups))]
+    return torch.stack([o[0] for o in outs]), torch.cat([o[1] for o in outs], dim=0)
   z = logits if logits.dtype == torch.float64 else logits.float()
   logp = torch.log_softmax(z, dim=1)
   batch, classes = z.shape

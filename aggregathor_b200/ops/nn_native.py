@@ -76,14 +76,14 @@ def alloc_out(m, n, dtype, device):
   return torch.empty((m, ld), dtype=dtype, device=device)[:, :n]
 
 
-def _gemm(a, b, out, M, N, K, a_mn, b_mn, bias, relu, splits, bn):
-  func = _lib().agb_gemm_bf16
+def _gemm(a, b, out, M, N, K, a_mn, b_mn, bias, relu, splits, bn, groups=1, group_stride=0):
+  func = _lib().agb_gemm_bf16_grouped
   out_fp32 = 1 if out.dtype == torch.float32 else 0
   if out.stride(1) != 1:
     raise RuntimeError("GEMM output must have unit inner stride")
   status = func(_ptr(a), _ptr(b), _ptr(out), ctypes.c_int(M), ctypes.c_int(N), ctypes.c_int(K), ctypes.c_longlong(a.stride(0)), ctypes.c_longlong(b.stride(0)),
                 ctypes.c_longlong(out.stride(0)), ctypes.c_int(1 if a_mn else 0), ctypes.c_int(1 if b_mn else 0), _ptr(bias), ctypes.c_int(1 if relu else 0),
-                ctypes.c_int(out_fp32), ctypes.c_int(splits), ctypes.c_int(bn), _stream())
+                ctypes.c_int(out_fp32), ctypes.c_int(splits), ctypes.c_int(bn), ctypes.c_int(groups), ctypes.c_longlong(group_stride), _stream())
   _check(status, "gemm_bf16")
   return out
 
@@ -117,18 +117,28 @@ def pick_splits(m_out, n_out, k, bn=128):
   return max(1, min(kblocks, want, 128))
 
 
-def mm_tn(x, y, out=None, splits=None, bn=0):
-  """x[K,M]^T @ y[K,N] -> fp32 [M,N]; split-K partial sums are accumulated with fp32 atomics (out is zeroed here)."""
+def _all_groups(out, groups, group_stride):
+  """[groups, *out.shape] strided view over every logical worker's copy of `out` (worker 0's view of the gradient matrix)."""
+  if groups == 1:
+    return out
+  return out.as_strided((groups,) + tuple(out.shape), (group_stride,) + tuple(out.stride()), out.storage_offset())
+
+
+def mm_tn(x, y, out=None, splits=None, bn=0, groups=1, group_stride=0):
+  """x[K,M]^T @ y[K,N] -> fp32 [M,N]; split-K partial sums are accumulated with fp32 atomics (out is zeroed here).
+  `groups` > 1: x and y hold `groups` consecutive blocks of K / groups rows, one product per block, written `group_stride`
+  elements apart starting at `out` (the per-worker weight gradients, one launch)."""
   x, y = _rows(x), _rows(y)
   K, M = x.shape
+  K //= groups
   N = y.shape[1]
   if out is None:
     out = torch.empty((M, N), dtype=torch.float32, device=x.device)
   if splits is None:
-    splits = pick_splits(M, N, K, 64 if N <= 64 else 128)
+    splits = max(1, pick_splits(M, N, K, 64 if N <= 64 else 128) // groups)
   if splits > 1:
-    out.zero_()
-  return _gemm(x, y, out, M, N, K, True, True, None, False, splits, bn)
+    _all_groups(out, groups, group_stride).zero_()
+  return _gemm(x, y, out, M, N, K, True, True, None, False, splits, bn, groups, group_stride)
 
 
 # ---------------------------------------------------------------------------- #
@@ -147,13 +157,13 @@ def linear_forward(x, weight, bias, relu):
   return mm_nt(x, weight, bias, relu)
 
 
-def linear_backward(dy, x, weight, y, relu, need_dx, grad_w, grad_b):
+def linear_backward(dy, x, weight, y, relu, need_dx, grad_w, grad_b, groups=1, group_stride=0):
   if not enabled("linear"):
     return NotImplemented
   dy = _rows(_masked(dy, y, relu))
-  mm_tn(dy, x, out=grad_w)
+  mm_tn(dy, x, out=grad_w, groups=groups, group_stride=group_stride)
   if grad_b is not None:
-    grad_b.copy_(colsum(dy))
+    colsum(dy, out=grad_b, groups=groups, group_stride=group_stride)
   return mm_nn(dy, weight) if need_dx else None
 
 
@@ -188,7 +198,7 @@ def conv2d_forward(x, weight, bias, stride, pads, relu):
   return None
 
 
-def conv2d_backward(dy, x, weight, y, stride, pads, relu, has_bias, need_dx, grad_w, grad_b):
+def conv2d_backward(dy, x, weight, y, stride, pads, relu, has_bias, need_dx, grad_w, grad_b, groups=1, group_stride=0):
   if not enabled("conv"):
     return NotImplemented
   if _is_pointwise(weight, stride, pads) and x.is_contiguous(memory_format=torch.channels_last) and x.shape[1] % 8 == 0 and weight.shape[0] % 8 == 0:
@@ -197,16 +207,16 @@ def conv2d_backward(dy, x, weight, y, stride, pads, relu, has_bias, need_dx, gra
     if not dy.is_contiguous(memory_format=torch.channels_last):
       dy = dy.contiguous(memory_format=torch.channels_last)
     dy2d = _as_rows(dy)
-    mm_tn(dy2d, _as_rows(x), out=grad_w.view(grad_w.shape[0], -1))
+    mm_tn(dy2d, _as_rows(x), out=grad_w.view(grad_w.shape[0], -1), groups=groups, group_stride=group_stride)
     if has_bias:
-      grad_b.copy_(colsum(dy2d))
+      colsum(dy2d, out=grad_b, groups=groups, group_stride=group_stride)
     if not need_dx:
       return None
     return _from_rows(mm_nn(dy2d, weight.reshape(weight.shape[0], -1)), n, h, w)
   if _implicit_ok(x, weight, stride, pads) and dy.dtype == torch.bfloat16:
-    return conv2d_backward_implicit(dy, x, weight, y, relu, has_bias, need_dx, grad_w, grad_b)
+    return conv2d_backward_implicit(dy, x, weight, y, relu, has_bias, need_dx, grad_w, grad_b, groups, group_stride)
   if enabled("convk") and _general_ok(x, weight) and dy.dtype == torch.bfloat16:
-    return conv2d_backward_general(dy, x, weight, y, stride, pads, relu, has_bias, need_dx, grad_w, grad_b)
+    return conv2d_backward_general(dy, x, weight, y, stride, pads, relu, has_bias, need_dx, grad_w, grad_b, groups, group_stride)
   return NotImplemented
 
 
@@ -246,7 +256,7 @@ def conv2d_forward_general(x, weight, bias, stride, pads, relu):
   return _from_rows(y if y.stride(0) == y.shape[1] else y.contiguous(), n, oh, ow)
 
 
-def conv2d_backward_general(dy, x, weight, y, stride, pads, relu, has_bias, need_dx, grad_w, grad_b):
+def conv2d_backward_general(dy, x, weight, y, stride, pads, relu, has_bias, need_dx, grad_w, grad_b, groups=1, group_stride=0):
   n, c, h, w = x.shape
   k = weight.shape[1]
   oh, ow = dy.shape[2], dy.shape[3]
@@ -255,10 +265,10 @@ def conv2d_backward_general(dy, x, weight, y, stride, pads, relu, has_bias, need
     dy = dy.contiguous(memory_format=torch.channels_last)
   dy2d = _as_rows(dy)
   col = _im2col(x, k, stride, pads, oh, ow)
-  mm_tn(dy2d, col, out=grad_w.view(grad_w.shape[0], -1))
+  mm_tn(dy2d, col, out=grad_w.view(grad_w.shape[0], -1), groups=groups, group_stride=group_stride)
   del col
   if has_bias:
-    grad_b.copy_(colsum(dy2d))
+    colsum(dy2d, out=grad_b, groups=groups, group_stride=group_stride)
   if not need_dx:
     return None
   if c % 8:
@@ -282,10 +292,10 @@ def _implicit_ok(x, weight, stride, pads):
           and weight.is_contiguous())
 
 
-def _conv_implicit(mode, act, other, out, n, h, w, cin, cout, k, bias=None, relu=False, splits=1, bn=0):
-  _check(_lib().agb_conv_implicit(ctypes.c_int(mode), _ptr(act), _ptr(other), _ptr(out), ctypes.c_int(n), ctypes.c_int(h), ctypes.c_int(w), ctypes.c_int(cin),
-                                  ctypes.c_int(cout), ctypes.c_int(k), _ptr(bias), ctypes.c_int(1 if relu else 0), ctypes.c_int(1 if out.dtype == torch.float32 else 0),
-                                  ctypes.c_int(splits), ctypes.c_int(bn), _stream()), "conv_implicit")
+def _conv_implicit(mode, act, other, out, n, h, w, cin, cout, k, bias=None, relu=False, splits=1, bn=0, groups=1, group_stride=0):
+  _check(_lib().agb_conv_implicit_grouped(ctypes.c_int(mode), _ptr(act), _ptr(other), _ptr(out), ctypes.c_int(n), ctypes.c_int(h), ctypes.c_int(w), ctypes.c_int(cin),
+                                          ctypes.c_int(cout), ctypes.c_int(k), _ptr(bias), ctypes.c_int(1 if relu else 0), ctypes.c_int(1 if out.dtype == torch.float32 else 0),
+                                          ctypes.c_int(splits), ctypes.c_int(bn), ctypes.c_int(groups), ctypes.c_longlong(group_stride), _stream()), "conv_implicit")
   return out
 
 
@@ -299,19 +309,19 @@ def conv2d_forward_implicit(x, weight, bias, relu):
   return y.permute(0, 3, 1, 2)
 
 
-def conv2d_backward_implicit(dy, x, weight, y, relu, has_bias, need_dx, grad_w, grad_b):
+def conv2d_backward_implicit(dy, x, weight, y, relu, has_bias, need_dx, grad_w, grad_b, groups=1, group_stride=0):
   n, cin, h, w = x.shape
   cout, k = weight.shape[0], weight.shape[1]
   dy = _masked(dy, y, relu)
   if not dy.is_contiguous(memory_format=torch.channels_last):
     dy = dy.contiguous(memory_format=torch.channels_last)
   tiles = k * k * ((cout + 127) // 128) * ((cin + 127) // 128)
-  kblocks = max(1, n * h * w // 64)
-  splits = max(1, min(kblocks, (2 * SM_COUNT + tiles - 1) // tiles, 64))
-  grad_w.zero_()
-  _conv_implicit(2, dy, x, grad_w, n, h, w, cin, cout, k, splits=splits)
+  kblocks = max(1, n * h * w // 64 // groups)
+  splits = max(1, min(kblocks, (2 * SM_COUNT + tiles * groups - 1) // (tiles * groups), 64))
+  _all_groups(grad_w, groups, group_stride).zero_()
+  _conv_implicit(2, dy, x, grad_w, n, h, w, cin, cout, k, splits=splits, groups=groups, group_stride=group_stride)
   if has_bias:
-    grad_b.copy_(colsum(_as_rows(dy)))
+    colsum(_as_rows(dy), out=grad_b, groups=groups, group_stride=group_stride)
   if not need_dx:
     return None
   dx = torch.empty((n, h, w, cin), dtype=torch.bfloat16, device=x.device)
@@ -337,15 +347,18 @@ def _cl_ok(*tensors):
   return all(t is None or (t.dtype == torch.bfloat16 and (t.dim() != 4 or t.is_contiguous(memory_format=torch.channels_last))) for t in tensors)
 
 
-def colsum(dy2d, y2d=None):
-  """fp32 column sums of a [rows, C] bf16 matrix (optionally masked by y > 0): bias gradients."""
+def colsum(dy2d, y2d=None, out=None, groups=1, group_stride=0):
+  """fp32 column sums of a [rows, C] bf16 matrix (optionally masked by y > 0): bias gradients. With `groups` > 1 one sum per
+  consecutive block of rows, written `group_stride` elements apart starting at `out`."""
   rows, c = dy2d.shape
+  if out is None:
+    out = torch.empty(c, dtype=torch.float32, device=dy2d.device)
   if c % 8 or dy2d.stride(0) != c:
     src = dy2d.float() if y2d is None else dy2d.float() * (y2d > 0)
-    return src.sum(dim=0)
-  out = torch.empty(c, dtype=torch.float32, device=dy2d.device)
-  sums = _workspace(dy2d.device, "colsum", 2 * c + 1, torch.float64)
-  _check(_lib().agb_colsum(_ptr(dy2d), _ptr(y2d), _ptr(out), _ptr(sums), ctypes.c_longlong(rows), ctypes.c_int(c), _stream()), "colsum")
+    _all_groups(out, groups, group_stride).copy_(src.reshape(groups, rows // groups, c).sum(dim=1) if groups > 1 else src.sum(dim=0))
+    return out
+  sums = _workspace(dy2d.device, "colsum", 2 * c * groups + 1, torch.float64)
+  _check(_lib().agb_colsum(_ptr(dy2d), _ptr(y2d), _ptr(out), _ptr(sums), ctypes.c_longlong(rows), ctypes.c_int(c), ctypes.c_int(groups), ctypes.c_longlong(group_stride), _stream()), "colsum")
   return out
 
 
@@ -363,7 +376,7 @@ def batchnorm_forward(x, gamma, beta, moving_mean, moving_var, decay, eps, relu,
   return y, stats[0], stats[1]
 
 
-def batchnorm_backward(dy, x, y, gamma, mean, rstd, relu, grad_gamma, grad_beta, groups=1):
+def batchnorm_backward(dy, x, y, gamma, mean, rstd, relu, grad_gamma, grad_beta, groups=1, group_stride=0):
   if not enabled("bn") or not _cl_ok(x, dy, y) or x.shape[1] % 8:
     return None
   if not dy.is_contiguous(memory_format=torch.channels_last):
@@ -374,7 +387,30 @@ def batchnorm_backward(dy, x, y, gamma, mean, rstd, relu, grad_gamma, grad_beta,
   sums = _workspace(x.device, "bn_sums", 2 * groups * c + 1, torch.float64)
   coef = _workspace(x.device, "bn_coef", 3 * groups * c, torch.float32)
   _check(_lib().agb_bn_backward(_ptr(dy), _ptr(x), _ptr(y if relu else None), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dx), _ptr(grad_gamma), _ptr(grad_beta),
-                                _ptr(sums), _ptr(coef), ctypes.c_longlong(rows), ctypes.c_int(c), ctypes.c_int(groups), _stream()), "bn_backward")
+                                _ptr(sums), _ptr(coef), ctypes.c_longlong(rows), ctypes.c_int(c), ctypes.c_int(groups), ctypes.c_longlong(group_stride), _stream()), "bn_backward")
+  return dx
+
+
+def layernorm_forward(x, gamma, beta, eps):
+  if not enabled("layernorm") or x.dtype != torch.bfloat16 or x.dim() != 2 or not x.is_contiguous() or x.shape[1] % 8 or x.shape[1] > 5632:
+    return None
+  rows, c = x.shape
+  y = torch.empty_like(x)
+  mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+  rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+  _check(_lib().agb_layernorm_forward(_ptr(x), _ptr(y), _ptr(gamma), _ptr(beta), _ptr(mean), _ptr(rstd), ctypes.c_longlong(rows), ctypes.c_int(c), ctypes.c_float(eps), _stream()), "layernorm_forward")
+  return y, mean, rstd
+
+
+def layernorm_backward(dy, x, gamma, mean, rstd, grad_gamma, grad_beta):
+  if not enabled("layernorm") or x.dtype != torch.bfloat16 or x.dim() != 2 or not x.is_contiguous() or x.shape[1] % 8 or x.shape[1] > 5632:
+    return None
+  dy = dy.contiguous()
+  rows, c = x.shape
+  dx = torch.empty_like(x)
+  grad_gamma.zero_()
+  grad_beta.zero_()
+  _check(_lib().agb_layernorm_backward(_ptr(dy), _ptr(x), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dx), _ptr(grad_gamma), _ptr(grad_beta), ctypes.c_longlong(rows), ctypes.c_int(c), _stream()), "layernorm_backward")
   return dx
 
 
@@ -436,15 +472,15 @@ def global_avgpool_backward(dy, shape):
   return dx
 
 
-def softmax_xent(logits, labels, label_smoothing):
+def softmax_xent(logits, labels, label_smoothing, groups=1):
   if not enabled("xent") or logits.dtype != torch.bfloat16 or logits.stride(1) != 1:
     return None
   batch, classes = logits.shape
   dlogits = torch.empty_strided(logits.shape, logits.stride(), dtype=torch.bfloat16, device=logits.device)
-  loss = torch.empty((), dtype=torch.float32, device=logits.device)
+  loss = torch.empty((groups,) if groups > 1 else (), dtype=torch.float32, device=logits.device)
   labels = labels if labels.dtype == torch.int64 else labels.long()
   _check(_lib().agb_softmax_xent(_ptr(logits), _ptr(labels), _ptr(dlogits), _ptr(loss), ctypes.c_int(batch), ctypes.c_int(classes), ctypes.c_longlong(logits.stride(0)),
-                                 ctypes.c_float(label_smoothing), _stream()), "softmax_xent")
+                                 ctypes.c_float(label_smoothing), ctypes.c_int(groups), _stream()), "softmax_xent")
   return loss, dlogits
 
 

@@ -95,6 +95,23 @@ def test_pools_and_eltwise():
   _close(ops.relu_backward("native", a, b), ops.relu_backward("torch", a, b), 1e-6)
 
 
+@pytest.mark.parametrize("rows,c", [(4096, 1024), (333, 384), (32, 4096), (50000, 64)])
+def test_layernorm(rows, c):
+  from aggregathor_b200.ops import nn as ops
+  x = (_rand((rows, c), 31) * 1.5 + 0.3)
+  dy = _rand((rows, c), 32)
+  gamma = torch.rand(c, device="cuda") + 0.5
+  beta = torch.randn(c, device="cuda") * 0.1
+  out = {}
+  for backend in ("torch", "native"):
+    y, mean, rstd = ops.layernorm_forward(backend, x, gamma, beta, 1e-5)
+    gg, gb = torch.zeros(c, device="cuda"), torch.zeros(c, device="cuda")
+    dx = ops.layernorm_backward(backend, dy, x, gamma, mean, rstd, gg, gb)
+    out[backend] = (y, mean, rstd, dx, gg, gb)
+  for a, b, tol in zip(out["native"], out["torch"], (2e-2, 1e-3, 1e-3, 3e-2, 2e-2, 2e-2)):
+    _close(a, b, tol)
+
+
 def test_softmax_xent_and_image_normalize():
   from aggregathor_b200.ops import nn as ops
   logits = _rand((32, 1000), 12) * 3
@@ -146,3 +163,48 @@ def test_model_gradients_native_vs_fp32(name, classes, batch, image):
   assert report["cos_native_fp32"] > min(0.97, report["cos_torch_fp32"] - 0.05), report
   ratio = float(grads["native"].norm() / grads["fp32"].norm())
   assert 0.85 < ratio < 1.15, (ratio, report)
+
+
+@pytest.mark.parametrize("name,classes,batch,image", [("resnet_v1_50", 1000, 8, 64), ("cnnet", 10, 8, 32), ("mlp", 10, 16, None)])
+def test_batched_workers_native(name, classes, batch, image):
+  """Native kernels with `ctx.groups` = 4 workers in one pass (grouped wgrad GEMM / conv, per-group BN, per-group loss) vs four
+  sequential native passes: same per-worker losses and gradient rows (up to atomics' summation order)."""
+  from aggregathor_b200.engine.flat import FlatLayout
+  from aggregathor_b200.models import Context, get_network
+  workers = 4
+  model = get_network(name, classes)
+  layout, shapes = FlatLayout(), {}
+  model.declare(layout, shapes)
+  layout.freeze()
+  init = torch.zeros(layout.padded_size)
+  init_states = {k: torch.zeros(v) for k, v in shapes.items()}
+  model.initialize(layout.views(init), init_states, torch.Generator().manual_seed(0))
+  params = init.cuda()
+  weights = params.to(torch.bfloat16)
+  xs = [(_rand((batch, 784), 40 + i).abs() if image is None else _rand((batch, model.input_shape[0], image, image), 40 + i)) for i in range(workers)]
+  ys = [torch.randint(0, classes, (batch,), device="cuda") for _ in range(workers)]
+
+  def context(rows):
+    ctx = Context("native", True, torch.bfloat16, "cuda")
+    ctx.master, ctx.weights = layout.views(params), layout.views(weights)
+    ctx.state = {k: v.clone().cuda() for k, v in init_states.items()}
+    ctx.grads = layout.views(rows)
+    return ctx
+
+  seq = torch.zeros((workers, layout.padded_size), device="cuda")
+  seq_losses = [float(model.loss_and_backward(x, y, context(seq[i]))) for i, (x, y) in enumerate(zip(xs, ys))]
+  bat = torch.zeros((workers, layout.padded_size), device="cuda")
+  ctx = context(bat[0])
+  ctx.groups, ctx.group_stride = workers, bat.stride(0)
+  x_all = torch.cat(xs, dim=0)
+  if image is not None:
+    x_all = x_all.contiguous(memory_format=torch.channels_last)
+  losses = model.loss_and_backward(x_all, torch.cat(ys), ctx)
+  assert losses.shape == (workers,)
+  for a, b in zip(losses.tolist(), seq_losses):
+    assert abs(a - b) <= 2e-2 * max(1.0, abs(b)), (losses.tolist(), seq_losses)
+  for i in range(workers):
+    cos = float(torch.nn.functional.cosine_similarity(bat[i], seq[i], dim=0))
+    assert cos > 0.995, (i, cos)
+    other = float(torch.nn.functional.cosine_similarity(bat[i], seq[(i + 1) % workers], dim=0))
+    assert other < 0.9, (i, other)   # rows are really per-worker, not a shared/summed gradient

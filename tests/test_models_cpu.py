@@ -107,5 +107,34 @@ def test_resnet_v2_units_and_depthwise_blocks():
   head = lambda c: [GlobalAvgPool("gap"), Conv2d("logits", c, 5, 1, padding="SAME", bias=True)]
   _check_stack([Conv2d("stem", 3, 16, 3, padding="SAME", bias=True), _PreactUnit("u1", 16, 32, 8, 1)] + head(32), (4, 3, 8, 8))
   _check_stack([Conv2d("stem", 3, 32, 7, stride=2, padding="explicit", bias=True), MaxPool("p", 3, 2, "SAME"), _PreactUnit("u1", 32, 32, 8, 2)] + head(32), (4, 3, 32, 32))
+  from aggregathor_b200.models.core import Dense, Flatten, LayerNorm
+  _check_stack([Flatten("f"), Dense("d1", 48, 24, relu=True), LayerNorm("ln", 24), Dense("d2", 24, 5)], (6, 3, 4, 4))
   _check_stack([Conv2d("stem", 3, 16, 3, stride=2, padding="SAME"), BatchNorm("bn0", 16), ReLU6("r0"), DepthwiseConv2d("dw", 16, 3, 2), BatchNorm("bn1", 16), ReLU6("r1"),
                 Conv2d("pw", 16, 24, 1, padding="SAME"), BatchNorm("bn2", 24), ReLU6("r2")] + head(24), (4, 3, 16, 16))
+
+
+@pytest.mark.parametrize("name,classes,shape", [("cnnet", 10, (2, 3, 32, 32)), ("resnet_v1_18", 7, (2, 3, 32, 32)), ("mlp", 10, (3, 784))])
+def test_batched_workers_match_sequential_workers(name, classes, shape):
+  """`ctx.groups` = W logical workers in one pass (per-worker BN statistics / loss means / gradient rows) == W separate passes."""
+  workers = 3
+  model, layout, params, states = _setup(name, classes, torch.float64)
+  torch.manual_seed(3)
+  xs = [torch.randn(shape, dtype=torch.float64) for _ in range(workers)]
+  if len(shape) == 4:
+    xs = [x.contiguous(memory_format=torch.channels_last) for x in xs]
+  ys = [torch.randint(0, classes, (shape[0],)) for _ in range(workers)]
+  rows = torch.zeros((workers, layout.padded_size), dtype=torch.float64)
+  sequential = [_loss(model, layout, params, states, x, y, rows[i])[0] for i, (x, y) in enumerate(zip(xs, ys))]
+  batched_rows = torch.zeros((workers, layout.padded_size), dtype=torch.float64)
+  ctx = Context("torch", True, torch.float64, "cpu")
+  ctx.master = ctx.weights = layout.views(params)
+  ctx.state = {k: v.clone() for k, v in states.items()}
+  ctx.grads = layout.views(batched_rows[0])
+  ctx.groups, ctx.group_stride = workers, batched_rows.stride(0)
+  x_all = torch.cat(xs, dim=0)
+  if len(shape) == 4:
+    x_all = x_all.contiguous(memory_format=torch.channels_last)
+  losses = model.loss_and_backward(x_all, torch.cat(ys), ctx)
+  assert losses.shape == (workers,)
+  assert torch.allclose(losses, torch.tensor(sequential, dtype=losses.dtype), rtol=1e-9, atol=1e-12)
+  assert torch.allclose(batched_rows, rows, rtol=1e-7, atol=1e-10)
