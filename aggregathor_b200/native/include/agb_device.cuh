@@ -11,7 +11,43 @@
     std::fprintf(stderr, "[agb] CUDA error %s at %s:%d: %s\n", cudaGetErrorName(err__), __FILE__, __LINE__, cudaGetErrorString(err__)); \
     return static_cast<int>(err__) ? static_cast<int>(err__) : 1; } } while (0)
 
+#include <cstdlib>
+#include <utility>
+
 namespace agb {
+
+// ---- programmatic dependent launch (PDL) ------------------------------------ //
+// Kernels launched through `launch_pdl` may start while their predecessor in the stream is still draining: everything before
+// `pdl_wait()` (barrier / TMEM / tensor-map set-up, shared-memory initialisation) overlaps the predecessor's tail; `pdl_wait()`
+// returns once the predecessor has completed and its memory is visible. `pdl_trigger()` lets the *next* kernel start launching.
+__device__ __forceinline__ void pdl_wait() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_trigger() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+inline bool pdl_enabled() {
+    static int enabled = -1;
+    if (enabled < 0) {
+        char const* env = std::getenv("AGB_PDL");
+        enabled = env ? (std::atoi(env) != 0) : 1;
+    }
+    return enabled != 0;
+}
+template<typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // ---- system-scope flags (cross-GPU) -------------------------------------- //
 __device__ __forceinline__ void st_release_sys(uint32_t* addr, uint32_t value) {

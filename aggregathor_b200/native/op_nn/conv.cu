@@ -99,6 +99,8 @@ __global__ void __launch_bounds__(kPersistentThreads, 1) conv_tcgen05_kernel(con
     __syncthreads();
     tc_fence_after();
     uint32_t const tmem_base = *tmem_slot;
+    pdl_trigger();   // set-up done: the next kernel may start its own; ...
+    pdl_wait();      // ... our inputs are complete only once the previous kernel has finished
 
     // Bytes that one stage really receives (boxes may be smaller than the tile): A box rows * 128 B per 64-wide chunk.
     uint32_t const a_bytes = MODE == kWgrad ? 2u * box_rows * 128u : static_cast<uint32_t>(box_rows) * 128u;
@@ -238,8 +240,7 @@ int launch_conv(CUtensorMap const& ta, CUtensorMap const& tb, GemmParams const& 
     }
     long long const items = static_cast<long long>(items_mn) * splits * ((MODE == kWgrad && cp.groups > 1) ? cp.groups : 1);
     int const grid = static_cast<int>(items < sms ? items : sms);
-    kernel<<<grid, kPersistentThreads, PCfg::kSmemBytes, stream>>>(ta, tb, p, cp, items_mn, splits);
-    AGB_CUDA_OK(cudaGetLastError());
+    AGB_CUDA_OK(launch_pdl(kernel, dim3(grid), dim3(kPersistentThreads), PCfg::kSmemBytes, stream, ta, tb, p, cp, items_mn, splits));
     return 0;
 }
 

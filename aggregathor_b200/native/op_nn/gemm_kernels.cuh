@@ -359,6 +359,8 @@ __global__ void __launch_bounds__(kPersistentThreads, 1) gemm_tcgen05_persistent
     __syncthreads();
     tc_fence_after();
     uint32_t const tmem_base = *tmem_slot;
+    pdl_trigger();   // set-up done: the next kernel may start its own; ...
+    pdl_wait();      // ... our inputs are complete only once the previous kernel has finished
 
     // item -> tile in grouped order (panels of 16 m-tiles, m fastest inside a panel, then n): the ~148 tiles in flight
     // cover a ~16 x 9 patch, so every A and B tile fetched from L2/HBM is reused by several CTAs of the same wave.
@@ -471,6 +473,8 @@ __global__ void __launch_bounds__(kThreads, BN <= 128 ? 2 : 1) gemm_tcgen05_kern
     __syncthreads();
     tc_fence_after();
     uint32_t const tmem_base = *tmem_slot;
+    pdl_trigger();   // set-up done: the next kernel may start its own; ...
+    pdl_wait();      // ... our inputs are complete only once the previous kernel has finished
 
     if (nkb > 0) {
         if (warp == 0) {
@@ -533,8 +537,7 @@ int launch_gemm(CUtensorMap const& ta, CUtensorMap const& tb, GemmParams const& 
         }
         long long const items = static_cast<long long>(m_tiles) * n_tiles * splits * (p.groups > 1 ? p.groups : 1);
         int const grid = static_cast<int>(items < sms ? items : sms);
-        kernel<<<grid, kPersistentThreads, PCfg::kSmemBytes, stream>>>(ta, tb, p, m_tiles, n_tiles, splits);
-        AGB_CUDA_OK(cudaGetLastError());
+        AGB_CUDA_OK(launch_pdl(kernel, dim3(grid), dim3(kPersistentThreads), PCfg::kSmemBytes, stream, ta, tb, p, m_tiles, n_tiles, splits));
         return 0;
     }
     if (p.groups > 1)

@@ -67,11 +67,13 @@ struct SumsFinalize {
 };
 
 template<int MODE>
-__device__ void finalize_sums(double const* sums, SumsFinalize const& f, int C, long long rows_per_group) {
+__device__ void finalize_sums(double* sums, SumsFinalize const& f, int C, long long rows_per_group) {
     double const n = static_cast<double>(rows_per_group), inv_n = 1.0 / n;
     for (int i = threadIdx.x; i < C * f.groups; i += blockDim.x) {
         int const c = i % C, g = i / C;
         double const s0 = __ldcg(sums + 2 * i), s1 = __ldcg(sums + 2 * i + 1);
+        sums[2 * i] = 0.;       // leave the workspace zeroed for the next statistics kernel (no memset between launches)
+        sums[2 * i + 1] = 0.;
         if (MODE == 0) {
             double const mean = s0 * inv_n;
             double var = fma(-mean, mean, s1 * inv_n);
@@ -109,6 +111,8 @@ __device__ void finalize_sums(double const* sums, SumsFinalize const& f, int C, 
 template<int MODE, int STRIP>
 __global__ void __launch_bounds__(kThreads) channel_sums_kernel(bf16 const* __restrict__ a, bf16 const* __restrict__ b, bf16 const* __restrict__ y, float const* __restrict__ mean,
                                     float const* __restrict__ rstd, double* __restrict__ out, long long rows_per_group, int C, int rows_per_cta, SumsFinalize const fin) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int kStripOctets = STRIP, kRowLanes = kThreads / STRIP;
     __shared__ float red[kRowLanes][kStripOctets * 16 + 1];
     __shared__ bool is_last;
@@ -226,6 +230,8 @@ __global__ void __launch_bounds__(kThreads) channel_sums_kernel(bf16 const* __re
 // whenever possible) so the coefficients stay in registers and no division happens in the loop.
 __global__ void __launch_bounds__(kThreads) bn_apply_kernel(bf16 const* __restrict__ x, bf16* __restrict__ y, float const* __restrict__ scale, float const* __restrict__ shift,
                                 long long total_octets, int C, long long rows_per_group, int relu) {
+    pdl_trigger();
+    pdl_wait();
     unsigned const octets = static_cast<unsigned>(C >> 3);
     long long const nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
     long long const stride = nthreads - nthreads % octets;   // multiple of `octets`: the octet of a thread never changes
@@ -280,6 +286,8 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(bf16 const* __restri
 // dx = a * dy' + b * x + c0 with per-(group, channel) coefficients prepared by the statistics kernel's last CTA.
 __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(bf16 const* __restrict__ dy, bf16 const* __restrict__ x, bf16 const* __restrict__ y, bf16* __restrict__ dx, float const* __restrict__ coef,
                                     long long total_octets, int C, long long rows_per_group) {
+    pdl_trigger();
+    pdl_wait();
     unsigned const octets = static_cast<unsigned>(C >> 3);
     long long const nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
     long long const stride = nthreads - nthreads % octets;
@@ -346,6 +354,8 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(bf16 const* __re
 
 // out = relu?(a + b) ; b may be null (plain ReLU)
 __global__ void add_relu_kernel(bf16 const* __restrict__ a, bf16 const* __restrict__ b, bf16* __restrict__ out, long long octets, int relu) {
+    pdl_trigger();
+    pdl_wait();
     long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     long long const stride = static_cast<long long>(gridDim.x) * blockDim.x;
     for (; i < octets; i += stride) {
@@ -369,6 +379,8 @@ __global__ void add_relu_kernel(bf16 const* __restrict__ a, bf16 const* __restri
 
 // dx = dy * (y > 0)
 __global__ void relu_bwd_kernel(bf16 const* __restrict__ dy, bf16 const* __restrict__ y, bf16* __restrict__ dx, long long octets) {
+    pdl_trigger();
+    pdl_wait();
     long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     long long const stride = static_cast<long long>(gridDim.x) * blockDim.x;
     for (; i < octets; i += stride) {
@@ -386,6 +398,8 @@ __global__ void relu_bwd_kernel(bf16 const* __restrict__ dy, bf16 const* __restr
 // Max pooling (k x k, stride s, explicit pads, -inf padding), NHWC. Forward also records the argmax (window-relative index).
 __global__ void maxpool_fwd_kernel(bf16 const* __restrict__ x, bf16* __restrict__ y, unsigned char* __restrict__ arg, int N, int H, int W, int C, int OH, int OW,
                                    int k, int s, int pad_t, int pad_l) {
+    pdl_trigger();
+    pdl_wait();
     int const octets = C >> 3;
     long long const total = static_cast<long long>(N) * OH * OW * octets;
     long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -435,6 +449,8 @@ __global__ void maxpool_fwd_kernel(bf16 const* __restrict__ x, bf16* __restrict_
 // Gather form: every input element sums the gradients of the windows whose argmax it is (no atomics).
 __global__ void maxpool_bwd_kernel(bf16 const* __restrict__ dy, unsigned char const* __restrict__ arg, bf16* __restrict__ dx, int N, int H, int W, int C, int OH, int OW,
                                    int k, int s, int pad_t, int pad_l) {
+    pdl_trigger();
+    pdl_wait();
     int const octets = C >> 3;
     long long const total = static_cast<long long>(N) * H * W * octets;
     long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -482,6 +498,8 @@ __global__ void maxpool_bwd_kernel(bf16 const* __restrict__ dy, unsigned char co
 
 // Global average pool: x [N, HW, C] -> y [N, C]; backward broadcasts dy / HW.
 __global__ void avgpool_fwd_kernel(bf16 const* __restrict__ x, bf16* __restrict__ y, int N, int HW, int C) {
+    pdl_trigger();
+    pdl_wait();
     int const octets = C >> 3;
     int const i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N * octets)
@@ -506,6 +524,8 @@ __global__ void avgpool_fwd_kernel(bf16 const* __restrict__ x, bf16* __restrict_
 }
 
 __global__ void avgpool_bwd_kernel(bf16 const* __restrict__ dy, bf16* __restrict__ dx, int N, int HW, int C) {
+    pdl_trigger();
+    pdl_wait();
     int const octets = C >> 3;
     long long const total = static_cast<long long>(N) * HW * octets;
     long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -528,6 +548,8 @@ __global__ void avgpool_bwd_kernel(bf16 const* __restrict__ dy, bf16* __restrict
 // loss += mean_b(-sum_k t_k log p_k) ; dlogits = (p - t) / B  (bf16, same leading dimension).
 __global__ void softmax_xent_kernel(bf16 const* __restrict__ logits, long long const* __restrict__ labels, bf16* __restrict__ dlogits, float* __restrict__ loss,
                                     int B, int K, long long ld, float smoothing, int rows_per_group) {
+    pdl_trigger();
+    pdl_wait();
     int const warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= B)
         return;
@@ -561,6 +583,8 @@ __global__ void softmax_xent_kernel(bf16 const* __restrict__ logits, long long c
 
 // uint8 NHWC image -> bf16 NHWC activations with C padded to `Cpad`: y = (x - mean[c]) * scale
 __global__ void image_normalize_kernel(unsigned char const* __restrict__ x, bf16* __restrict__ y, long long pixels, int C, int Cpad, float m0, float m1, float m2, float scale) {
+    pdl_trigger();
+    pdl_wait();
     long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     long long const stride = static_cast<long long>(gridDim.x) * blockDim.x;
     for (; i < pixels; i += stride) {
@@ -579,6 +603,8 @@ __global__ void image_normalize_kernel(unsigned char const* __restrict__ x, bf16
 // im2col: x NHWC [N,H,W,C] -> col [N*OH*OW, ldcol] with column order (kh, kw, c); zero padding, zero tail columns.
 // One thread per (output pixel, kh, kw, channel octet) when C % 8 == 0, scalar path otherwise (the 3-channel stem).
 __global__ void im2col_kernel(bf16 const* __restrict__ x, bf16* __restrict__ col, int N, int H, int W, int C, int OH, int OW, int k, int s, int pad_t, int pad_l, long long ldcol) {
+    pdl_trigger();
+    pdl_wait();
     if ((C & 7) == 0) {
         int const octets = C >> 3;
         long long const total = static_cast<long long>(N) * OH * OW * k * k * octets;
@@ -643,6 +669,8 @@ __global__ void im2col_kernel(bf16 const* __restrict__ x, bf16* __restrict__ col
 
 // col2im (gather form): dx[n,h,w,c] = sum over (kh,kw) of dcol[n, oh, ow, (kh,kw,c)] for the windows covering (h,w). C % 8 == 0.
 __global__ void col2im_kernel(bf16 const* __restrict__ dcol, bf16* __restrict__ dx, int N, int H, int W, int C, int OH, int OW, int k, int s, int pad_t, int pad_l, long long ldcol) {
+    pdl_trigger();
+    pdl_wait();
     int const octets = C >> 3;
     long long const total = static_cast<long long>(N) * H * W * octets;
     long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -713,14 +741,15 @@ inline SumsPlan plan_sums(long long rows_per_group, int C, int groups) {
 }
 
 template<int MODE>
-void launch_sums(SumsPlan const& plan, cudaStream_t s, bf16 const* a, bf16 const* b, bf16 const* y, float const* mean, float const* rstd, double* out,
+int launch_sums(SumsPlan const& plan, cudaStream_t s, bf16 const* a, bf16 const* b, bf16 const* y, float const* mean, float const* rstd, double* out,
                  long long rows_per_group, int C, SumsFinalize const& fin) {
     if (plan.strip == 32)
-        channel_sums_kernel<MODE, 32><<<plan.grid, kThreads, 0, s>>>(a, b, y, mean, rstd, out, rows_per_group, C, plan.rows_per_cta, fin);
+        AGB_CUDA_OK(launch_pdl(channel_sums_kernel<MODE, 32>, dim3(plan.grid), dim3(kThreads), 0, s, a, b, y, mean, rstd, out, rows_per_group, C, plan.rows_per_cta, fin));
     else if (plan.strip == 16)
-        channel_sums_kernel<MODE, 16><<<plan.grid, kThreads, 0, s>>>(a, b, y, mean, rstd, out, rows_per_group, C, plan.rows_per_cta, fin);
+        AGB_CUDA_OK(launch_pdl(channel_sums_kernel<MODE, 16>, dim3(plan.grid), dim3(kThreads), 0, s, a, b, y, mean, rstd, out, rows_per_group, C, plan.rows_per_cta, fin));
     else
-        channel_sums_kernel<MODE, 8><<<plan.grid, kThreads, 0, s>>>(a, b, y, mean, rstd, out, rows_per_group, C, plan.rows_per_cta, fin);
+        AGB_CUDA_OK(launch_pdl(channel_sums_kernel<MODE, 8>, dim3(plan.grid), dim3(kThreads), 0, s, a, b, y, mean, rstd, out, rows_per_group, C, plan.rows_per_cta, fin));
+    return 0;
 }
 
 } // namespace
@@ -737,7 +766,6 @@ int agb_bn_forward(void const* x, void* y, void const* gamma, void const* beta, 
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     long long const rpg = rows / groups;
     // workspace: [groups*C*2] doubles, then one zeroed ticket word (zeroed together with the sums)
-    AGB_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(double) * (2 * C * groups + 1), s));
     SumsFinalize fin{};
     fin.ticket = reinterpret_cast<unsigned*>(static_cast<double*>(sums) + 2 * C * groups);
     fin.gamma = static_cast<float const*>(gamma); fin.beta = static_cast<float const*>(beta);
@@ -746,9 +774,10 @@ int agb_bn_forward(void const* x, void* y, void const* gamma, void const* beta, 
     fin.moving_mean = static_cast<float*>(moving_mean); fin.moving_var = static_cast<float*>(moving_var);
     fin.groups = groups; fin.eps = eps; fin.decay = decay;
     SumsPlan plan = plan_sums(rpg, C, groups);
-    launch_sums<0>(plan, s, static_cast<bf16 const*>(x), nullptr, nullptr, nullptr, nullptr, static_cast<double*>(sums), rpg, C, fin);
+    if (int status = launch_sums<0>(plan, s, static_cast<bf16 const*>(x), nullptr, nullptr, nullptr, nullptr, static_cast<double*>(sums), rpg, C, fin))
+        return status;
     long long const octets = rows * (C >> 3);
-    bn_apply_kernel<<<grid_for(octets), kThreads, 0, s>>>(static_cast<bf16 const*>(x), static_cast<bf16*>(y), static_cast<float const*>(scale), static_cast<float const*>(shift), octets, C, rpg, relu);
+    AGB_CUDA_OK(launch_pdl(bn_apply_kernel, dim3(grid_for(octets)), dim3(kThreads), 0, s, static_cast<bf16 const*>(x), static_cast<bf16*>(y), static_cast<float const*>(scale), static_cast<float const*>(shift), octets, C, rpg, relu));
     AGB_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -759,7 +788,6 @@ int agb_bn_backward(void const* dy, void const* x, void const* y, void const* ga
         return 301;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     long long const rpg = rows / groups;
-    AGB_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(double) * (2 * C * groups + 1), s));
     SumsFinalize fin{};
     fin.ticket = reinterpret_cast<unsigned*>(static_cast<double*>(sums) + 2 * C * groups);
     fin.gamma = static_cast<float const*>(gamma);
@@ -768,11 +796,12 @@ int agb_bn_backward(void const* dy, void const* x, void const* y, void const* ga
     fin.dgamma = static_cast<float*>(dgamma); fin.dbeta = static_cast<float*>(dbeta);
     fin.groups = groups; fin.group_stride = group_stride;
     SumsPlan plan = plan_sums(rpg, C, groups);
-    launch_sums<1>(plan, s, static_cast<bf16 const*>(dy), static_cast<bf16 const*>(x), static_cast<bf16 const*>(y), static_cast<float const*>(save_mean),
-                   static_cast<float const*>(save_rstd), static_cast<double*>(sums), rpg, C, fin);
+    if (int status = launch_sums<1>(plan, s, static_cast<bf16 const*>(dy), static_cast<bf16 const*>(x), static_cast<bf16 const*>(y), static_cast<float const*>(save_mean),
+                   static_cast<float const*>(save_rstd), static_cast<double*>(sums), rpg, C, fin))
+        return status;
     long long const octets = rows * (C >> 3);
-    bn_bwd_apply_kernel<<<grid_for(octets), kThreads, 0, s>>>(static_cast<bf16 const*>(dy), static_cast<bf16 const*>(x), static_cast<bf16 const*>(y), static_cast<bf16*>(dx),
-        static_cast<float const*>(coef), octets, C, rpg);
+    AGB_CUDA_OK(launch_pdl(bn_bwd_apply_kernel, dim3(grid_for(octets)), dim3(kThreads), 0, s, static_cast<bf16 const*>(dy), static_cast<bf16 const*>(x), static_cast<bf16 const*>(y), static_cast<bf16*>(dx),
+        static_cast<float const*>(coef), octets, C, rpg));
     AGB_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -783,13 +812,13 @@ int agb_colsum(void const* dy, void const* y, void* out, void* sums, long long r
     if ((C & 7) || groups < 1 || rows % groups)
         return 301;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    AGB_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(double) * (2 * C * groups + 1), s));
     SumsFinalize fin{};
     fin.ticket = reinterpret_cast<unsigned*>(static_cast<double*>(sums) + 2 * C * groups);
     fin.dbeta = static_cast<float*>(out);
     fin.groups = groups; fin.group_stride = group_stride;
     SumsPlan plan = plan_sums(rows / groups, C, groups);
-    launch_sums<2>(plan, s, static_cast<bf16 const*>(dy), nullptr, static_cast<bf16 const*>(y), nullptr, nullptr, static_cast<double*>(sums), rows / groups, C, fin);
+    if (int status = launch_sums<2>(plan, s, static_cast<bf16 const*>(dy), nullptr, static_cast<bf16 const*>(y), nullptr, nullptr, static_cast<double*>(sums), rows / groups, C, fin))
+        return status;
     AGB_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -797,7 +826,7 @@ int agb_colsum(void const* dy, void const* y, void* out, void* sums, long long r
 int agb_add_relu(void const* a, void const* b, void* out, long long n, int relu, void* stream) {
     if (n & 7)
         return 301;
-    add_relu_kernel<<<grid_for(n / 8), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<bf16 const*>(a), static_cast<bf16 const*>(b), static_cast<bf16*>(out), n / 8, relu);
+    AGB_CUDA_OK(launch_pdl(add_relu_kernel, dim3(grid_for(n / 8)), dim3(kThreads), 0, static_cast<cudaStream_t>(stream), static_cast<bf16 const*>(a), static_cast<bf16 const*>(b), static_cast<bf16*>(out), n / 8, relu));
     AGB_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -805,7 +834,7 @@ int agb_add_relu(void const* a, void const* b, void* out, long long n, int relu,
 int agb_relu_backward(void const* dy, void const* y, void* dx, long long n, void* stream) {
     if (n & 7)
         return 301;
-    relu_bwd_kernel<<<grid_for(n / 8), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<bf16 const*>(dy), static_cast<bf16 const*>(y), static_cast<bf16*>(dx), n / 8);
+    AGB_CUDA_OK(launch_pdl(relu_bwd_kernel, dim3(grid_for(n / 8)), dim3(kThreads), 0, static_cast<cudaStream_t>(stream), static_cast<bf16 const*>(dy), static_cast<bf16 const*>(y), static_cast<bf16*>(dx), n / 8));
     AGB_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -814,7 +843,7 @@ int agb_maxpool_forward(void const* x, void* y, void* arg, int N, int H, int W, 
     if ((C & 7) || k * k > 255)
         return 301;
     long long const work = static_cast<long long>(N) * OH * OW * (C >> 3);
-    maxpool_fwd_kernel<<<grid_for(work), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<bf16 const*>(x), static_cast<bf16*>(y), static_cast<unsigned char*>(arg), N, H, W, C, OH, OW, k, s, pad_t, pad_l);
+    AGB_CUDA_OK(launch_pdl(maxpool_fwd_kernel, dim3(grid_for(work)), dim3(kThreads), 0, static_cast<cudaStream_t>(stream), static_cast<bf16 const*>(x), static_cast<bf16*>(y), static_cast<unsigned char*>(arg), N, H, W, C, OH, OW, k, s, pad_t, pad_l));
     AGB_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -823,7 +852,7 @@ int agb_maxpool_backward(void const* dy, void const* arg, void* dx, int N, int H
     if (C & 7)
         return 301;
     long long const work = static_cast<long long>(N) * H * W * (C >> 3);
-    maxpool_bwd_kernel<<<grid_for(work), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<bf16 const*>(dy), static_cast<unsigned char const*>(arg), static_cast<bf16*>(dx), N, H, W, C, OH, OW, k, s, pad_t, pad_l);
+    AGB_CUDA_OK(launch_pdl(maxpool_bwd_kernel, dim3(grid_for(work)), dim3(kThreads), 0, static_cast<cudaStream_t>(stream), static_cast<bf16 const*>(dy), static_cast<unsigned char const*>(arg), static_cast<bf16*>(dx), N, H, W, C, OH, OW, k, s, pad_t, pad_l));
     AGB_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -831,7 +860,7 @@ int agb_maxpool_backward(void const* dy, void const* arg, void* dx, int N, int H
 int agb_avgpool_forward(void const* x, void* y, int N, int HW, int C, void* stream) {
     if (C & 7)
         return 301;
-    avgpool_fwd_kernel<<<(N * (C >> 3) + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<bf16 const*>(x), static_cast<bf16*>(y), N, HW, C);
+    AGB_CUDA_OK(launch_pdl(avgpool_fwd_kernel, dim3((N * (C >> 3) + 127) / 128), dim3(128), 0, static_cast<cudaStream_t>(stream), static_cast<bf16 const*>(x), static_cast<bf16*>(y), N, HW, C));
     AGB_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -840,7 +869,7 @@ int agb_avgpool_backward(void const* dy, void* dx, int N, int HW, int C, void* s
     if (C & 7)
         return 301;
     long long const work = static_cast<long long>(N) * HW * (C >> 3);
-    avgpool_bwd_kernel<<<grid_for(work), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<bf16 const*>(dy), static_cast<bf16*>(dx), N, HW, C);
+    AGB_CUDA_OK(launch_pdl(avgpool_bwd_kernel, dim3(grid_for(work)), dim3(kThreads), 0, static_cast<cudaStream_t>(stream), static_cast<bf16 const*>(dy), static_cast<bf16*>(dx), N, HW, C));
     AGB_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -851,14 +880,14 @@ int agb_softmax_xent(void const* logits, void const* labels, void* dlogits, void
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     AGB_CUDA_OK(cudaMemsetAsync(loss, 0, sizeof(float) * groups, s));
     int const warps_per_cta = 4;
-    softmax_xent_kernel<<<(B + warps_per_cta - 1) / warps_per_cta, warps_per_cta * 32, 0, s>>>(static_cast<bf16 const*>(logits), static_cast<long long const*>(labels),
-        static_cast<bf16*>(dlogits), static_cast<float*>(loss), B, K, ld, smoothing, B / groups);
+    AGB_CUDA_OK(launch_pdl(softmax_xent_kernel, dim3((B + warps_per_cta - 1) / warps_per_cta), dim3(warps_per_cta * 32), 0, s, static_cast<bf16 const*>(logits), static_cast<long long const*>(labels),
+        static_cast<bf16*>(dlogits), static_cast<float*>(loss), B, K, ld, smoothing, B / groups));
     AGB_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
 int agb_image_normalize(void const* x, void* y, long long pixels, int C, int Cpad, float m0, float m1, float m2, float scale, void* stream) {
-    image_normalize_kernel<<<grid_for(pixels), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<unsigned char const*>(x), static_cast<bf16*>(y), pixels, C, Cpad, m0, m1, m2, scale);
+    AGB_CUDA_OK(launch_pdl(image_normalize_kernel, dim3(grid_for(pixels)), dim3(kThreads), 0, static_cast<cudaStream_t>(stream), static_cast<unsigned char const*>(x), static_cast<bf16*>(y), pixels, C, Cpad, m0, m1, m2, scale));
     AGB_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -867,7 +896,7 @@ int agb_im2col(void const* x, void* col, int N, int H, int W, int C, int OH, int
     if (ldcol & 7)
         return 301;
     long long const work = (C & 7) == 0 ? static_cast<long long>(N) * OH * OW * k * k * (C >> 3) : static_cast<long long>(N) * OH * OW * (ldcol >> 3);
-    im2col_kernel<<<grid_for(work, kThreads, 148 * 16), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<bf16 const*>(x), static_cast<bf16*>(col), N, H, W, C, OH, OW, k, s, pad_t, pad_l, ldcol);
+    AGB_CUDA_OK(launch_pdl(im2col_kernel, dim3(grid_for(work, kThreads, 148 * 16)), dim3(kThreads), 0, static_cast<cudaStream_t>(stream), static_cast<bf16 const*>(x), static_cast<bf16*>(col), N, H, W, C, OH, OW, k, s, pad_t, pad_l, ldcol));
     AGB_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -876,7 +905,7 @@ int agb_col2im(void const* dcol, void* dx, int N, int H, int W, int C, int OH, i
     if ((C & 7) || (ldcol & 7))
         return 301;
     long long const work = static_cast<long long>(N) * H * W * (C >> 3);
-    col2im_kernel<<<grid_for(work, kThreads, 148 * 16), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<bf16 const*>(dcol), static_cast<bf16*>(dx), N, H, W, C, OH, OW, k, s, pad_t, pad_l, ldcol);
+    AGB_CUDA_OK(launch_pdl(col2im_kernel, dim3(grid_for(work, kThreads, 148 * 16)), dim3(kThreads), 0, static_cast<cudaStream_t>(stream), static_cast<bf16 const*>(dcol), static_cast<bf16*>(dx), N, H, W, C, OH, OW, k, s, pad_t, pad_l, ldcol));
     AGB_CUDA_OK(cudaGetLastError());
     return 0;
 }

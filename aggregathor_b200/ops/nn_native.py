@@ -339,7 +339,7 @@ def _workspace(device, name, numel, dtype):
   key = (device, name, dtype)
   buf = _workspaces.get(key)
   if buf is None or buf.numel() < numel:
-    buf = _workspaces[key] = torch.empty(max(numel, 4096), dtype=dtype, device=device)
+    buf = _workspaces[key] = torch.zeros(max(numel, 4096), dtype=dtype, device=device)   # statistics kernels expect (and leave) zeros
   return buf
 
 
