@@ -30,7 +30,7 @@ inline bool pdl_enabled() {
     static int enabled = -1;
     if (enabled < 0) {
         char const* env = std::getenv("AGB_PDL");
-        enabled = env ? (std::atoi(env) != 0) : 1;
+        enabled = env ? (std::atoi(env) != 0) : 0;   // opt-in: measured neutral under CUDA-graph replay on B200 (profiles/README.md)
     }
     return enabled != 0;
 }
