@@ -40,6 +40,7 @@ class Context:
     self.grads = None           # name -> fp32 gradient view of the current worker
     self.state = None           # name -> non-trainable state tensor (BN moving statistics)
     self.generator = None       # torch.Generator for dropout
+    self.aux_heads = []         # `AuxHead`s that produced side logits during the current training forward
     self.need_input_grad = False
     self.groups = 1             # logical workers batched in one pass (their batches are consecutive along dim 0)
     self.group_stride = 0       # elements between two workers' gradient rows (`grads` are worker 0's views)
@@ -90,26 +91,28 @@ def same_padding(size, k, stride):
 
 
 class Conv2d(Module):
-  """2-D convolution, NHWC / OHWI. `padding`: "SAME" (TF semantics), "VALID", or an int (symmetric explicit,
-  the `conv2d_same` convention of slim's resnet_utils: pad (k-1)//2, k-1-(k-1)//2 then VALID)."""
+  """2-D convolution, NHWC / OHWI. `k`: int or (kh, kw) (the 1x7 / 7x1 / 1x3 / 3x1 factorised kernels of the Inception
+  families). `padding`: "SAME" (TF semantics), "VALID", or anything else = symmetric explicit, the `conv2d_same` convention
+  of slim's resnet_utils: pad (k-1)//2, k-1-(k-1)//2 then VALID."""
 
   def __init__(self, name, cin, cout, k, stride=1, padding="SAME", bias=False, relu=False, init="variance_scaling", init_std=None, bias_init=0.0):
     super().__init__(name)
+    self.kh, self.kw = (k, k) if isinstance(k, int) else tuple(k)
     self.cin, self.cout, self.k, self.stride, self.padding = cin, cout, k, stride, padding
     self.bias, self.relu, self.init, self.init_std, self.bias_init = bias, relu, init, init_std, bias_init
 
   def declare(self, layout, states):
-    layout.add(self.name + "/weights", (self.cout, self.k, self.k, self.cin))
+    layout.add(self.name + "/weights", (self.cout, self.kh, self.kw, self.cin))
     if self.bias:
       layout.add(self.name + "/biases", (self.cout,))
 
   def initialize(self, master, states, generator):
     w = master[self.name + "/weights"]
-    fan_in = self.k * self.k * self.cin
+    fan_in = self.kh * self.kw * self.cin
     if self.init == "truncated_normal":
       _trunc_normal_(w, self.init_std, generator)
     elif self.init == "xavier":
-      limit = math.sqrt(6.0 / (fan_in + self.k * self.k * self.cout))
+      limit = math.sqrt(6.0 / (fan_in + self.kh * self.kw * self.cout))
       w.uniform_(-limit, limit, generator=generator)
     else:  # slim variance_scaling_initializer(): truncated normal, stddev = sqrt(2 / fan_in) / .8796...
       _trunc_normal_(w, math.sqrt(2.0 / fan_in) / 0.87962566103423978, generator)
@@ -118,11 +121,11 @@ class Conv2d(Module):
 
   def _pads(self, h, w):
     if self.padding == "SAME":
-      return same_padding(h, self.k, self.stride) + same_padding(w, self.k, self.stride)
+      return same_padding(h, self.kh, self.stride) + same_padding(w, self.kw, self.stride)
     if self.padding == "VALID":
       return (0, 0, 0, 0)
-    total = self.k - 1
-    return (total // 2, total - total // 2, total // 2, total - total // 2)
+    th, tw = self.kh - 1, self.kw - 1
+    return (th // 2, th - th // 2, tw // 2, tw - tw // 2)
 
   def forward(self, x, ctx):
     n, c, h, w = x.shape
@@ -299,20 +302,34 @@ class GlobalAvgPool(Module):
 
 
 class AvgPool(Module):
-  """Average pooling (VALID), used by a few slim nets."""
+  """Average pooling, "VALID" or TF "SAME" (padded positions are excluded from the divisor, as `tf.nn.avg_pool` does)."""
 
-  def __init__(self, name, k, stride):
+  def __init__(self, name, k, stride, padding="VALID"):
     super().__init__(name)
-    self.k, self.stride = k, stride
+    self.k, self.stride, self.padding = k, stride, padding
+    self._counts = {}
+
+  def _count(self, h, w, pads, like):
+    key = (h, w, like.dtype, like.device)
+    if key not in self._counts:
+      ones = F.pad(torch.ones((1, 1, h, w), dtype=torch.float32, device=like.device), (pads[2], pads[3], pads[0], pads[1]))
+      self._counts[key] = (1.0 / F.avg_pool2d(ones, self.k, self.stride, divisor_override=1)).to(like.dtype)
+    return self._counts[key]
 
   def forward(self, x, ctx):
-    self._saved_shape = x.shape
-    return F.avg_pool2d(x, self.k, self.stride)
+    n, c, h, w = x.shape
+    pads = (same_padding(h, self.k, self.stride) + same_padding(w, self.k, self.stride)) if self.padding == "SAME" else (0, 0, 0, 0)
+    xp = F.pad(x, (pads[2], pads[3], pads[0], pads[1])) if any(pads) else x
+    self._saved = (xp.shape, (h, w), pads)
+    y = F.avg_pool2d(xp, self.k, self.stride, divisor_override=1) * self._count(h, w, pads, x)
+    return y.contiguous(memory_format=torch.channels_last)
 
   def backward(self, dy, ctx):
-    n, c, h, w = self._saved_shape
-    ones = torch.ones((c, 1, self.k, self.k), dtype=dy.dtype, device=dy.device) / (self.k * self.k)
-    return F.conv_transpose2d(dy, ones, stride=self.stride, groups=c, output_padding=((h - self.k) % self.stride, (w - self.k) % self.stride)).contiguous(memory_format=torch.channels_last)
+    shape, (h, w), pads = self._saved
+    dy = (dy * self._count(h, w, pads, dy)).contiguous(memory_format=torch.channels_last)
+    proto = torch.empty(shape, dtype=dy.dtype, device=dy.device).contiguous(memory_format=torch.channels_last)
+    dxp = torch.ops.aten.avg_pool2d_backward(dy, proto, [self.k, self.k], [self.stride, self.stride], [0, 0], False, True, 1)
+    return dxp[:, :, pads[0]:pads[0] + h, pads[2]:pads[2] + w].contiguous(memory_format=torch.channels_last)
 
 
 class Subsample(Module):
@@ -470,6 +487,232 @@ class Branches(Module):
     return total
 
 
+class DepthwiseConv2d(Module):
+  """Depthwise k x k convolution (TF "SAME" padding), `multiplier` output channels per input channel (slim
+  `separable_conv2d(..., depth_multiplier)` first half). Weights [C * multiplier, k, k, 1]. Runs through the aten provider
+  (grouped convolution): a depthwise filter has no GEMM shape to put on the tensor cores."""
+
+  def __init__(self, name, channels, k, stride, multiplier=1, init_std=0.09):
+    super().__init__(name)
+    self.channels, self.k, self.stride, self.multiplier, self.init_std = channels, k, stride, multiplier, init_std
+
+  def declare(self, layout, states):
+    layout.add(self.name + "/depthwise_weights", (self.channels * self.multiplier, self.k, self.k, 1))
+
+  def initialize(self, master, states, generator):
+    _trunc_normal_(master[self.name + "/depthwise_weights"], self.init_std, generator)
+
+  def forward(self, x, ctx):
+    n, c, h, w = x.shape
+    t, b = same_padding(h, self.k, self.stride)
+    l, r = same_padding(w, self.k, self.stride)
+    xp = F.pad(x, (l, r, t, b))
+    self._saved = (xp, (t, b, l, r), (h, w))
+    weight = ctx.weights[self.name + "/depthwise_weights"].permute(0, 3, 1, 2)
+    return F.conv2d(xp, weight, None, self.stride, 0, 1, c).contiguous(memory_format=torch.channels_last)
+
+  def backward(self, dy, ctx):
+    xp, (t, b, l, r), (h, w) = self._saved
+    self._saved = None
+    weight = ctx.weights[self.name + "/depthwise_weights"].permute(0, 3, 1, 2)
+    pieces = []
+    for g, (dy_g, xp_g) in enumerate(zip(dy.chunk(ctx.groups, dim=0), xp.chunk(ctx.groups, dim=0))):
+      dxp, dw, _ = torch.ops.aten.convolution_backward(dy_g, xp_g, weight, None, [self.stride] * 2, [0, 0], [1, 1], False, [0, 0], self.channels, [True, True, False])
+      nn_ops.group_view(ctx.grads[self.name + "/depthwise_weights"], g, ctx.group_stride).copy_(dw.permute(0, 2, 3, 1))
+      pieces.append(dxp)
+    dxp = pieces[0] if len(pieces) == 1 else torch.cat(pieces, dim=0)
+    return dxp[:, :, t:t + h, l:l + w].contiguous(memory_format=torch.channels_last)
+
+
+class ReLU6(Module):
+  def forward(self, x, ctx):
+    self._saved_x = x
+    return torch.clamp(x, 0.0, 6.0)
+
+  def backward(self, dy, ctx):
+    x, self._saved_x = self._saved_x, None
+    return dy * ((x > 0) & (x < 6)).to(dy.dtype)
+
+
+class Scale(Module):
+  """y = factor * x (residual scaling of Inception-ResNet blocks)."""
+
+  def __init__(self, name, factor):
+    super().__init__(name)
+    self.factor = factor
+
+  def forward(self, x, ctx):
+    return x * self.factor
+
+  def backward(self, dy, ctx):
+    return dy * self.factor
+
+
+class OffsetSubsample(Module):
+  """y[i, j] = x[stride * i + offset, stride * j + offset] (zero beyond the border), output ceil(size / stride): the
+  zero-pad + crop + 1x1 strided average pool of NASNet's `factorized_reduction` second path."""
+
+  def __init__(self, name, stride=2, offset=1):
+    super().__init__(name)
+    self.stride, self.offset = stride, offset
+
+  def forward(self, x, ctx):
+    n, c, h, w = x.shape
+    self._saved_shape = x.shape
+    oh, ow = -(-h // self.stride), -(-w // self.stride)
+    picked = x[:, :, self.offset::self.stride, self.offset::self.stride]
+    if picked.shape[2] == oh and picked.shape[3] == ow:
+      return picked.contiguous(memory_format=torch.channels_last)
+    y = torch.zeros((n, c, oh, ow), dtype=x.dtype, device=x.device).contiguous(memory_format=torch.channels_last)
+    y[:, :, :picked.shape[2], :picked.shape[3]] = picked
+    return y
+
+  def backward(self, dy, ctx):
+    n, c, h, w = self._saved_shape
+    dx = torch.zeros((n, c, h, w), dtype=dy.dtype, device=dy.device).contiguous(memory_format=torch.channels_last)
+    target = dx[:, :, self.offset::self.stride, self.offset::self.stride]
+    target.copy_(dy[:, :, :target.shape[2], :target.shape[3]])
+    return dx
+
+
+class DropPath(Module):
+  """Training-time stochastic depth on a cell branch (NASNet `_apply_drop_path`): each sample of the batch keeps the branch with
+  probability `keep_prob` (scaled by 1 / keep_prob). The cell-depth scaling of the drop rate is folded into `keep_prob` by
+  the model builder; the reference's additional training-progress scaling needs the total step count and is not applied."""
+
+  def __init__(self, name, keep_prob):
+    super().__init__(name)
+    self.keep_prob = keep_prob
+
+  def forward(self, x, ctx):
+    if not ctx.training or self.keep_prob >= 1.0:
+      self._saved_mask = None
+      return x
+    mask = (torch.rand((x.shape[0], 1, 1, 1), device=x.device, generator=ctx.generator) < self.keep_prob).to(x.dtype) / self.keep_prob
+    self._saved_mask = mask
+    return x * mask
+
+  def backward(self, dy, ctx):
+    mask, self._saved_mask = self._saved_mask, None
+    return dy if mask is None else dy * mask
+
+
+class Add(Module):
+  """Multi-input node of a `Graph`: element-wise sum of its inputs."""
+
+  multi_input = True
+
+  def forward(self, xs, ctx):
+    self._saved_count = len(xs)
+    total = xs[0]
+    for x in xs[1:]:
+      total = nn_ops.add_forward(ctx.backend, total, x)
+    return total
+
+  def backward(self, dy, ctx):
+    return [dy] * self._saved_count
+
+
+class Concat(Module):
+  """Multi-input node of a `Graph`: channel concatenation."""
+
+  multi_input = True
+
+  def forward(self, xs, ctx):
+    self._saved_split = [x.shape[1] for x in xs]
+    return torch.cat(xs, dim=1).contiguous(memory_format=torch.channels_last)
+
+  def backward(self, dy, ctx):
+    return [piece.contiguous(memory_format=torch.channels_last) for piece in torch.split(dy, self._saved_split, dim=1)]
+
+
+class Graph(Module):
+  """Static DAG of modules (NASNet / PNASNet cells, where a hidden state feeds several later nodes).
+
+  Values are numbered: 0 .. `nb_inputs`-1 are the graph inputs, node i (in list order = a topological order) produces value
+  `nb_inputs + i`. `nodes` = [(module, input_ids)]; a module flagged `multi_input` receives the list of its inputs and returns
+  a list of input gradients, any other module takes exactly one input. The output is value `output` (default: the last one).
+  Backward walks the nodes in reverse and sums the gradients of a value consumed several times.
+  With `nb_inputs` == 1, forward takes the tensor itself; otherwise a list."""
+
+  def __init__(self, name, nodes, nb_inputs=1, output=None):
+    super().__init__(name)
+    self.nodes = [(module, tuple(inputs)) for module, inputs in nodes]
+    self.nb_inputs = nb_inputs
+    self.output = output if output is not None else nb_inputs + len(self.nodes) - 1
+    self.multi_input = nb_inputs > 1
+
+  def children(self):
+    return [module for module, _ in self.nodes]
+
+  def declare(self, layout, states):
+    for module, _ in self.nodes:
+      module.declare(layout, states)
+
+  def initialize(self, master, states, generator):
+    for module, _ in self.nodes:
+      module.initialize(master, states, generator)
+
+  def forward(self, x, ctx):
+    values = list(x) if self.nb_inputs > 1 else [x]
+    for module, inputs in self.nodes:
+      if getattr(module, "multi_input", False):
+        values.append(module.forward([values[i] for i in inputs], ctx))
+      else:
+        values.append(module.forward(values[inputs[0]], ctx))
+    return values[self.output]
+
+  def backward(self, dy, ctx):
+    grads = {self.output: dy}
+    for index in range(len(self.nodes) - 1, -1, -1):
+      module, inputs = self.nodes[index]
+      g = grads.pop(self.nb_inputs + index, None)
+      if g is None:  # value never used downstream of the output
+        continue
+      back = module.backward(g, ctx)
+      if not getattr(module, "multi_input", False):
+        back = [back]
+      for i, gi in zip(inputs, back):
+        if gi is None:
+          continue
+        grads[i] = gi if i not in grads else nn_ops.add_forward(ctx.backend, grads[i], gi)
+    if self.nb_inputs > 1:
+      return [grads.get(i) for i in range(self.nb_inputs)]
+    return grads.get(0)
+
+
+class AuxHead(Module):
+  """Auxiliary classifier tapped off the trunk (Inception v3/v4, Inception-ResNet-v2, NASNet, PNASNet): the trunk activation
+  passes through unchanged; in training the side `head` produces extra logits whose softmax cross-entropy enters the loss with
+  `weight` (reference: `experiments/slims.py:122-125`, 0.4 x aux loss). The model's loss head fills `_saved_dlogits`."""
+
+  def __init__(self, name, head, weight=0.4):
+    super().__init__(name)
+    self.head, self.weight = head, weight
+
+  def children(self):
+    return (self.head,)
+
+  def declare(self, layout, states):
+    self.head.declare(layout, states)
+
+  def initialize(self, master, states, generator):
+    self.head.initialize(master, states, generator)
+
+  def forward(self, x, ctx):
+    if ctx.training:
+      logits = self.head.forward(x, ctx)
+      self._saved_shape = logits.shape
+      self._saved_logits = logits.reshape(logits.shape[0], -1)
+      ctx.aux_heads.append(self)
+    return x
+
+  def backward(self, dy, ctx):
+    dlogits, self._saved_dlogits, self._saved_logits = self._saved_dlogits, None, None
+    dx = self.head.backward(dlogits, ctx)
+    return nn_ops.add_forward(ctx.backend, dy, dx)
+
+
 class Model:
   """A root module + input description + loss head."""
 
@@ -486,7 +729,7 @@ class Model:
       kids = list(module.children())
       if not kids:
         return module if isinstance(module, (Conv2d, Dense)) else None
-      if isinstance(module, (Residual, Branches)):
+      if isinstance(module, (Residual, Branches, Graph)):
         return None
       module = kids[0]
 
@@ -497,6 +740,7 @@ class Model:
     self.root.initialize(master, states, generator)
 
   def logits(self, x, ctx):
+    ctx.aux_heads = []
     y = self.root.forward(x, ctx)
     self._raw_shape = y.shape
     return y.reshape(y.shape[0], -1)
@@ -506,11 +750,19 @@ class Model:
     workers are batched: each worker's loss is the mean over its own slice of the batch)."""
     logits = self.logits(x, ctx)
     loss, dlogits = nn_ops.softmax_xent(ctx.backend, logits, labels, self.label_smoothing, ctx.groups)
-    dlogits = dlogits.to(ctx.dtype).reshape(self._raw_shape)
-    if dlogits.dim() == 4:
-      dlogits = dlogits.contiguous(memory_format=torch.channels_last)
+    dlogits = self._shaped(dlogits, self._raw_shape, ctx)
+    for aux in ctx.aux_heads:
+      aux_loss, aux_dlogits = nn_ops.softmax_xent(ctx.backend, aux._saved_logits, labels, self.label_smoothing, ctx.groups)
+      loss = loss + aux.weight * aux_loss
+      aux._saved_dlogits = self._shaped(aux_dlogits * aux.weight, aux._saved_shape, ctx)
+    ctx.aux_heads = []
     self.root.backward(dlogits, ctx)
     return loss
+
+  @staticmethod
+  def _shaped(dlogits, shape, ctx):
+    dlogits = dlogits.to(ctx.dtype).reshape(shape)
+    return dlogits.contiguous(memory_format=torch.channels_last) if dlogits.dim() == 4 else dlogits
 
   def accuracy(self, x, labels, ctx):
     logits = self.logits(x, ctx)

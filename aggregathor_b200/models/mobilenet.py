@@ -2,54 +2,7 @@
 ReLU6, 1x1 pointwise + BN + ReLU6), global average pool, dropout, 1x1 conv logits. Depthwise convolutions
 run through the torch provider (grouped conv); pointwise 1x1 convolutions are plain GEMMs."""
 
-import torch
-import torch.nn.functional as F
-
-from .core import BatchNorm, Conv2d, Dropout, GlobalAvgPool, Model, Module, Sequential, same_padding, _trunc_normal_
-
-
-class DepthwiseConv2d(Module):
-  def __init__(self, name, channels, k, stride):
-    super().__init__(name)
-    self.channels, self.k, self.stride = channels, k, stride
-
-  def declare(self, layout, states):
-    layout.add(self.name + "/depthwise_weights", (self.channels, self.k, self.k, 1))
-
-  def initialize(self, master, states, generator):
-    _trunc_normal_(master[self.name + "/depthwise_weights"], 0.09, generator)
-
-  def forward(self, x, ctx):
-    n, c, h, w = x.shape
-    t, b = same_padding(h, self.k, self.stride)
-    l, r = same_padding(w, self.k, self.stride)
-    xp = F.pad(x, (l, r, t, b))
-    self._saved = (xp, (t, b, l, r), (h, w))
-    weight = ctx.weights[self.name + "/depthwise_weights"].permute(0, 3, 1, 2)
-    return F.conv2d(xp, weight, None, self.stride, 0, 1, c).contiguous(memory_format=torch.channels_last)
-
-  def backward(self, dy, ctx):
-    xp, (t, b, l, r), (h, w) = self._saved
-    self._saved = None
-    weight = ctx.weights[self.name + "/depthwise_weights"].permute(0, 3, 1, 2)
-    from ..ops.nn import group_view
-    pieces = []
-    for g, (dy_g, xp_g) in enumerate(zip(dy.chunk(ctx.groups, dim=0), xp.chunk(ctx.groups, dim=0))):
-      dxp, dw, _ = torch.ops.aten.convolution_backward(dy_g, xp_g, weight, None, [self.stride] * 2, [0, 0], [1, 1], False, [0, 0], self.channels, [True, True, False])
-      group_view(ctx.grads[self.name + "/depthwise_weights"], g, ctx.group_stride).copy_(dw.permute(0, 2, 3, 1))
-      pieces.append(dxp)
-    dxp = pieces[0] if len(pieces) == 1 else torch.cat(pieces, dim=0)
-    return dxp[:, :, t:t + h, l:l + w].contiguous(memory_format=torch.channels_last)
-
-
-class ReLU6(Module):
-  def forward(self, x, ctx):
-    self._saved_x = x
-    return torch.clamp(x, 0.0, 6.0)
-
-  def backward(self, dy, ctx):
-    x, self._saved_x = self._saved_x, None
-    return dy * ((x > 0) & (x < 6)).to(dy.dtype)
+from .core import BatchNorm, Conv2d, DepthwiseConv2d, Dropout, GlobalAvgPool, Identity, Model, ReLU6, Residual, Sequential
 
 
 def mobilenet_v1(num_classes=1001, multiplier=1.0, name="mobilenet_v1"):
@@ -68,4 +21,39 @@ def mobilenet_v1(num_classes=1001, multiplier=1.0, name="mobilenet_v1"):
     cin = cout
   layers += [GlobalAvgPool(s + "/AvgPool_1a"), Dropout(s + "/Dropout_1b", 0.999),
              Conv2d(s + "/Logits/Conv2d_1c_1x1", cin, num_classes, 1, padding="SAME", bias=True, init="truncated_normal", init_std=0.09)]
+  return Model(name, Sequential(name, layers), (3, 224, 224), num_classes)
+
+
+def _make_divisible(value, divisor=8, min_value=8):
+  new = max(min_value, int(value + divisor / 2) // divisor * divisor)
+  return new + divisor if new < 0.9 * value else new
+
+
+def mobilenet_v2(num_classes=1001, multiplier=1.0, name="mobilenet_v2"):
+  """MobileNet v2 (slim `mobilenet_v2.V2_DEF`): 3x3/2 stem, 17 inverted-residual `expanded_conv` blocks (1x1 expansion x6 +
+  BN + ReLU6, 3x3 depthwise + BN + ReLU6, linear 1x1 projection + BN, identity shortcut when stride 1 and the depth is kept),
+  1x1 conv to 1280 (not shrunk for multipliers < 1), global average pool, dropout 0.8, 1x1 conv logits."""
+  s = "MobilenetV2"
+  bn = lambda base, c: BatchNorm(base + "/BatchNorm", c, decay=0.997, epsilon=0.001)
+  depth = lambda d: _make_divisible(d * multiplier)
+  cin = depth(32)
+  layers = [Conv2d(s + "/Conv", 3, cin, 3, stride=2, padding="SAME", init="truncated_normal", init_std=0.09), bn(s + "/Conv", cin), ReLU6(s + "/Conv/Relu6")]
+  spec = [(1, 16, 1), (6, 24, 2), (6, 24, 1), (6, 32, 2), (6, 32, 1), (6, 32, 1), (6, 64, 2), (6, 64, 1), (6, 64, 1), (6, 64, 1), (6, 96, 1), (6, 96, 1), (6, 96, 1),
+          (6, 160, 2), (6, 160, 1), (6, 160, 1), (6, 320, 1)]
+  for i, (expansion, cout, stride) in enumerate(spec):
+    base = s + ("/expanded_conv" if i == 0 else "/expanded_conv_%d" % i)
+    cout = depth(cout)
+    inner = cin if expansion == 1 else _make_divisible(cin * expansion)
+    block = []
+    if inner > cin:
+      block += [Conv2d(base + "/expand", cin, inner, 1, padding="SAME", init="truncated_normal", init_std=0.09), bn(base + "/expand", inner), ReLU6(base + "/expand/Relu6")]
+    block += [DepthwiseConv2d(base + "/depthwise", inner, 3, stride), bn(base + "/depthwise", inner), ReLU6(base + "/depthwise/Relu6"),
+              Conv2d(base + "/project", inner, cout, 1, padding="SAME", init="truncated_normal", init_std=0.09), bn(base + "/project", cout)]
+    block = Sequential(base, block)
+    layers.append(Residual(base + "/add", Identity(base + "/shortcut"), block, relu=False) if (stride == 1 and cin == cout) else block)
+    cin = cout
+  last = 1280 if multiplier < 1.0 else depth(1280)
+  layers += [Conv2d(s + "/Conv_1", cin, last, 1, padding="SAME", init="truncated_normal", init_std=0.09), bn(s + "/Conv_1", last), ReLU6(s + "/Conv_1/Relu6"),
+             GlobalAvgPool(s + "/Logits/AvgPool"), Dropout(s + "/Logits/Dropout", 0.8),
+             Conv2d(s + "/Logits/Conv2d_1c_1x1", last, num_classes, 1, padding="SAME", bias=True, init="truncated_normal", init_std=0.09)]
   return Model(name, Sequential(name, layers), (3, 224, 224), num_classes)

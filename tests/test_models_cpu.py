@@ -67,15 +67,27 @@ def test_parameter_counts_match_reference():
     assert layout.size == count, (name, layout.size)
 
 
-def test_unbuilt_networks_raise_user_exception():
+def test_every_slim_name_builds():
+  """All 33 names of the reference's slim factory (`external/slim/nets/nets_factory.py:39-72`) are constructible; unknown names raise."""
   from aggregathor_b200 import tools
-  with pytest.raises(tools.UserException):
-    get_network("inception_v3", 1000)
+  from aggregathor_b200.models import nets_factory
+  assert len(nets_factory.networks_map) == 33
+  sizes = {}
+  for name in nets_factory.networks_map:
+    model = get_network(name, 1001)
+    layout, states = FlatLayout(), {}
+    model.declare(layout, states)
+    sizes[name] = layout.size
+    assert model.input_shape[1] == nets_factory.default_image_size(name), name
+  # published trainable-parameter counts (1001 classes)
+  assert sizes["mobilenet_v2"] == 3506153
+  assert 6.5e6 < sizes["inception_v1"] < 6.7e6 and 27.0e6 < sizes["inception_v3"] < 27.3e6
+  assert 5.2e6 < sizes["nasnet_mobile"] - 2.5e6 < 5.4e6  # 5.3 M without the auxiliary head
   with pytest.raises(tools.UserException):
     get_network("nope", 10)
 
 
-def _check_stack(layers, shape, classes=5):
+def _check_stack(layers, shape, classes=5, every=1):
   """Per-variable directional derivatives of a small custom stack (float64)."""
   from aggregathor_b200.models.core import Model, Sequential
   model = Model("t", Sequential("t", layers), shape[1:], classes)
@@ -90,7 +102,7 @@ def _check_stack(layers, shape, classes=5):
   x = torch.randn(shape, dtype=torch.float64).contiguous(memory_format=torch.channels_last)
   labels = torch.randint(0, classes, (shape[0],))
   _, grad = _loss(model, layout, params, states, x, labels)
-  for name in layout.names:
+  for name in layout.names[::every]:
     direction = torch.zeros_like(params)
     layout.view(direction, name).normal_()
     direction /= direction.norm()
@@ -138,3 +150,53 @@ def test_batched_workers_match_sequential_workers(name, classes, shape):
   assert losses.shape == (workers,)
   assert torch.allclose(losses, torch.tensor(sequential, dtype=losses.dtype), rtol=1e-9, atol=1e-12)
   assert torch.allclose(batched_rows, rows, rtol=1e-7, atol=1e-10)
+
+
+def test_inception_pieces():
+  """Rectangular kernels, SAME average pooling (stride 1 and 2, odd maps), scaled residual block, auxiliary head."""
+  from aggregathor_b200.models.core import AuxHead, AvgPool, BatchNorm, Branches, Conv2d, Dense, Flatten, GlobalAvgPool, Identity, MaxPool, Residual, Scale, Sequential
+  head = lambda c: [GlobalAvgPool("gap"), Conv2d("logits", c, 5, 1, padding="SAME", bias=True)]
+  towers = Branches("mixed", [
+    Sequential("b0", [Conv2d("b0/1x7", 8, 6, (1, 7)), BatchNorm("b0/bn", 6, relu=True, scale=False), Conv2d("b0/7x1", 6, 6, (7, 1))]),
+    Sequential("b1", [AvgPool("b1/pool", 3, 1, "SAME"), Conv2d("b1/1x1", 8, 4, 1)]),
+    Sequential("b2", [Conv2d("b2/3x1", 8, 4, (3, 1), padding="VALID"), Conv2d("b2/1x3", 4, 4, (1, 3), padding="VALID"), Conv2d("b2/fix", 4, 4, 3, padding="explicit")])])
+  # b2 shrinks the map by 2 in each dimension: keep it out of the concat by using its own stack below
+  towers.branches.pop()
+  res = Residual("res", Identity("sc"), Sequential("r", [towers, Conv2d("up", 10, 8, 1, bias=True), Scale("scale", 0.17)]), relu=True)
+  aux = AuxHead("aux", Sequential("auxh", [AvgPool("aux/pool", 5, 3, "VALID"), Conv2d("aux/conv", 8, 6, 1), Flatten("aux/flat"), Dense("aux/fc", 6, 5)]))
+  _check_stack([Conv2d("stem", 3, 8, 3, stride=1, padding="SAME"), res, aux, AvgPool("red", 3, 2, "SAME"), MaxPool("mp", 3, 2, "SAME")] + head(8), (3, 3, 7, 7))
+  _check_stack([Conv2d("stem", 3, 8, 3, padding="SAME"), Conv2d("b2/3x1", 8, 4, (3, 1), padding="VALID"), Conv2d("b2/1x3", 4, 4, (1, 3), stride=2, padding="SAME")] + head(4), (2, 3, 9, 8))
+
+
+@pytest.mark.parametrize("family", ["nasnet", "pnasnet"])
+def test_searched_cells(family):
+  """A miniature NASNet-A / PNASNet-5 (cifar stem, 3 cells with both reductions, 4 filters): DAG backward vs finite differences."""
+  from aggregathor_b200.models import nasnet
+  model = nasnet._build("tiny", family, 5, 20, "cifar", num_cells=3, filters=4, stem_multiplier=1.0, drop_path_keep_prob=1.0, dense_keep_prob=1.0, skip_reduction_input=(family == "pnasnet"))
+  _check_stack([model.root], (2, 3, 20, 20), every=3)
+
+
+def test_imagenet_stem_cells():
+  from aggregathor_b200.models import nasnet
+  model = nasnet._build("tiny", "nasnet", 5, 83, "imagenet", num_cells=3, filters=8, stem_multiplier=0.25, drop_path_keep_prob=1.0, dense_keep_prob=1.0, skip_reduction_input=True)
+  _check_stack([model.root], (2, 3, 83, 83), every=9)
+
+
+@pytest.mark.parametrize("name,shape", [("mobilenet_v2_035", (2, 3, 64, 64)), ("inception_v1", (2, 3, 64, 64)), ("nasnet_cifar", (2, 3, 32, 32))])
+def test_new_families_step(name, shape):
+  """fp32 smoke step at a reduced resolution: finite loss, gradient reaches the first and the last variable, drop-path / dropout active."""
+  model, layout, params, states = _setup(name, 11, dtype=torch.float32)
+  torch.manual_seed(3)
+  x = torch.randn(shape).contiguous(memory_format=torch.channels_last)
+  labels = torch.randint(0, 11, (shape[0],))
+  ctx = Context("torch", True, torch.float32, "cpu")
+  ctx.master = ctx.weights = layout.views(params)
+  ctx.state = {k: v.clone() for k, v in states.items()}
+  grads = torch.zeros_like(params)
+  ctx.grads = layout.views(grads)
+  ctx.generator = torch.Generator().manual_seed(5)
+  loss = float(model.loss_and_backward(x, labels, ctx))
+  assert loss == loss and loss < 1e3
+  assert float(layout.view(grads, layout.names[0]).abs().sum()) > 0 and float(layout.view(grads, layout.names[-1]).abs().sum()) > 0
+  ctx.training = False
+  assert 0.0 <= float(model.accuracy(x, labels, ctx)) <= 1.0
