@@ -131,8 +131,10 @@ def test_regularization_and_mnist_attack_experiment():
 def test_experiment_registry_covers_reference_names():
   names = set(experiments.itemize())
   assert {"mnist", "mnistAttack", "cnnet", "slim-resnet_v1_50-imagenet", "slim-resnet_v1_18-cifar10", "slim-vgg_16-imagenet", "slim-inception_v3-imagenet"} <= names
+  assert len([name for name in names if name.startswith("slim-") and name.endswith("-imagenet")]) == 33
+  assert experiments.instantiate("slim-inception_v3-imagenet", []).model().input_shape == (3, 299, 299)
   with pytest.raises(tools.UserException):
-    experiments.instantiate("slim-inception_v3-imagenet", []).model()
+    experiments.instantiate("slim-nope-imagenet", [])
 
 
 def test_cnnet_step_on_cpu():
