@@ -48,6 +48,42 @@ def enabled(op):
 
 
 # ---------------------------------------------------------------------------- #
+# Weight-gradient side stream: the weight gradient of a layer is off the critical path of the backward chain, so it can run
+# next to the data gradient of the same layer (fork before, join after; under CUDA-graph capture this becomes two parallel
+# branches of the graph). Opt-in with AGB_WGRAD_STREAM=1.
+
+_WGRAD_STREAM = os.environ.get("AGB_WGRAD_STREAM", "0") not in ("", "0")
+_side_streams = {}
+
+
+class _Fork:
+  """`with _Fork() as fork:` runs the body on the side stream after everything issued so far on the current stream;
+  `fork.join()` makes the current stream wait for it. A no-op pair when the side stream is disabled."""
+
+  def __enter__(self):
+    self.side = None
+    if _WGRAD_STREAM:
+      self.main = torch.cuda.current_stream()
+      key = self.main.device_index
+      if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=self.main.device)
+      self.side = _side_streams[key]
+      self.side.wait_stream(self.main)
+      self._ctx = torch.cuda.stream(self.side)
+      self._ctx.__enter__()
+    return self
+
+  def __exit__(self, *exc):
+    if self.side is not None:
+      self._ctx.__exit__(*exc)
+    return False
+
+  def join(self):
+    if self.side is not None:
+      self.main.wait_stream(self.side)
+
+
+# ---------------------------------------------------------------------------- #
 # GEMM
 
 def _rows(t):
@@ -161,10 +197,13 @@ def linear_backward(dy, x, weight, y, relu, need_dx, grad_w, grad_b, groups=1, g
   if not enabled("linear"):
     return NotImplemented
   dy = _rows(_masked(dy, y, relu))
-  mm_tn(dy, x, out=grad_w, groups=groups, group_stride=group_stride)
-  if grad_b is not None:
-    colsum(dy, out=grad_b, groups=groups, group_stride=group_stride)
-  return mm_nn(dy, weight) if need_dx else None
+  with _Fork() as fork:
+    mm_tn(dy, x, out=grad_w, groups=groups, group_stride=group_stride)
+    if grad_b is not None:
+      colsum(dy, out=grad_b, groups=groups, group_stride=group_stride)
+  dx = mm_nn(dy, weight) if need_dx else None
+  fork.join()
+  return dx
 
 
 # ---------------------------------------------------------------------------- #
@@ -207,12 +246,13 @@ def conv2d_backward(dy, x, weight, y, stride, pads, relu, has_bias, need_dx, gra
     if not dy.is_contiguous(memory_format=torch.channels_last):
       dy = dy.contiguous(memory_format=torch.channels_last)
     dy2d = _as_rows(dy)
-    mm_tn(dy2d, _as_rows(x), out=grad_w.view(grad_w.shape[0], -1), groups=groups, group_stride=group_stride)
-    if has_bias:
-      colsum(dy2d, out=grad_b, groups=groups, group_stride=group_stride)
-    if not need_dx:
-      return None
-    return _from_rows(mm_nn(dy2d, weight.reshape(weight.shape[0], -1)), n, h, w)
+    with _Fork() as fork:
+      mm_tn(dy2d, _as_rows(x), out=grad_w.view(grad_w.shape[0], -1), groups=groups, group_stride=group_stride)
+      if has_bias:
+        colsum(dy2d, out=grad_b, groups=groups, group_stride=group_stride)
+    dx = _from_rows(mm_nn(dy2d, weight.reshape(weight.shape[0], -1)), n, h, w) if need_dx else None
+    fork.join()
+    return dx
   if _implicit_ok(x, weight, stride, pads) and dy.dtype == torch.bfloat16:
     return conv2d_backward_implicit(dy, x, weight, y, relu, has_bias, need_dx, grad_w, grad_b, groups, group_stride)
   if enabled("convk") and _general_ok(x, weight) and dy.dtype == torch.bfloat16:
@@ -264,20 +304,22 @@ def conv2d_backward_general(dy, x, weight, y, stride, pads, relu, has_bias, need
   if not dy.is_contiguous(memory_format=torch.channels_last):
     dy = dy.contiguous(memory_format=torch.channels_last)
   dy2d = _as_rows(dy)
-  col = _im2col(x, k, stride, pads, oh, ow)
-  mm_tn(dy2d, col, out=grad_w.view(grad_w.shape[0], -1), groups=groups, group_stride=group_stride)
-  del col
-  if has_bias:
-    colsum(dy2d, out=grad_b, groups=groups, group_stride=group_stride)
-  if not need_dx:
-    return None
-  if c % 8:
+  if need_dx and c % 8:
     return NotImplemented
+  col = _im2col(x, k, stride, pads, oh, ow)
+  with _Fork() as fork:
+    mm_tn(dy2d, col, out=grad_w.view(grad_w.shape[0], -1), groups=groups, group_stride=group_stride)
+    if has_bias:
+      colsum(dy2d, out=grad_b, groups=groups, group_stride=group_stride)
+  if not need_dx:
+    fork.join()
+    return None
   dcol = mm_nn(dy2d, _weight_rows(weight))
   dx = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=x.device)
   func = _lib().agb_col2im
   _check(func(_ptr(dcol), _ptr(dx), ctypes.c_int(n), ctypes.c_int(h), ctypes.c_int(w), ctypes.c_int(c), ctypes.c_int(oh), ctypes.c_int(ow), ctypes.c_int(k),
               ctypes.c_int(stride), ctypes.c_int(pads[0]), ctypes.c_int(pads[2]), ctypes.c_longlong(dcol.stride(0)), _stream()), "col2im")
+  fork.join()
   return dx.permute(0, 3, 1, 2)
 
 
@@ -318,15 +360,18 @@ def conv2d_backward_implicit(dy, x, weight, y, relu, has_bias, need_dx, grad_w, 
   tiles = k * k * ((cout + 127) // 128) * ((cin + 127) // 128)
   kblocks = max(1, n * h * w // 64 // groups)
   splits = max(1, min(kblocks, (2 * SM_COUNT + tiles * groups - 1) // (tiles * groups), 64))
-  _all_groups(grad_w, groups, group_stride).zero_()
-  _conv_implicit(2, dy, x, grad_w, n, h, w, cin, cout, k, splits=splits, groups=groups, group_stride=group_stride)
-  if has_bias:
-    colsum(_as_rows(dy), out=grad_b, groups=groups, group_stride=group_stride)
-  if not need_dx:
-    return None
-  dx = torch.empty((n, h, w, cin), dtype=torch.bfloat16, device=x.device)
-  _conv_implicit(1, dy, weight, dx, n, h, w, cin, cout, k)
-  return dx.permute(0, 3, 1, 2)
+  with _Fork() as fork:
+    _all_groups(grad_w, groups, group_stride).zero_()
+    _conv_implicit(2, dy, x, grad_w, n, h, w, cin, cout, k, splits=splits, groups=groups, group_stride=group_stride)
+    if has_bias:
+      colsum(_as_rows(dy), out=grad_b, groups=groups, group_stride=group_stride)
+  dx = None
+  if need_dx:
+    dx = torch.empty((n, h, w, cin), dtype=torch.bfloat16, device=x.device)
+    _conv_implicit(1, dy, weight, dx, n, h, w, cin, cout, k)
+    dx = dx.permute(0, 3, 1, 2)
+  fork.join()
+  return dx
 
 
 # ---------------------------------------------------------------------------- #

@@ -208,3 +208,78 @@ def test_batched_workers_native(name, classes, batch, image):
     assert cos > 0.995, (i, cos)
     other = float(torch.nn.functional.cosine_similarity(bat[i], seq[(i + 1) % workers], dim=0))
     assert other < 0.9, (i, other)   # rows are really per-worker, not a shared/summed gradient
+
+
+def _strip_randomness(module):
+  from aggregathor_b200.models.core import DropPath, Dropout
+  if isinstance(module, (Dropout, DropPath)):
+    module.keep_prob = 1.0
+  for child in module.children():
+    _strip_randomness(child)
+
+
+def _model_run(model, layout, params, weights, init_states, x, labels, backend, dtype):
+  from aggregathor_b200.models import Context
+  ctx = Context(backend, True, dtype, "cuda")
+  ctx.master = layout.views(params)
+  ctx.weights = ctx.master if dtype == torch.float32 else layout.views(weights)
+  ctx.state = {k: v.clone().cuda() for k, v in init_states.items()}
+  g = torch.zeros(layout.padded_size, device="cuda")
+  ctx.grads = layout.views(g)
+  return float(model.loss_and_backward(x.to(dtype), labels, ctx)), g
+
+
+@pytest.mark.parametrize("name,batch", [("inception_v3", 4), ("mobilenet_v2", 8), ("nasnet_mobile", 4), ("inception_resnet_v2", 2)])
+def test_searched_and_inception_families_native(name, batch):
+  """The Inception / MobileNet-v2 / NASNet graphs (branches, DAG cells, auxiliary heads, rectangular and depthwise kernels) run on
+  the native provider at their default resolution and agree with an fp32 library run as well as the bf16 library provider does."""
+  from aggregathor_b200.engine.flat import FlatLayout
+  from aggregathor_b200.models import get_network
+  torch.backends.cudnn.allow_tf32 = False
+  torch.backends.cuda.matmul.allow_tf32 = False
+  model = get_network(name, 101)
+  _strip_randomness(model.root)
+  layout, shapes = FlatLayout(), {}
+  model.declare(layout, shapes)
+  layout.freeze()
+  init = torch.zeros(layout.padded_size)
+  init_states = {k: torch.zeros(v) for k, v in shapes.items()}
+  model.initialize(layout.views(init), init_states, torch.Generator().manual_seed(0))
+  params = init.cuda()
+  weights = params.to(torch.bfloat16)
+  x = _rand((batch,) + tuple(model.input_shape), 30)
+  labels = torch.randint(0, 101, (batch,), device="cuda")
+  losses, grads = {}, {}
+  for tag, backend, dtype in (("fp32", "torch", torch.float32), ("torch", "torch", torch.bfloat16), ("native", "native", torch.bfloat16)):
+    losses[tag], grads[tag] = _model_run(model, layout, params, weights, init_states, x, labels, backend, dtype)
+  cos = lambda a, b: float(torch.nn.functional.cosine_similarity(grads[a], grads[b], dim=0))
+  report = {"loss": losses, "cos_native_fp32": cos("native", "fp32"), "cos_torch_fp32": cos("torch", "fp32")}
+  print(name, report)
+  assert all(v == v for v in losses.values()), report
+  assert abs(losses["native"] - losses["fp32"]) < 5e-2 * max(1.0, abs(losses["fp32"])), report
+  assert report["cos_native_fp32"] > min(0.95, report["cos_torch_fp32"] - 0.1), report
+
+
+def test_wgrad_side_stream_matches(monkeypatch):
+  """Weight gradients computed on the side stream (fork / join around each layer's data gradient) equal the single-stream ones."""
+  from aggregathor_b200.engine.flat import FlatLayout
+  from aggregathor_b200.models import get_network
+  from aggregathor_b200.ops import nn_native
+  model = get_network("resnet_v1_50", 100)
+  layout, shapes = FlatLayout(), {}
+  model.declare(layout, shapes)
+  layout.freeze()
+  init = torch.zeros(layout.padded_size)
+  init_states = {k: torch.zeros(v) for k, v in shapes.items()}
+  model.initialize(layout.views(init), init_states, torch.Generator().manual_seed(0))
+  params = init.cuda()
+  weights = params.to(torch.bfloat16)
+  x = _rand((8, 3, 64, 64), 31)
+  labels = torch.randint(0, 100, (8,), device="cuda")
+  monkeypatch.setattr(nn_native, "_WGRAD_STREAM", False)
+  loss_a, grad_a = _model_run(model, layout, params, weights, init_states, x, labels, "native", torch.bfloat16)
+  monkeypatch.setattr(nn_native, "_WGRAD_STREAM", True)
+  loss_b, grad_b = _model_run(model, layout, params, weights, init_states, x, labels, "native", torch.bfloat16)
+  torch.cuda.synchronize()
+  assert abs(loss_a - loss_b) < 1e-6
+  assert float(torch.nn.functional.cosine_similarity(grad_a, grad_b, dim=0)) > 0.9999

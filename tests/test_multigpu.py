@@ -48,3 +48,14 @@ def test_training_keeps_replicas_identical(tmp_path):
   assert code == 0, out[-4000:]
   assert "Replica divergence" not in out and "Step 11: total loss" in out
   assert (tmp_path / "c" / "model-12.index").exists()
+
+
+@pytest.mark.skipif(_gpus() < 2, reason="needs at least 2 GPUs")
+def test_own_collectives_match_nccl(tmp_path):
+  """All-reduce / all-gather kernels over peer-mapped memory (`parallel/collectives.py`) vs the NCCL results, every dtype and the
+  uneven all-gather; replicas must end with identical bits."""
+  nproc = 2 if _gpus() < 4 else 4
+  code, out = _torchrun(nproc, [str(ROOT / "benchmarks" / "coll_bench.py"), "--coll-numel", "2000003", "--coll-iters", "3", "--coll-out", str(tmp_path)])
+  assert code == 0, out[-4000:]
+  report = json.loads((tmp_path / ("coll_bench_%d.json" % nproc)).read_text())
+  assert report["failures"] == [] and report["allreduce"]["ours_ms"] > 0
