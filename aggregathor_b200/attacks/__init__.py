@@ -17,6 +17,8 @@ __all__ = ["_Attack", "register", "instantiate", "itemize"]
 
 
 class _Attack:
+  forges = False  # True: the attack tampers with the row *after* it was signed (only meaningful with `--authenticate`)
+
   def __init__(self, nbworkers, nbbyzwrks, args):
     raise NotImplementedError
 

@@ -11,6 +11,9 @@
               each 65 000-byte chunk of the serialized gradient is lost with probability `rate` and replaced by
               NaN (`fill:nan`, the intent of the reference), zeros (`fill:zero`, what its byte-fill actually did) or the
               bytes of the previous gradient (`fill:clever`, the reference's `CLEVER=1`).
+* `forge`     in-flight tampering: scales the first `fraction` of the row by `factor` *after* the row was signed, so that gradient
+              authentication (`runner.py --authenticate`, `parallel/signing.py`) must reject exactly the touched slices; without
+              authentication it behaves like a partial `flip`.
 """
 
 import torch
@@ -109,7 +112,17 @@ class DropChunksAttack(_Simple):
       state["previous"] = current
 
 
+class ForgeAttack(_Simple):
+  defaults = {"factor": -1.0, "fraction": 1.0}
+  forges = True
+
+  def apply(self, row, worker, step, state):
+    count = max(1, min(row.numel(), int(row.numel() * self.args["fraction"])))
+    row[:count].mul_(self.args["factor"])
+
+
 register("flip", FlipAttack)
+register("forge", ForgeAttack)
 register("random", RandomAttack)
 register("nan", NaNAttack)
 register("inf", InfAttack)

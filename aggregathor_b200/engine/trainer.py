@@ -42,7 +42,7 @@ class Manager:
 
   def __init__(self, experiment, aggregator, nbworkers, optimizer="sgd", optimizer_args=None, learning_rate="fixed", learning_rate_args=None,
                regularizations=(-1., -1.), trace=False, *, attack=None, nb_real_byz=0, device=None, group=None, engine="auto", backend="auto",
-               dtype=None, seed=0, placement=None, debug_checksum=False, engine_args=None, use_graphs=None):
+               dtype=None, seed=0, placement=None, debug_checksum=False, engine_args=None, use_graphs=None, authenticate=False):
     self.device = torch.device(device) if device is not None else _default_device()
     if self.device.type == "cuda" and self.device.index is None:
       self.device = torch.device("cuda", torch.cuda.current_device())
@@ -128,6 +128,11 @@ class Manager:
     self.attack = attack
     self.byzantine = set(range(nbworkers - nb_real_byz, nbworkers)) if (attack is not None and nb_real_byz > 0) else set()
     self._attack_state = {i: {} for i in self.byzantine}
+    # -- gradient authentication (opt-in; reference: signed worker -> PS messages of the hardened transport) -- #
+    self.authenticator = None
+    if authenticate:
+      from ..parallel.signing import Authenticator
+      self.authenticator = Authenticator(self.layout, nbworkers, group)
     # -- counters ------------------------------------------------------------------- #
     self.step = 0
     self.total_loss = None
@@ -213,16 +218,34 @@ class Manager:
       for j in range(len(self.local_workers)):
         self.grads[self.placement[self.local_workers[j]][1]].add_(reg_grad)
         losses[j] = losses[j] + reg_loss
+    forging = self.authenticator is not None and getattr(self.attack, "forges", False)
     for j, i in enumerate(self.local_workers):
-      if i in self.byzantine:
+      if i in self.byzantine and not forging:
         self.attack.apply(self.grads[self.placement[i][1]], i, self.step, self._attack_state[i])
     return losses
+
+  def authenticate_gradients(self):
+    """Sign the local rows, let forging attackers tamper with theirs, exchange the records, verify what this rank will consume."""
+    auth = self.authenticator
+    local = [(i, self.grads[self.placement[i][1]]) for i in self.local_workers]
+
+    def tamper():
+      if getattr(self.attack, "forges", False):
+        for i in self.local_workers:
+          if i in self.byzantine:
+            self.attack.apply(self.grads[self.placement[i][1]], i, self.step, self._attack_state[i])
+
+    records = auth.publish(self.step, local, after_sign=tamper)
+    return auth.verify(self.step, self.aggregation.visible_rows(), records, self.aggregation.consumed_slices())
 
   def train(self):
     """One synchronous training step (the reference's `sess.run(train_tn)`); returns the total loss as a 0-d device tensor."""
     rate = self.rate(self.step)
     with self.tracer.span("Workers: loss and gradient computation"):
       losses = self.compute_gradients()
+    if self.authenticator is not None:
+      with self.tracer.span("Authentication: sign, exchange, verify"):
+        self.authenticate_gradients()
     with self.tracer.span("Master: aggregated gradient computation and application"):
       self.aggregation.step(rate)
     self._refresh_weights()

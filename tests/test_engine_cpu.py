@@ -142,3 +142,56 @@ def test_cnnet_step_on_cpu():
   a = float(mgr.train())
   b = float(mgr.train())
   assert a == a and b == b and 0.0 <= mgr.evaluate()["top1-X-acc"] <= 1.0
+
+
+def test_authentication_rejects_forged_rows():
+  """ed25519-signed gradient digests: honest rows pass, a row tampered with after signing is dropped (NaN) and Krum trains on."""
+  honest = _manager("krum", 7, 2, authenticate=True)
+  for _ in range(3):
+    loss = float(honest.train())
+  assert loss == loss and honest.authenticator.rejected_total == 0
+  forged = _manager("krum", 7, 2, attacks.instantiate("forge", 7, 2, ["factor:-1e6", "fraction:0.5"]), 2, authenticate=True)
+  first = float(forged.train())
+  for _ in range(20):
+    last = float(forged.train())
+  assert forged.authenticator.rejected_total == 21 * 2  # two forging workers, one (single-rank) slice each, every step
+  assert last == last and last < first and forged.evaluate()["top1-X-acc"] > 0.5
+  # without authentication the same tampering reaches the aggregator as a plain attack
+  naive = _manager("average", 7, 2, attacks.instantiate("forge", 7, 2, ["factor:-1e6", "fraction:0.5"]), 2)
+  for _ in range(10):
+    loss = float(naive.train())
+  assert not (loss == loss and loss < first)
+
+
+def test_authenticator_signature_checks():
+  from aggregathor_b200.engine.flat import FlatLayout
+  from aggregathor_b200.parallel.signing import Authenticator
+  layout = FlatLayout()
+  layout.add("theta", (1000,))
+  layout.freeze()
+  auth = Authenticator(layout, 3)
+  rows = {i: torch.randn(layout.padded_size) for i in range(3)}
+  records = auth.publish(5, list(rows.items()))
+  assert auth.verify(5, rows, records, [0]) == []
+  assert auth.verify(6, {0: rows[0].clone()}, records, [0]) == [(0, 0)]                      # replayed record of another step
+  bad = dict(records)
+  bad[1] = (records[1][0], bytes(64))
+  probe = {1: rows[1].clone()}
+  assert auth.verify(5, probe, bad, [0]) == [(1, 0)] and bool(torch.isnan(probe[1]).all())   # forged signature -> whole slice dropped
+  missing = {2: rows[2].clone()}
+  assert auth.verify(5, missing, {}, [0]) == [(2, 0)]                                        # no record at all
+
+
+def test_two_process_authenticated_run(tmp_path):
+  """2 ranks x 2 workers (gloo): one forging worker on rank 1; every rank must drop its slices and replicas stay identical."""
+  port = 29100 + os.getpid() % 300
+  launcher = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", str(port)]
+  args = ["--server", '{"ps": ["127.0.0.1:7000"], "workers": ["127.0.0.1:7001", "127.0.0.1:7002"], "eval": ["127.0.0.1:7000"]}', "--no-wait",
+          "--experiment", "mnist", "--aggregator", "average-nan", "--nb-workers", "4", "--nb-decl-byz-workers", "1", "--nb-real-byz-workers", "1", "--attack", "forge",
+          "--attack-args", "factor:-1e9", "fraction:0.2", "--authenticate", "--max-step", "6", "--learning-rate-args", "initial-rate:0.05", "--evaluation-file", "-",
+          "--checkpoint-dir", str(tmp_path / "c"), "--checkpoint-delta", "-1", "--checkpoint-period", "-1", "--summary-dir", "-", "--debug-checksum"]
+  code, out = _run(args, timeout=600, launcher=launcher)
+  assert code == 0, out
+  assert "failing authentication" in out and "Replica divergence" not in out and "Step 5: total loss" in out
+  losses = [float(x) for x in re.findall(r"Step \d+: total loss = ([0-9.eE+-]+)", out)]
+  assert all(l == l and l < 100 for l in losses), losses
