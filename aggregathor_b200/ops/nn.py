@@ -174,7 +174,9 @@ def batchnorm_backward(backend, dy, x, y, gamma, mean, rstd, relu, grad_gamma, g
     return torch.cat(pieces, dim=0).contiguous(memory_format=_CL)
   if relu:
     dy = _relu_mask(dy, y)
-  dx, dgamma, dbeta = torch.ops.aten.native_batch_norm_backward(dy, x, gamma, None, None, mean, rstd, True, 1e-5, [True, gamma is not None, True])
+  # without gamma (slim `scale=False`) a unit weight is passed: the CUDA kernel returns an empty bias gradient for an undefined weight
+  weight = gamma if gamma is not None else torch.ones(x.shape[1], dtype=mean.dtype, device=x.device)
+  dx, dgamma, dbeta = torch.ops.aten.native_batch_norm_backward(dy, x, weight, None, None, mean, rstd, True, 1e-5, [True, gamma is not None, True])
   if grad_gamma is not None:
     grad_gamma.copy_(dgamma)
   grad_beta.copy_(dbeta)
