@@ -189,6 +189,15 @@ class Manager:
 
   def _run_workers(self, batches, trace):
     """Forward + backward of every local worker -> fp32 tensor of per-worker losses."""
+    if self.backend == "native" and self.device.type == "cuda" and not os.environ.get("AGB_NO_PREZERO"):
+      # one fill of the whole gradient matrix instead of one per split-K weight gradient
+      from ..ops import nn_native
+      self.grads.zero_()
+      with nn_native.prezeroed_gradients():
+        return self._run_workers_inner(batches, trace)
+    return self._run_workers_inner(batches, trace)
+
+  def _run_workers_inner(self, batches, trace):
     if self.batched and trace is None:
       return self.experiment.losses_batched(self.model, batches, self.batched_ctx).float()
     losses = self.experiment.losses(self.model, batches, self.contexts, trace)

@@ -132,9 +132,10 @@ class Conv2d(Module):
     pads = self._pads(h, w)
     weight = ctx.weights[self.name + "/weights"]
     bias = ctx.master[self.name + "/biases"] if self.bias else None
-    y = nn_ops.conv2d_forward(ctx.backend, x, weight, bias, self.stride, pads, self.relu)
+    aux = {} if ctx.training else None
+    y = nn_ops.conv2d_forward(ctx.backend, x, weight, bias, self.stride, pads, self.relu, aux)
     if ctx.training:
-      self._saved_x, self._saved_y, self._saved_pads = x, (y if self.relu else None), pads
+      self._saved_x, self._saved_y, self._saved_pads, self._saved_aux = x, (y if self.relu else None), pads, aux
     return y
 
   def backward(self, dy, ctx):
@@ -142,8 +143,9 @@ class Conv2d(Module):
     weight = ctx.weights[self.name + "/weights"]
     need_dx = ctx.need_input_grad or not getattr(self, "is_first", False)
     dx, dw, db = nn_ops.conv2d_backward(ctx.backend, dy, x, weight, self._saved_y, self.stride, pads, self.relu, self.bias, need_dx,
-                                        ctx.grads[self.name + "/weights"], ctx.grads[self.name + "/biases"] if self.bias else None, ctx.groups, ctx.group_stride)
-    self._saved_x = self._saved_y = None
+                                        ctx.grads[self.name + "/weights"], ctx.grads[self.name + "/biases"] if self.bias else None, ctx.groups, ctx.group_stride,
+                                        self._saved_aux)
+    self._saved_x = self._saved_y = self._saved_aux = None
     return dx
 
 

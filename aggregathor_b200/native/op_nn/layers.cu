@@ -740,6 +740,268 @@ inline SumsPlan plan_sums(long long rows_per_group, int C, int groups) {
     return plan;
 }
 
+// ---------------------------------------------------------------------------- //
+// Single-launch batch-norm (training) forward / backward.
+//
+// The two-kernel path above (statistics, then apply) pays two launches and reads the activation twice. At per-GPU batch
+// sizes most BN tensors of a ResNet are 2..26 MB — smaller than the 148 x 192 KB of shared memory on the chip. This kernel
+// runs one CTA per SM: phase 1 streams the CTA's row chunk once, *keeps it in shared memory* and accumulates the per-channel
+// partial sums (fp32 per thread, fixed-order fold per CTA, one fp64 atomic per channel and CTA); a grid-wide barrier
+// (atomic counter, every CTA is resident: grid <= #SMs, 1 CTA/SM by shared-memory footprint); phase 2 turns the sums into
+// per-channel coefficients in registers and applies them to the resident tile, so the activation crosses the memory
+// system once in and once out. Rows beyond the on-chip capacity are simply re-read in phase 2 (L2 hits at these sizes).
+// Workspace: two halves used alternately (device-side toggle); a launch zeroes the half the next launch will use.
+
+constexpr int kFusedThreads = 512;
+constexpr int kFusedScratchBytes = kFusedThreads * 16 * 4;      // CTA reduction scratch: [lanes][octets * 16] floats
+constexpr int kFusedStashBytes = 192 * 1024;                    // resident tile(s)
+constexpr long long kFusedHalfBytes = 16 + 2ll * 8 * 16384;     // barrier word + sums for up to 16384 (group, channel) pairs
+
+struct BnFused {
+    bf16 const* a;              // forward: x            backward: dy
+    bf16 const* b;              //                       backward: x
+    bf16 const* mask;           //                       backward: y of a fused ReLU (or null)
+    bf16* out;                  // forward: y            backward: dx
+    float const* gamma;
+    float const* beta;
+    float* moving_mean;
+    float* moving_var;
+    float* save_mean;           // forward: out          backward: in
+    float* save_rstd;
+    float* dgamma;
+    float* dbeta;
+    long long group_stride;
+    unsigned* state;            // [0]: which half of `ws` this launch uses
+    unsigned char* ws;
+    long long rows_per_group, rows_per_cta;
+    int C, groups, ctas_per_group, stash_vecs, relu;
+    float eps, decay;
+};
+
+__device__ __forceinline__ unsigned ld_acquire_gpu(unsigned const* addr) {
+    unsigned value;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(value) : "l"(addr) : "memory");
+    return value;
+}
+
+template<bool BWD>
+__global__ void __launch_bounds__(kFusedThreads, 1) bn_fused_kernel(BnFused const p) {
+    extern __shared__ __align__(16) unsigned char fused_smem[];
+    float* red = reinterpret_cast<float*>(fused_smem);
+    uint4* stash_a = reinterpret_cast<uint4*>(fused_smem + kFusedScratchBytes);
+    uint4* stash_b = stash_a + p.stash_vecs;
+    int const octets = p.C >> 3;
+    unsigned const slot = __ldcg(p.state) & 1u;
+    unsigned char* mine = p.ws + slot * kFusedHalfBytes;
+    unsigned* bar = reinterpret_cast<unsigned*>(mine);
+    double* sums = reinterpret_cast<double*>(mine + 16);
+    {   // clear the other half for whoever launches next
+        uint4* other = reinterpret_cast<uint4*>(p.ws + (slot ^ 1u) * kFusedHalfBytes);
+        for (long long i = static_cast<long long>(blockIdx.x) * kFusedThreads + threadIdx.x; i < kFusedHalfBytes / 16; i += static_cast<long long>(gridDim.x) * kFusedThreads)
+            other[i] = make_uint4(0, 0, 0, 0);
+    }
+    int const group = blockIdx.x / p.ctas_per_group, chunk = blockIdx.x % p.ctas_per_group;
+    long long const row_begin = static_cast<long long>(chunk) * p.rows_per_cta;
+    long long const row_end = min(p.rows_per_group, row_begin + p.rows_per_cta);
+    long long const nvec = row_end > row_begin ? (row_end - row_begin) * octets : 0;
+    long long const base = (static_cast<long long>(group) * p.rows_per_group + row_begin) * octets;
+    uint4 const* ga = reinterpret_cast<uint4 const*>(p.a) + base;
+    uint4 const* gb = BWD ? reinterpret_cast<uint4 const*>(p.b) + base : nullptr;
+    uint4 const* gm = (BWD && p.mask) ? reinterpret_cast<uint4 const*>(p.mask) + base : nullptr;
+    uint4* gout = reinterpret_cast<uint4*>(p.out) + base;
+    int const stride = kFusedThreads - kFusedThreads % octets;      // a thread keeps the same channel octet for all its vectors
+    int const lanes = stride / octets;
+    bool const active = static_cast<int>(threadIdx.x) < stride;
+    int const o = threadIdx.x % octets, lane = threadIdx.x / octets;
+    int const cbase = group * p.C + o * 8;
+    float s0[8], s1[8], mu[8], rs[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        s0[j] = 0.f;
+        s1[j] = 0.f;
+        mu[j] = (BWD && active) ? p.save_mean[cbase + j] : 0.f;
+        rs[j] = (BWD && active) ? p.save_rstd[cbase + j] : 0.f;
+    }
+    // ---- phase 1: stream the chunk once, stash it, accumulate ------------------------------------------------------ //
+    if (active) {
+        constexpr int U = BWD ? 2 : 4;
+        for (long long i0 = threadIdx.x; i0 < nvec; i0 += static_cast<long long>(stride) * U) {
+            uint4 ra[U], rb[U], rm[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                long long const i = i0 + static_cast<long long>(u) * stride;
+                if (i < nvec) {
+                    ra[u] = ga[i];
+                    if (BWD)
+                        rb[u] = gb[i];
+                    if (BWD && gm)
+                        rm[u] = gm[i];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                long long const i = i0 + static_cast<long long>(u) * stride;
+                if (i >= nvec)
+                    continue;
+                float va[8];
+                unpack8(ra[u], va);
+                if (!BWD) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        s0[j] += va[j];
+                        s1[j] += va[j] * va[j];
+                    }
+                    if (i < p.stash_vecs)
+                        stash_a[i] = ra[u];
+                } else {
+                    if (gm) {
+                        float vy[8];
+                        unpack8(rm[u], vy);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            va[j] = vy[j] > 0.f ? va[j] : 0.f;
+                    }
+                    float vx[8];
+                    unpack8(rb[u], vx);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        s0[j] += va[j];
+                        s1[j] += va[j] * (vx[j] - mu[j]) * rs[j];
+                    }
+                    if (i < p.stash_vecs) {
+                        stash_a[i] = gm ? pack8(va) : ra[u];    // the masked gradient (exact: masking only zeroes lanes)
+                        stash_b[i] = rb[u];
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            red[lane * (octets * 16) + o * 16 + j] = s0[j];
+            red[lane * (octets * 16) + o * 16 + 8 + j] = s1[j];
+        }
+    }
+    __syncthreads();
+    if (nvec > 0) {
+        for (int t = threadIdx.x; t < octets * 16; t += kFusedThreads) {
+            float total = 0.f;
+            for (int l = 0; l < lanes; ++l)
+                total += red[l * (octets * 16) + t];
+            atomicAdd(sums + (static_cast<long long>(group) * p.C + (t >> 4) * 8 + (t & 7)) * 2 + ((t >> 3) & 1), static_cast<double>(total));
+        }
+    }
+    // ---- grid barrier ----------------------------------------------------------------------------------------------- //
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        atomicAdd(bar, 1u);
+        unsigned spins = 0;
+        while (ld_acquire_gpu(bar) < gridDim.x) {
+            __nanosleep(40);
+            if (++spins > (1u << 24)) {   // ~1 s: a CTA of this grid never arrived
+                printf("[agb] bn_fused_kernel: grid barrier timeout (block %d, %u of %u arrived)\n", static_cast<int>(blockIdx.x), ld_acquire_gpu(bar), gridDim.x);
+                __trap();
+            }
+        }
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        *p.state = slot ^ 1u;
+    if (!active)
+        return;
+    // ---- phase 2: coefficients in registers, apply to the resident tile ------------------------------------------------ //
+    double const n = static_cast<double>(p.rows_per_group), inv_n = 1.0 / n;
+    float c0[8], c1[8], c2[8];
+    bool const writer = chunk == 0 && lane == 0;   // one thread per (group, channel octet) publishes the per-channel results
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        int const c = o * 8 + j;
+        double const t0 = __ldcg(sums + static_cast<long long>(cbase + j) * 2), t1 = __ldcg(sums + static_cast<long long>(cbase + j) * 2 + 1);
+        float const gmj = p.gamma ? p.gamma[c] : 1.f;
+        if (!BWD) {
+            double const mean = t0 * inv_n;
+            double var = fma(-mean, mean, t1 * inv_n);
+            if (var < 0.)
+                var = 0.;
+            float const rstd = rsqrtf(static_cast<float>(var) + p.eps);
+            c0[j] = gmj * rstd;
+            c1[j] = p.beta[c] - static_cast<float>(mean) * gmj * rstd;
+            c2[j] = 0.f;
+            if (writer) {
+                p.save_mean[cbase + j] = static_cast<float>(mean);
+                p.save_rstd[cbase + j] = rstd;
+                if (p.moving_mean && group == 0) {   // unbiased variance in the moving average, as TF's fused batch norm
+                    double const unbiased = n > 1. ? var * n / (n - 1.) : var;
+                    p.moving_mean[c] = p.decay * p.moving_mean[c] + (1.f - p.decay) * static_cast<float>(mean);
+                    p.moving_var[c] = p.decay * p.moving_var[c] + (1.f - p.decay) * static_cast<float>(unbiased);
+                }
+            }
+        } else {
+            float const inv = static_cast<float>(inv_n);
+            c0[j] = gmj * rs[j];
+            c1[j] = -gmj * rs[j] * rs[j] * static_cast<float>(t1) * inv;
+            c2[j] = -gmj * rs[j] * static_cast<float>(t0) * inv - c1[j] * mu[j];
+            if (writer) {
+                if (p.dgamma)
+                    p.dgamma[group * p.group_stride + c] = static_cast<float>(t1);
+                p.dbeta[group * p.group_stride + c] = static_cast<float>(t0);
+            }
+        }
+    }
+    for (long long i = threadIdx.x; i < nvec; i += stride) {
+        bool const resident = i < p.stash_vecs;
+        float va[8];
+        unpack8(resident ? stash_a[i] : ga[i], va);
+        if (!BWD) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                va[j] = va[j] * c0[j] + c1[j];
+                if (p.relu)
+                    va[j] = fmaxf(va[j], 0.f);
+            }
+        } else {
+            if (!resident && gm) {
+                float vy[8];
+                unpack8(gm[i], vy);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    va[j] = vy[j] > 0.f ? va[j] : 0.f;
+            }
+            float vx[8];
+            unpack8(resident ? stash_b[i] : gb[i], vx);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                va[j] = c0[j] * va[j] + c1[j] * vx[j] + c2[j];
+        }
+        gout[i] = pack8(va);
+    }
+}
+
+// Returns 0 when the fused kernel was launched, 399 when the shape is outside its envelope (the caller uses the two-kernel path).
+template<bool BWD>
+int launch_bn_fused(BnFused p, long long rows, cudaStream_t s) {
+    int const octets = p.C >> 3;
+    if ((p.C & 7) || octets > kFusedThreads || p.groups < 1 || p.groups > 148 || rows % p.groups || static_cast<long long>(p.C) * p.groups > 16384)
+        return 399;
+    static bool configured = false;
+    int const smem = kFusedScratchBytes + kFusedStashBytes;
+    if (!configured) {
+        AGB_CUDA_OK(cudaFuncSetAttribute(bn_fused_kernel<BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    p.rows_per_group = rows / p.groups;
+    long long const vecs = p.rows_per_group * octets;
+    long long const min_vecs = octets * 32ll > 2048 ? octets * 32ll : 2048;    // at least 32 rows / 32 KB per CTA
+    long long want = (vecs + min_vecs - 1) / min_vecs;
+    int const cap = 148 / p.groups;
+    p.ctas_per_group = static_cast<int>(want < 1 ? 1 : (want > cap ? cap : want));
+    p.rows_per_cta = (p.rows_per_group + p.ctas_per_group - 1) / p.ctas_per_group;
+    p.stash_vecs = kFusedStashBytes / 16 / (BWD ? 2 : 1);
+    AGB_CUDA_OK(launch_pdl(bn_fused_kernel<BWD>, dim3(p.groups * p.ctas_per_group), dim3(kFusedThreads), static_cast<size_t>(smem), s, p));
+    AGB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 template<int MODE>
 int launch_sums(SumsPlan const& plan, cudaStream_t s, bf16 const* a, bf16 const* b, bf16 const* y, float const* mean, float const* rstd, double* out,
                  long long rows_per_group, int C, SumsFinalize const& fin) {
@@ -804,6 +1066,35 @@ int agb_bn_backward(void const* dy, void const* x, void const* y, void const* ga
         static_cast<float const*>(coef), octets, C, rpg));
     AGB_CUDA_OK(cudaGetLastError());
     return 0;
+}
+
+// Single-launch variants; `ws` = zero-initialised workspace of agb_bn_fused_workspace_bytes() bytes, private to each direction.
+long long agb_bn_fused_workspace_bytes() {
+    return 16 + 2 * kFusedHalfBytes;
+}
+
+int agb_bn_forward_fused(void const* x, void* y, void const* gamma, void const* beta, void* moving_mean, void* moving_var, void* save_mean, void* save_rstd,
+                         void* ws, long long rows, int C, int groups, float eps, float decay, int relu, void* stream) {
+    BnFused p{};
+    p.a = static_cast<bf16 const*>(x); p.out = static_cast<bf16*>(y);
+    p.gamma = static_cast<float const*>(gamma); p.beta = static_cast<float const*>(beta);
+    p.moving_mean = static_cast<float*>(moving_mean); p.moving_var = static_cast<float*>(moving_var);
+    p.save_mean = static_cast<float*>(save_mean); p.save_rstd = static_cast<float*>(save_rstd);
+    p.state = static_cast<unsigned*>(ws); p.ws = static_cast<unsigned char*>(ws) + 16;
+    p.C = C; p.groups = groups; p.eps = eps; p.decay = decay; p.relu = relu;
+    return launch_bn_fused<false>(p, rows, static_cast<cudaStream_t>(stream));
+}
+
+int agb_bn_backward_fused(void const* dy, void const* x, void const* y, void const* gamma, void const* save_mean, void const* save_rstd, void* dx, void* dgamma, void* dbeta,
+                          void* ws, long long rows, int C, int groups, long long group_stride, void* stream) {
+    BnFused p{};
+    p.a = static_cast<bf16 const*>(dy); p.b = static_cast<bf16 const*>(x); p.mask = static_cast<bf16 const*>(y); p.out = static_cast<bf16*>(dx);
+    p.gamma = static_cast<float const*>(gamma);
+    p.save_mean = const_cast<float*>(static_cast<float const*>(save_mean)); p.save_rstd = const_cast<float*>(static_cast<float const*>(save_rstd));
+    p.dgamma = static_cast<float*>(dgamma); p.dbeta = static_cast<float*>(dbeta); p.group_stride = group_stride;
+    p.state = static_cast<unsigned*>(ws); p.ws = static_cast<unsigned char*>(ws) + 16;
+    p.C = C; p.groups = groups;
+    return launch_bn_fused<true>(p, rows, static_cast<cudaStream_t>(stream));
 }
 
 // out[g * group_stride + c] = sum over the rows of group g of dy[r][c] (masked by y > 0 when y != null);

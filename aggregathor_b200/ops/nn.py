@@ -58,9 +58,10 @@ def _chunks(tensor, groups):
 # ---------------------------------------------------------------------------- #
 # Convolution
 
-def conv2d_forward(backend, x, weight, bias, stride, pads, relu):
+def conv2d_forward(backend, x, weight, bias, stride, pads, relu, aux=None):
+  """`aux`: dict owned by the calling layer, handed back to `conv2d_backward` (provider-private forward by-products)."""
   if backend == "native" and x.is_cuda:
-    out = _native().conv2d_forward(x, weight, bias, stride, pads, relu)
+    out = _native().conv2d_forward(x, weight, bias, stride, pads, relu, aux)
     if out is not None:
       return out
     _fallback("conv2d_forward")
@@ -71,11 +72,11 @@ def conv2d_forward(backend, x, weight, bias, stride, pads, relu):
   return y.contiguous(memory_format=_CL)
 
 
-def conv2d_backward(backend, dy, x, weight, y, stride, pads, relu, has_bias, need_dx, grad_w, grad_b, groups=1, group_stride=0):
+def conv2d_backward(backend, dy, x, weight, y, stride, pads, relu, has_bias, need_dx, grad_w, grad_b, groups=1, group_stride=0, aux=None):
   """Writes dW into `grad_w` ([Cout, kh, kw, Cin] fp32 view) and db into `grad_b`; returns dx or None. With `groups` > 1 the batch
   is `groups` consecutive per-worker batches and worker g's gradients go `g * group_stride` elements after worker 0's."""
   if backend == "native" and x.is_cuda:
-    out = _native().conv2d_backward(dy, x, weight, y, stride, pads, relu, has_bias, need_dx, grad_w, grad_b, groups, group_stride)
+    out = _native().conv2d_backward(dy, x, weight, y, stride, pads, relu, has_bias, need_dx, grad_w, grad_b, groups, group_stride, aux)
     if out is not NotImplemented:
       return out, None, None
     _fallback("conv2d_backward")

@@ -48,6 +48,27 @@ def enabled(op):
 
 
 # ---------------------------------------------------------------------------- #
+# Pre-zeroed gradient rows: split-K weight gradients accumulate with fp32 atomics and need a zeroed destination. The trainer
+# clears the whole [workers, d] gradient matrix with ONE fill before the backward pass and declares it here, which replaces
+# one small fill launch per layer (53 for ResNet-50).
+
+_prezeroed = False
+
+
+class prezeroed_gradients:
+  """`with prezeroed_gradients():` — destinations passed as `out=` / `grad_w` are already zero."""
+
+  def __enter__(self):
+    global _prezeroed
+    self._previous, _prezeroed = _prezeroed, True
+
+  def __exit__(self, *exc):
+    global _prezeroed
+    _prezeroed = self._previous
+    return False
+
+
+# ---------------------------------------------------------------------------- #
 # Weight-gradient side stream: the weight gradient of a layer is off the critical path of the backward chain, so it can run
 # next to the data gradient of the same layer (fork before, join after; under CUDA-graph capture this becomes two parallel
 # branches of the graph). Opt-in with AGB_WGRAD_STREAM=1.
@@ -168,11 +189,12 @@ def mm_tn(x, y, out=None, splits=None, bn=0, groups=1, group_stride=0):
   K, M = x.shape
   K //= groups
   N = y.shape[1]
-  if out is None:
+  fresh = out is None
+  if fresh:
     out = torch.empty((M, N), dtype=torch.float32, device=x.device)
   if splits is None:
     splits = max(1, pick_splits(M, N, K, 64 if N <= 64 else 128) // groups)
-  if splits > 1:
+  if splits > 1 and (fresh or not _prezeroed):
     _all_groups(out, groups, group_stride).zero_()
   return _gemm(x, y, out, M, N, K, True, True, None, False, splits, bn, groups, group_stride)
 
@@ -223,7 +245,8 @@ def _is_pointwise(weight, stride, pads):
   return weight.shape[1] == 1 and weight.shape[2] == 1 and stride == 1 and not any(pads)
 
 
-def conv2d_forward(x, weight, bias, stride, pads, relu):
+def conv2d_forward(x, weight, bias, stride, pads, relu, aux=None):
+  """`aux`: optional dict that lives until the matching backward call; the im2col path leaves its column matrix there."""
   if not enabled("conv"):
     return None
   if _is_pointwise(weight, stride, pads) and x.is_contiguous(memory_format=torch.channels_last) and x.shape[1] % 8 == 0:
@@ -233,11 +256,11 @@ def conv2d_forward(x, weight, bias, stride, pads, relu):
   if _implicit_ok(x, weight, stride, pads):
     return conv2d_forward_implicit(x, weight, bias, relu)
   if enabled("convk") and _general_ok(x, weight):
-    return conv2d_forward_general(x, weight, bias, stride, pads, relu)
+    return conv2d_forward_general(x, weight, bias, stride, pads, relu, aux)
   return None
 
 
-def conv2d_backward(dy, x, weight, y, stride, pads, relu, has_bias, need_dx, grad_w, grad_b, groups=1, group_stride=0):
+def conv2d_backward(dy, x, weight, y, stride, pads, relu, has_bias, need_dx, grad_w, grad_b, groups=1, group_stride=0, aux=None):
   if not enabled("conv"):
     return NotImplemented
   if _is_pointwise(weight, stride, pads) and x.is_contiguous(memory_format=torch.channels_last) and x.shape[1] % 8 == 0 and weight.shape[0] % 8 == 0:
@@ -256,7 +279,7 @@ def conv2d_backward(dy, x, weight, y, stride, pads, relu, has_bias, need_dx, gra
   if _implicit_ok(x, weight, stride, pads) and dy.dtype == torch.bfloat16:
     return conv2d_backward_implicit(dy, x, weight, y, relu, has_bias, need_dx, grad_w, grad_b, groups, group_stride)
   if enabled("convk") and _general_ok(x, weight) and dy.dtype == torch.bfloat16:
-    return conv2d_backward_general(dy, x, weight, y, stride, pads, relu, has_bias, need_dx, grad_w, grad_b, groups, group_stride)
+    return conv2d_backward_general(dy, x, weight, y, stride, pads, relu, has_bias, need_dx, grad_w, grad_b, groups, group_stride, aux)
   return NotImplemented
 
 
@@ -287,16 +310,18 @@ def _general_ok(x, weight):
   return x.is_contiguous(memory_format=torch.channels_last) and x.dtype == torch.bfloat16 and weight.shape[0] % 8 == 0 and weight.shape[1] == weight.shape[2]
 
 
-def conv2d_forward_general(x, weight, bias, stride, pads, relu):
+def conv2d_forward_general(x, weight, bias, stride, pads, relu, aux=None):
   n, c, h, w = x.shape
   k = weight.shape[1]
   oh, ow = _out_size(h, k, stride, pads[0], pads[1]), _out_size(w, k, stride, pads[2], pads[3])
   col = _im2col(x, k, stride, pads, oh, ow)
+  if aux is not None:
+    aux["col"] = col  # the weight gradient multiplies by the same matrix: keep it instead of rebuilding it
   y = mm_nt(col, _weight_rows(weight), bias, relu)
   return _from_rows(y if y.stride(0) == y.shape[1] else y.contiguous(), n, oh, ow)
 
 
-def conv2d_backward_general(dy, x, weight, y, stride, pads, relu, has_bias, need_dx, grad_w, grad_b, groups=1, group_stride=0):
+def conv2d_backward_general(dy, x, weight, y, stride, pads, relu, has_bias, need_dx, grad_w, grad_b, groups=1, group_stride=0, aux=None):
   n, c, h, w = x.shape
   k = weight.shape[1]
   oh, ow = dy.shape[2], dy.shape[3]
@@ -306,7 +331,9 @@ def conv2d_backward_general(dy, x, weight, y, stride, pads, relu, has_bias, need
   dy2d = _as_rows(dy)
   if need_dx and c % 8:
     return NotImplemented
-  col = _im2col(x, k, stride, pads, oh, ow)
+  col = aux.pop("col", None) if aux is not None else None
+  if col is None or col.shape[0] != n * oh * ow:
+    col = _im2col(x, k, stride, pads, oh, ow)
   with _Fork() as fork:
     mm_tn(dy2d, col, out=grad_w.view(grad_w.shape[0], -1), groups=groups, group_stride=group_stride)
     if has_bias:
@@ -361,7 +388,8 @@ def conv2d_backward_implicit(dy, x, weight, y, relu, has_bias, need_dx, grad_w, 
   kblocks = max(1, n * h * w // 64 // groups)
   splits = max(1, min(kblocks, (2 * SM_COUNT + tiles * groups - 1) // (tiles * groups), 64))
   with _Fork() as fork:
-    _all_groups(grad_w, groups, group_stride).zero_()
+    if not _prezeroed:
+      _all_groups(grad_w, groups, group_stride).zero_()
     _conv_implicit(2, dy, x, grad_w, n, h, w, cin, cout, k, splits=splits, groups=groups, group_stride=group_stride)
     if has_bias:
       colsum(_as_rows(dy), out=grad_b, groups=groups, group_stride=group_stride)
@@ -407,6 +435,22 @@ def colsum(dy2d, y2d=None, out=None, groups=1, group_stride=0):
   return out
 
 
+_BN_FUSED = os.environ.get("AGB_BN_FUSED", "1") not in ("", "0")
+_BN_UNSUPPORTED = 399
+
+
+def set_bn_fused(flag):
+  """Select the single-launch (resident-tile) batch-norm kernels or the statistics + apply pair."""
+  global _BN_FUSED
+  _BN_FUSED = bool(flag)
+
+
+def _bn_fused_workspace(device, name):
+  lib = _lib()
+  lib.agb_bn_fused_workspace_bytes.restype = ctypes.c_longlong
+  return _workspace(device, name, int(lib.agb_bn_fused_workspace_bytes()), torch.uint8)
+
+
 def batchnorm_forward(x, gamma, beta, moving_mean, moving_var, decay, eps, relu, groups=1):
   if not enabled("bn") or not _cl_ok(x) or x.shape[1] % 8:
     return None
@@ -414,6 +458,13 @@ def batchnorm_forward(x, gamma, beta, moving_mean, moving_var, decay, eps, relu,
   rows = n * h * w
   y = torch.empty_like(x, memory_format=torch.channels_last)
   stats = torch.empty((4, groups * c), dtype=torch.float32, device=x.device)  # save_mean, save_rstd, scale, shift
+  if _BN_FUSED:
+    status = _lib().agb_bn_forward_fused(_ptr(x), _ptr(y), _ptr(gamma), _ptr(beta), _ptr(moving_mean), _ptr(moving_var), _ptr(stats[0]), _ptr(stats[1]),
+                                         _ptr(_bn_fused_workspace(x.device, "bn_fused_fwd")), ctypes.c_longlong(rows), ctypes.c_int(c), ctypes.c_int(groups),
+                                         ctypes.c_float(eps), ctypes.c_float(decay), ctypes.c_int(1 if relu else 0), _stream())
+    if status != _BN_UNSUPPORTED:
+      _check(status, "bn_forward_fused")
+      return y, stats[0], stats[1]
   sums = _workspace(x.device, "bn_sums", 2 * groups * c + 1, torch.float64)
   _check(_lib().agb_bn_forward(_ptr(x), _ptr(y), _ptr(gamma), _ptr(beta), _ptr(moving_mean), _ptr(moving_var), _ptr(stats[0]), _ptr(stats[1]), _ptr(sums),
                                _ptr(stats[2]), _ptr(stats[3]), ctypes.c_longlong(rows), ctypes.c_int(c), ctypes.c_int(groups), ctypes.c_float(eps),
@@ -429,6 +480,13 @@ def batchnorm_backward(dy, x, y, gamma, mean, rstd, relu, grad_gamma, grad_beta,
   n, c, h, w = x.shape
   rows = n * h * w
   dx = torch.empty_like(x, memory_format=torch.channels_last)
+  if _BN_FUSED:
+    status = _lib().agb_bn_backward_fused(_ptr(dy), _ptr(x), _ptr(y if relu else None), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dx), _ptr(grad_gamma), _ptr(grad_beta),
+                                          _ptr(_bn_fused_workspace(x.device, "bn_fused_bwd")), ctypes.c_longlong(rows), ctypes.c_int(c), ctypes.c_int(groups),
+                                          ctypes.c_longlong(group_stride), _stream())
+    if status != _BN_UNSUPPORTED:
+      _check(status, "bn_backward_fused")
+      return dx
   sums = _workspace(x.device, "bn_sums", 2 * groups * c + 1, torch.float64)
   coef = _workspace(x.device, "bn_coef", 3 * groups * c, torch.float32)
   _check(_lib().agb_bn_backward(_ptr(dy), _ptr(x), _ptr(y if relu else None), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dx), _ptr(grad_gamma), _ptr(grad_beta),

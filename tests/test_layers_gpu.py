@@ -20,10 +20,14 @@ def _close(a, b, tol):
   assert err <= tol * scale, (err, scale)
 
 
-@pytest.mark.parametrize("shape", [(32, 64, 56, 56), (8, 256, 14, 14), (4, 2048, 7, 7), (16, 192, 5, 5)])
+@pytest.mark.parametrize("shape", [(32, 64, 56, 56), (8, 256, 14, 14), (4, 2048, 7, 7), (16, 192, 5, 5), (32, 64, 112, 112), (2, 24, 3, 3)])
 @pytest.mark.parametrize("relu", [False, True])
-def test_batchnorm(shape, relu):
-  from aggregathor_b200.ops import nn as ops
+@pytest.mark.parametrize("fused", [True, False])
+def test_batchnorm(shape, relu, fused):
+  """`fused`: the single-launch resident-tile kernels (the 51 MB shape exceeds the on-chip stash and takes the re-read path) vs
+  the statistics + apply kernel pair."""
+  from aggregathor_b200.ops import nn as ops, nn_native
+  nn_native.set_bn_fused(fused)
   x = _rand(shape, 1) * 2 + 0.5
   dy = _rand(shape, 2)
   c = shape[1]
@@ -36,9 +40,39 @@ def test_batchnorm(shape, relu):
     gg, gb = torch.zeros(c, device="cuda"), torch.zeros(c, device="cuda")
     dx = ops.batchnorm_backward(backend, dy, x, y if relu else None, gamma, mean, rstd, relu, gg, gb)
     out[backend] = (y, mean, rstd, dx, gg, gb, mm, mv)
+  nn_native.set_bn_fused(True)
   tols = (2e-2, 1e-3, 1e-3, 3e-2, 2e-2, 2e-2, 1e-3, 1e-3)
   for a, b, tol in zip(out["native"], out["torch"], tols):
     _close(a, b, tol)
+
+
+def test_batchnorm_fused_groups_and_repeats():
+  """Per-worker statistics (groups) in the single-launch kernels, many back-to-back launches of different widths (the two
+  workspace halves alternate and must always be found zeroed), bit-stable results."""
+  from aggregathor_b200.ops import nn as ops, nn_native
+  results = {}
+  for fused in (True, False):
+    nn_native.set_bn_fused(fused)
+    outs = []
+    for rep in range(3):
+      for c, hw, groups in ((64, 28, 4), (512, 7, 8), (256, 14, 2), (1024, 4, 1)):
+        x = _rand((8 * groups, c, hw, hw), 50 + c) + 0.25
+        dy = _rand((8 * groups, c, hw, hw), 60 + c)
+        gamma, beta = torch.rand(c, device="cuda") + 0.5, torch.zeros(c, device="cuda")
+        mm, mv = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+        y, mean, rstd = ops.batchnorm_forward("native", x, gamma, beta, mm, mv, 0.9, 1e-5, True, groups)
+        grads = torch.zeros((groups, 2, c), device="cuda")
+        dx = ops.batchnorm_backward("native", dy, x, y, gamma, mean, rstd, True, grads[0, 0], grads[0, 1], groups, grads.stride(0))
+        outs.append((y, mean, rstd, dx, grads))
+    results[fused] = outs
+  nn_native.set_bn_fused(True)
+  torch.cuda.synchronize()
+  for got, want in zip(results[True], results[False]):
+    for a, b, tol in zip(got, want, (1e-2, 1e-4, 1e-4, 2e-2, 1e-3)):
+      _close(a, b, tol)
+  for a, b in zip(results[True][:4], results[True][8:12]):   # same inputs, later launches: identical statistics
+    _close(a[1], b[1], 1e-6)
+    _close(a[2], b[2], 1e-6)
 
 
 @pytest.mark.parametrize("cin,cout,k,stride,hw,pads", [(64, 64, 3, 1, 56, (1, 1, 1, 1)), (128, 128, 3, 2, 28, (1, 1, 1, 1)), (3, 64, 7, 2, 224, (3, 3, 3, 3)),
