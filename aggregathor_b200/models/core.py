@@ -228,6 +228,25 @@ class BatchNorm(Module):
     self._saved = None
     return dx
 
+  # -- closing layer of a residual unit: y = relu(bn(x) + shortcut) in one pass ------------------------------------------ #
+  def forward_add_relu(self, x, shortcut, ctx):
+    gamma = ctx.master[self.name + "/gamma"] if self.scale else None
+    beta = ctx.master[self.name + "/beta"]
+    mean, var = ctx.state[self.name + "/moving_mean"], ctx.state[self.name + "/moving_variance"]
+    if not ctx.training:
+      return nn_ops.add_relu_forward(ctx.backend, nn_ops.batchnorm_inference(ctx.backend, x, gamma, beta, mean, var, self.epsilon, False), shortcut, True)
+    y, batch_mean, batch_rstd = nn_ops.batchnorm_add_relu_forward(ctx.backend, x, gamma, beta, mean, var, self.decay, self.epsilon, shortcut, ctx.groups)
+    self._saved = (x, y, batch_mean, batch_rstd)
+    return y
+
+  def backward_add_relu(self, dy, ctx):
+    """-> (gradient of x, gradient of the shortcut input)."""
+    x, y, batch_mean, batch_rstd = self._saved
+    gamma = ctx.master[self.name + "/gamma"] if self.scale else None
+    self._saved = None
+    return nn_ops.batchnorm_add_relu_backward(ctx.backend, dy, x, y, gamma, batch_mean, batch_rstd, ctx.grads[self.name + "/gamma"] if self.scale else None,
+                                              ctx.grads[self.name + "/beta"], ctx.groups, ctx.group_stride)
+
 
 class LayerNorm(Module):
   """Layer normalisation over the feature dimension of a [rows, features] activation (trainable gamma / beta)."""
@@ -433,8 +452,21 @@ class Residual(Module):
     self.shortcut.initialize(master, states, generator)
     self.residual.initialize(master, states, generator)
 
+  def _closing_norm(self):
+    """The residual branch's last layer when the unit ends with BN -> add -> ReLU (ResNet v1): those three fuse into one pass."""
+    if not self.relu or not isinstance(self.residual, Sequential) or not self.residual.layers:
+      return None
+    last = self.residual.layers[-1]
+    return last if (isinstance(last, BatchNorm) and not last.relu) else None
+
   def forward(self, x, ctx):
     a = self.shortcut.forward(x, ctx)
+    norm = self._closing_norm()
+    if norm is not None:
+      b = x
+      for layer in self.residual.layers[:-1]:
+        b = layer.forward(b, ctx)
+      return norm.forward_add_relu(b, a, ctx)
     b = self.residual.forward(x, ctx)
     y = nn_ops.add_relu_forward(ctx.backend, a, b, self.relu)
     if ctx.training and self.relu:
@@ -442,6 +474,13 @@ class Residual(Module):
     return y
 
   def backward(self, dy, ctx):
+    norm = self._closing_norm()
+    if norm is not None:
+      db, dy = norm.backward_add_relu(dy, ctx)
+      for layer in reversed(self.residual.layers[:-1]):
+        db = layer.backward(db, ctx)
+      da = self.shortcut.backward(dy, ctx)
+      return nn_ops.add_forward(ctx.backend, da, db)
     if self.relu:
       dy = nn_ops.relu_backward(ctx.backend, dy, self._saved_y)
       self._saved_y = None

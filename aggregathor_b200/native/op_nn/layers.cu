@@ -759,9 +759,10 @@ constexpr long long kFusedHalfBytes = 16 + 2ll * 8 * 16384;     // barrier word 
 
 struct BnFused {
     bf16 const* a;              // forward: x            backward: dy
-    bf16 const* b;              //                       backward: x
+    bf16 const* b;              // forward: residual added before the ReLU (or null)   backward: x
     bf16 const* mask;           //                       backward: y of a fused ReLU (or null)
     bf16* out;                  // forward: y            backward: dx
+    bf16* out2;                 //                       backward: the masked dy (gradient of the residual input), or null
     float const* gamma;
     float const* beta;
     float* moving_mean;
@@ -806,7 +807,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bn_fused_kernel(BnFused cons
     long long const nvec = row_end > row_begin ? (row_end - row_begin) * octets : 0;
     long long const base = (static_cast<long long>(group) * p.rows_per_group + row_begin) * octets;
     uint4 const* ga = reinterpret_cast<uint4 const*>(p.a) + base;
-    uint4 const* gb = BWD ? reinterpret_cast<uint4 const*>(p.b) + base : nullptr;
+    uint4 const* gb = p.b ? reinterpret_cast<uint4 const*>(p.b) + base : nullptr;
+    uint4* gout2 = (BWD && p.out2) ? reinterpret_cast<uint4*>(p.out2) + base : nullptr;
     uint4 const* gm = (BWD && p.mask) ? reinterpret_cast<uint4 const*>(p.mask) + base : nullptr;
     uint4* gout = reinterpret_cast<uint4*>(p.out) + base;
     int const stride = kFusedThreads - kFusedThreads % octets;      // a thread keeps the same channel octet for all its vectors
@@ -860,6 +862,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bn_fused_kernel(BnFused cons
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
                             va[j] = vy[j] > 0.f ? va[j] : 0.f;
+                        if (gout2)
+                            gout2[i] = pack8(va);
                     }
                     float vx[8];
                     unpack8(rb[u], vx);
@@ -953,9 +957,12 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bn_fused_kernel(BnFused cons
         float va[8];
         unpack8(resident ? stash_a[i] : ga[i], va);
         if (!BWD) {
+            float vr[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (gb)
+                unpack8(gb[i], vr);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                va[j] = va[j] * c0[j] + c1[j];
+                va[j] = va[j] * c0[j] + c1[j] + vr[j];
                 if (p.relu)
                     va[j] = fmaxf(va[j], 0.f);
             }
@@ -1073,10 +1080,11 @@ long long agb_bn_fused_workspace_bytes() {
     return 16 + 2 * kFusedHalfBytes;
 }
 
-int agb_bn_forward_fused(void const* x, void* y, void const* gamma, void const* beta, void* moving_mean, void* moving_var, void* save_mean, void* save_rstd,
+// `residual` (optional, same shape as x): y = relu?(bn(x) + residual) — the closing add + ReLU of a residual unit.
+int agb_bn_forward_fused(void const* x, void const* residual, void* y, void const* gamma, void const* beta, void* moving_mean, void* moving_var, void* save_mean, void* save_rstd,
                          void* ws, long long rows, int C, int groups, float eps, float decay, int relu, void* stream) {
     BnFused p{};
-    p.a = static_cast<bf16 const*>(x); p.out = static_cast<bf16*>(y);
+    p.a = static_cast<bf16 const*>(x); p.b = static_cast<bf16 const*>(residual); p.out = static_cast<bf16*>(y);
     p.gamma = static_cast<float const*>(gamma); p.beta = static_cast<float const*>(beta);
     p.moving_mean = static_cast<float*>(moving_mean); p.moving_var = static_cast<float*>(moving_var);
     p.save_mean = static_cast<float*>(save_mean); p.save_rstd = static_cast<float*>(save_rstd);
@@ -1085,10 +1093,14 @@ int agb_bn_forward_fused(void const* x, void* y, void const* gamma, void const* 
     return launch_bn_fused<false>(p, rows, static_cast<cudaStream_t>(stream));
 }
 
-int agb_bn_backward_fused(void const* dy, void const* x, void const* y, void const* gamma, void const* save_mean, void const* save_rstd, void* dx, void* dgamma, void* dbeta,
-                          void* ws, long long rows, int C, int groups, long long group_stride, void* stream) {
+// `dmasked` (optional, needs y): also stores dy * (y > 0), the gradient flowing into the residual input of the fused add + ReLU.
+int agb_bn_backward_fused(void const* dy, void const* x, void const* y, void const* gamma, void const* save_mean, void const* save_rstd, void* dx, void* dmasked, void* dgamma,
+                          void* dbeta, void* ws, long long rows, int C, int groups, long long group_stride, void* stream) {
     BnFused p{};
     p.a = static_cast<bf16 const*>(dy); p.b = static_cast<bf16 const*>(x); p.mask = static_cast<bf16 const*>(y); p.out = static_cast<bf16*>(dx);
+    p.out2 = static_cast<bf16*>(dmasked);
+    if (p.out2 && !p.mask)
+        return 302;
     p.gamma = static_cast<float const*>(gamma);
     p.save_mean = const_cast<float*>(static_cast<float const*>(save_mean)); p.save_rstd = const_cast<float*>(static_cast<float const*>(save_rstd));
     p.dgamma = static_cast<float*>(dgamma); p.dbeta = static_cast<float*>(dbeta); p.group_stride = group_stride;

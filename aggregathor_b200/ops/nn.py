@@ -156,6 +156,26 @@ def batchnorm_forward(backend, x, gamma, beta, moving_mean, moving_var, decay, e
   return y, mean, rstd
 
 
+def batchnorm_add_relu_forward(backend, x, gamma, beta, moving_mean, moving_var, decay, eps, residual, groups=1):
+  """y = relu(bn(x) + residual): the closing batch norm, shortcut add and ReLU of a residual unit in one pass. Returns (y, mean, rstd)."""
+  if backend == "native" and x.is_cuda:
+    out = _native().batchnorm_forward(x, gamma, beta, moving_mean, moving_var, decay, eps, True, groups, residual)
+    if out is not None:
+      return out
+  y, mean, rstd = batchnorm_forward(backend, x, gamma, beta, moving_mean, moving_var, decay, eps, False, groups)
+  return add_relu_forward(backend, y, residual, True), mean, rstd
+
+
+def batchnorm_add_relu_backward(backend, dy, x, y, gamma, mean, rstd, grad_gamma, grad_beta, groups=1, group_stride=0):
+  """Backward of `batchnorm_add_relu_forward`: returns (dx, g) with g = dy * (y > 0), the gradient of the residual input."""
+  if backend == "native" and x.is_cuda:
+    out = _native().batchnorm_backward(dy, x, y, gamma, mean, rstd, True, grad_gamma, grad_beta, groups, group_stride, True)
+    if out is not None:
+      return out
+  g = relu_backward(backend, dy, y)
+  return batchnorm_backward(backend, g, x, None, gamma, mean, rstd, False, grad_gamma, grad_beta, groups, group_stride), g
+
+
 def batchnorm_inference(backend, x, gamma, beta, moving_mean, moving_var, eps, relu):
   y = F.batch_norm(x, moving_mean, moving_var, gamma, beta, False, 0.0, eps)
   return torch.relu_(y) if relu else y
