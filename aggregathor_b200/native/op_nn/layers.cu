@@ -755,6 +755,7 @@ inline SumsPlan plan_sums(long long rows_per_group, int C, int groups) {
 constexpr int kFusedThreads = 512;
 constexpr int kFusedScratchBytes = kFusedThreads * 16 * 4;      // CTA reduction scratch: [lanes][octets * 16] floats
 constexpr int kFusedStashBytes = 192 * 1024;                    // resident tile(s)
+using FusedSum = float;                                          // fp32 reductions in L2 (`RED.ADD.F32`): fp64 atomics serialise far more slowly
 constexpr long long kFusedHalfBytes = 16 + 2ll * 8 * 16384;     // barrier word + sums for up to 16384 (group, channel) pairs
 
 struct BnFused {
@@ -792,16 +793,27 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bn_fused_kernel(BnFused cons
     uint4* stash_a = reinterpret_cast<uint4*>(fused_smem + kFusedScratchBytes);
     uint4* stash_b = stash_a + p.stash_vecs;
     int const octets = p.C >> 3;
-    unsigned const slot = __ldcg(p.state) & 1u;
+    // Per-channel vectors (pivot / saved statistics, later the coefficients) are fetched by ONE thread per channel and handed to
+    // the others through shared memory: 16 warps x 148 CTAs all asking L2 for the same few cache lines costs tens of microseconds.
+    __shared__ unsigned slot_shared;
+    float* chan = red;          // [3][C] floats, aliasing the reduction scratch (used before / after it)
+    int const group = blockIdx.x / p.ctas_per_group, chunk = blockIdx.x % p.ctas_per_group;
+    if (threadIdx.x == 0)
+        slot_shared = __ldcg(p.state) & 1u;
+    for (int c = threadIdx.x; c < p.C; c += kFusedThreads) {
+        chan[c] = BWD ? p.save_mean[group * p.C + c] : (p.moving_mean ? p.moving_mean[c] : 0.f);
+        chan[p.C + c] = BWD ? p.save_rstd[group * p.C + c] : 0.f;
+    }
+    __syncthreads();
+    unsigned const slot = slot_shared;
     unsigned char* mine = p.ws + slot * kFusedHalfBytes;
     unsigned* bar = reinterpret_cast<unsigned*>(mine);
-    double* sums = reinterpret_cast<double*>(mine + 16);
+    FusedSum* sums = reinterpret_cast<FusedSum*>(mine + 16);
     {   // clear the other half for whoever launches next
         uint4* other = reinterpret_cast<uint4*>(p.ws + (slot ^ 1u) * kFusedHalfBytes);
         for (long long i = static_cast<long long>(blockIdx.x) * kFusedThreads + threadIdx.x; i < kFusedHalfBytes / 16; i += static_cast<long long>(gridDim.x) * kFusedThreads)
             other[i] = make_uint4(0, 0, 0, 0);
     }
-    int const group = blockIdx.x / p.ctas_per_group, chunk = blockIdx.x % p.ctas_per_group;
     long long const row_begin = static_cast<long long>(chunk) * p.rows_per_cta;
     long long const row_end = min(p.rows_per_group, row_begin + p.rows_per_cta);
     long long const nvec = row_end > row_begin ? (row_end - row_begin) * octets : 0;
@@ -816,17 +828,20 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bn_fused_kernel(BnFused cons
     bool const active = static_cast<int>(threadIdx.x) < stride;
     int const o = threadIdx.x % octets, lane = threadIdx.x / octets;
     int const cbase = group * p.C + o * 8;
+    // forward: `mu` is a per-channel pivot (the moving mean): sums of (x - pivot) and (x - pivot)^2 keep E[x^2] - E[x]^2 well
+    // conditioned in fp32 even when |mean| >> std; backward: the saved batch statistics.
     float s0[8], s1[8], mu[8], rs[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         s0[j] = 0.f;
         s1[j] = 0.f;
-        mu[j] = (BWD && active) ? p.save_mean[cbase + j] : 0.f;
-        rs[j] = (BWD && active) ? p.save_rstd[cbase + j] : 0.f;
+        mu[j] = active ? chan[o * 8 + j] : 0.f;
+        rs[j] = active ? chan[p.C + o * 8 + j] : 0.f;
     }
+    __syncthreads();            // `chan` aliases `red`: everybody has its copy before the scratch is reused
     // ---- phase 1: stream the chunk once, stash it, accumulate ------------------------------------------------------ //
     if (active) {
-        constexpr int U = BWD ? 2 : 4;
+        constexpr int U = BWD ? 4 : 8;
         for (long long i0 = threadIdx.x; i0 < nvec; i0 += static_cast<long long>(stride) * U) {
             uint4 ra[U], rb[U], rm[U];
 #pragma unroll
@@ -850,8 +865,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bn_fused_kernel(BnFused cons
                 if (!BWD) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        s0[j] += va[j];
-                        s1[j] += va[j] * va[j];
+                        float const d = va[j] - mu[j];
+                        s0[j] += d;
+                        s1[j] += d * d;
                     }
                     if (i < p.stash_vecs)
                         stash_a[i] = ra[u];
@@ -891,7 +907,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bn_fused_kernel(BnFused cons
             float total = 0.f;
             for (int l = 0; l < lanes; ++l)
                 total += red[l * (octets * 16) + t];
-            atomicAdd(sums + (static_cast<long long>(group) * p.C + (t >> 4) * 8 + (t & 7)) * 2 + ((t >> 3) & 1), static_cast<double>(total));
+            atomicAdd(sums + (static_cast<long long>(group) * p.C + (t >> 4) * 8 + (t & 7)) * 2 + ((t >> 3) & 1), static_cast<FusedSum>(total));
         }
     }
     // ---- grid barrier ----------------------------------------------------------------------------------------------- //
@@ -901,8 +917,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bn_fused_kernel(BnFused cons
         atomicAdd(bar, 1u);
         unsigned spins = 0;
         while (ld_acquire_gpu(bar) < gridDim.x) {
-            __nanosleep(40);
-            if (++spins > (1u << 24)) {   // ~1 s: a CTA of this grid never arrived
+            __nanosleep(200);
+            if (++spins > (1u << 22)) {   // ~1 s: a CTA of this grid never arrived
                 printf("[agb] bn_fused_kernel: grid barrier timeout (block %d, %u of %u arrived)\n", static_cast<int>(blockIdx.x), ld_acquire_gpu(bar), gridDim.x);
                 __trap();
             }
@@ -911,46 +927,55 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bn_fused_kernel(BnFused cons
     __syncthreads();
     if (blockIdx.x == 0 && threadIdx.x == 0)
         *p.state = slot ^ 1u;
-    if (!active)
-        return;
-    // ---- phase 2: coefficients in registers, apply to the resident tile ------------------------------------------------ //
-    double const n = static_cast<double>(p.rows_per_group), inv_n = 1.0 / n;
-    float c0[8], c1[8], c2[8];
-    bool const writer = chunk == 0 && lane == 0;   // one thread per (group, channel octet) publishes the per-channel results
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        int const c = o * 8 + j;
-        double const t0 = __ldcg(sums + static_cast<long long>(cbase + j) * 2), t1 = __ldcg(sums + static_cast<long long>(cbase + j) * 2 + 1);
-        float const gmj = p.gamma ? p.gamma[c] : 1.f;
-        if (!BWD) {
-            double const mean = t0 * inv_n;
-            double var = fma(-mean, mean, t1 * inv_n);
-            if (var < 0.)
-                var = 0.;
-            float const rstd = rsqrtf(static_cast<float>(var) + p.eps);
-            c0[j] = gmj * rstd;
-            c1[j] = p.beta[c] - static_cast<float>(mean) * gmj * rstd;
-            c2[j] = 0.f;
-            if (writer) {
-                p.save_mean[cbase + j] = static_cast<float>(mean);
-                p.save_rstd[cbase + j] = rstd;
-                if (p.moving_mean && group == 0) {   // unbiased variance in the moving average, as TF's fused batch norm
-                    double const unbiased = n > 1. ? var * n / (n - 1.) : var;
-                    p.moving_mean[c] = p.decay * p.moving_mean[c] + (1.f - p.decay) * static_cast<float>(mean);
-                    p.moving_var[c] = p.decay * p.moving_var[c] + (1.f - p.decay) * static_cast<float>(unbiased);
+    // ---- phase 2: one thread per channel turns the sums into coefficients (shared memory), then apply to the resident tile -- //
+    {
+        double const n = static_cast<double>(p.rows_per_group), inv_n = 1.0 / n;
+        for (int c = threadIdx.x; c < p.C; c += kFusedThreads) {
+            long long const idx = static_cast<long long>(group) * p.C + c;
+            double const t0 = __ldcg(sums + idx * 2), t1 = __ldcg(sums + idx * 2 + 1);
+            float const gmc = p.gamma ? p.gamma[c] : 1.f;
+            if (!BWD) {
+                float const pivot = p.moving_mean ? p.moving_mean[c] : 0.f;
+                double const shifted = t0 * inv_n;
+                double const mean = shifted + static_cast<double>(pivot);
+                double var = fma(-shifted, shifted, t1 * inv_n);
+                if (var < 0.)
+                    var = 0.;
+                float const rstd = rsqrtf(static_cast<float>(var) + p.eps);
+                chan[c] = gmc * rstd;
+                chan[p.C + c] = p.beta[c] - static_cast<float>(mean) * gmc * rstd;
+                if (chunk == 0) {
+                    p.save_mean[idx] = static_cast<float>(mean);
+                    p.save_rstd[idx] = rstd;
+                    if (p.moving_mean && group == 0) {   // unbiased variance in the moving average, as TF's fused batch norm
+                        double const unbiased = n > 1. ? var * n / (n - 1.) : var;
+                        p.moving_mean[c] = p.decay * pivot + (1.f - p.decay) * static_cast<float>(mean);
+                        p.moving_var[c] = p.decay * p.moving_var[c] + (1.f - p.decay) * static_cast<float>(unbiased);
+                    }
+                }
+            } else {
+                float const inv = static_cast<float>(inv_n), rsc = p.save_rstd[idx], muc = p.save_mean[idx];
+                float const b1 = -gmc * rsc * rsc * static_cast<float>(t1) * inv;
+                chan[c] = gmc * rsc;
+                chan[p.C + c] = b1;
+                chan[2 * p.C + c] = -gmc * rsc * static_cast<float>(t0) * inv - b1 * muc;
+                if (chunk == 0) {
+                    if (p.dgamma)
+                        p.dgamma[group * p.group_stride + c] = static_cast<float>(t1);
+                    p.dbeta[group * p.group_stride + c] = static_cast<float>(t0);
                 }
             }
-        } else {
-            float const inv = static_cast<float>(inv_n);
-            c0[j] = gmj * rs[j];
-            c1[j] = -gmj * rs[j] * rs[j] * static_cast<float>(t1) * inv;
-            c2[j] = -gmj * rs[j] * static_cast<float>(t0) * inv - c1[j] * mu[j];
-            if (writer) {
-                if (p.dgamma)
-                    p.dgamma[group * p.group_stride + c] = static_cast<float>(t1);
-                p.dbeta[group * p.group_stride + c] = static_cast<float>(t0);
-            }
         }
+    }
+    __syncthreads();
+    if (!active)
+        return;
+    float c0[8], c1[8], c2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        c0[j] = chan[o * 8 + j];
+        c1[j] = chan[p.C + o * 8 + j];
+        c2[j] = BWD ? chan[2 * p.C + o * 8 + j] : 0.f;
     }
     for (long long i = threadIdx.x; i < nvec; i += stride) {
         bool const resident = i < p.stash_vecs;
@@ -988,7 +1013,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bn_fused_kernel(BnFused cons
 template<bool BWD>
 int launch_bn_fused(BnFused p, long long rows, cudaStream_t s) {
     int const octets = p.C >> 3;
-    if ((p.C & 7) || octets > kFusedThreads || p.groups < 1 || p.groups > 148 || rows % p.groups || static_cast<long long>(p.C) * p.groups > 16384)
+    if ((p.C & 7) || 3 * p.C * 4 > kFusedScratchBytes || p.groups < 1 || p.groups > 148 || rows % p.groups || static_cast<long long>(p.C) * p.groups > 16384)
         return 399;
     static bool configured = false;
     int const smem = kFusedScratchBytes + kFusedStashBytes;

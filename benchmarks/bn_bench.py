@@ -15,9 +15,13 @@ parser = argparse.ArgumentParser()
 parser.add_argument("--batch", type=int, default=32)
 parser.add_argument("--reps", type=int, default=20)
 parser.add_argument("--out", default="gpurun_out/bn_bench.json")
+parser.add_argument("--only", default="", help="C,HW: a single shape")
+parser.add_argument("--eager", action="store_true", help="no CUDA graph: plain launches (for ncu)")
 args = parser.parse_args()
 torch.cuda.set_device(0)
 shapes = [(64, 112), (64, 56), (256, 56), (128, 28), (512, 28), (256, 14), (1024, 14), (512, 7), (2048, 7)]
+if args.only:
+  shapes = [tuple(int(v) for v in args.only.split(","))]
 flush = torch.empty(64 << 20, dtype=torch.float32, device="cuda")  # 256 MB > L2
 results = []
 for c, hw in shapes:
@@ -35,10 +39,17 @@ for c, hw in shapes:
       for _ in range(3):
         fn()
       torch.cuda.synchronize()
-      graph = torch.cuda.CUDAGraph()
-      with torch.cuda.graph(graph):
-        for _ in range(args.reps):
-          fn()
+      if args.eager:
+        class graph:  # noqa: N801 - same interface as a captured graph
+          @staticmethod
+          def replay():
+            for _ in range(args.reps):
+              fn()
+      else:
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+          for _ in range(args.reps):
+            fn()
       graph.replay()
       torch.cuda.synchronize()
       times = []
