@@ -19,6 +19,7 @@ the numerical reference and as the baseline arm.
 """
 
 import math
+import os
 
 import torch
 import torch.nn.functional as F
@@ -454,7 +455,7 @@ class Residual(Module):
 
   def _closing_norm(self):
     """The residual branch's last layer when the unit ends with BN -> add -> ReLU (ResNet v1): those three fuse into one pass."""
-    if not self.relu or not isinstance(self.residual, Sequential) or not self.residual.layers:
+    if not self.relu or not isinstance(self.residual, Sequential) or not self.residual.layers or os.environ.get("AGB_FUSE_RESIDUAL", "1") == "0":
       return None
     last = self.residual.layers[-1]
     return last if (isinstance(last, BatchNorm) and not last.relu) else None

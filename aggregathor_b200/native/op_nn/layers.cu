@@ -754,8 +754,12 @@ inline SumsPlan plan_sums(long long rows_per_group, int C, int groups) {
 
 constexpr int kFusedThreads = 512;
 constexpr int kFusedScratchBytes = kFusedThreads * 16 * 4;      // CTA reduction scratch: [lanes][octets * 16] floats
-constexpr int kFusedStashBytes = 192 * 1024;                    // resident tile(s)
-using FusedSum = float;                                          // fp32 reductions in L2 (`RED.ADD.F32`): fp64 atomics serialise far more slowly
+constexpr int kFusedPivotBytes = 12 * 1024;                     // the forward pivot per channel, kept from phase 0 to phase 2
+constexpr int kFusedStashBytes = 180 * 1024;                    // resident tile(s)
+// fp64 accumulation of the CTAs' fp32 partial sums is exact (53-bit mantissa vs <= 148 addends of 24 bits), hence independent of
+// the arrival order: statistics are bit-reproducible from run to run. To keep the atomics off a handful of hot L2 lines when C
+// is small, the CTAs of a group spread over `replicas` copies of the sums, folded in a fixed order in phase 2.
+using FusedSum = double;
 constexpr long long kFusedHalfBytes = 16 + 2ll * 8 * 16384;     // barrier word + sums for up to 16384 (group, channel) pairs
 
 struct BnFused {
@@ -776,7 +780,7 @@ struct BnFused {
     unsigned* state;            // [0]: which half of `ws` this launch uses
     unsigned char* ws;
     long long rows_per_group, rows_per_cta;
-    int C, groups, ctas_per_group, stash_vecs, relu;
+    int C, groups, ctas_per_group, stash_vecs, relu, replicas;
     float eps, decay;
 };
 
@@ -790,7 +794,8 @@ template<bool BWD>
 __global__ void __launch_bounds__(kFusedThreads, 1) bn_fused_kernel(BnFused const p) {
     extern __shared__ __align__(16) unsigned char fused_smem[];
     float* red = reinterpret_cast<float*>(fused_smem);
-    uint4* stash_a = reinterpret_cast<uint4*>(fused_smem + kFusedScratchBytes);
+    float* pivot_s = reinterpret_cast<float*>(fused_smem + kFusedScratchBytes);
+    uint4* stash_a = reinterpret_cast<uint4*>(fused_smem + kFusedScratchBytes + kFusedPivotBytes);
     uint4* stash_b = stash_a + p.stash_vecs;
     int const octets = p.C >> 3;
     // Per-channel vectors (pivot / saved statistics, later the coefficients) are fetched by ONE thread per channel and handed to
@@ -803,6 +808,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bn_fused_kernel(BnFused cons
     for (int c = threadIdx.x; c < p.C; c += kFusedThreads) {
         chan[c] = BWD ? p.save_mean[group * p.C + c] : (p.moving_mean ? p.moving_mean[c] : 0.f);
         chan[p.C + c] = BWD ? p.save_rstd[group * p.C + c] : 0.f;
+        if (!BWD)
+            pivot_s[c] = chan[c];   // phase 2 must use the value read HERE: by then another CTA has updated the moving mean
     }
     __syncthreads();
     unsigned const slot = slot_shared;
@@ -907,7 +914,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bn_fused_kernel(BnFused cons
             float total = 0.f;
             for (int l = 0; l < lanes; ++l)
                 total += red[l * (octets * 16) + t];
-            atomicAdd(sums + (static_cast<long long>(group) * p.C + (t >> 4) * 8 + (t & 7)) * 2 + ((t >> 3) & 1), static_cast<FusedSum>(total));
+            long long const slot_index = (static_cast<long long>(chunk % p.replicas) * p.groups + group) * p.C + (t >> 4) * 8 + (t & 7);
+            atomicAdd(sums + slot_index * 2 + ((t >> 3) & 1), static_cast<FusedSum>(total));
         }
     }
     // ---- grid barrier ----------------------------------------------------------------------------------------------- //
@@ -932,10 +940,15 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bn_fused_kernel(BnFused cons
         double const n = static_cast<double>(p.rows_per_group), inv_n = 1.0 / n;
         for (int c = threadIdx.x; c < p.C; c += kFusedThreads) {
             long long const idx = static_cast<long long>(group) * p.C + c;
-            double const t0 = __ldcg(sums + idx * 2), t1 = __ldcg(sums + idx * 2 + 1);
+            double t0 = 0., t1 = 0.;
+            for (int r = 0; r < p.replicas; ++r) {
+                long long const slot_index = static_cast<long long>(r) * p.groups * p.C + idx;
+                t0 += __ldcg(sums + slot_index * 2);
+                t1 += __ldcg(sums + slot_index * 2 + 1);
+            }
             float const gmc = p.gamma ? p.gamma[c] : 1.f;
             if (!BWD) {
-                float const pivot = p.moving_mean ? p.moving_mean[c] : 0.f;
+                float const pivot = pivot_s[c];
                 double const shifted = t0 * inv_n;
                 double const mean = shifted + static_cast<double>(pivot);
                 double var = fma(-shifted, shifted, t1 * inv_n);
@@ -977,50 +990,88 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bn_fused_kernel(BnFused cons
         c1[j] = chan[p.C + o * 8 + j];
         c2[j] = BWD ? chan[2 * p.C + o * 8 + j] : 0.f;
     }
-    for (long long i = threadIdx.x; i < nvec; i += stride) {
-        bool const resident = i < p.stash_vecs;
-        float va[8];
-        unpack8(resident ? stash_a[i] : ga[i], va);
+    auto finish = [&](float (&va)[8], float const (&vx)[8]) {   // vx: forward = residual (zeros when absent), backward = x
         if (!BWD) {
-            float vr[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            if (gb)
-                unpack8(gb[i], vr);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                va[j] = va[j] * c0[j] + c1[j] + vr[j];
+                va[j] = va[j] * c0[j] + c1[j] + vx[j];
                 if (p.relu)
                     va[j] = fmaxf(va[j], 0.f);
             }
         } else {
-            if (!resident && gm) {
-                float vy[8];
-                unpack8(gm[i], vy);
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    va[j] = vy[j] > 0.f ? va[j] : 0.f;
-            }
-            float vx[8];
-            unpack8(resident ? stash_b[i] : gb[i], vx);
 #pragma unroll
             for (int j = 0; j < 8; ++j)
                 va[j] = c0[j] * va[j] + c1[j] * vx[j] + c2[j];
         }
-        gout[i] = pack8(va);
+        return pack8(va);
+    };
+    long long const resident_end = nvec < p.stash_vecs ? nvec : static_cast<long long>(p.stash_vecs);
+    long long i = threadIdx.x;
+    for (; i < resident_end; i += stride) {            // the tile kept on chip
+        float va[8], vx[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        unpack8(stash_a[i], va);
+        if (BWD)
+            unpack8(stash_b[i], vx);
+        else if (gb)
+            unpack8(gb[i], vx);
+        gout[i] = finish(va, vx);
+    }
+    constexpr int V = BWD ? 2 : 4;                     // the rest is streamed again (L2 / HBM), several loads in flight per thread
+    for (; i < nvec; i += static_cast<long long>(stride) * V) {
+        uint4 ra[V], rb[V], rm[V];
+#pragma unroll
+        for (int u = 0; u < V; ++u) {
+            long long const k = i + static_cast<long long>(u) * stride;
+            if (k < nvec) {
+                ra[u] = ga[k];
+                if (gb)
+                    rb[u] = gb[k];
+                if (BWD && gm)
+                    rm[u] = gm[k];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < V; ++u) {
+            long long const k = i + static_cast<long long>(u) * stride;
+            if (k >= nvec)
+                continue;
+            float va[8], vx[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            unpack8(ra[u], va);
+            if (gb)
+                unpack8(rb[u], vx);
+            if (BWD && gm) {
+                float vy[8];
+                unpack8(rm[u], vy);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    va[j] = vy[j] > 0.f ? va[j] : 0.f;
+            }
+            gout[k] = finish(va, vx);
+        }
     }
 }
+
+long long g_fused_max_mb[2] = {72, 40};   // forward, backward
+long long g_fused_min_rows = 4096;
 
 // Returns 0 when the fused kernel was launched, 399 when the shape is outside its envelope (the caller uses the two-kernel path).
 template<bool BWD>
 int launch_bn_fused(BnFused p, long long rows, cudaStream_t s) {
     int const octets = p.C >> 3;
-    if ((p.C & 7) || 3 * p.C * 4 > kFusedScratchBytes || p.groups < 1 || p.groups > 148 || rows % p.groups || static_cast<long long>(p.C) * p.groups > 16384)
+    if ((p.C & 7) || 3 * p.C * 4 > kFusedScratchBytes || p.C * 4 > kFusedPivotBytes || p.groups < 1 || p.groups > 148 || rows % p.groups || static_cast<long long>(p.C) * p.groups > 16384)
         return 399;
     static bool configured = false;
-    int const smem = kFusedScratchBytes + kFusedStashBytes;
+    int const smem = kFusedScratchBytes + kFusedPivotBytes + kFusedStashBytes;
     if (!configured) {
         AGB_CUDA_OK(cudaFuncSetAttribute(bn_fused_kernel<BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
+    // measured envelope (benchmarks/bn_bench.py, B200): the resident-tile kernel wins from a few thousand rows up to tensors a few
+    // times the on-chip capacity; tiny tensors and very large ones are served better by the many-CTA kernel pair
+    bool const extra = BWD ? p.out2 != nullptr : p.b != nullptr;   // closing add + ReLU fused in: worth one more separate kernel
+    long long const bytes = rows * p.C * 2;
+    if (rows < (extra ? g_fused_min_rows / 4 : g_fused_min_rows) || bytes > g_fused_max_mb[BWD ? 1 : 0] << 20)
+        return 399;
     p.rows_per_group = rows / p.groups;
     long long const vecs = p.rows_per_group * octets;
     long long const min_vecs = octets * 32ll > 2048 ? octets * 32ll : 2048;    // at least 32 rows / 32 KB per CTA
@@ -1029,6 +1080,10 @@ int launch_bn_fused(BnFused p, long long rows, cudaStream_t s) {
     p.ctas_per_group = static_cast<int>(want < 1 ? 1 : (want > cap ? cap : want));
     p.rows_per_cta = (p.rows_per_group + p.ctas_per_group - 1) / p.ctas_per_group;
     p.stash_vecs = kFusedStashBytes / 16 / (BWD ? 2 : 1);
+    long long const room = 16384 / (static_cast<long long>(p.C) * p.groups);
+    p.replicas = static_cast<int>(room < 1 ? 1 : (room > 8 ? 8 : room));
+    if (p.replicas > p.ctas_per_group)
+        p.replicas = p.ctas_per_group;
     AGB_CUDA_OK(launch_pdl(bn_fused_kernel<BWD>, dim3(p.groups * p.ctas_per_group), dim3(kFusedThreads), static_cast<size_t>(smem), s, p));
     AGB_CUDA_OK(cudaGetLastError());
     return 0;
@@ -1101,6 +1156,13 @@ int agb_bn_backward(void const* dy, void const* x, void const* y, void const* ga
 }
 
 // Single-launch variants; `ws` = zero-initialised workspace of agb_bn_fused_workspace_bytes() bytes, private to each direction.
+int agb_bn_fused_set_limits(long long forward_mb, long long backward_mb, long long min_rows) {
+    g_fused_max_mb[0] = forward_mb;
+    g_fused_max_mb[1] = backward_mb;
+    g_fused_min_rows = min_rows;
+    return 0;
+}
+
 long long agb_bn_fused_workspace_bytes() {
     return 16 + 2 * kFusedHalfBytes;
 }

@@ -445,6 +445,11 @@ def set_bn_fused(flag):
   _BN_FUSED = bool(flag)
 
 
+def set_bn_fused_limits(forward_mb=72, backward_mb=40, min_rows=4096):
+  """Envelope of the single-launch kernels: largest tensor (MB) per direction and fewest rows (defaults = measured on B200)."""
+  _lib().agb_bn_fused_set_limits(ctypes.c_longlong(forward_mb), ctypes.c_longlong(backward_mb), ctypes.c_longlong(min_rows))
+
+
 def _bn_fused_workspace(device, name):
   lib = _lib()
   lib.agb_bn_fused_workspace_bytes.restype = ctypes.c_longlong

@@ -16,9 +16,12 @@ parser.add_argument("--batch", type=int, default=32)
 parser.add_argument("--reps", type=int, default=20)
 parser.add_argument("--out", default="gpurun_out/bn_bench.json")
 parser.add_argument("--only", default="", help="C,HW: a single shape")
+parser.add_argument("--no-limits", action="store_true", help="lift the size envelope of the single-launch kernels")
 parser.add_argument("--eager", action="store_true", help="no CUDA graph: plain launches (for ncu)")
 args = parser.parse_args()
 torch.cuda.set_device(0)
+if args.no_limits:
+  nn_native.set_bn_fused_limits(1 << 20, 1 << 20, 1)
 shapes = [(64, 112), (64, 56), (256, 56), (128, 28), (512, 28), (256, 14), (1024, 14), (512, 7), (2048, 7)]
 if args.only:
   shapes = [tuple(int(v) for v in args.only.split(","))]
