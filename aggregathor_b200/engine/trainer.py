@@ -236,7 +236,9 @@ class Manager:
   def authenticate_gradients(self):
     """Sign the local rows, let forging attackers tamper with theirs, exchange the records, verify what this rank will consume."""
     auth = self.authenticator
-    local = [(i, self.grads[self.placement[i][1]]) for i in self.local_workers]
+    # rows are identified by their slot in the gathered matrix (rank * w + local row): the cluster allocation may spread the
+    # logical workers over the ranks in any order, the aggregation engines and the records only know slots
+    local = [(self.rank * self.w + self.placement[i][1], self.grads[self.placement[i][1]]) for i in self.local_workers]
 
     def tamper():
       if getattr(self.attack, "forges", False):

@@ -99,21 +99,38 @@ template<typename T, bool MC> __global__ void __launch_bounds__(512) allreduce_k
     long long const total = a.offs[1];
     long long const lo = total * a.rank / a.R, hi = total * (a.rank + 1) / a.R;
     long long const stride = static_cast<long long>(gridDim.x) * blockDim.x;
-    for (long long v = lo + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < hi; v += stride) {
-        if constexpr (MC) {  // fp32 only: the switch adds the R copies and fans the result out
-            float4 sum = multimem_ld_reduce_add_f4(reinterpret_cast<float const*>(a.mc + v * 16));
-            if (a.mean) {
-                float const scale = 1.f / static_cast<float>(a.R);
-                sum.x *= scale; sum.y *= scale; sum.z *= scale; sum.w *= scale;
-            }
-            multimem_st_f4(reinterpret_cast<float*>(a.mc + v * 16), sum);
-        } else {
-            Vec16<T> sum = ld_vec<T>(a.buf[0], v);  // fixed rank order: every rank would compute the same bits
-            for (int r = 1; r < a.R; ++r) {
-                Vec16<T> const other = ld_vec<T>(a.buf[r], v);
+    if constexpr (MC) {  // fp32 only: the switch adds the R copies and fans the result out; 4 independent round trips per thread
+        constexpr int U = 4;
+        float const scale = a.mean ? 1.f / static_cast<float>(a.R) : 1.f;
+        for (long long v0 = lo + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v0 < hi; v0 += stride * U) {
+            float4 sum[U];
 #pragma unroll
-                for (int i = 0; i < Vec16<T>::kLanes; ++i)
-                    sum.v[i] += other.v[i];
+            for (int u = 0; u < U; ++u)
+                if (v0 + u * stride < hi)
+                    sum[u] = multimem_ld_reduce_add_f4(reinterpret_cast<float const*>(a.mc + (v0 + u * stride) * 16));
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (v0 + u * stride < hi) {
+                    sum[u].x *= scale; sum[u].y *= scale; sum[u].z *= scale; sum[u].w *= scale;
+                    multimem_st_f4(reinterpret_cast<float*>(a.mc + (v0 + u * stride) * 16), sum[u]);
+                }
+        }
+    } else {
+        for (long long v = lo + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < hi; v += stride) {
+            Vec16<T> parts[kMaxRanks > 8 ? 8 : kMaxRanks];
+            Vec16<T> sum = ld_vec<T>(a.buf[0], v);  // fixed rank order: every rank would compute the same bits
+            for (int r0 = 1; r0 < a.R; r0 += 8) {   // up to 8 peer loads in flight
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (r0 + k < a.R)
+                        parts[k] = ld_vec<T>(a.buf[r0 + k], v);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (r0 + k < a.R) {
+#pragma unroll
+                        for (int i = 0; i < Vec16<T>::kLanes; ++i)
+                            sum.v[i] += parts[k].v[i];
+                    }
             }
             if (a.mean) {
 #pragma unroll

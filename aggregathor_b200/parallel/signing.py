@@ -109,7 +109,7 @@ class Authenticator:
 
   # -- protocol ----------------------------------------------------------------------- #
   def publish(self, step, local_rows, after_sign=None):
-    """`local_rows`: [(worker index, flat fp32 row)] of this rank. Returns every rank's records {worker: (digests, signature)}.
+    """`local_rows`: [(row slot = rank * w + local row, flat fp32 row)] of this rank. Returns every rank's records {slot: (digests, signature)}.
     `after_sign()` runs between signing and the exchange (fault injection: tampering with an already signed row)."""
     mine = {}
     for worker, row in local_rows:

@@ -193,5 +193,9 @@ def test_two_process_authenticated_run(tmp_path):
   code, out = _run(args, timeout=600, launcher=launcher)
   assert code == 0, out
   assert "failing authentication" in out and "Replica divergence" not in out and "Step 5: total loss" in out
+  # only the tampered part is dropped: the forger touches the first 20 % of its row = slice 0 of 2, on every rank, every step
+  dropped = re.findall(r"dropped (\d+) gradient slice\(s\) failing authentication: \[\((\d+), (\d+)\)\]", out)
+  assert len(dropped) == 12 and all(count == "1" and piece == "0" for count, _, piece in dropped), dropped
+  assert len({slot for _, slot, _ in dropped}) == 1
   losses = [float(x) for x in re.findall(r"Step \d+: total loss = ([0-9.eE+-]+)", out)]
   assert all(l == l and l < 100 for l in losses), losses

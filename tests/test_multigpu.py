@@ -59,3 +59,20 @@ def test_own_collectives_match_nccl(tmp_path):
   assert code == 0, out[-4000:]
   report = json.loads((tmp_path / ("coll_bench_%d.json" % nproc)).read_text())
   assert report["failures"] == [] and report["allreduce"]["ours_ms"] > 0
+
+
+@pytest.mark.skipif(_gpus() < 2, reason="needs at least 2 GPUs")
+def test_authenticated_training_drops_only_forged_slices(tmp_path):
+  """`--authenticate` on 2 ranks x 4 workers with the fused engine: digests are recomputed through the peer mapping; the two forging
+  workers lose the slice they tampered with (the first 40 % of the row = slice 0), honest rows pass, Krum keeps training."""
+  args = [str(ROOT / "runner.py"), "--server", '{"ps": ["127.0.0.1:7000"], "workers": ["127.0.0.1:7001", "127.0.0.1:7002"], "eval": ["127.0.0.1:7000"]}', "--no-wait",
+          "--experiment", "cnnet", "--experiment-args", "batch-size:16", "--aggregator", "krum", "--nb-workers", "8", "--nb-decl-byz-workers", "2",
+          "--nb-real-byz-workers", "2", "--attack", "forge", "--attack-args", "factor:-50", "fraction:0.4", "--authenticate", "--max-step", "8", "--use-gpu", "--reuse-gpu",
+          "--debug-checksum", "--evaluation-file", "-", "--checkpoint-dir", str(tmp_path / "c"), "--checkpoint-delta", "-1", "--checkpoint-period", "-1", "--summary-dir", "-"]
+  code, out = _torchrun(2, args)
+  assert code == 0, out[-4000:]
+  assert "Replica divergence" not in out and "Step 7: total loss" in out
+  import re
+  dropped = re.findall(r"dropped (\d+) gradient slice\(s\) failing authentication: (\[[^\]]*\])", out)
+  assert dropped and all(count == "2" for count, _ in dropped), dropped[:4]          # rank 0 (owner of slice 0) drops the two forgers' slice, every step
+  assert all(piece.count(", 0)") == 2 for _, piece in dropped), dropped[:4]
