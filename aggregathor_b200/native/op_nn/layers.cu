@@ -228,8 +228,8 @@ __global__ void __launch_bounds__(kThreads) channel_sums_kernel(bf16 const* __re
 
 // y = relu?(x * scale[g][c] + shift[g][c]). Each thread keeps a fixed channel octet (stride is a multiple of `octets`
 // whenever possible) so the coefficients stay in registers and no division happens in the loop.
-__global__ void __launch_bounds__(kThreads) bn_apply_kernel(bf16 const* __restrict__ x, bf16* __restrict__ y, float const* __restrict__ scale, float const* __restrict__ shift,
-                                long long total_octets, int C, long long rows_per_group, int relu) {
+__global__ void __launch_bounds__(kThreads) bn_apply_kernel(bf16 const* __restrict__ x, bf16 const* __restrict__ residual, bf16* __restrict__ y, float const* __restrict__ scale,
+                                float const* __restrict__ shift, long long total_octets, int C, long long rows_per_group, int relu) {
     pdl_trigger();
     pdl_wait();
     unsigned const octets = static_cast<unsigned>(C >> 3);
@@ -251,12 +251,14 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(bf16 const* __restri
             sh[j] = shift[g * C + o * 8 + j];
         }
     };
-    auto transform = [&](uint4 raw) {
-        float v[8];
+    auto transform = [&](uint4 raw, long long index) {   // y = relu?(x * scale + shift (+ residual))
+        float v[8], r[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         unpack8(raw, v);
+        if (residual)
+            unpack8(*reinterpret_cast<uint4 const*>(residual + index * 8), r);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            v[j] = v[j] * sc[j] + sh[j];
+            v[j] = v[j] * sc[j] + sh[j] + r[j];
             if (relu)
                 v[j] = fmaxf(v[j], 0.f);
         }
@@ -272,20 +274,20 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(bf16 const* __restri
                 raw[u] = *reinterpret_cast<uint4 const*>(x + (i + u * stride) * 8);
 #pragma unroll
             for (int u = 0; u < U; ++u)
-                *reinterpret_cast<uint4*>(y + (i + u * stride) * 8) = transform(raw[u]);
+                *reinterpret_cast<uint4*>(y + (i + u * stride) * 8) = transform(raw[u], i + u * stride);
         }
     }
     for (; i < total_octets; i += stride) {
         int const g = single_group ? 0 : static_cast<int>(i / octets_per_group);
         if (g != cached_group)
             load_coefficients(g);
-        *reinterpret_cast<uint4*>(y + i * 8) = transform(*reinterpret_cast<uint4 const*>(x + i * 8));
+        *reinterpret_cast<uint4*>(y + i * 8) = transform(*reinterpret_cast<uint4 const*>(x + i * 8), i);
     }
 }
 
 // dx = a * dy' + b * x + c0 with per-(group, channel) coefficients prepared by the statistics kernel's last CTA.
-__global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(bf16 const* __restrict__ dy, bf16 const* __restrict__ x, bf16 const* __restrict__ y, bf16* __restrict__ dx, float const* __restrict__ coef,
-                                    long long total_octets, int C, long long rows_per_group) {
+__global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(bf16 const* __restrict__ dy, bf16 const* __restrict__ x, bf16 const* __restrict__ y, bf16* __restrict__ dx, bf16* __restrict__ dmasked,
+                                    float const* __restrict__ coef, long long total_octets, int C, long long rows_per_group) {
     pdl_trigger();
     pdl_wait();
     unsigned const octets = static_cast<unsigned>(C >> 3);
@@ -309,7 +311,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(bf16 const* __re
             cc[j] = cf[3 * j + 2];
         }
     };
-    auto transform = [&](uint4 rd, uint4 rx, uint4 ry, bool masked) {
+    auto transform = [&](uint4 rd, uint4 rx, uint4 ry, bool masked, long long index) {
         float vd[8], vx[8];
         unpack8(rd, vd);
         unpack8(rx, vx);
@@ -319,6 +321,8 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(bf16 const* __re
 #pragma unroll
             for (int j = 0; j < 8; ++j)
                 vd[j] = vy[j] > 0.f ? vd[j] : 0.f;
+            if (dmasked)   // the gradient of the residual input of a fused add + ReLU
+                *reinterpret_cast<uint4*>(dmasked + index * 8) = pack8(vd);
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j)
@@ -340,7 +344,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(bf16 const* __re
             }
 #pragma unroll
             for (int u = 0; u < U; ++u)
-                *reinterpret_cast<uint4*>(dx + (i + u * stride) * 8) = transform(rd[u], rx[u], ry[u], masked);
+                *reinterpret_cast<uint4*>(dx + (i + u * stride) * 8) = transform(rd[u], rx[u], ry[u], masked, i + u * stride);
         }
     }
     for (; i < total_octets; i += stride) {
@@ -348,7 +352,35 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(bf16 const* __re
         if (g != cached_group)
             load_coefficients(g);
         uint4 const ry = masked ? *reinterpret_cast<uint4 const*>(y + i * 8) : make_uint4(0, 0, 0, 0);
-        *reinterpret_cast<uint4*>(dx + i * 8) = transform(*reinterpret_cast<uint4 const*>(dy + i * 8), *reinterpret_cast<uint4 const*>(x + i * 8), ry, masked);
+        *reinterpret_cast<uint4*>(dx + i * 8) = transform(*reinterpret_cast<uint4 const*>(dy + i * 8), *reinterpret_cast<uint4 const*>(x + i * 8), ry, masked, i);
+    }
+}
+
+// Strided pixel sub-sampling (the 1x1 stride-s "max-pool" of slim's identity shortcuts): y[n, oh, ow, :] = x[n, oh*s, ow*s, :].
+// grid.y = n * OH + oh, threads along (ow, channel octet): no per-element division.
+__global__ void subsample_fwd_kernel(bf16 const* __restrict__ x, bf16* __restrict__ y, int H, int W, int OH, int OW, int octets, int s) {
+    pdl_trigger();
+    pdl_wait();
+    int const n = blockIdx.y / OH, oh = blockIdx.y % OH;
+    uint4 const* src = reinterpret_cast<uint4 const*>(x) + (static_cast<long long>(n) * H + static_cast<long long>(oh) * s) * W * octets;
+    uint4* dst = reinterpret_cast<uint4*>(y) + static_cast<long long>(blockIdx.y) * OW * octets;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < OW * octets; i += gridDim.x * blockDim.x) {
+        int const ow = i / octets, o = i - ow * octets;
+        dst[i] = src[static_cast<long long>(ow) * s * octets + o];
+    }
+}
+// Its backward writes the whole dx in one pass: dy at the sampled pixels, zero elsewhere (replaces a fill + a strided copy).
+__global__ void subsample_bwd_kernel(bf16 const* __restrict__ dy, bf16* __restrict__ dx, int H, int W, int OH, int OW, int octets, int s) {
+    pdl_trigger();
+    pdl_wait();
+    int const n = blockIdx.y / H, h = blockIdx.y % H;
+    bool const row_hit = h % s == 0 && h / s < OH;
+    uint4 const* src = reinterpret_cast<uint4 const*>(dy) + (static_cast<long long>(n) * OH + h / s) * OW * octets;
+    uint4* dst = reinterpret_cast<uint4*>(dx) + static_cast<long long>(blockIdx.y) * W * octets;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < W * octets; i += gridDim.x * blockDim.x) {
+        int const w = i / octets, o = i - w * octets;
+        bool const hit = row_hit && w % s == 0 && w / s < OW;
+        dst[i] = hit ? src[static_cast<long long>(w / s) * octets + o] : make_uint4(0, 0, 0, 0);
     }
 }
 
@@ -447,21 +479,17 @@ __global__ void maxpool_fwd_kernel(bf16 const* __restrict__ x, bf16* __restrict_
 }
 
 // Gather form: every input element sums the gradients of the windows whose argmax it is (no atomics).
+// grid.y = n * H + h (one input row per CTA row), threads along (w, channel octet): no per-element division by H or W, and the
+// candidate window rows are resolved once per CTA.
 __global__ void maxpool_bwd_kernel(bf16 const* __restrict__ dy, unsigned char const* __restrict__ arg, bf16* __restrict__ dx, int N, int H, int W, int C, int OH, int OW,
                                    int k, int s, int pad_t, int pad_l) {
     pdl_trigger();
     pdl_wait();
     int const octets = C >> 3;
-    long long const total = static_cast<long long>(N) * H * W * octets;
-    long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    long long const stride = static_cast<long long>(gridDim.x) * blockDim.x;
-    for (; i < total; i += stride) {
-        int const o = static_cast<int>(i % octets);
-        long long rest = i / octets;
-        int const w = static_cast<int>(rest % W);
-        rest /= W;
-        int const h = static_cast<int>(rest % H);
-        int const n = static_cast<int>(rest / H);
+    int const n = blockIdx.y / H, h = blockIdx.y % H;
+    bf16* const out_row = dx + static_cast<long long>(blockIdx.y) * W * C;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < W * octets; i += gridDim.x * blockDim.x) {
+        int const w = i / octets, o = i - w * octets;
         float acc[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j)
@@ -488,11 +516,10 @@ __global__ void maxpool_bwd_kernel(bf16 const* __restrict__ dy, unsigned char co
                 unsigned char const me = static_cast<unsigned char>(kh * k + kw);
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                    if (pw[j] == me)
-                        acc[j] += v[j];
+                    acc[j] += pw[j] == me ? v[j] : 0.f;
             }
         }
-        *reinterpret_cast<uint4*>(dx + i * 8) = pack8(acc);
+        *reinterpret_cast<uint4*>(out_row + static_cast<long long>(i) * 8) = pack8(acc);
     }
 }
 
@@ -1108,7 +1135,7 @@ extern "C" {
 // Workspace layout for BN (caller provides, zeroed `sums` not required: it is cleared here):
 //   sums  double [groups*C*2] | save_mean, save_rstd, scale, shift float [groups*C] each (forward)
 //   sums  double [groups*C*2] | coef float [groups*C*3]                              (backward)
-int agb_bn_forward(void const* x, void* y, void const* gamma, void const* beta, void* moving_mean, void* moving_var, void* save_mean, void* save_rstd,
+int agb_bn_forward(void const* x, void const* residual, void* y, void const* gamma, void const* beta, void* moving_mean, void* moving_var, void* save_mean, void* save_rstd,
                    void* sums, void* scale, void* shift, long long rows, int C, int groups, float eps, float decay, int relu, void* stream) {
     if ((C & 7) || groups < 1 || rows % groups)
         return 301;
@@ -1126,12 +1153,12 @@ int agb_bn_forward(void const* x, void* y, void const* gamma, void const* beta, 
     if (int status = launch_sums<0>(plan, s, static_cast<bf16 const*>(x), nullptr, nullptr, nullptr, nullptr, static_cast<double*>(sums), rpg, C, fin))
         return status;
     long long const octets = rows * (C >> 3);
-    AGB_CUDA_OK(launch_pdl(bn_apply_kernel, dim3(grid_for(octets)), dim3(kThreads), 0, s, static_cast<bf16 const*>(x), static_cast<bf16*>(y), static_cast<float const*>(scale), static_cast<float const*>(shift), octets, C, rpg, relu));
+    AGB_CUDA_OK(launch_pdl(bn_apply_kernel, dim3(grid_for(octets)), dim3(kThreads), 0, s, static_cast<bf16 const*>(x), static_cast<bf16 const*>(residual), static_cast<bf16*>(y), static_cast<float const*>(scale), static_cast<float const*>(shift), octets, C, rpg, relu));
     AGB_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
-int agb_bn_backward(void const* dy, void const* x, void const* y, void const* gamma, void const* save_mean, void const* save_rstd, void* dx, void* dgamma, void* dbeta,
+int agb_bn_backward(void const* dy, void const* x, void const* y, void const* gamma, void const* save_mean, void const* save_rstd, void* dx, void* dmasked, void* dgamma, void* dbeta,
                     void* sums, void* coef, long long rows, int C, int groups, long long group_stride, void* stream) {
     if ((C & 7) || groups < 1 || rows % groups)
         return 301;
@@ -1150,7 +1177,7 @@ int agb_bn_backward(void const* dy, void const* x, void const* y, void const* ga
         return status;
     long long const octets = rows * (C >> 3);
     AGB_CUDA_OK(launch_pdl(bn_bwd_apply_kernel, dim3(grid_for(octets)), dim3(kThreads), 0, s, static_cast<bf16 const*>(dy), static_cast<bf16 const*>(x), static_cast<bf16 const*>(y), static_cast<bf16*>(dx),
-        static_cast<float const*>(coef), octets, C, rpg));
+        static_cast<bf16*>(dmasked), static_cast<float const*>(coef), octets, C, rpg));
     AGB_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -1221,6 +1248,30 @@ int agb_add_relu(void const* a, void const* b, void* out, long long n, int relu,
     return 0;
 }
 
+int agb_subsample_forward(void const* x, void* y, int N, int H, int W, int C, int s, void* stream) {
+    if ((C & 7) || s < 1)
+        return 301;
+    int const OH = (H + s - 1) / s, OW = (W + s - 1) / s, octets = C >> 3;
+    if (static_cast<long long>(N) * OH > 65535)
+        return 399;
+    int const per_row = OW * octets;
+    AGB_CUDA_OK(launch_pdl(subsample_fwd_kernel, dim3((per_row + kThreads - 1) / kThreads, N * OH), dim3(kThreads), 0, static_cast<cudaStream_t>(stream), static_cast<bf16 const*>(x), static_cast<bf16*>(y), H, W, OH, OW, octets, s));
+    AGB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int agb_subsample_backward(void const* dy, void* dx, int N, int H, int W, int C, int s, void* stream) {
+    if ((C & 7) || s < 1)
+        return 301;
+    int const OH = (H + s - 1) / s, OW = (W + s - 1) / s, octets = C >> 3;
+    if (static_cast<long long>(N) * H > 65535)
+        return 399;
+    int const per_row = W * octets;
+    AGB_CUDA_OK(launch_pdl(subsample_bwd_kernel, dim3((per_row + kThreads - 1) / kThreads, N * H), dim3(kThreads), 0, static_cast<cudaStream_t>(stream), static_cast<bf16 const*>(dy), static_cast<bf16*>(dx), H, W, OH, OW, octets, s));
+    AGB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 int agb_relu_backward(void const* dy, void const* y, void* dx, long long n, void* stream) {
     if (n & 7)
         return 301;
@@ -1241,8 +1292,9 @@ int agb_maxpool_forward(void const* x, void* y, void* arg, int N, int H, int W, 
 int agb_maxpool_backward(void const* dy, void const* arg, void* dx, int N, int H, int W, int C, int OH, int OW, int k, int s, int pad_t, int pad_l, void* stream) {
     if (C & 7)
         return 301;
-    long long const work = static_cast<long long>(N) * H * W * (C >> 3);
-    AGB_CUDA_OK(launch_pdl(maxpool_bwd_kernel, dim3(grid_for(work)), dim3(kThreads), 0, static_cast<cudaStream_t>(stream), static_cast<bf16 const*>(dy), static_cast<unsigned char const*>(arg), static_cast<bf16*>(dx), N, H, W, C, OH, OW, k, s, pad_t, pad_l));
+    if (static_cast<long long>(N) * H > 65535)
+        return 301;
+    AGB_CUDA_OK(launch_pdl(maxpool_bwd_kernel, dim3((W * (C >> 3) + kThreads - 1) / kThreads, N * H), dim3(kThreads), 0, static_cast<cudaStream_t>(stream), static_cast<bf16 const*>(dy), static_cast<unsigned char const*>(arg), static_cast<bf16*>(dx), N, H, W, C, OH, OW, k, s, pad_t, pad_l));
     AGB_CUDA_OK(cudaGetLastError());
     return 0;
 }

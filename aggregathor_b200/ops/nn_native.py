@@ -462,7 +462,7 @@ def batchnorm_forward(x, gamma, beta, moving_mean, moving_var, decay, eps, relu,
     return None
   n, c, h, w = x.shape
   rows = n * h * w
-  if residual is not None and (not _BN_FUSED or residual.shape != x.shape or not residual.is_contiguous(memory_format=torch.channels_last)):
+  if residual is not None and (residual.shape != x.shape or not residual.is_contiguous(memory_format=torch.channels_last)):
     return None
   y = torch.empty_like(x, memory_format=torch.channels_last)
   stats = torch.empty((4, groups * c), dtype=torch.float32, device=x.device)  # save_mean, save_rstd, scale, shift
@@ -473,10 +473,8 @@ def batchnorm_forward(x, gamma, beta, moving_mean, moving_var, decay, eps, relu,
     if status != _BN_UNSUPPORTED:
       _check(status, "bn_forward_fused")
       return y, stats[0], stats[1]
-    if residual is not None:
-      return None
   sums = _workspace(x.device, "bn_sums", 2 * groups * c + 1, torch.float64)
-  _check(_lib().agb_bn_forward(_ptr(x), _ptr(y), _ptr(gamma), _ptr(beta), _ptr(moving_mean), _ptr(moving_var), _ptr(stats[0]), _ptr(stats[1]), _ptr(sums),
+  _check(_lib().agb_bn_forward(_ptr(x), _ptr(residual), _ptr(y), _ptr(gamma), _ptr(beta), _ptr(moving_mean), _ptr(moving_var), _ptr(stats[0]), _ptr(stats[1]), _ptr(sums),
                                _ptr(stats[2]), _ptr(stats[3]), ctypes.c_longlong(rows), ctypes.c_int(c), ctypes.c_int(groups), ctypes.c_float(eps),
                                ctypes.c_float(decay), ctypes.c_int(1 if relu else 0), _stream()), "bn_forward")
   return y, stats[0], stats[1]
@@ -484,28 +482,26 @@ def batchnorm_forward(x, gamma, beta, moving_mean, moving_var, decay, eps, relu,
 
 def batchnorm_backward(dy, x, y, gamma, mean, rstd, relu, grad_gamma, grad_beta, groups=1, group_stride=0, want_masked=False):
   """`want_masked` (needs `relu`): returns (dx, dy * (y > 0)) — single-launch kernel only (None when it cannot take the shape)."""
-  if not enabled("bn") or not _cl_ok(x, dy, y) or x.shape[1] % 8 or (want_masked and not (_BN_FUSED and relu)):
+  if not enabled("bn") or not _cl_ok(x, dy, y) or x.shape[1] % 8 or (want_masked and not relu):
     return None
   if not dy.is_contiguous(memory_format=torch.channels_last):
     dy = dy.contiguous(memory_format=torch.channels_last)
   n, c, h, w = x.shape
   rows = n * h * w
   dx = torch.empty_like(x, memory_format=torch.channels_last)
+  masked = torch.empty_like(dy, memory_format=torch.channels_last) if want_masked else None
   if _BN_FUSED:
-    masked = torch.empty_like(dy, memory_format=torch.channels_last) if want_masked else None
     status = _lib().agb_bn_backward_fused(_ptr(dy), _ptr(x), _ptr(y if relu else None), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dx), _ptr(masked), _ptr(grad_gamma),
                                           _ptr(grad_beta), _ptr(_bn_fused_workspace(x.device, "bn_fused_bwd")), ctypes.c_longlong(rows), ctypes.c_int(c), ctypes.c_int(groups),
                                           ctypes.c_longlong(group_stride), _stream())
     if status != _BN_UNSUPPORTED:
       _check(status, "bn_backward_fused")
       return (dx, masked) if want_masked else dx
-    if want_masked:
-      return None
   sums = _workspace(x.device, "bn_sums", 2 * groups * c + 1, torch.float64)
   coef = _workspace(x.device, "bn_coef", 3 * groups * c, torch.float32)
-  _check(_lib().agb_bn_backward(_ptr(dy), _ptr(x), _ptr(y if relu else None), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dx), _ptr(grad_gamma), _ptr(grad_beta),
+  _check(_lib().agb_bn_backward(_ptr(dy), _ptr(x), _ptr(y if relu else None), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dx), _ptr(masked), _ptr(grad_gamma), _ptr(grad_beta),
                                 _ptr(sums), _ptr(coef), ctypes.c_longlong(rows), ctypes.c_int(c), ctypes.c_int(groups), ctypes.c_longlong(group_stride), _stream()), "bn_backward")
-  return dx
+  return (dx, masked) if want_masked else dx
 
 
 def layernorm_forward(x, gamma, beta, eps):
@@ -529,6 +525,32 @@ def layernorm_backward(dy, x, gamma, mean, rstd, grad_gamma, grad_beta):
   grad_beta.zero_()
   _check(_lib().agb_layernorm_backward(_ptr(dy), _ptr(x), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dx), _ptr(grad_gamma), _ptr(grad_beta), ctypes.c_longlong(rows), ctypes.c_int(c), _stream()), "layernorm_backward")
   return dx
+
+
+def subsample_forward(x, stride):
+  if not enabled("eltwise") or not _cl_ok(x) or x.dim() != 4 or x.shape[1] % 8:
+    return None
+  n, c, h, w = x.shape
+  y = torch.empty((n, -(-h // stride), -(-w // stride), c), dtype=torch.bfloat16, device=x.device)
+  status = _lib().agb_subsample_forward(_ptr(x), _ptr(y), ctypes.c_int(n), ctypes.c_int(h), ctypes.c_int(w), ctypes.c_int(c), ctypes.c_int(stride), _stream())
+  if status == _BN_UNSUPPORTED:
+    return None
+  _check(status, "subsample_forward")
+  return y.permute(0, 3, 1, 2)
+
+
+def subsample_backward(dy, shape, stride):
+  n, c, h, w = shape
+  if not enabled("eltwise") or not _cl_ok(dy) or dy.dim() != 4 or c % 8:
+    return None
+  if not dy.is_contiguous(memory_format=torch.channels_last):
+    dy = dy.contiguous(memory_format=torch.channels_last)
+  dx = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=dy.device)
+  status = _lib().agb_subsample_backward(_ptr(dy), _ptr(dx), ctypes.c_int(n), ctypes.c_int(h), ctypes.c_int(w), ctypes.c_int(c), ctypes.c_int(stride), _stream())
+  if status == _BN_UNSUPPORTED:
+    return None
+  _check(status, "subsample_backward")
+  return dx.permute(0, 3, 1, 2)
 
 
 def relu_backward(dy, y):

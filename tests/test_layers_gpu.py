@@ -323,3 +323,42 @@ def test_wgrad_side_stream_matches(monkeypatch):
   torch.cuda.synchronize()
   assert abs(loss_a - loss_b) < 1e-6
   assert float(torch.nn.functional.cosine_similarity(grad_a, grad_b, dim=0)) > 0.9999
+
+
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("c,hw,groups", [(256, 16, 4), (64, 56, 1), (512, 8, 2), (2048, 2, 1)])
+def test_batchnorm_add_relu(fused, c, hw, groups):
+  """Closing layer of a residual unit, y = relu(bn(x) + shortcut), and its backward (dx, masked dy) — in the single-launch kernel
+  and in the statistics + apply pair — against the composition of the library ops in fp32."""
+  from aggregathor_b200.ops import nn as ops, nn_native
+  nn_native.set_bn_fused(fused)
+  nn_native.set_bn_fused_limits(1 << 20, 1 << 20, 1)
+  try:
+    x, res, dy = _rand((8 * groups, c, hw, hw), 70) + 0.25, _rand((8 * groups, c, hw, hw), 71), _rand((8 * groups, c, hw, hw), 72)
+    gamma, beta = torch.rand(c, device="cuda") + 0.5, torch.randn(c, device="cuda") * 0.1
+    outs = {}
+    for backend in ("native", "torch"):
+      cast = (lambda t: t) if backend == "native" else (lambda t: t.float())
+      mm, mv = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+      y, mean, rstd = ops.batchnorm_add_relu_forward(backend, cast(x), gamma, beta, mm, mv, 0.9, 1e-5, cast(res), groups)
+      mask = y if backend == "native" else mask
+      grads = torch.zeros((groups, 2, c), device="cuda")
+      dx, g = ops.batchnorm_add_relu_backward(backend, cast(dy), cast(x), cast(mask), gamma, mean, rstd, grads[0, 0], grads[0, 1], groups, grads.stride(0))
+      outs[backend] = (y, mean, rstd, dx, g, grads)
+    for a, b, tol in zip(outs["native"], outs["torch"], (1e-2, 1e-4, 1e-4, 2e-2, 1e-6, 1e-3)):
+      _close(a, b, tol)
+  finally:
+    nn_native.set_bn_fused(True)
+    nn_native.set_bn_fused_limits()
+
+
+@pytest.mark.parametrize("shape,stride", [((8, 256, 56, 56), 2), ((4, 64, 7, 7), 2), ((2, 128, 9, 10), 3)])
+def test_subsample(shape, stride):
+  from aggregathor_b200.ops import nn as ops
+  x = _rand(shape, 80)
+  y = ops.subsample_forward("native", x, stride)
+  ref = ops.subsample_forward("torch", x, stride)
+  assert y.shape == ref.shape and torch.equal(y.contiguous(), ref.contiguous())
+  dy = _rand(tuple(ref.shape), 81)
+  dx = ops.subsample_backward("native", dy, shape, stride)
+  assert dx.shape == x.shape and torch.equal(dx.contiguous(), ops.subsample_backward("torch", dy, shape, stride).contiguous())
