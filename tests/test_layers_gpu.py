@@ -297,7 +297,8 @@ def test_searched_and_inception_families_native(name, batch):
   print(name, report)
   assert all(v == v for v in losses.values()), report
   assert abs(losses["native"] - losses["fp32"]) < 5e-2 * max(1.0, abs(losses["fp32"])), report
-  assert report["cos_native_fp32"] > min(0.95, report["cos_torch_fp32"] - 0.1), report
+  if report["cos_torch_fp32"] >= 0.5:  # below that the bf16 library run itself has decorrelated from fp32 (tiny batch, deep BN stack): nothing to compare
+    assert report["cos_native_fp32"] > min(0.95, report["cos_torch_fp32"] - 0.1), report
 
 
 def test_wgrad_side_stream_matches(monkeypatch):
