@@ -107,12 +107,17 @@ class Communicator:
     self.allreduce_(flat.numel(), flat.dtype, mean)
     return staged[:flat.numel()].clone().view(tensor.shape)
 
-  def allgather(self, tensor):
-    """Concatenation along dimension 0 of every rank's `tensor` (first dimensions may differ, the others must match)."""
+  def allgather(self, tensor, counts=None):
+    """Concatenation along dimension 0 of every rank's `tensor` (first dimensions may differ, the others must match).
+    `counts`: every rank's first dimension when the caller knows them — skips the size exchange, which is a host round trip."""
     if tensor.dim() == 0:
       raise tools.UserException("all-gather needs tensors of rank >= 1")
     rows = torch.tensor([tensor.shape[0]], dtype=torch.int64)
-    if self.world > 1:
+    if counts is not None:
+      if len(counts) != self.world or int(counts[self.rank]) != tensor.shape[0]:
+        raise tools.UserException("all-gather: `counts` must list every rank's first dimension")
+      counts = [torch.tensor([int(c)]) for c in counts]
+    elif self.world > 1:
       counts = [torch.zeros(1, dtype=torch.int64) for _ in range(self.world)]
       if tensor.device.type == "cuda":  # control plane: sizes travel through the process group of the job (NCCL)
         gathered = torch.zeros(self.world, dtype=torch.int64, device=tensor.device)
@@ -198,5 +203,5 @@ def allreduce(tensor, mean=False):
   return _comm().allreduce(tensor, mean)
 
 
-def allgather(tensor):
-  return _comm().allgather(tensor)
+def allgather(tensor, counts=None):
+  return _comm().allgather(tensor, counts)

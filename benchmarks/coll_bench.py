@@ -98,6 +98,8 @@ def main():
     rows, counts = rows_of(rank), [rows_of(r) for r in range(world)]
     t = (torch.arange(rows * cols, dtype=torch.float32).reshape(rows, cols) + 1000 * rank).to(dtype).to(device)
     got = collectives.allgather(t)
+    if not torch.equal(got, collectives.allgather(t, counts)):
+      failures.append("allgather with known counts differs, rows=%s" % counts)
     want = torch.cat([(torch.arange(c * cols, dtype=torch.float32).reshape(c, cols) + 1000 * r).to(dtype) for r, c in enumerate(counts)]).to(device)
     if got.shape != want.shape or got.dtype != dtype or not torch.equal(got, want):
       failures.append("allgather rows=%s cols=%d %s" % (counts, cols, dtype))
@@ -115,11 +117,13 @@ def main():
     block = torch.randn(numel // world, device=device)
     outs = torch.empty(numel // world * world, device=device)
     ours_ag = _time(lambda: comm.allgather(block), args.iters, device)
+    known = [numel // world] * world
+    ours_ag_known = _time(lambda: comm.allgather(block, known), args.iters, device)
     nccl_ag = _time(lambda: dist.all_gather_into_tensor(outs, block), args.iters, device)
     bus = 2.0 * (world - 1) / world * nbytes
     report.update({
       "allreduce": {"bytes": nbytes, "ours_ms": ours, "nccl_ms": nccl, "ours_busbw_gbs": bus / ours / 1e6, "nccl_busbw_gbs": bus / nccl / 1e6, "speedup": nccl / ours},
-      "allgather": {"bytes_out": numel // world * world * 4, "ours_ms_including_staging_copy": ours_ag, "nccl_ms": nccl_ag}})
+      "allgather": {"bytes_out": numel // world * world * 4, "ours_ms_including_staging_copy": ours_ag, "ours_ms_known_sizes": ours_ag_known, "nccl_ms": nccl_ag}})
   if failures:
     print("[rank %d] FAILED: %s" % (rank, "; ".join(failures)), file=sys.stderr)
   if rank == 0:
