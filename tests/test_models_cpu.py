@@ -200,3 +200,37 @@ def test_new_families_step(name, shape):
   assert float(layout.view(grads, layout.names[0]).abs().sum()) > 0 and float(layout.view(grads, layout.names[-1]).abs().sum()) > 0
   ctx.training = False
   assert 0.0 <= float(model.accuracy(x, labels, ctx)) <= 1.0
+
+
+def test_drop_path_and_dropout_masks():
+  """Per-sample drop-path and element-wise dropout: kept entries are rescaled by 1 / keep_prob, backward applies the same mask,
+  evaluation is the identity."""
+  from aggregathor_b200.models.core import DropPath, Dropout
+  ctx = Context("torch", True, torch.float32, "cpu")
+  ctx.generator = torch.Generator().manual_seed(3)
+  x = torch.ones((64, 4, 3, 3))
+  for module, per_sample in ((DropPath("dp", 0.75), True), (Dropout("do", 0.75), False)):
+    y = module.forward(x, ctx)
+    kept = y != 0
+    assert torch.allclose(y[kept], torch.full_like(y[kept], 1 / 0.75))
+    assert 0.5 < float(kept.float().mean()) < 0.95
+    if per_sample:
+      flat = kept.reshape(64, -1)
+      assert bool((flat.all(dim=1) | (~flat).all(dim=1)).all())     # a sample is kept or dropped as a whole
+    dx = module.backward(torch.ones_like(x), ctx)
+    assert torch.equal(dx, y)
+    ctx.training = False
+    assert module.forward(x, ctx) is x
+    ctx.training = True
+
+
+def test_graph_module_accumulates_fanout_gradients():
+  """A value consumed by several nodes receives the sum of their gradients; multi-input graphs return one gradient per input."""
+  from aggregathor_b200.models.core import Add, Concat, Graph, Scale
+  ctx = Context("torch", True, torch.float64, "cpu")
+  graph = Graph("g", [(Scale("a", 2.0), (0,)), (Scale("b", 3.0), (0,)), (Add("sum"), (2, 3)), (Concat("cat"), (4, 1)), (Scale("c", 0.5), (5,))], nb_inputs=2)
+  x0, x1 = torch.randn(2, 3, 4, 4, dtype=torch.float64), torch.randn(2, 5, 4, 4, dtype=torch.float64)
+  y = graph.forward([x0, x1], ctx)
+  assert torch.allclose(y, 0.5 * torch.cat([5.0 * x0, x1], dim=1))
+  g0, g1 = graph.backward(torch.ones_like(y), ctx)
+  assert torch.allclose(g0, torch.full_like(x0, 2.5)) and torch.allclose(g1, torch.full_like(x1, 0.5))
