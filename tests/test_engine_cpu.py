@@ -199,3 +199,21 @@ def test_two_process_authenticated_run(tmp_path):
   assert len({slot for _, slot, _ in dropped}) == 1
   losses = [float(x) for x in re.findall(r"Step \d+: total loss = ([0-9.eE+-]+)", out)]
   assert all(l == l and l < 100 for l in losses), losses
+
+
+def test_deploy_local_cluster_with_lossy_workers(tmp_path):
+  """`deploy.py --deploy` on a local cluster specification: two CPU ranks as child processes, `--UDP 1` turns one worker into a
+  lossy-transport (drop-chunks) worker, the NaN-aware rule trains through it, the deployer exits 0 when its ranks are done."""
+  port = 7200 + os.getpid() % 500
+  cluster = '{"ps": ["127.0.0.1:%d"], "workers": ["127.0.0.1:%d", "127.0.0.1:%d"]}' % (port, port + 1, port + 2)
+  runner = ("--experiment mnist --aggregator average-nan --nb-workers 4 --nb-decl-byz-workers 1 --max-step 5 --learning-rate-args initial-rate:0.05 "
+            "--evaluation-file - --checkpoint-dir %s --checkpoint-delta -1 --checkpoint-period -1 --summary-dir -" % (tmp_path / "c"))
+  env = dict(os.environ, AGB_NUM_THREADS="2", OMP_NUM_THREADS="2")
+  proc = subprocess.run([sys.executable, str(ROOT / "deploy.py"), "--cluster", cluster, "--deploy", "--UDP", "1", "--MPI", "--runner", runner],
+                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600, env=env, cwd=str(ROOT))
+  out = proc.stdout.decode(errors="replace")
+  assert proc.returncode == 0, out[-3000:]
+  assert "rank 0/2" in out and "rank 1/2" in out and "'--MPI' is accepted for compatibility" in out
+  losses = [float(x) for x in re.findall(r"Step \d+: total loss = ([0-9.eE+-]+)", out)]
+  assert len(losses) == 5 and all(l == l for l in losses) and losses[-1] < losses[0]
+  assert "drop-chunks" in out
