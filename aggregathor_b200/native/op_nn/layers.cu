@@ -1292,9 +1292,16 @@ int agb_maxpool_forward(void const* x, void* y, void* arg, int N, int H, int W, 
 int agb_maxpool_backward(void const* dy, void const* arg, void* dx, int N, int H, int W, int C, int OH, int OW, int k, int s, int pad_t, int pad_l, void* stream) {
     if (C & 7)
         return 301;
-    if (static_cast<long long>(N) * H > 65535)
+    if (H > 65535)
         return 301;
-    AGB_CUDA_OK(launch_pdl(maxpool_bwd_kernel, dim3((W * (C >> 3) + kThreads - 1) / kThreads, N * H), dim3(kThreads), 0, static_cast<cudaStream_t>(stream), static_cast<bf16 const*>(dy), static_cast<unsigned char const*>(arg), static_cast<bf16*>(dx), N, H, W, C, OH, OW, k, s, pad_t, pad_l));
+    // grid.y = images x rows is limited to 65535: very large batches go in slices of whole images
+    int const per_launch = 65535 / H;
+    for (int n0 = 0; n0 < N; n0 += per_launch) {
+        int const count = N - n0 < per_launch ? N - n0 : per_launch;
+        AGB_CUDA_OK(launch_pdl(maxpool_bwd_kernel, dim3((W * (C >> 3) + kThreads - 1) / kThreads, count * H), dim3(kThreads), 0, static_cast<cudaStream_t>(stream),
+            static_cast<bf16 const*>(dy) + static_cast<long long>(n0) * OH * OW * C, static_cast<unsigned char const*>(arg) + static_cast<long long>(n0) * OH * OW * C,
+            static_cast<bf16*>(dx) + static_cast<long long>(n0) * H * W * C, count, H, W, C, OH, OW, k, s, pad_t, pad_l));
+    }
     AGB_CUDA_OK(cudaGetLastError());
     return 0;
 }
