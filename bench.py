@@ -198,7 +198,7 @@ def main():
     line = {
       "metric": "steps/sec (whole box, device-timed, max over ranks) ResNet-50 slim + Krum f=2", "value": value, "unit": "steps/s", "n_gpus": world,
       "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-      "dtype": str(manager.dtype).replace("torch.", ""), "data": "synthetic (ImageNet-shaped uint8 images, random-init weights)", "impl": args.impl,
+      "dtype": {"bfloat16": "bf16", "float16": "fp16", "float32": "fp32"}.get(str(manager.dtype).replace("torch.", ""), str(manager.dtype)), "data": "synthetic (ImageNet-shaped uint8 images, random-init weights)", "impl": args.impl,
       "config": {"model": "slim-" + args.model + "-" + args.dataset, "aggregator": args.aggregator, "nb_workers": n, "nb_decl_byz_workers": f,
                  "global_batch": n * args.batch_size, "per_worker_batch": args.batch_size, "image_size": manager.model.input_shape[-1], "seq_len": None,
                  "parallelism": "dp%d (x%d logical workers per GPU)" % (world, n // world), "engine": manager.aggregation.name, "nn_backend": manager.backend,
