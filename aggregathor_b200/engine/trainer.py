@@ -162,8 +162,8 @@ class Manager:
 
   @staticmethod
   def _has_dropout(module):
-    from ..models.core import Dropout
-    if isinstance(module, Dropout):
+    from ..models.core import DropPath, Dropout
+    if isinstance(module, (Dropout, DropPath)) and module.keep_prob < 1.0:
       return True
     return any(Manager._has_dropout(child) for child in module.children())
 
