@@ -38,6 +38,9 @@ def parse():
   parser.add_argument("--aggregator", type=str, default="krum")
   parser.add_argument("--nb-workers", type=int, default=8)
   parser.add_argument("--nb-decl-byz-workers", type=int, default=2)
+  parser.add_argument("--nb-real-byz-workers", type=int, default=0, help="the last k logical workers run --attack (BASELINE.json config 5: 2 + flip)")
+  parser.add_argument("--attack", type=str, default="")
+  parser.add_argument("--attack-args", nargs="*", default=[])
   parser.add_argument("--batch-size", type=int, default=32, help="per logical worker")
   parser.add_argument("--image-size", type=int, default=0)
   parser.add_argument("--nn-backend", type=str, default="auto")
@@ -95,7 +98,7 @@ def main():
   import torch
   import torch.distributed as dist
   sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-  from aggregathor_b200 import aggregators, experiments, tools
+  from aggregathor_b200 import aggregators, attacks, experiments, tools
   from aggregathor_b200.engine.trainer import Manager
   from aggregathor_b200.ops import counters
 
@@ -124,7 +127,9 @@ def main():
   gar = aggregators.instantiate(args.aggregator, n, f, [])
   engine = args.engine or ("fused" if args.impl == "ours" else "baseline")
   backend = args.nn_backend if args.impl == "ours" else "torch"
-  manager = Manager(experiment, gar, n, "sgd", [], "fixed", ["initial-rate:0.01"], device=device, engine=engine, backend=backend, seed=0)
+  attack = attacks.instantiate(args.attack, n, f, args.attack_args) if (args.attack and args.nb_real_byz_workers > 0) else None
+  manager = Manager(experiment, gar, n, "sgd", [], "fixed", ["initial-rate:0.01"], device=device, engine=engine, backend=backend, seed=0,
+                    attack=attack, nb_real_byz=args.nb_real_byz_workers if attack is not None else 0)
 
   def sync():
     torch.cuda.synchronize(device)
@@ -193,10 +198,13 @@ def main():
     e2e = {"value": args.steps / (e2e_ms / 1000.0), "unit": "steps/s", "ms_per_step": e2e_ms / args.steps,
            "h2d_bytes_per_step": int(h2d.item()), "d2h_bytes_per_step": 4 * world, "last_loss": losses[-1] if losses else None}
 
+  headline = (args.model, args.aggregator, n, f, attack) == ("resnet_v1_50", "krum", 8, 2, None)
+  metric = "steps/sec (whole box, device-timed, max over ranks) ResNet-50 slim + Krum f=2" if headline else (
+    "steps/sec (whole box, device-timed, max over ranks) %s + %s n=%d f=%d%s" % (args.model, args.aggregator, n, f, (" attack=" + args.attack) if attack is not None else ""))
   if rank == 0:
     sys.stdout = sys.__stdout__
     line = {
-      "metric": "steps/sec (whole box, device-timed, max over ranks) ResNet-50 slim + Krum f=2", "value": value, "unit": "steps/s", "n_gpus": world,
+      "metric": metric, "value": value, "unit": "steps/s", "n_gpus": world,
       "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
       "dtype": {"bfloat16": "bf16", "float16": "fp16", "float32": "fp32"}.get(str(manager.dtype).replace("torch.", ""), str(manager.dtype)), "data": "synthetic (ImageNet-shaped uint8 images, random-init weights)", "impl": args.impl,
       "config": {"model": "slim-" + args.model + "-" + args.dataset, "aggregator": args.aggregator, "nb_workers": n, "nb_decl_byz_workers": f,
