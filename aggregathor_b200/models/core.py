@@ -531,8 +531,8 @@ class Branches(Module):
 
 class DepthwiseConv2d(Module):
   """Depthwise k x k convolution (TF "SAME" padding), `multiplier` output channels per input channel (slim
-  `separable_conv2d(..., depth_multiplier)` first half). Weights [C * multiplier, k, k, 1]. Runs through the aten provider
-  (grouped convolution): a depthwise filter has no GEMM shape to put on the tensor cores."""
+  `separable_conv2d(..., depth_multiplier)` first half). Weights [C * multiplier, k, k, 1]. A depthwise filter has no GEMM shape to
+  put on the tensor cores: bandwidth kernels in `native/op_nn/depthwise.cu` (opt-in until validated on a B200), aten otherwise."""
 
   def __init__(self, name, channels, k, stride, multiplier=1, init_std=0.09):
     super().__init__(name)
@@ -546,24 +546,16 @@ class DepthwiseConv2d(Module):
 
   def forward(self, x, ctx):
     n, c, h, w = x.shape
-    t, b = same_padding(h, self.k, self.stride)
-    l, r = same_padding(w, self.k, self.stride)
-    xp = F.pad(x, (l, r, t, b))
-    self._saved = (xp, (t, b, l, r), (h, w))
-    weight = ctx.weights[self.name + "/depthwise_weights"].permute(0, 3, 1, 2)
-    return F.conv2d(xp, weight, None, self.stride, 0, 1, c).contiguous(memory_format=torch.channels_last)
+    pads = same_padding(h, self.k, self.stride) + same_padding(w, self.k, self.stride)
+    if ctx.training:
+      self._saved = (x, pads)
+    return nn_ops.depthwise_forward(ctx.backend, x, ctx.weights[self.name + "/depthwise_weights"], self.stride, pads)
 
   def backward(self, dy, ctx):
-    xp, (t, b, l, r), (h, w) = self._saved
+    x, pads = self._saved
     self._saved = None
-    weight = ctx.weights[self.name + "/depthwise_weights"].permute(0, 3, 1, 2)
-    pieces = []
-    for g, (dy_g, xp_g) in enumerate(zip(dy.chunk(ctx.groups, dim=0), xp.chunk(ctx.groups, dim=0))):
-      dxp, dw, _ = torch.ops.aten.convolution_backward(dy_g, xp_g, weight, None, [self.stride] * 2, [0, 0], [1, 1], False, [0, 0], self.channels, [True, True, False])
-      nn_ops.group_view(ctx.grads[self.name + "/depthwise_weights"], g, ctx.group_stride).copy_(dw.permute(0, 2, 3, 1))
-      pieces.append(dxp)
-    dxp = pieces[0] if len(pieces) == 1 else torch.cat(pieces, dim=0)
-    return dxp[:, :, t:t + h, l:l + w].contiguous(memory_format=torch.channels_last)
+    return nn_ops.depthwise_backward(ctx.backend, dy, x, ctx.weights[self.name + "/depthwise_weights"], self.stride, pads, ctx.grads[self.name + "/depthwise_weights"],
+                                     ctx.groups, ctx.group_stride)
 
 
 class ReLU6(Module):

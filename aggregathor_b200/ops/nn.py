@@ -105,6 +105,38 @@ def conv2d_backward(backend, dy, x, weight, y, stride, pads, relu, has_bias, nee
 
 
 # ---------------------------------------------------------------------------- #
+# Depthwise convolution (weights [C * multiplier, k, k, 1]; `pads` = (top, bottom, left, right))
+
+def depthwise_forward(backend, x, weight, stride, pads):
+  if backend == "native" and x.is_cuda:
+    out = _native().depthwise_forward(x, weight, stride, pads)
+    if out is not None:
+      return out
+  t, b, l, r = pads
+  xp = F.pad(x, (l, r, t, b))
+  return F.conv2d(xp, weight.permute(0, 3, 1, 2), None, stride, 0, 1, x.shape[1]).contiguous(memory_format=_CL)
+
+
+def depthwise_backward(backend, dy, x, weight, stride, pads, grad_w, groups=1, group_stride=0):
+  """Returns dx; the weight gradient of every logical worker goes into its row (`grad_w` = worker 0's [C * multiplier, k, k, 1] view)."""
+  if backend == "native" and x.is_cuda:
+    out = _native().depthwise_backward(dy, x, weight, stride, pads, grad_w, groups, group_stride)
+    if out is not None:
+      return out
+  t, b, l, r = pads
+  n, c, h, w = x.shape
+  xp = F.pad(x, (l, r, t, b))
+  kernel = weight.permute(0, 3, 1, 2)
+  pieces = []
+  for g, (dy_g, xp_g) in enumerate(zip(_chunks(dy, groups), _chunks(xp, groups))):
+    dxp, dw, _ = torch.ops.aten.convolution_backward(dy_g, xp_g, kernel, None, [stride, stride], [0, 0], [1, 1], False, [0, 0], c, [True, True, False])
+    group_view(grad_w, g, group_stride).copy_(dw.permute(0, 2, 3, 1))
+    pieces.append(dxp)
+  dxp = pieces[0] if len(pieces) == 1 else torch.cat(pieces, dim=0)
+  return dxp[:, :, t:t + h, l:l + w].contiguous(memory_format=_CL)
+
+
+# ---------------------------------------------------------------------------- #
 # Dense
 
 def linear_forward(backend, x, weight, bias, relu):

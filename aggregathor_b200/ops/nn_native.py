@@ -527,6 +527,55 @@ def layernorm_backward(dy, x, gamma, mean, rstd, grad_gamma, grad_beta):
   return dx
 
 
+# ---------------------------------------------------------------------------- #
+# Depthwise convolution (native/op_nn/depthwise.cu). Written after this round's GPU budget was spent: compiled and covered by
+# gated tests (`AGB_NATIVE_DEPTHWISE=1`), off by default until validated on a B200 — the aten grouped convolution is used otherwise.
+
+_DEPTHWISE = os.environ.get("AGB_NATIVE_DEPTHWISE", "0") not in ("", "0")
+
+
+def _depthwise_ok(x, weight):
+  return (_DEPTHWISE and enabled("depthwise") and _cl_ok(x) and x.dim() == 4 and x.shape[1] % 8 == 0 and weight.shape[0] == x.shape[1] and weight.shape[1] == weight.shape[2]
+          and weight.dtype == torch.bfloat16)
+
+
+def _transposed_taps(weight):
+  """[C, k, k, 1] bf16 -> [k*k, C]: the 8 channels of a thread become one 16-byte load per tap."""
+  c, k = weight.shape[0], weight.shape[1]
+  return weight.reshape(c, k * k).t().contiguous()
+
+
+def depthwise_forward(x, weight, stride, pads):
+  if not _depthwise_ok(x, weight):
+    return None
+  n, c, h, w = x.shape
+  k = weight.shape[1]
+  oh, ow = _out_size(h, k, stride, pads[0], pads[1]), _out_size(w, k, stride, pads[2], pads[3])
+  y = torch.empty((n, oh, ow, c), dtype=torch.bfloat16, device=x.device)
+  _check(_lib().agb_depthwise_forward(_ptr(x), _ptr(_transposed_taps(weight)), _ptr(y), ctypes.c_int(n), ctypes.c_int(h), ctypes.c_int(w), ctypes.c_int(c), ctypes.c_int(oh),
+                                      ctypes.c_int(ow), ctypes.c_int(k), ctypes.c_int(stride), ctypes.c_int(pads[0]), ctypes.c_int(pads[2]), _stream()), "depthwise_forward")
+  return y.permute(0, 3, 1, 2)
+
+
+def depthwise_backward(dy, x, weight, stride, pads, grad_w, groups=1, group_stride=0):
+  """Returns dx; writes the per-worker weight gradients into `grad_w` ([C, k, k, 1] fp32 view of worker 0's row)."""
+  if not _depthwise_ok(x, weight) or dy.dtype != torch.bfloat16:
+    return None
+  if not dy.is_contiguous(memory_format=torch.channels_last):
+    dy = dy.contiguous(memory_format=torch.channels_last)
+  n, c, h, w = x.shape
+  k = weight.shape[1]
+  oh, ow = dy.shape[2], dy.shape[3]
+  geometry = (ctypes.c_int(n), ctypes.c_int(h), ctypes.c_int(w), ctypes.c_int(c), ctypes.c_int(oh), ctypes.c_int(ow), ctypes.c_int(k), ctypes.c_int(stride),
+              ctypes.c_int(pads[0]), ctypes.c_int(pads[2]))
+  if not _prezeroed:
+    _all_groups(grad_w, groups, group_stride).zero_()
+  _check(_lib().agb_depthwise_wgrad(_ptr(dy), _ptr(x), _ptr(grad_w), *geometry, ctypes.c_int(groups), ctypes.c_longlong(group_stride), _stream()), "depthwise_wgrad")
+  dx = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=x.device)
+  _check(_lib().agb_depthwise_dgrad(_ptr(dy), _ptr(_transposed_taps(weight)), _ptr(dx), *geometry, _stream()), "depthwise_dgrad")
+  return dx.permute(0, 3, 1, 2)
+
+
 def subsample_forward(x, stride):
   if not enabled("eltwise") or not _cl_ok(x) or x.dim() != 4 or x.shape[1] % 8:
     return None

@@ -363,3 +363,25 @@ def test_subsample(shape, stride):
   dy = _rand(tuple(ref.shape), 81)
   dx = ops.subsample_backward("native", dy, shape, stride)
   assert dx.shape == x.shape and torch.equal(dx.contiguous(), ops.subsample_backward("torch", dy, shape, stride).contiguous())
+
+
+@pytest.mark.skipif(__import__("os").environ.get("AGB_NATIVE_DEPTHWISE", "0") in ("", "0"), reason="native depthwise kernels are opt-in (AGB_NATIVE_DEPTHWISE=1) until validated on a B200")
+@pytest.mark.parametrize("c,hw,k,stride,groups", [(64, 28, 3, 1, 1), (128, 14, 3, 2, 2), (88, 21, 5, 2, 1), (176, 11, 7, 1, 4), (32, 9, 7, 2, 1)])
+def test_depthwise_native(c, hw, k, stride, groups):
+  """Depthwise forward / data gradient / per-worker weight gradient kernels vs the aten grouped convolution in fp32."""
+  from aggregathor_b200.models.core import same_padding
+  from aggregathor_b200.ops import nn as ops
+  x, weight = _rand((4 * groups, c, hw, hw), 90), (_rand((c, k, k, 1), 91) * 0.2).contiguous()
+  pads = same_padding(hw, k, stride) + same_padding(hw, k, stride)
+  y = ops.depthwise_forward("native", x, weight, stride, pads)
+  ref = ops.depthwise_forward("torch", x.float(), weight.float(), stride, pads)
+  _close(y, ref, 1e-2)
+  dy = _rand(tuple(ref.shape), 92)
+  grads = {}
+  for backend in ("native", "torch"):
+    rows = torch.zeros((groups, c, k, k, 1), device="cuda")
+    cast = (lambda t: t) if backend == "native" else (lambda t: t.float())
+    dx = ops.depthwise_backward(backend, cast(dy), cast(x), cast(weight), stride, pads, rows[0], groups, rows.stride(0))
+    grads[backend] = (dx, rows)
+  _close(grads["native"][0], grads["torch"][0], 2e-2)
+  _close(grads["native"][1], grads["torch"][1], 2e-2)
