@@ -341,13 +341,20 @@ class AvgPool(Module):
   def forward(self, x, ctx):
     n, c, h, w = x.shape
     pads = (same_padding(h, self.k, self.stride) + same_padding(w, self.k, self.stride)) if self.padding == "SAME" else (0, 0, 0, 0)
+    native = nn_ops.avgpool2d_forward(ctx.backend, x, self.k, self.stride, pads)
+    if native is not None:
+      self._saved = (tuple(x.shape), None, pads)
+      return native
     xp = F.pad(x, (pads[2], pads[3], pads[0], pads[1])) if any(pads) else x
     self._saved = (xp.shape, (h, w), pads)
     y = F.avg_pool2d(xp, self.k, self.stride, divisor_override=1) * self._count(h, w, pads, x)
     return y.contiguous(memory_format=torch.channels_last)
 
   def backward(self, dy, ctx):
-    shape, (h, w), pads = self._saved
+    shape, size, pads = self._saved
+    if size is None:
+      return nn_ops.avgpool2d_backward(ctx.backend, dy, shape, self.k, self.stride, pads)
+    h, w = size
     dy = (dy * self._count(h, w, pads, dy)).contiguous(memory_format=torch.channels_last)
     proto = torch.empty(shape, dtype=dy.dtype, device=dy.device).contiguous(memory_format=torch.channels_last)
     dxp = torch.ops.aten.avg_pool2d_backward(dy, proto, [self.k, self.k], [self.stride, self.stride], [0, 0], False, True, 1)
@@ -561,11 +568,11 @@ class DepthwiseConv2d(Module):
 class ReLU6(Module):
   def forward(self, x, ctx):
     self._saved_x = x
-    return torch.clamp(x, 0.0, 6.0)
+    return nn_ops.relu6_forward(ctx.backend, x)
 
   def backward(self, dy, ctx):
     x, self._saved_x = self._saved_x, None
-    return dy * ((x > 0) & (x < 6)).to(dy.dtype)
+    return nn_ops.relu6_backward(ctx.backend, dy, x)
 
 
 class Scale(Module):

@@ -203,3 +203,141 @@ int agb_depthwise_wgrad(void const* dy, void const* x, void* dw, int N, int H, i
 }
 
 } // extern "C"
+
+// ---------------------------------------------------------------------------- //
+// Average pooling with TF "SAME" semantics (the divisor counts only the pixels inside the image) and ReLU6 — the remaining
+// element-wise layers of the Inception / MobileNet / NASNet graphs.
+
+namespace {
+
+// y[n, oh, ow, c] = mean over the in-image pixels of the k x k window at (oh*s - pad_t, ow*s - pad_l)
+__global__ void __launch_bounds__(kThreads) avgpool2d_fwd_kernel(bf16 const* __restrict__ x, bf16* __restrict__ y, Geometry const g, int first_image) {
+    int const octets = g.C >> 3;
+    int const n = first_image + blockIdx.y / g.OH, oh = blockIdx.y % g.OH;
+    int const h0 = max(0, oh * g.s - g.pad_t), h1 = min(g.H, oh * g.s - g.pad_t + g.k);
+    uint4* const out_row = reinterpret_cast<uint4*>(y) + (static_cast<long long>(n) * g.OH + oh) * g.OW * octets;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < g.OW * octets; i += gridDim.x * blockDim.x) {
+        int const ow = i / octets, o = i - ow * octets;
+        int const w0 = max(0, ow * g.s - g.pad_l), w1 = min(g.W, ow * g.s - g.pad_l + g.k);
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int ih = h0; ih < h1; ++ih)
+            for (int iw = w0; iw < w1; ++iw) {
+                float v[8];
+                unpack8(reinterpret_cast<uint4 const*>(x)[((static_cast<long long>(n) * g.H + ih) * g.W + iw) * octets + o], v);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    acc[j] += v[j];
+            }
+        float const inv = 1.f / static_cast<float>(max(1, (h1 - h0) * (w1 - w0)));
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            acc[j] *= inv;
+        out_row[i] = pack8(acc);
+    }
+}
+
+// dx[n, h, w, c] = sum over the windows containing (h, w) of dy[n, oh, ow, c] / (in-image size of that window)
+__global__ void __launch_bounds__(kThreads) avgpool2d_bwd_kernel(bf16 const* __restrict__ dy, bf16* __restrict__ dx, Geometry const g, int first_image) {
+    int const octets = g.C >> 3;
+    int const n = first_image + blockIdx.y / g.H, h = blockIdx.y % g.H;
+    uint4* const out_row = reinterpret_cast<uint4*>(dx) + (static_cast<long long>(n) * g.H + h) * g.W * octets;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < g.W * octets; i += gridDim.x * blockDim.x) {
+        int const w = i / octets, o = i - w * octets;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int kh = 0; kh < g.k; ++kh) {
+            int const th = h + g.pad_t - kh;
+            if (th < 0 || th % g.s)
+                continue;
+            int const oh = th / g.s;
+            if (oh >= g.OH)
+                continue;
+            int const rows = min(g.H, oh * g.s - g.pad_t + g.k) - max(0, oh * g.s - g.pad_t);
+            for (int kw = 0; kw < g.k; ++kw) {
+                int const tw = w + g.pad_l - kw;
+                if (tw < 0 || tw % g.s)
+                    continue;
+                int const ow = tw / g.s;
+                if (ow >= g.OW)
+                    continue;
+                int const cols = min(g.W, ow * g.s - g.pad_l + g.k) - max(0, ow * g.s - g.pad_l);
+                float v[8];
+                unpack8(reinterpret_cast<uint4 const*>(dy)[((static_cast<long long>(n) * g.OH + oh) * g.OW + ow) * octets + o], v);
+                float const inv = 1.f / static_cast<float>(max(1, rows * cols));
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    acc[j] += v[j] * inv;
+            }
+        }
+        out_row[i] = pack8(acc);
+    }
+}
+
+// forward: y = min(max(x, 0), 6); backward: dx = dy where 0 < x < 6
+__global__ void __launch_bounds__(kThreads) relu6_kernel(bf16 const* __restrict__ x, bf16 const* __restrict__ dy, bf16* __restrict__ out, long long octets) {
+    long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    long long const stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (; i < octets; i += stride) {
+        float v[8];
+        unpack8(reinterpret_cast<uint4 const*>(x)[i], v);
+        if (dy) {
+            float d[8];
+            unpack8(reinterpret_cast<uint4 const*>(dy)[i], d);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                v[j] = (v[j] > 0.f && v[j] < 6.f) ? d[j] : 0.f;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                v[j] = fminf(fmaxf(v[j], 0.f), 6.f);
+        }
+        reinterpret_cast<uint4*>(out)[i] = pack8(v);
+    }
+}
+
+} // namespace
+
+extern "C" {
+
+int agb_avgpool2d_forward(void const* x, void* y, int N, int H, int W, int C, int OH, int OW, int k, int s, int pad_t, int pad_l, void* stream) {
+    Geometry const g{N, H, W, C, OH, OW, k, s, pad_t, pad_l};
+    if (int status = check(g))
+        return status;
+    int const per_launch = 65535 / OH;
+    for (int n0 = 0; n0 < N; n0 += per_launch) {
+        int const count = N - n0 < per_launch ? N - n0 : per_launch;
+        AGB_CUDA_OK(launch_pdl(avgpool2d_fwd_kernel, dim3((OW * (C >> 3) + kThreads - 1) / kThreads, count * OH), dim3(kThreads), 0, static_cast<cudaStream_t>(stream),
+                               static_cast<bf16 const*>(x), static_cast<bf16*>(y), g, n0));
+    }
+    AGB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int agb_avgpool2d_backward(void const* dy, void* dx, int N, int H, int W, int C, int OH, int OW, int k, int s, int pad_t, int pad_l, void* stream) {
+    Geometry const g{N, H, W, C, OH, OW, k, s, pad_t, pad_l};
+    if (int status = check(g))
+        return status;
+    int const per_launch = 65535 / H;
+    for (int n0 = 0; n0 < N; n0 += per_launch) {
+        int const count = N - n0 < per_launch ? N - n0 : per_launch;
+        AGB_CUDA_OK(launch_pdl(avgpool2d_bwd_kernel, dim3((W * (C >> 3) + kThreads - 1) / kThreads, count * H), dim3(kThreads), 0, static_cast<cudaStream_t>(stream),
+                               static_cast<bf16 const*>(dy), static_cast<bf16*>(dx), g, n0));
+    }
+    AGB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// dy == null: forward clamp of x; otherwise the backward mask applied to dy.
+int agb_relu6(void const* x, void const* dy, void* out, long long n, void* stream) {
+    if (n & 7)
+        return 301;
+    long long const octets = n / 8;
+    long long blocks = (octets + kThreads - 1) / kThreads;
+    if (blocks > 148 * 16)
+        blocks = 148 * 16;
+    AGB_CUDA_OK(launch_pdl(relu6_kernel, dim3(static_cast<unsigned>(blocks < 1 ? 1 : blocks)), dim3(kThreads), 0, static_cast<cudaStream_t>(stream), static_cast<bf16 const*>(x),
+                           static_cast<bf16 const*>(dy), static_cast<bf16*>(out), octets));
+    AGB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+} // extern "C"

@@ -331,6 +331,35 @@ def maxpool_backward(backend, dy, shape, index, k, stride, pads, x, y):
   return dxp[:, :, t:t + h, l:l + w].contiguous(memory_format=_CL)
 
 
+def avgpool2d_forward(backend, x, k, stride, pads):
+  """Native k x k average pool with the TF "SAME" divisor, or None (the caller keeps its aten implementation)."""
+  if backend == "native" and x.is_cuda:
+    return _native().avgpool2d_forward(x, k, stride, pads)
+  return None
+
+
+def avgpool2d_backward(backend, dy, shape, k, stride, pads):
+  if backend == "native" and dy.is_cuda:
+    return _native().avgpool2d_backward(dy, shape, k, stride, pads)
+  return None
+
+
+def relu6_forward(backend, x):
+  if backend == "native" and x.is_cuda:
+    out = _native().relu6(x)
+    if out is not None:
+      return out
+  return torch.clamp(x, 0.0, 6.0)
+
+
+def relu6_backward(backend, dy, x):
+  if backend == "native" and x.is_cuda:
+    out = _native().relu6(x, dy)
+    if out is not None:
+      return out
+  return dy * ((x > 0) & (x < 6)).to(dy.dtype)
+
+
 def global_avgpool_forward(backend, x):
   if backend == "native" and x.is_cuda:
     out = _native().global_avgpool_forward(x)

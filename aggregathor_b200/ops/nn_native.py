@@ -528,10 +528,11 @@ def layernorm_backward(dy, x, gamma, mean, rstd, grad_gamma, grad_beta):
 
 
 # ---------------------------------------------------------------------------- #
-# Depthwise convolution (native/op_nn/depthwise.cu). Written after this round's GPU budget was spent: compiled and covered by
-# gated tests (`AGB_NATIVE_DEPTHWISE=1`), off by default until validated on a B200 — the aten grouped convolution is used otherwise.
+# Depthwise convolution, SAME average pooling, ReLU6 (native/op_nn/depthwise.cu). Written after this round's GPU budget was spent:
+# compiled, index arithmetic checked against torch by a CPU emulation, covered by gated tests (`AGB_NATIVE_PREVIEW=1`), off by
+# default until validated on a B200 — the aten provider is used otherwise.
 
-_DEPTHWISE = os.environ.get("AGB_NATIVE_DEPTHWISE", "0") not in ("", "0")
+_DEPTHWISE = os.environ.get("AGB_NATIVE_PREVIEW", os.environ.get("AGB_NATIVE_DEPTHWISE", "0")) not in ("", "0")
 
 
 def _depthwise_ok(x, weight):
@@ -574,6 +575,43 @@ def depthwise_backward(dy, x, weight, stride, pads, grad_w, groups=1, group_stri
   dx = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=x.device)
   _check(_lib().agb_depthwise_dgrad(_ptr(dy), _ptr(_transposed_taps(weight)), _ptr(dx), *geometry, _stream()), "depthwise_dgrad")
   return dx.permute(0, 3, 1, 2)
+
+
+def avgpool2d_forward(x, k, stride, pads):
+  if not (_DEPTHWISE and enabled("pool") and _cl_ok(x) and x.dim() == 4 and x.shape[1] % 8 == 0):
+    return None
+  n, c, h, w = x.shape
+  oh, ow = _out_size(h, k, stride, pads[0], pads[1]), _out_size(w, k, stride, pads[2], pads[3])
+  y = torch.empty((n, oh, ow, c), dtype=torch.bfloat16, device=x.device)
+  _check(_lib().agb_avgpool2d_forward(_ptr(x), _ptr(y), ctypes.c_int(n), ctypes.c_int(h), ctypes.c_int(w), ctypes.c_int(c), ctypes.c_int(oh), ctypes.c_int(ow), ctypes.c_int(k),
+                                      ctypes.c_int(stride), ctypes.c_int(pads[0]), ctypes.c_int(pads[2]), _stream()), "avgpool2d_forward")
+  return y.permute(0, 3, 1, 2)
+
+
+def avgpool2d_backward(dy, shape, k, stride, pads):
+  n, c, h, w = shape
+  if not (_DEPTHWISE and enabled("pool") and _cl_ok(dy) and dy.dim() == 4 and c % 8 == 0):
+    return None
+  if not dy.is_contiguous(memory_format=torch.channels_last):
+    dy = dy.contiguous(memory_format=torch.channels_last)
+  dx = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=dy.device)
+  _check(_lib().agb_avgpool2d_backward(_ptr(dy), _ptr(dx), ctypes.c_int(n), ctypes.c_int(h), ctypes.c_int(w), ctypes.c_int(c), ctypes.c_int(dy.shape[2]), ctypes.c_int(dy.shape[3]),
+                                       ctypes.c_int(k), ctypes.c_int(stride), ctypes.c_int(pads[0]), ctypes.c_int(pads[2]), _stream()), "avgpool2d_backward")
+  return dx.permute(0, 3, 1, 2)
+
+
+def relu6(x, dy=None):
+  """Forward clamp (dy None) or backward mask of ReLU6."""
+  tensors = (x,) if dy is None else (x, dy)
+  if not (_DEPTHWISE and enabled("eltwise")) or any(t.dtype != torch.bfloat16 or t.numel() % 8 for t in tensors):
+    return None
+  if dy is not None and (dy.stride() != x.stride() or dy.shape != x.shape):
+    return None
+  if not (x.is_contiguous() or x.is_contiguous(memory_format=torch.channels_last)):
+    return None
+  out = torch.empty_like(x)
+  _check(_lib().agb_relu6(_ptr(x), _ptr(dy), _ptr(out), ctypes.c_longlong(x.numel()), _stream()), "relu6")
+  return out
 
 
 def subsample_forward(x, stride):

@@ -365,7 +365,11 @@ def test_subsample(shape, stride):
   assert dx.shape == x.shape and torch.equal(dx.contiguous(), ops.subsample_backward("torch", dy, shape, stride).contiguous())
 
 
-@pytest.mark.skipif(__import__("os").environ.get("AGB_NATIVE_DEPTHWISE", "0") in ("", "0"), reason="native depthwise kernels are opt-in (AGB_NATIVE_DEPTHWISE=1) until validated on a B200")
+_PREVIEW = __import__("os").environ.get("AGB_NATIVE_PREVIEW", __import__("os").environ.get("AGB_NATIVE_DEPTHWISE", "0")) not in ("", "0")
+_preview = pytest.mark.skipif(not _PREVIEW, reason="depthwise / SAME average pool / ReLU6 kernels are opt-in (AGB_NATIVE_PREVIEW=1) until validated on a B200")
+
+
+@_preview
 @pytest.mark.parametrize("c,hw,k,stride,groups", [(64, 28, 3, 1, 1), (128, 14, 3, 2, 2), (88, 21, 5, 2, 1), (176, 11, 7, 1, 4), (32, 9, 7, 2, 1)])
 def test_depthwise_native(c, hw, k, stride, groups):
   """Depthwise forward / data gradient / per-worker weight gradient kernels vs the aten grouped convolution in fp32."""
@@ -385,3 +389,23 @@ def test_depthwise_native(c, hw, k, stride, groups):
     grads[backend] = (dx, rows)
   _close(grads["native"][0], grads["torch"][0], 2e-2)
   _close(grads["native"][1], grads["torch"][1], 2e-2)
+
+
+@_preview
+@pytest.mark.parametrize("shape,k,stride,padding", [((4, 64, 35, 35), 3, 1, "SAME"), ((2, 128, 17, 18), 3, 2, "SAME"), ((2, 768, 17, 17), 5, 3, "VALID"), ((3, 32, 8, 8), 2, 2, "SAME")])
+def test_avgpool2d_and_relu6_native(shape, k, stride, padding):
+  """SAME / VALID average pooling (divisor = in-image window size) and ReLU6, forward and backward, native vs the aten path of the modules."""
+  from aggregathor_b200.models.core import AvgPool, Context, ReLU6
+  x, outs = _rand(shape, 95) * 4, {}
+  for backend in ("native", "torch"):
+    ctx = Context(backend, True, torch.bfloat16 if backend == "native" else torch.float32, "cuda")
+    pool, act = AvgPool("p", k, stride, padding), ReLU6("r")
+    xin = x if backend == "native" else x.float()
+    y = pool.forward(xin, ctx)
+    dy = _rand(tuple(y.shape), 96)
+    dx = pool.backward(dy if backend == "native" else dy.float(), ctx)
+    a = act.forward(xin, ctx)
+    da = act.backward(_rand(shape, 97) if backend == "native" else _rand(shape, 97).float(), ctx)
+    outs[backend] = (y, dx, a, da)
+  for got, want, tol in zip(outs["native"], outs["torch"], (1e-2, 1e-2, 1e-2, 1e-2)):
+    _close(got, want, tol)
