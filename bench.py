@@ -33,6 +33,7 @@ def parse():
   parser.add_argument("--steps", type=int, default=10)
   parser.add_argument("--warmup", type=int, default=3)
   parser.add_argument("--impl", type=str, default="ours", choices=("ours", "baseline", "reference"))
+  parser.add_argument("--experiment", type=str, default="", help="experiment name overriding slim-<model>-<dataset> (e.g. cnnet: BASELINE.json configuration 2)")
   parser.add_argument("--model", type=str, default="resnet_v1_50")
   parser.add_argument("--dataset", type=str, default="imagenet")
   parser.add_argument("--aggregator", type=str, default="krum")
@@ -123,7 +124,10 @@ def main():
   exp_args = ["batch-size:" + str(args.batch_size), "synthetic-samples:" + str(max(256, 4 * args.batch_size))]
   if args.image_size:
     exp_args.append("image-size:" + str(args.image_size))
-  experiment = experiments.instantiate("slim-" + args.model + "-" + args.dataset, exp_args)
+  experiment_name = args.experiment or ("slim-" + args.model + "-" + args.dataset)
+  if args.experiment:
+    exp_args = [a for a in exp_args if not a.startswith("image-size:")]
+  experiment = experiments.instantiate(experiment_name, exp_args)
   gar = aggregators.instantiate(args.aggregator, n, f, [])
   engine = args.engine or ("fused" if args.impl == "ours" else "baseline")
   backend = args.nn_backend if args.impl == "ours" else "torch"
@@ -198,16 +202,16 @@ def main():
     e2e = {"value": args.steps / (e2e_ms / 1000.0), "unit": "steps/s", "ms_per_step": e2e_ms / args.steps,
            "h2d_bytes_per_step": int(h2d.item()), "d2h_bytes_per_step": 4 * world, "last_loss": losses[-1] if losses else None}
 
-  headline = (args.model, args.aggregator, n, f, attack) == ("resnet_v1_50", "krum", 8, 2, None)
+  headline = (experiment_name, args.aggregator, n, f, attack) == ("slim-resnet_v1_50-imagenet", "krum", 8, 2, None)
   metric = "steps/sec (whole box, device-timed, max over ranks) ResNet-50 slim + Krum f=2" if headline else (
-    "steps/sec (whole box, device-timed, max over ranks) %s + %s n=%d f=%d%s" % (args.model, args.aggregator, n, f, (" attack=" + args.attack) if attack is not None else ""))
+    "steps/sec (whole box, device-timed, max over ranks) %s + %s n=%d f=%d%s" % (experiment_name, args.aggregator, n, f, (" attack=" + args.attack) if attack is not None else ""))
   if rank == 0:
     sys.stdout = sys.__stdout__
     line = {
       "metric": metric, "value": value, "unit": "steps/s", "n_gpus": world,
       "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
       "dtype": {"bfloat16": "bf16", "float16": "fp16", "float32": "fp32"}.get(str(manager.dtype).replace("torch.", ""), str(manager.dtype)), "data": "synthetic (ImageNet-shaped uint8 images, random-init weights)", "impl": args.impl,
-      "config": {"model": "slim-" + args.model + "-" + args.dataset, "aggregator": args.aggregator, "nb_workers": n, "nb_decl_byz_workers": f,
+      "config": {"model": experiment_name, "aggregator": args.aggregator, "nb_workers": n, "nb_decl_byz_workers": f,
                  "global_batch": n * args.batch_size, "per_worker_batch": args.batch_size, "image_size": manager.model.input_shape[-1], "seq_len": None,
                  "parallelism": "dp%d (x%d logical workers per GPU)" % (world, n // world), "engine": manager.aggregation.name, "nn_backend": manager.backend,
                  "d": manager.layout.size, "l2": "per-step working set (activations + 8 x 102 MB gradients) exceeds the 126 MB L2; no explicit flush"},
