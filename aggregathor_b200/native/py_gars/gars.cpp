@@ -163,9 +163,110 @@ template<class T> int average_nan(T const* g, size_t n, size_t d, T* out) {
     return 0;
 }
 
+// ------------------------------------------------------------------------ //
+// Coordinate-wise selections. For up to kRankWorkers workers the order statistics come from rank counting on blocks of
+// coordinates: rank_i = #{j : before(v_j, j, v_i, i)} with the keys made total (non-finite -> +inf, ties -> lower index), i.e. n^2
+// branch-free compare-and-adds per coordinate over kBlock contiguous coordinates of every row — streaming loads and loops the
+// compiler vectorises, instead of an index sort per coordinate with strided gathers. Larger n: std::nth_element on indices.
+// (Same definition as the device kernels, `native/op_gar/gar.cu`; the reference does nth_element per coordinate, `native.cpp:678-748`.)
+constexpr size_t kRankWorkers = 32;
+constexpr size_t kBlock = 32;
+
+template<class T> struct Block {
+    T val[kRankWorkers][kBlock];     // original values
+    T key[kRankWorkers][kBlock];     // non-finite -> +inf
+    int rank[kRankWorkers][kBlock];
+};
+
+template<class T> inline void load_block(T const* g, size_t n, size_t d, size_t x0, size_t len, Block<T>& blk) {
+    T const inf = std::numeric_limits<T>::infinity();
+    for (size_t i = 0; i < n; ++i) {
+        T const* row = g + i * d + x0;
+        for (size_t c = 0; c < kBlock; ++c) {
+            T const v = c < len ? row[c] : T(0);
+            blk.val[i][c] = v;
+            blk.key[i][c] = (v - v == T(0)) ? v : inf;   // v - v is NaN for NaN and +-inf
+        }
+    }
+}
+
+template<class T> inline void rank_block(size_t n, T const (*key)[kBlock], int (*rank)[kBlock]) {
+    for (size_t i = 0; i < n; ++i) {
+        int* const r = rank[i];
+        for (size_t c = 0; c < kBlock; ++c)
+            r[c] = 0;
+        for (size_t j = 0; j < n; ++j) {
+            T const* kj = key[j];
+            T const* ki = key[i];
+            if (j < i) {
+                for (size_t c = 0; c < kBlock; ++c)
+                    r[c] += kj[c] <= ki[c];       // equal keys: the lower index comes first
+            } else if (j > i) {
+                for (size_t c = 0; c < kBlock; ++c)
+                    r[c] += kj[c] < ki[c];
+            }
+        }
+    }
+}
+
+template<class T> inline void make_keys(size_t rows, Block<T>& blk) {
+    T const inf = std::numeric_limits<T>::infinity();
+    for (size_t i = 0; i < rows; ++i)
+        for (size_t c = 0; c < kBlock; ++c) {
+            T const v = blk.val[i][c];
+            blk.key[i][c] = (v - v == T(0)) ? v : inf;
+        }
+}
+
+// res[c] = mean of the `beta` values of column c of blk.val[0 .. rows) closest to their (upper) median, added in row order.
+template<class T> inline void averaged_median_of_block(size_t rows, size_t beta, Block<T>& blk, T* res) {
+    int const target = static_cast<int>(rows / 2), keep = static_cast<int>(beta);
+    T const inf = std::numeric_limits<T>::infinity();
+    rank_block<T>(rows, blk.key, blk.rank);
+    T med[kBlock];
+    for (size_t c = 0; c < kBlock; ++c)
+        med[c] = T(0);
+    for (size_t i = 0; i < rows; ++i)
+        for (size_t c = 0; c < kBlock; ++c)
+            med[c] = blk.rank[i][c] == target ? blk.val[i][c] : med[c];
+    for (size_t i = 0; i < rows; ++i)           // second key: distance to the median (non-finite -> +inf)
+        for (size_t c = 0; c < kBlock; ++c) {
+            T const dev = std::fabs(blk.val[i][c] - med[c]);
+            blk.key[i][c] = (dev - dev == T(0)) ? dev : inf;
+        }
+    rank_block<T>(rows, blk.key, blk.rank);
+    for (size_t c = 0; c < kBlock; ++c)
+        res[c] = T(0);
+    for (size_t i = 0; i < rows; ++i)
+        for (size_t c = 0; c < kBlock; ++c)
+            res[c] += blk.rank[i][c] < keep ? blk.val[i][c] : T(0);
+    for (size_t c = 0; c < kBlock; ++c)
+        res[c] /= static_cast<T>(beta);
+}
+
 template<class T> int median(T const* g, size_t n, size_t d, T* out) {
     if (n == 0 || n > kMaxWorkers)
         return 1;
+    if (n <= kRankWorkers) {
+        agb::parallel_for(0, (d + kBlock - 1) / kBlock, kGrainCoord / kBlock, [&](size_t b, size_t e) {
+            Block<T> blk;
+            int const target = static_cast<int>(n / 2);   // upper median for even n
+            for (size_t blk_i = b; blk_i < e; ++blk_i) {
+                size_t const x0 = blk_i * kBlock, len = std::min(kBlock, d - x0);
+                load_block(g, n, d, x0, len, blk);
+                rank_block<T>(n, blk.key, blk.rank);
+                T res[kBlock];
+                for (size_t c = 0; c < kBlock; ++c)
+                    res[c] = T(0);
+                for (size_t i = 0; i < n; ++i)
+                    for (size_t c = 0; c < kBlock; ++c)
+                        res[c] = blk.rank[i][c] == target ? blk.val[i][c] : res[c];
+                for (size_t c = 0; c < len; ++c)
+                    out[x0 + c] = res[c];
+            }
+        });
+        return 0;
+    }
     agb::parallel_for(0, d, kGrainCoord, [&](size_t b, size_t e) {
         std::vector<size_t> idx(n);
         for (size_t x = b; x < e; ++x) {
@@ -183,6 +284,20 @@ template<class T> int median(T const* g, size_t n, size_t d, T* out) {
 template<class T> int averaged_median(T const* g, size_t n, size_t d, size_t beta, T* out) {
     if (n == 0 || n > kMaxWorkers || beta == 0 || beta > n)
         return 1;
+    if (n <= kRankWorkers) {
+        agb::parallel_for(0, (d + kBlock - 1) / kBlock, kGrainCoord / kBlock, [&](size_t b, size_t e) {
+            Block<T> blk;
+            T res[kBlock];
+            for (size_t blk_i = b; blk_i < e; ++blk_i) {
+                size_t const x0 = blk_i * kBlock, len = std::min(kBlock, d - x0);
+                load_block(g, n, d, x0, len, blk);
+                averaged_median_of_block<T>(n, beta, blk, res);
+                for (size_t c = 0; c < len; ++c)
+                    out[x0 + c] = res[c];
+            }
+        });
+        return 0;
+    }
     agb::parallel_for(0, d, kGrainCoord, [&](size_t b, size_t e) {
         std::vector<size_t> idx(n);
         std::vector<T> dev(n);
@@ -288,6 +403,33 @@ template<class T> int bulyan(T const* g, size_t n, size_t d, size_t f, size_t m,
         for (size_t i = 0; i < n; ++i)
             if (weights[k * n + i] != T(0))
                 members[k].push_back(i);
+    if (theta <= kRankWorkers) {
+        agb::parallel_for(0, (d + kBlock - 1) / kBlock, kGrainCoord / 4 / kBlock, [&](size_t b, size_t e) {
+            Block<T> blk;
+            T res[kBlock];
+            for (size_t blk_i = b; blk_i < e; ++blk_i) {
+                size_t const x0 = blk_i * kBlock, len = std::min(kBlock, d - x0);
+                for (size_t k = 0; k < theta; ++k) {     // the theta intermediate gradients of this block (members added in index order)
+                    T* const row = blk.val[k];
+                    for (size_t c = 0; c < kBlock; ++c)
+                        row[c] = T(0);
+                    for (size_t i: members[k]) {
+                        T const* src = g + i * d + x0;
+                        for (size_t c = 0; c < len; ++c)
+                            row[c] += src[c];
+                    }
+                    T const count = static_cast<T>(members[k].size());
+                    for (size_t c = 0; c < kBlock; ++c)
+                        row[c] /= count;
+                }
+                make_keys<T>(theta, blk);
+                averaged_median_of_block<T>(theta, beta, blk, res);
+                for (size_t c = 0; c < len; ++c)
+                    out[x0 + c] = res[c];
+            }
+        });
+        return 0;
+    }
     agb::parallel_for(0, d, kGrainCoord / 4, [&](size_t b, size_t e) {
         std::vector<T> inter(theta), dev(theta);
         std::vector<size_t> idx(theta);
