@@ -39,6 +39,29 @@ template<class T> inline bool before(T a, size_t ia, T b, size_t ib) {
 
 // ------------------------------------------------------------------------ //
 // Pairwise squared distances, deterministic: per-chunk partial matrices folded in chunk order.
+// sum_{k in [b, e)} (x[k] - y[k])^2 with 16 interleaved partial sums folded in a fixed tree: the association is fixed (hence
+// deterministic) but no longer one serial chain, so the loop vectorises instead of waiting 4 cycles per addition.
+template<class T> inline T squared_difference(T const* x, T const* y, size_t b, size_t e) {
+    constexpr size_t kLanes = 16;
+    T acc[kLanes];
+    for (size_t u = 0; u < kLanes; ++u)
+        acc[u] = T(0);
+    size_t k = b;
+    for (; k + kLanes <= e; k += kLanes)
+        for (size_t u = 0; u < kLanes; ++u) {
+            T const delta = x[k + u] - y[k + u];
+            acc[u] += delta * delta;
+        }
+    for (size_t u = 0; k < e; ++k, ++u) {
+        T const delta = x[k] - y[k];
+        acc[u] += delta * delta;
+    }
+    for (size_t width = kLanes / 2; width > 0; width /= 2)
+        for (size_t u = 0; u < width; ++u)
+            acc[u] += acc[u + width];
+    return acc[0];
+}
+
 template<class T> void pairwise_distances(T const* g, size_t n, size_t d, T* dist /* [n*n] */) {
     size_t const grain = kGrainCoord;
     size_t const chunks = ThreadPool::chunk_count(0, d, grain);
@@ -51,12 +74,7 @@ template<class T> void pairwise_distances(T const* g, size_t n, size_t d, T* dis
             T const* x = g + i * d;
             for (size_t j = i + 1; j < n; ++j, ++p) {
                 T const* y = g + j * d;
-                T sum = 0;
-                for (size_t k = b; k < e; ++k) {
-                    T delta = x[k] - y[k];
-                    sum += delta * delta;
-                }
-                out[p] = sum;
+                out[p] = squared_difference(x, y, b, e);
             }
         }
     });
@@ -467,14 +485,7 @@ template<class T> int bulyan(T const* g, size_t n, size_t d, size_t f, size_t m,
 template<class T> T squared_distance(T const* a, T const* b, size_t d) {
     size_t const chunks = ThreadPool::chunk_count(0, d, kGrainCoord);
     std::vector<T> partial(chunks, T(0));
-    global_pool().run(0, d, kGrainCoord, [&](size_t chunk, size_t lo, size_t hi) {
-        T sum = 0;
-        for (size_t k = lo; k < hi; ++k) {
-            T delta = a[k] - b[k];
-            sum += delta * delta;
-        }
-        partial[chunk] = sum;
-    });
+    global_pool().run(0, d, kGrainCoord, [&](size_t chunk, size_t lo, size_t hi) { partial[chunk] = squared_difference(a, b, lo, hi); });
     T sum = 0;
     for (T v: partial)
         sum += v;
