@@ -122,3 +122,13 @@ def test_learning_rates_and_optimizer_table():
     build(learning_rates, "learning rate decay", "cosine", [])
   adam = build(optimizers, "optimizer", "adam", ["adam-beta1:0.8", "unknown:1"])
   assert adam.hyper["beta1"] == 0.8 and adam.nbslots == 2
+
+
+def test_clock_sampler_without_nvidia_smi():
+  """On a box without nvidia-smi the sampler reports that instead of failing (bench.py records it in its JSON line)."""
+  from aggregathor_b200.utils.clocks import ClockSampler
+  sampler = ClockSampler(0)
+  sampler.start()
+  report = sampler.stop()
+  assert set(report) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+  assert report["sm_mhz"] is None or report["sm_mhz"] > 0
