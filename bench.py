@@ -56,9 +56,9 @@ def main():
     return 0
   import torch
   import torch.distributed as dist
-  from aggregathor_b200.utils.clocks import ClockSampler
   sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
   from aggregathor_b200 import aggregators, attacks, experiments, tools
+  from aggregathor_b200.utils.clocks import ClockSampler
   from aggregathor_b200.engine.trainer import Manager
   from aggregathor_b200.ops import counters
 
