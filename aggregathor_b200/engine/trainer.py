@@ -21,7 +21,6 @@ import time
 import torch
 import torch.distributed as dist
 
-from .. import attacks as attacks_pkg
 from .. import tools
 from ..models import Context
 from ..ops import gar as gar_ops

@@ -8,7 +8,6 @@ experiment the reference intended. `severity:1` = scale by -100, `severity:2` = 
 """
 
 import numpy as np
-import torch
 
 from .. import tools
 from . import register

@@ -8,7 +8,6 @@ one-hot labels (+ label smoothing). Images are uint8 NHWC on the host; `vgg` pre
 `inception` preprocessing (scale to [-1, 1]) happens on the device, fused with the bf16 cast.
 """
 
-import torch
 
 from .. import tools
 from ..models import nets_factory

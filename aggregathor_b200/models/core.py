@@ -24,7 +24,6 @@ import os
 import torch
 import torch.nn.functional as F
 
-from .. import tools
 from ..ops import nn as nn_ops
 
 

@@ -10,7 +10,7 @@ no activation) whenever the depth changes and `subsample` (1x1 max-pool) otherwi
 canonical basic-block ResNet-18. `resnet_v1_50` has 25 557 032 trainable parameters at 1000 classes.
 """
 
-from .core import BatchNorm, Conv2d, GlobalAvgPool, Identity, MaxPool, Model, Module, Residual, Sequential, Subsample
+from .core import BatchNorm, Conv2d, GlobalAvgPool, MaxPool, Model, Module, Residual, Sequential, Subsample
 
 
 def _conv_bn(name, cin, cout, k, stride=1, relu=True):

@@ -5,7 +5,6 @@ take the others down). Usage: gemm_check.py {nt|nn|tn} ; appends JSON lines to g
 import json
 import os
 import sys
-import time
 
 import torch
 

@@ -6,7 +6,6 @@ import collections
 import pathlib
 import re
 import subprocess
-import sys
 
 ROOT = pathlib.Path(__file__).resolve().parent.parent
 NATIVE = ROOT / "aggregathor_b200" / "native"
