@@ -299,6 +299,11 @@ class Manager:
             "layout": self.layout.describe(), "time": time.time()}
 
   def load_state_dict(self, state):
+    if "tf_variables" in state:  # a checkpoint of the reference: variables by name in TensorFlow's layouts, optimizer slots not carried over
+      from ..tools import tf_checkpoint
+      flat, states, step = tf_checkpoint.to_layout(state["tf_variables"], self.layout, self.states)
+      tools.info("Imported the TensorFlow checkpoint %r (global step %s); optimizer slots start from zero" % (state.get("source", "?"), step), context="restore")
+      state = {"params": flat, "states": states, "optimizer": None, "global_step": step if step is not None else 0}
     if state["params"].numel() != self.params.numel():
       raise tools.UserException("Checkpoint holds %d parameters, the model needs %d" % (state["params"].numel(), self.params.numel()))
     self.params.copy_(state["params"].to(self.device))
@@ -307,7 +312,7 @@ class Manager:
         self.states[name].copy_(value.to(self.device))
     if state.get("optimizer") == self.optimizer.name:
       self.aggregation.load_state_dict(state["aggregation"])
-    else:
+    elif state.get("optimizer") is not None:
       tools.warning("Checkpoint was written with optimizer %r, now using %r: slots are reset" % (state.get("optimizer"), self.optimizer.name))
     self.step = int(state["global_step"])
     self._refresh_weights(force=True)

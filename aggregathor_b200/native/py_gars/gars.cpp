@@ -494,6 +494,34 @@ template<class T> T squared_distance(T const* a, T const* b, size_t d) {
 
 } // namespace
 
+// CRC32C (Castagnoli), table driven, 8 bytes per step: checksums of TensorFlow-format files (checkpoint tensors, TFRecords).
+extern "C" uint32_t agb_crc32c(uint8_t const* data, size_t size, uint32_t crc) {
+    static uint32_t table[8][256];
+    static bool ready = false;
+    if (!ready) {
+        for (uint32_t i = 0; i < 256; ++i) {
+            uint32_t c = i;
+            for (int k = 0; k < 8; ++k)
+                c = (c & 1) ? (c >> 1) ^ 0x82F63B78u : c >> 1;
+            table[0][i] = c;
+        }
+        for (uint32_t i = 0; i < 256; ++i)
+            for (int t = 1; t < 8; ++t)
+                table[t][i] = (table[t - 1][i] >> 8) ^ table[0][table[t - 1][i] & 0xFF];
+        ready = true;
+    }
+    crc = ~crc;
+    size_t i = 0;
+    for (; i + 8 <= size; i += 8) {
+        uint32_t const lo = crc ^ (static_cast<uint32_t>(data[i]) | static_cast<uint32_t>(data[i + 1]) << 8 | static_cast<uint32_t>(data[i + 2]) << 16 | static_cast<uint32_t>(data[i + 3]) << 24);
+        crc = table[7][lo & 0xFF] ^ table[6][(lo >> 8) & 0xFF] ^ table[5][(lo >> 16) & 0xFF] ^ table[4][lo >> 24]
+            ^ table[3][data[i + 4]] ^ table[2][data[i + 5]] ^ table[1][data[i + 6]] ^ table[0][data[i + 7]];
+    }
+    for (; i < size; ++i)
+        crc = table[0][(crc ^ data[i]) & 0xFF] ^ (crc >> 8);
+    return ~crc;
+}
+
 #define AGB_EXPORT(T, S) \
     extern "C" int agb_cpu_average_##S(T const* g, size_t n, size_t d, T* out) { return average<T>(g, n, d, out); } \
     extern "C" int agb_cpu_average_nan_##S(T const* g, size_t n, size_t d, T* out) { return average_nan<T>(g, n, d, out); } \

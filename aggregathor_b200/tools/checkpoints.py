@@ -66,6 +66,9 @@ class Checkpoints:
       path = self.latest()
       if path is None:
         raise UserException("No storage file to restore")
+    from . import tf_checkpoint
+    if tf_checkpoint.is_tf_bundle(path):  # written by the reference (tf.train.Saver): the trainer maps the variables onto its layout
+      return {"tf_variables": tf_checkpoint.read_bundle(path), "source": str(path)}
     return torch.load(str(path) + _DATA_SUFFIX, map_location=map_location, weights_only=False)
 
   def save(self, state, step, meta=None):

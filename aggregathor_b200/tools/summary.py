@@ -26,7 +26,24 @@ for _i in range(256):
   _CRC_TABLE.append(_c)
 
 
+_native_crc = None
+
+
 def _crc32c(data):
+  """CRC32C of a bytes-like object: the C++ routine of `native/py_gars` for anything sizeable, the table loop otherwise / as fallback."""
+  global _native_crc
+  if len(data) >= 4096 and _native_crc is not False:
+    if _native_crc is None:
+      try:
+        import ctypes
+        from .. import native
+        _native_crc = native.library("py_gars").agb_crc32c
+        _native_crc.restype = ctypes.c_uint32
+        _native_crc.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_uint32]
+      except Exception:
+        _native_crc = False
+    if _native_crc:
+      return int(_native_crc(bytes(data), len(data), 0))
   crc = 0xFFFFFFFF
   for byte in data:
     crc = _CRC_TABLE[(crc ^ byte) & 0xFF] ^ (crc >> 8)
