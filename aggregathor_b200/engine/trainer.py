@@ -139,7 +139,8 @@ class Manager:
     self.h2d_bytes_per_step = sum(getattr(s, "h2d_bytes", 0) for s in self.streams)
     # -- CUDA graph of the workers' forward/backward ---------------------------------- #
     if use_graphs is None:
-      use_graphs = cuda and not os.environ.get("AGB_NO_GRAPH") and not self._has_dropout(self.model.root) and type(experiment).losses is type(experiment).__mro__[-2].losses
+      use_graphs = (cuda and not os.environ.get("AGB_NO_GRAPH") and not self._has_dropout(self.model.root) and not getattr(experiment, "stochastic_preprocess", False)
+                    and type(experiment).losses is type(experiment).__mro__[-2].losses)
     self.use_graphs = bool(use_graphs) and cuda
     self._graph = None
     self._graph_warmup = 2       # eager steps before capture (lazy kernel attributes, workspaces, autotuning)

@@ -35,6 +35,7 @@ class CNNetExperiment(_Experiment):
     if self.data.synthetic:
       tools.warning("CIFAR-10 files not found: using the synthetic CIFAR-10-shaped dataset", context="cnnet")
     self._streams = {}
+    self.stochastic_preprocess = True   # the random flip of `cifarnet` preprocessing: no CUDA-graph replay of the step
 
   def model(self):
     return simple.cnnet(10)

@@ -3,7 +3,7 @@
 
 Args: `batch-size:32`, `eval-batch-size:1024`, `weight-decay:4e-5` (accepted; as in the reference the
 regularisation losses are *not* added to the training loss, `slims.py:122-125`), `label-smoothing:0`,
-`labels-offset:0`, `preprocessing:<model default>`, `image-size:<model default>`. Loss = softmax cross-entropy on
+`labels-offset:0`, `preprocessing:<model default>`, `image-size:<model default>`, `augment:none|flip|crop-flip`. Loss = softmax cross-entropy on
 one-hot labels (+ label smoothing). Images are uint8 NHWC on the host; `vgg` preprocessing (mean subtraction) or
 `inception` preprocessing (scale to [-1, 1]) happens on the device, fused with the bf16 cast.
 """
@@ -32,7 +32,12 @@ class SlimExperiment(_Experiment):
   def __init__(self, dataset, model, args):
     self.args = tools.parse_keyval(args if args is not None else [], defaults={
       "batch-size": 32, "eval-batch-size": 1024, "weight-decay": 0.00004, "label-smoothing": 0., "labels-offset": 0,
-      "nb-fetcher-threads": 1, "nb-batcher-threads": 1, "image-size": nets_factory.default_image_size(model), "seed": 0, "synthetic-samples": 512})
+      "nb-fetcher-threads": 1, "nb-batcher-threads": 1, "image-size": nets_factory.default_image_size(model), "seed": 0, "synthetic-samples": 512,
+      "augment": "none"})
+    if self.args["augment"] not in ("none", "flip", "crop-flip"):
+      raise tools.UserException("augment must be one of none, flip, crop-flip")
+    # random augmentation draws from the device generator every step: such a step cannot be replayed from a CUDA graph
+    self.stochastic_preprocess = self.args["augment"] != "none"
     if self.args["batch-size"] <= 0:
       raise tools.UserException("Cannot make batches of non-positive size")
     self.dataset_name, self.model_name = dataset, model
@@ -63,7 +68,25 @@ class SlimExperiment(_Experiment):
       self._eval_stream = BatchStream(self.data.x_test, self.data.y_test, min(self.args["eval-batch-size"], len(self.data.y_test)), device, shuffle=False, transform=self._offset)
     return next(self._eval_stream)
 
+  def _augment(self, images, generator):
+    """Training-time augmentation on the device, uint8 NHWC in and out: random horizontal flip, optionally preceded by a random
+    crop of the image padded by 1/8 of its size on every side (a light stand-in for slim's random-resize-and-crop)."""
+    import torch
+    batch, height, width, _ = images.shape
+    if self.args["augment"] == "crop-flip":
+      pad_h, pad_w = max(1, height // 8), max(1, width // 8)
+      padded = torch.nn.functional.pad(images.permute(0, 3, 1, 2), (pad_w, pad_w, pad_h, pad_h), mode="replicate").permute(0, 2, 3, 1)
+      top = torch.randint(0, 2 * pad_h + 1, (batch,), device=images.device, generator=generator)
+      left = torch.randint(0, 2 * pad_w + 1, (batch,), device=images.device, generator=generator)
+      rows = top[:, None] + torch.arange(height, device=images.device)[None, :]
+      cols = left[:, None] + torch.arange(width, device=images.device)[None, :]
+      images = padded[torch.arange(batch, device=images.device)[:, None, None], rows[:, :, None], cols[:, None, :]]
+    flip = torch.rand(batch, device=images.device, generator=generator) < 0.5
+    return torch.where(flip.view(-1, 1, 1, 1), images.flip(2), images)
+
   def preprocess(self, inputs, ctx, training):
+    if training and self.stochastic_preprocess:
+      inputs = self._augment(inputs, ctx.generator)
     if self.preprocessing == "cifarnet":
       return cifarnet_preprocess(inputs, ctx.dtype, training, ctx.generator)
     from ..ops import nn as nn_ops

@@ -217,3 +217,22 @@ def test_deploy_local_cluster_with_lossy_workers(tmp_path):
   losses = [float(x) for x in re.findall(r"Step \d+: total loss = ([0-9.eE+-]+)", out)]
   assert len(losses) == 5 and all(l == l for l in losses) and losses[-1] < losses[0]
   assert "drop-chunks" in out
+
+
+def test_slim_augmentation_options():
+  """`augment:flip` / `augment:crop-flip`: every output image is a (possibly mirrored) window of the replicate-padded input, evaluation is untouched."""
+  exp = experiments.instantiate("slim-resnet_v1_18-cifar10", ["batch-size:4", "synthetic-samples:64", "augment:crop-flip", "image-size:16"])
+  assert exp.stochastic_preprocess
+  generator = torch.Generator().manual_seed(1)
+  images = torch.randint(0, 255, (6, 16, 16, 3), dtype=torch.uint8)
+  out = exp._augment(images, generator)
+  assert out.shape == images.shape and out.dtype == torch.uint8
+  pad = 2
+  padded = torch.nn.functional.pad(images.permute(0, 3, 1, 2), (pad,) * 4, mode="replicate").permute(0, 2, 3, 1)
+  for b in range(6):
+    windows = [padded[b, t:t + 16, l:l + 16] for t in range(2 * pad + 1) for l in range(2 * pad + 1)]
+    assert any(torch.equal(out[b], w) or torch.equal(out[b], w.flip(1)) for w in windows)
+  plain = experiments.instantiate("slim-resnet_v1_18-cifar10", ["batch-size:4", "synthetic-samples:64", "image-size:16"])
+  assert not plain.stochastic_preprocess
+  with pytest.raises(tools.UserException):
+    experiments.instantiate("slim-resnet_v1_18-cifar10", ["augment:rotate"])
