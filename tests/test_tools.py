@@ -132,3 +132,21 @@ def test_clock_sampler_without_nvidia_smi():
   report = sampler.stop()
   assert set(report) >= {"sm_mhz", "sm_max_mhz", "reasons"}
   assert report["sm_mhz"] is None or report["sm_mhz"] > 0
+
+
+def test_cadence_delta_and_period_semantics():
+  """Step-delta and wall-clock triggers of the evaluation / checkpoint / summary services (reference: `runner.py:356-494`): fire at
+  start, then every `delta` steps or `period` seconds, whichever comes first; both negative = never; a restored run counts from its step."""
+  from aggregathor_b200.engine.services import Cadence
+  cadence = Cadence(5, -1)
+  assert not cadence.disabled and cadence.due(0, 100.0)                   # first trigger right away
+  cadence.mark(0)
+  assert not cadence.due(4, 1e9) and cadence.due(5, 0.0)
+  timed = Cadence(-1, 10.0)
+  assert timed.due(0, 0.0)
+  timed.mark(0)
+  mark_time = timed.last_time
+  assert not timed.due(10 ** 6, mark_time + 9.9) and timed.due(1, mark_time + 10.0)
+  assert Cadence(-1, -1).disabled and not Cadence(-1, -1).due(10 ** 6, 1e12)
+  restored = Cadence(5, -1, restored=True, step=300)
+  assert not restored.due(303, 0.0) and restored.due(305, 0.0)            # no immediate trigger after a restore
