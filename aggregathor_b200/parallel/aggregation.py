@@ -233,14 +233,29 @@ class FusedAggregation(_AggregationBase):
     return full
 
 
+def _single_host(group=None):
+  """Whether every rank of the group runs on the same machine (collective call). Peer-mapped memory — hence the fused engine —
+  only exists inside one NVLink domain; ranks spread over several hosts (deploy.py over SSH) go through NCCL."""
+  if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+    return True
+  import socket
+  hosts = [None] * dist.get_world_size(group)
+  dist.all_gather_object(hosts, socket.gethostname(), group=group)
+  return len(set(hosts)) == 1
+
+
 def make_aggregation(kind, gar, layout, nbworkers, optimizer, group=None, device="cpu", **kwargs):
-  """`kind` in {"auto", "fused", "baseline", "host"}; "auto" = fused on CUDA when the rule has a kernel, host on CPU."""
+  """`kind` in {"auto", "fused", "baseline", "host"}; "auto" = fused on CUDA when the rule has a kernel and all ranks share one
+  machine, the NCCL baseline engine on CUDA otherwise, host on CPU."""
   device = torch.device(device)
   if kind == "auto":
     if device.type != "cuda":
       kind = "host"
     elif gar.fused_spec() is not None and nbworkers <= gar_ops.MAX_WORKERS:
       kind = "fused"
+      if not _single_host(group):
+        tools.warning("The ranks span several hosts: no peer-mapped memory between them, using the NCCL all-gather engine", context="fused")
+        kind = "baseline"
     else:
       kind = "baseline"
   if kind == "fused":

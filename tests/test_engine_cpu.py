@@ -236,3 +236,46 @@ def test_slim_augmentation_options():
   assert not plain.stochastic_preprocess
   with pytest.raises(tools.UserException):
     experiments.instantiate("slim-resnet_v1_18-cifar10", ["augment:rotate"])
+
+
+def test_engine_selection(monkeypatch):
+  """`auto`: host engine on CPU; on CUDA the fused engine when the rule has a kernel and every rank shares one machine, the NCCL
+  baseline when the ranks span hosts or the rule has no kernel (engines replaced by stand-ins: no GPU needed to check the choice)."""
+  from aggregathor_b200.engine.flat import FlatLayout
+  from aggregathor_b200.engine.optimizers import optimizers
+  from aggregathor_b200.engine.schedules import build
+  from aggregathor_b200.parallel import aggregation
+  layout = FlatLayout()
+  layout.add("theta", (10,))
+  layout.freeze()
+  sgd = build(optimizers, "optimizer", "sgd", [])
+  made = []
+  for name in ("FusedAggregation", "BaselineAggregation"):
+    monkeypatch.setattr(aggregation, name, lambda *a, _name=name, **k: made.append(_name) or _name)
+  krum = aggregators.instantiate("krum", 7, 2, [])
+  assert aggregation.make_aggregation("auto", krum, layout, 7, sgd, device="cpu").name == "host"
+  monkeypatch.setattr(aggregation, "_single_host", lambda group=None: True)
+  assert aggregation.make_aggregation("auto", krum, layout, 7, sgd, device="cuda:0") == "FusedAggregation"
+  monkeypatch.setattr(aggregation, "_single_host", lambda group=None: False)
+  assert aggregation.make_aggregation("auto", krum, layout, 7, sgd, device="cuda:0") == "BaselineAggregation"
+  assert aggregation.make_aggregation("fused", krum, layout, 7, sgd, device="cuda:0") == "FusedAggregation"      # an explicit choice is honoured
+
+  class Custom(aggregators._GAR):
+    def __init__(self):
+      pass
+    def aggregate(self, gradients):
+      return gradients[0]
+  monkeypatch.setattr(aggregation, "_single_host", lambda group=None: True)
+  assert aggregation.make_aggregation("auto", Custom(), layout, 7, sgd, device="cuda:0") == "BaselineAggregation"
+  assert aggregation._single_host.__name__ == "<lambda>"
+
+
+def test_single_host_detection_across_processes(tmp_path):
+  script = tmp_path / "probe.py"
+  script.write_text("import sys, torch.distributed as dist\nsys.path.insert(0, %r)\nfrom aggregathor_b200.parallel.aggregation import _single_host\n"
+                    "dist.init_process_group('gloo')\nprint('single host:', _single_host())\ndist.destroy_process_group()\n" % str(ROOT))
+  port = 29050 + os.getpid() % 40
+  proc = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=300, cwd=str(ROOT))
+  out = proc.stdout.decode(errors="replace")
+  assert proc.returncode == 0 and out.count("single host: True") == 2, out[-2000:]
