@@ -1,4 +1,7 @@
-"""MobileNet v1 (slim `mobilenet_v1`): 3x3/2 stem conv + 13 depthwise-separable blocks (3x3 depthwise + BN +
+"""MobileNet v1 / v2 — `mobilenet_v1[_075|_050|_025]`, `mobilenet_v2[_140|_035]` of the reference's slim factory
+(`external/slim/nets/nets_factory.py:39-72`; the definitions live in the tensorflow/models checkout it expects).
+
+MobileNet v1 (slim `mobilenet_v1`): 3x3/2 stem conv + 13 depthwise-separable blocks (3x3 depthwise + BN +
 ReLU6, 1x1 pointwise + BN + ReLU6), global average pool, dropout, 1x1 conv logits. Depthwise convolutions
 run through the torch provider (grouped conv); pointwise 1x1 convolutions are plain GEMMs."""
 

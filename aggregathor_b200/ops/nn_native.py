@@ -1,4 +1,5 @@
-"""sm_100a providers of the nn ops (`native/op_nn`).
+"""sm_100a providers of the nn ops (`native/op_nn`) — what TensorFlow's cuDNN / cuBLAS kernels are to the reference's experiments
+(`experiments/cnnet.py:58-95`, `experiments/slims.py:100-125`: every layer there is a library call placed by TF).
 
 Every function returns None (forward ops) or NotImplemented (backward ops whose legitimate result may be None) when it
 does not handle the given arguments; `ops/nn.py` then either falls back to the torch provider or raises
