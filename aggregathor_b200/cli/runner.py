@@ -304,6 +304,10 @@ def main(argv=None):
           if service is not None:
             service.run(graph_mgr.step)
           cadence.mark(graph_mgr.step)
+      if value & (services.FLAG_EVAL | services.FLAG_CHECKPOINT | services.FLAG_SUMMARY):
+        # rank 0 just spent an arbitrary time evaluating / writing files: re-align the ranks on the host before anyone launches
+        # the next step's aggregation kernel (whose entry barrier spins on every peer's flag)
+        dist.barrier()
       return bool(value & services.FLAG_STOP)
 
     if world > 1:

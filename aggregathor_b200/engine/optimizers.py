@@ -73,5 +73,6 @@ optimizers = {
               {"initial-accumulator-value": (0.1, "initial_accumulator_value")}),
   "adam": (lambda beta1=None, beta2=None: OptimizerSpec("adam", 2, beta1=beta1, beta2=beta2, epsilon=1e-8),
            {"adam-beta1": (0.9, "beta1"), "adam-beta2": (0.999, "beta2")}),
-  "rmsprop": (lambda: OptimizerSpec("rmsprop", 2, decay=0.9, momentum=0.0, epsilon=1e-10), {}),
+  # TF 1.x `RMSPropOptimizer._create_slots`: the mean-square slot "rms" starts at ONE, "momentum" at zero (first update ~ lr * g)
+  "rmsprop": (lambda: OptimizerSpec("rmsprop", 2, slot_init=(1.0, 0.0), decay=0.9, momentum=0.0, epsilon=1e-10), {}),
   "sgd": (lambda: OptimizerSpec("sgd", 0), {})}

@@ -167,7 +167,12 @@ class BatchStream:
         self._thread = threading.Thread(target=self._producer, name="input", daemon=True)
         self._thread.start()
       x, y, done = self._queue.get()
-      torch.cuda.current_stream(self.device).wait_event(done)
+      consumer = torch.cuda.current_stream(self.device)
+      consumer.wait_event(done)
+      # allocated on the producer's side stream, consumed here: tell the caching allocator, or the block could be handed back to the
+      # producer's next H2D copy while kernels of this stream still read it
+      x.record_stream(consumer)
+      y.record_stream(consumer)
     return (x, y) if self.transform is None else self.transform(x, y)
 
   def close(self):

@@ -34,11 +34,13 @@ class MNIST(_Experiment):
     return self.data.x_train, self.data.y_train
 
   def train_stream(self, worker, nbworkers, device):
-    key = 0 if self.args["shared-batch"] else worker
-    if key not in self._streams:
+    if worker not in self._streams:
       images, labels = self._train_arrays(worker, nbworkers)
-      self._streams[key] = BatchStream(images, labels, self.args["batch-size"], device, seed=self.args["seed"] + key)
-    return self._streams[key]
+      # `shared-batch:1` (the reference's quirk, `experiments/mnist.py:76-81,124`): every worker draws THE SAME batch each step — one
+      # stream object per worker (a shared iterator would hand consecutive, i.e. different, batches to the workers), all seeded alike
+      seed = self.args["seed"] + (0 if self.args["shared-batch"] else worker)
+      self._streams[worker] = BatchStream(images, labels, self.args["batch-size"], device, seed=seed)
+    return self._streams[worker]
 
   def eval_batch(self, device):
     count = self.args["eval-batch-size"] or len(self.data.y_test)

@@ -23,7 +23,9 @@ at a few seconds per file and keeps the kernels independent from the torch ABI:
 wrappers pass `tensor.data_ptr()` and the current `cudaStream_t`.
 """
 
+import contextlib
 import ctypes
+import fcntl
 import os
 import pathlib
 import shlex
@@ -91,6 +93,38 @@ def _run(libname, command, quiet):
   return proc.returncode == 0
 
 
+@contextlib.contextmanager
+def _process_lock():
+  """Serialise builds across PROCESSES (every rank of a torchrun / deploy.py job calls `library()` at the same moment on a
+  fresh checkout): an exclusive `flock` on a lock file beside the libraries. Products are additionally written under a
+  temporary name and renamed into place, so a concurrent `CDLL` never maps a half-written file."""
+  try:
+    handle = open(_HERE / ".build.lock", "a+")
+  except OSError:   # read-only install: nothing can be built anyway
+    yield
+    return
+  try:
+    fcntl.flock(handle, fcntl.LOCK_EX)
+    yield
+  finally:
+    try:
+      fcntl.flock(handle, fcntl.LOCK_UN)
+    finally:
+      handle.close()
+
+
+def _run_into(libname, command, product, quiet):
+  """Run `command` (whose output file argument is the literal "@OUT@") writing to a temporary sibling of `product`, then rename."""
+  tmp = product.with_name(product.name + ".tmp" + str(os.getpid()))
+  ok = _run(libname, [str(tmp) if c == "@OUT@" else c for c in command], quiet)
+  if ok:
+    os.replace(tmp, product)
+  else:
+    with contextlib.suppress(OSError):
+      tmp.unlink()
+  return ok
+
+
 def _stale(product, sources):
   if not product.exists():
     return True
@@ -156,20 +190,20 @@ def _build(libdir, stack, quiet):
   for src in cpps:
     obj = pathlib.Path(str(src) + ".o")
     if _stale(obj, headers + shared_headers + [src]):
-      if not _run(name, [_CXX] + _CXX_FLAGS + incl + ["-c", "-o", str(obj), str(src)], quiet):
+      if not _run_into(name, [_CXX] + _CXX_FLAGS + incl + ["-c", "-o", "@OUT@", str(src)], obj, quiet):
         raise RuntimeError("C++ source " + repr(src.name) + " did not compile")
     objects.append(obj)
   for src in cudas:
     obj = pathlib.Path(str(src) + ".o")
     if _stale(obj, headers + shared_headers + [src]):
-      if not _run(name, [_NVCC] + _NVCC_FLAGS + incl + ["-c", "-o", str(obj), str(src)], quiet):
+      if not _run_into(name, [_NVCC] + _NVCC_FLAGS + incl + ["-c", "-o", "@OUT@", str(src)], obj, quiet):
         raise RuntimeError("CUDA source " + repr(src.name) + " did not compile")
     objects.append(obj)
   so_path = _so_path(libdir)
   if _stale(so_path, objects + dep_sos):
     linker = [_NVCC, "-shared", "-Xcompiler", "-fPIC", "-Xlinker", "-rpath=$ORIGIN", "-Xlinker", "--no-as-needed"] if cudas else [_CXX] + _LINK_FLAGS
-    command = linker + ["-o", str(so_path)] + [str(o) for o in objects] + ["-L" + str(_HERE)] + ["-l:" + p.name for p in dep_sos]
-    if not _run(name, command, quiet):
+    command = linker + ["-o", "@OUT@"] + [str(o) for o in objects] + ["-L" + str(_HERE)] + ["-l:" + p.name for p in dep_sos]
+    if not _run_into(name, command, so_path, quiet):
       raise RuntimeError("final shared object " + repr(so_path.name) + " could not be linked")
   return so_path
 
@@ -210,7 +244,8 @@ def library(name, quiet=True):
       if os.environ.get("AGB_NATIVE_NO_BUILD") and _so_path(libdir).exists():
         so_path = _so_path(libdir)
       else:
-        so_path = _build(libdir, [], quiet)
+        with _process_lock():
+          so_path = _build(libdir, [], quiet)
       return _load(libdir, so_path)
     except Exception as err:
       _failed[name] = str(err)
@@ -238,7 +273,8 @@ def build_all(quiet=True, load=True, strict=False):
       if not any(_scan(libdir)[2:]):
         continue  # nothing to compile (yet)
       try:
-        so_path = _build(libdir, [], quiet)
+        with _process_lock():
+          so_path = _build(libdir, [], quiet)
         results[libdir.name] = so_path
         if load and libdir.name not in _libs:
           _load(libdir, so_path)

@@ -61,17 +61,34 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(uint32_t const* addr) {
 __device__ __forceinline__ void fence_sys() {
     asm volatile("fence.acq_rel.sys;" ::: "memory");
 }
-// Spin until *addr reaches `target` (monotonic epochs, wrap-safe signed difference). The
-// iteration bound turns a protocol bug into a trap instead of a hung GPU.
+// Spin until *addr reaches `target` (monotonic epochs, wrap-safe signed difference). A peer may legitimately be late by a long
+// time (rank 0 evaluating or writing a checkpoint, a first-use build, CUDA-graph capture): the bound is wall-clock
+// (%globaltimer), generous (default 120 s) and configurable per library through `set_flag_timeout` (AGB_FLAG_TIMEOUT_S);
+// 0 = wait forever. Expiry is reported and the kernel trapped: a dead peer must not hang the whole box silently.
+static __device__ unsigned long long g_flag_timeout_ns = 120ull * 1000000000ull;
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void wait_flag_sys(uint32_t const* addr, uint32_t target) {
-    unsigned long long spins = 0;
+    if (static_cast<int32_t>(ld_acquire_sys(addr) - target) >= 0)
+        return;
+    unsigned long long const start = globaltimer_ns(), limit = g_flag_timeout_ns;
+    unsigned spins = 0;
     while (static_cast<int32_t>(ld_acquire_sys(addr) - target) < 0) {
-        __nanosleep(64);
-        if (++spins > (1ull << 26)) { // several seconds
-            printf("[agb] wait_flag_sys timeout: flag %p = %u, expected >= %u (block %d)\n", (void const*) addr, ld_acquire_sys(addr), target, (int) blockIdx.x);
+        __nanosleep(spins < 64 ? 32 : 256);
+        if ((++spins & 0x3ffu) == 0 && limit != 0 && globaltimer_ns() - start > limit) {
+            printf("[agb] wait_flag_sys: no signal after %llu s: flag %p = %u, expected >= %u (block %d) - a peer rank died or never launched\n",
+                   limit / 1000000000ull, (void const*) addr, ld_acquire_sys(addr), target, (int) blockIdx.x);
             __trap();
         }
     }
+}
+inline int set_flag_timeout(double seconds) {
+    unsigned long long const ns = seconds <= 0. ? 0ull : static_cast<unsigned long long>(seconds * 1e9);
+    AGB_CUDA_OK(cudaMemcpyToSymbol(g_flag_timeout_ns, &ns, sizeof(ns)));
+    return 0;
 }
 
 // ---- streaming 128-bit accesses ------------------------------------------ //

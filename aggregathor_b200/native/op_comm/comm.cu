@@ -189,6 +189,11 @@ char const* agb_op_list() {
     return "comm_alloc,comm_free,comm_ipc_handle,comm_ipc_open,comm_ipc_close,comm_enable_peer,comm_can_access_peer,comm_p2p_copy,comm_barrier_test,comm_allreduce,comm_allgather";
 }
 
+// Wall-clock bound (seconds, 0 = none) of the cross-GPU flag waits of this library's kernels.
+int agb_comm_set_flag_timeout(double seconds) {
+    return set_flag_timeout(seconds);
+}
+
 int agb_comm_alloc(unsigned long long size, unsigned long long* out) {
     void* ptr = nullptr;
     AGB_CUDA_OK(cudaMalloc(&ptr, size));

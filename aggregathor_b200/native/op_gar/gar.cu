@@ -597,6 +597,11 @@ char const* agb_op_list() {
     return "gar_fused,gar_max_ctas,sgd,drop_chunks,checksum,cast_bf16";
 }
 
+// Wall-clock bound (seconds, 0 = none) of the cross-GPU flag waits of this library's kernels.
+int agb_gar_set_flag_timeout(double seconds) {
+    return set_flag_timeout(seconds);
+}
+
 // Upper bound of the grid the fused kernel may use (to size `cta_partials`: [ctas][120] floats).
 int agb_gar_max_ctas() {
     int device = 0, sms = 0;

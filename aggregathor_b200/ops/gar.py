@@ -7,6 +7,7 @@ the reference, which only ever had a CPU kernel: `native/op_krum/op.cpp:98-107`)
 """
 
 import ctypes
+import os
 
 import torch
 
@@ -66,6 +67,10 @@ class FusedLauncher:
     self._floats = (ctypes.c_float * 4)()
     self._func = _lib().agb_gar_fused
     self._func.restype = ctypes.c_int
+    timeout = os.environ.get("AGB_FLAG_TIMEOUT_S")
+    if timeout is not None:   # bound of the cross-GPU flag waits (default 120 s, 0 = wait forever)
+      with torch.cuda.device(self.device):
+        _check(_lib().agb_gar_set_flag_timeout(ctypes.c_double(float(timeout))), "gar_set_flag_timeout")
 
   def launch(self, spec, rows, lo, hi, *, agg_out=None, opt="none", lr=0.0, hyper=(0.0, 0.0, 0.0), param=None,
              slot0=None, slot1=None, param_dst=None, param_mc=0, param_bf16_dst=None, rank=0, R=1, signals=None, mailboxes=None,

@@ -18,6 +18,16 @@ unit that is signed is the digest of a published row, split along the same coord
   on every rank, the coordinate-wise rules ignore the NaN coordinates).
 
 This costs a host round trip per step and is therefore opt-in (`runner.py --authenticate`), like the reference's transport.
+
+Limits, stated plainly (weaker than per-message signatures over a socket):
+* on GPUs the signed digest is the 64-bit position-dependent mixing sum of `native/op_gar` (`checksum_kernel`), not a
+  cryptographic hash: the ed25519 signature authenticates the digest, but an adversary that can search millions of free
+  coordinates could craft a second row with the same digest. The host path uses blake2b. A keyed / cryptographic device
+  digest is the obvious hardening; the protocol does not change.
+* verify-then-use: the consumer verifies the peer-mapped row in place and its aggregation kernel re-reads the same memory
+  afterwards. The owner of the row could rewrite it in between (it is its own memory). Ranks are separate processes of one
+  job on one trusted box — the threat model the feature covers is a *corrupted* or *forged-in-flight* row (fault injection
+  `--attack forge`), not a malicious co-resident process racing the verifier.
 """
 
 import hashlib

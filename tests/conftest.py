@@ -6,11 +6,21 @@ import pytest
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
+def pytest_addoption(parser):
+  parser.addoption("--runslow", action="store_true", default=False, help="also run the tests marked `slow` (or set AGB_RUN_SLOW=1)")
+
+
 def pytest_configure(config):
   config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `pytest -m gpu`)")
+  config.addinivalue_line("markers", "slow: multi-second CPU test (finite differences over whole networks); run with --runslow / AGB_RUN_SLOW=1")
 
 
 def pytest_collection_modifyitems(config, items):
+  if not (config.getoption("--runslow") or os.environ.get("AGB_RUN_SLOW")):
+    skip_slow = pytest.mark.skip(reason="slow test: --runslow / AGB_RUN_SLOW=1")
+    for item in items:
+      if "slow" in item.keywords:
+        item.add_marker(skip_slow)
   try:
     import torch
     has_gpu = torch.cuda.is_available()

@@ -119,6 +119,31 @@ def test_optimizers_decrease_loss_and_checkpoint_roundtrip(opt):
     assert torch.equal(a, b)
 
 
+def test_mnist_shared_batch_gives_every_worker_the_same_batch():
+  shared = experiments.instantiate("mnist", ["batch-size:8", "shared-batch:1"])
+  a, b = shared.train_stream(0, 2, "cpu"), shared.train_stream(1, 2, "cpu")
+  assert a is not b
+  for _ in range(3):
+    (xa, ya), (xb, yb) = next(a), next(b)
+    assert torch.equal(xa, xb) and torch.equal(ya, yb)
+  own = experiments.instantiate("mnist", ["batch-size:8"])
+  (xa, _), (xb, _) = next(own.train_stream(0, 2, "cpu")), next(own.train_stream(1, 2, "cpu"))
+  assert not torch.equal(xa, xb)
+
+
+def test_rmsprop_first_step_matches_tensorflow():
+  """TF 1.x RMSPropOptimizer: rms slot starts at 1, momentum at 0 => first update = lr * g / sqrt(0.9 + 0.1 g^2 + eps)."""
+  from aggregathor_b200.engine.optimizers import optimizers
+  from aggregathor_b200.engine.schedules import build
+  spec = build(optimizers, "optimizer", "rmsprop", [])
+  param, grad = torch.tensor([1.0, -2.0, 0.5]), torch.tensor([0.5, -4.0, 0.0])
+  slots = spec.make_slots(param)
+  assert torch.equal(slots[0], torch.ones(3)) and torch.equal(slots[1], torch.zeros(3))
+  expected = param - 0.01 * grad / torch.sqrt(0.9 + 0.1 * grad * grad + 1e-10)
+  spec.apply_torch(param, grad, slots, 0.01, 1)
+  assert torch.allclose(param, expected, atol=1e-7)
+
+
 def test_regularization_and_mnist_attack_experiment():
   mgr = _manager("average", 2, 0, regularizations=(1e-4, 1e-3))
   assert float(mgr.train()) > 0

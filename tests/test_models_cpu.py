@@ -168,7 +168,7 @@ def test_inception_pieces():
   _check_stack([Conv2d("stem", 3, 8, 3, padding="SAME"), Conv2d("b2/3x1", 8, 4, (3, 1), padding="VALID"), Conv2d("b2/1x3", 4, 4, (1, 3), stride=2, padding="SAME")] + head(4), (2, 3, 9, 8))
 
 
-@pytest.mark.parametrize("family", ["nasnet", "pnasnet"])
+@pytest.mark.parametrize("family", ["nasnet", pytest.param("pnasnet", marks=pytest.mark.slow)])
 def test_searched_cells(family):
   """A miniature NASNet-A / PNASNet-5 (cifar stem, 3 cells with both reductions, 4 filters): DAG backward vs finite differences."""
   from aggregathor_b200.models import nasnet
@@ -176,6 +176,7 @@ def test_searched_cells(family):
   _check_stack([model.root], (2, 3, 20, 20), every=3)
 
 
+@pytest.mark.slow
 def test_imagenet_stem_cells():
   from aggregathor_b200.models import nasnet
   model = nasnet._build("tiny", "nasnet", 5, 83, "imagenet", num_cells=3, filters=8, stem_multiplier=0.25, drop_path_keep_prob=1.0, dense_keep_prob=1.0, skip_reduction_input=True)

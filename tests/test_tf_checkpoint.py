@@ -73,7 +73,7 @@ def test_prefix_compressed_blocks_are_decoded(tmp_path):
   assert sorted(back) == sorted(names) and all(np.array_equal(back[n], a) for n, a in zip(names, arrays))
 
 
-@pytest.mark.parametrize("name,classes", [("cnnet", 10), ("resnet_v1_18", 7), ("mobilenet_v1_025", 5), ("vgg_a", 3)])
+@pytest.mark.parametrize("name,classes", [("cnnet", 10), ("resnet_v1_18", 7), ("mobilenet_v1_025", 5), pytest.param("vgg_a", 3, marks=pytest.mark.slow)])
 def test_layout_conversion_roundtrip(name, classes):
   """from_layout -> TensorFlow shapes (HWIO kernels, [in, out] dense, [kh, kw, C, 1] depthwise) -> to_layout gives the parameters back."""
   model = get_network(name, classes)
