@@ -16,10 +16,16 @@ Same flags as the reference:
   --runner "..."             arguments passed to `runner.py` on every rank
   --UDP n                    the first n workers use the lossy transport: mapped to `--nb-real-byz-workers n --attack drop-chunks`
                              (the emulation of the reference's UDP path) unless `--runner` already selects an attack
+  --ship auto|always|never   NFS-free deployment (reference: `deploy.py:201-229` pipes its own source into `ssh host python`): the
+                             framework's source tree (package, entry points, native sources and built libraries) is packed into
+                             a tarball and piped through the SSH connection; the remote side unpacks it into a temporary directory,
+                             runs its rank from there and removes it afterwards — no shared filesystem, no pre-installed checkout.
+                             `auto` (default) ships to remote hosts only, `never` expects the same checkout path on every host.
 Stays in the foreground until SIGINT/SIGTERM (or until orphaned), then terminates what it started.
 """
 
 import argparse
+import io
 import os
 import pathlib
 import shlex
@@ -96,16 +102,62 @@ def plan(cluster, wk_job="workers", ps_job="ps"):
   return master_host, int(master_port), ranks
 
 
+_BUNDLE_SUFFIXES = {".py", ".cu", ".cuh", ".cpp", ".hpp", ".h", ".so", ".sh", ".md", ".toml", ""}
+_bundle_cache = None
+
+
+def source_bundle():
+  """gzip-compressed tarball (bytes) of everything a rank needs: the package (sources + built native libraries), the entry points."""
+  global _bundle_cache
+  if _bundle_cache is not None:
+    return _bundle_cache
+  import tarfile
+  buffer = io.BytesIO()
+  with tarfile.open(fileobj=buffer, mode="w:gz", compresslevel=3) as tar:
+    for entry in ("runner.py", "deploy.py", "pyproject.toml"):
+      if (REPO / entry).is_file():
+        tar.add(str(REPO / entry), arcname=entry)
+    package = REPO / "aggregathor_b200"
+    for path in sorted(package.rglob("*")):
+      relative = path.relative_to(REPO)
+      if "__pycache__" in relative.parts or not path.is_file() or path.name.endswith(".o") or ".tmp" in path.name:
+        continue
+      if path.suffix in _BUNDLE_SUFFIXES or path.name in ("DEPS",):
+        tar.add(str(path), arcname=str(relative))
+      elif path.is_symlink():
+        tar.add(str(path), arcname=str(relative))
+  _bundle_cache = buffer.getvalue()
+  return _bundle_cache
+
+
+def remote_script(env, runner_args, nice):
+  """Shell run by `ssh host`: unpack the tarball arriving on stdin into a private directory, run the rank there, clean up."""
+  assignments = " ".join(k + "=" + shlex.quote(v) for k, v in env.items())
+  command = ("nice -n 19 " if nice else "") + "python3 runner.py " + " ".join(shlex.quote(c) for c in runner_args)
+  return ("set -e; d=$(mktemp -d -t agb-rank-XXXXXX); trap 'rm -rf \"$d\"' EXIT; tar xzf - -C \"$d\"; cd \"$d\"; "
+          "env " + assignments + " AGB_SHIPPED=1 " + command + " < /dev/null")
+
+
 def rank_command(runner_args, nice):
   cmd = [sys.executable, str(REPO / "runner.py")] + runner_args
   return (["nice", "-n", "19"] if nice else []) + cmd
 
 
-def start_rank(job, index, host, rank, local, world, master_host, master_port, runner_args, nice):
+def start_rank(job, index, host, rank, local, world, master_host, master_port, runner_args, nice, ship="auto", ssh=("ssh", "-o", "BatchMode=yes")):
   env = {"RANK": str(rank), "WORLD_SIZE": str(world), "LOCAL_RANK": str(local), "LOCAL_WORLD_SIZE": str(world), "MASTER_ADDR": master_host, "MASTER_PORT": str(master_port)}
   command = rank_command(runner_args, nice)
-  if _is_local(host):
+  local_host = _is_local(host)
+  if local_host and ship != "always":
     child = subprocess.Popen(command, env=dict(os.environ, **env), cwd=str(REPO))
+  elif ship != "never":
+    # NFS-free: the source tree travels through the connection itself
+    launcher = ["sh", "-c"] if local_host else list(ssh) + [host]
+    child = subprocess.Popen(launcher + [remote_script(env, runner_args, nice)], stdin=subprocess.PIPE)
+    try:
+      child.stdin.write(source_bundle())
+      child.stdin.close()
+    except BrokenPipeError:
+      pass
   else:
     remote = "cd " + shlex.quote(str(REPO)) + " && env " + " ".join(k + "=" + shlex.quote(v) for k, v in env.items()) + " " + " ".join(shlex.quote(c) for c in command)
     child = subprocess.Popen(["ssh", "-o", "BatchMode=yes", host, remote])
@@ -126,6 +178,7 @@ def main(argv=None):
   parser.add_argument("--MPI", action="store_true", default=False, help="Accepted for compatibility with the reference (grpc+mpi transport); ignored")
   parser.add_argument("--runner", type=str, default="", help="Arguments passed to runner.py on every rank")
   parser.add_argument("--UDP", type=int, default=0, help="Number of workers running over the lossy transport (could be seen as Byzantine)")
+  parser.add_argument("--ship", type=str, default="auto", choices=("auto", "always", "never"), help="Ship the source tree through the SSH pipe (NFS-free deployment): remote hosts only (auto), every rank, or never")
   args = parser.parse_args(sys.argv[1:] if argv is None else argv)
   cluster = cluster_parse(args.cluster)
   nices = args.nice if args.nice is not None else []
@@ -172,7 +225,7 @@ def main(argv=None):
         print("\033[1;30m[" + job + ":" + str(index) + "]\033[1;34m No server running\033[0m")
         continue
       if args.deploy or own:
-        start_rank(job, index, host, rank, local, world, master_host, master_port, runner_args, job in nices)
+        start_rank(job, index, host, rank, local, world, master_host, master_port, runner_args, job in nices, ship=args.ship)
   sys.stdout.flush()
   while not exit_pending:
     time.sleep(1)

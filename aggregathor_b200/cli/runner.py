@@ -99,11 +99,77 @@ def _init_distributed(use_gpu):
   return rank, world, local, device
 
 
+
+# ---------------------------------------------------------------------------- #
+# Argument post-processing (same user-visible rules and messages as the reference's `runner.py:233-297`, table-driven here)
+
+def _tee_streams(args):
+  """`--stdout-to/--stderr-to FILE`: duplicate (not redirect) the stream into FILE, colours stripped."""
+  for attr, stream_name, label in (("stdout_to", "stdout", "standard output"), ("stderr_to", "stderr", "standard error output")):
+    target = getattr(args, attr)
+    if target == "-":
+      continue
+    path = pathlib.Path(target)
+    tee = tools.MethodCallReplicator(getattr(sys, stream_name), tools.ContextIOWrapper(path.open("w"), nocolor=True))
+    setattr(sys, stream_name, tee)
+    tee.write("Duplicating " + label + " to " + repr(str(path.resolve())) + os.linesep)
+
+
+def _validate(args):
+  """Fatal problems raise `UserException`, suspicious settings only warn; list arguments left out become empty lists."""
+  n, f, real = args.nb_workers, args.nb_decl_byz_workers, args.nb_real_byz_workers
+  if bool(args.client) == bool(args.server):
+    raise tools.UserException("One and only one of '--client' and '--server' must be specified")
+  if args.server:
+    args.server = tools.cluster_parse(args.server)
+    missing = [job for job in (args.ps_job_name, args.wk_job_name, args.ev_job_name) if job not in args.server]
+    if missing:
+      raise tools.UserException("Given cluster specification does not include a " + repr(missing[0]) + " job")
+  fatal = (
+    (n <= 0, "Expected at least one non-Byzantine worker"),
+    (n < real, "Got more real Byzantine workers (" + repr(real) + ") than total number of workers (" + repr(n) + ")"))
+  for failed, message in fatal:
+    if failed:
+      raise tools.UserException(message)
+  advisories = (
+    (n <= 2 * f, "Got more declared Byzantine workers (" + repr(f) + ") than half the total number of workers (" + repr(n) + ")"),
+    (f < real, "Got more real Byzantine workers (" + repr(real) + ") than declared number of Byzantine workers (" + repr(f) + ")"),
+    (args.use_tpu or args.reuse_tpu, "There is no TPU on a B200 box: '--use-tpu/--reuse-tpu' are accepted and ignored"),
+    (args.MPI, "'--MPI' is accepted for compatibility: ranks communicate through peer-mapped memory (NVLink) and NCCL/gloo"))
+  for suspicious, message in advisories:
+    if suspicious:
+      tools.warning(message)
+  for name in ("experiment_args", "aggregator_args", "learning_rate_args", "optimizer_args", "attack_args"):
+    if getattr(args, name) is None:
+      setattr(args, name, [])
+
+
+def _resolve_outputs(args):
+  """Evaluation file and summary directory default into the checkpoint directory; "-" switches either off."""
+  def resolve(value, default):
+    if value == "-":
+      return ""
+    return value if value else default
+  base = args.checkpoint_dir
+  args.evaluation_file = resolve(args.evaluation_file, str(pathlib.PurePath(base) / config.default_evaluation_file_name) if base else "")
+  args.summary_dir = resolve(args.summary_dir, base if base else "")
+
+
+def _device_preferences(args):
+  """(preference order of device types, types that may host several entities): TPU > GPU > CPU; `--reuse-X` implies `--use-X`."""
+  args.use_gpu = args.use_gpu or args.reuse_gpu
+  args.use_tpu = args.use_tpu or args.reuse_tpu
+  wanted = [("TPU", args.use_tpu, args.reuse_tpu), ("GPU", args.use_gpu, args.reuse_gpu), ("CPU", True, True)]
+  return tuple(kind for kind, use, _ in wanted if use), tuple(kind for kind, _, reuse in wanted if reuse)
+
+
 def main(argv=None):
   global exit_pending
   exit_pending = False
   tools.install()
   tools.success("Python module loading phase...")
+  if os.environ.get("AGB_PRINT_ROOT"):
+    print("package root: " + str(pathlib.Path(__file__).resolve().parents[2]))
   if threading.current_thread() is threading.main_thread():
     signal.signal(signal.SIGINT, mark_exit)
     signal.signal(signal.SIGTERM, mark_exit)
@@ -113,57 +179,11 @@ def main(argv=None):
   parser = make_parser()
   with tools.Context("args", "info"):
     args = parser.parse_args(sys.argv[1:] if argv is None else argv)
-    if args.stdout_to != "-":
-      path = pathlib.Path(args.stdout_to)
-      sys.stdout = tools.MethodCallReplicator(sys.stdout, tools.ContextIOWrapper(path.open("w"), nocolor=True))
-      sys.stdout.write("Duplicating standard output to " + repr(str(path.resolve())) + os.linesep)
-    if args.stderr_to != "-":
-      path = pathlib.Path(args.stderr_to)
-      sys.stderr = tools.MethodCallReplicator(sys.stderr, tools.ContextIOWrapper(path.open("w"), nocolor=True))
-      sys.stderr.write("Duplicating standard error output to " + repr(str(path.resolve())) + os.linesep)
-    if args.client and args.server or not (args.client or args.server):
-      raise tools.UserException("One and only one of '--client' and '--server' must be specified")
-    if args.server:
-      args.server = tools.cluster_parse(args.server)
-      for job in (args.ps_job_name, args.wk_job_name, args.ev_job_name):
-        if job not in args.server:
-          raise tools.UserException("Given cluster specification does not include a " + repr(job) + " job")
-    if args.nb_workers <= 0:
-      raise tools.UserException("Expected at least one non-Byzantine worker")
-    if args.nb_workers < args.nb_real_byz_workers:
-      raise tools.UserException("Got more real Byzantine workers (" + repr(args.nb_real_byz_workers) + ") than total number of workers (" + repr(args.nb_workers) + ")")
-    if args.nb_workers <= 2 * args.nb_decl_byz_workers:
-      tools.warning("Got more declared Byzantine workers (" + repr(args.nb_decl_byz_workers) + ") than half the total number of workers (" + repr(args.nb_workers) + ")")
-    if args.nb_decl_byz_workers < args.nb_real_byz_workers:
-      tools.warning("Got more real Byzantine workers (" + repr(args.nb_real_byz_workers) + ") than declared number of Byzantine workers (" + repr(args.nb_decl_byz_workers) + ")")
-    if args.use_tpu or args.reuse_tpu:
-      tools.warning("There is no TPU on a B200 box: '--use-tpu/--reuse-tpu' are accepted and ignored")
-    if args.MPI:
-      tools.warning("'--MPI' is accepted for compatibility: ranks communicate through peer-mapped memory (NVLink) and NCCL/gloo")
-    for name in ("experiment_args", "aggregator_args", "learning_rate_args", "optimizer_args", "attack_args"):
-      if getattr(args, name) is None:
-        setattr(args, name, [])
-    if args.checkpoint_dir:
-      if not args.evaluation_file:
-        args.evaluation_file = str(pathlib.PurePath(args.checkpoint_dir) / config.default_evaluation_file_name)
-      elif args.evaluation_file == "-":
-        args.evaluation_file = ""
-      if not args.summary_dir:
-        args.summary_dir = args.checkpoint_dir
-      elif args.summary_dir == "-":
-        args.summary_dir = ""
-    else:
-      if args.evaluation_file == "-":
-        args.evaluation_file = ""
-      if args.summary_dir == "-":
-        args.summary_dir = ""
+    _tee_streams(args)
+    _validate(args)
+    _resolve_outputs(args)
     nb_nonbyz_workers = args.nb_workers - args.nb_real_byz_workers
-    if args.reuse_gpu:
-      args.use_gpu = True
-    if args.reuse_tpu:
-      args.use_tpu = True
-    device_prefs = (("TPU",) if args.use_tpu else ()) + (("GPU",) if args.use_gpu else ()) + ("CPU",)
-    device_reuse = (("TPU",) if args.reuse_tpu else ()) + (("GPU",) if args.reuse_gpu else ()) + ("CPU",)
+    device_prefs, device_reuse = _device_preferences(args)
     rank, world, local, device = _init_distributed(args.use_gpu)
     if rank != 0:
       tools.set_rank_tag("r" + str(rank))

@@ -8,11 +8,19 @@ plus noise (learnable, so the training loop still shows a falling loss / rising 
 
 `BatchStream` is the input pipeline: a background thread assembles batches into pinned host buffers and issues the
 host->device copies on a side stream, double-buffered, so the step never waits on the input unless it outruns it.
+
+Datasets that do not fit in host memory (ImageNet at 256x256 is ~250 GB) are *streamed*: `tools/datasets.py --shards N` writes
+`<name>/train-00000-of-000NN.agbshard` files of fixed-size records and `ShardStream` feeds the same pinned ring from the native
+reader (`native/py_loader`: reader threads -> shuffle pool -> batch), the counterpart of slim's `DatasetDataProvider(num_readers)`
++ `tf.train.batch` + `prefetch_queue` (reference: `experiments/slims.py:100-111`, `experiments/cnnet.py:123-132`).
 """
 
+import ctypes
+import json
 import os
 import pathlib
 import queue
+import struct
 import threading
 
 import numpy as np
@@ -28,6 +36,61 @@ _SHAPES = {  # name -> (train size, test size, (H, W, C), classes)
   "cifar100": (50000, 10000, (32, 32, 3), 100),
   "flowers": (3320, 350, (224, 224, 3), 5),
   "imagenet": (1281167, 50000, (224, 224, 3), 1000)}
+
+
+SHARD_MAGIC = b"AGBSHRD1"
+SHARD_SUFFIX = ".agbshard"
+
+
+def write_shard(path, images, labels):
+  """One shard file: 64-byte header, `count` uint8 HWC records, `count` int64 labels (layout of `native/py_loader/loader.cpp`)."""
+  images = np.ascontiguousarray(images, dtype=np.uint8)
+  labels = np.ascontiguousarray(labels, dtype=np.int64).reshape(-1)
+  if images.ndim == 3:
+    images = images[..., None]
+  count, h, w, c = images.shape
+  if len(labels) != count:
+    raise tools.UserException("write_shard: %d images but %d labels" % (count, len(labels)))
+  header = SHARD_MAGIC + struct.pack("<QIIIIQ", count, h, w, c, 8, h * w * c) + bytes(24)
+  with open(path, "wb") as fd:
+    fd.write(header)
+    fd.write(images.tobytes())
+    fd.write(labels.tobytes())
+  return path
+
+
+def read_shard_header(path):
+  with open(path, "rb") as fd:
+    raw = fd.read(64)
+  if len(raw) != 64 or raw[:8] != SHARD_MAGIC:
+    raise tools.UserException("Not a shard file: " + repr(str(path)))
+  count, h, w, c, label_bytes, record_bytes = struct.unpack("<QIIIIQ", raw[8:40])
+  return {"count": count, "shape": (h, w, c), "record_bytes": record_bytes, "label_bytes": label_bytes}
+
+
+def read_shard(path, limit=None):
+  """Whole shard (or its first `limit` records) in memory: the evaluation split, tests."""
+  header = read_shard_header(path)
+  count = header["count"] if limit is None else min(header["count"], limit)
+  with open(path, "rb") as fd:
+    fd.seek(64)
+    images = np.frombuffer(fd.read(count * header["record_bytes"]), dtype=np.uint8).reshape((count,) + header["shape"])
+    fd.seek(64 + header["count"] * header["record_bytes"])
+    labels = np.frombuffer(fd.read(count * 8), dtype=np.int64)
+  return images, labels
+
+
+def _dataset_roots():
+  return (DATASETS_DIR, pathlib.Path(os.environ.get("AGB_DATASETS", "/nonexistent")))
+
+
+def find_shards(name, split):
+  """Sorted shard files `<root>/<name>/<split>-*.agbshard` of a streamed dataset ([] when there are none)."""
+  for root in _dataset_roots():
+    files = sorted((root / name).glob(split + "-*" + SHARD_SUFFIX)) if (root / name).is_dir() else []
+    if files:
+      return files
+  return []
 
 
 def known_datasets():
@@ -53,6 +116,24 @@ class Dataset:
 
   def __init__(self, name, image_size=None, synthetic_limit=4096, seed=1234):
     self.name = name
+    self.streaming = False
+    self.train_shards = find_shards(name, "train")
+    if self.train_shards:
+      # streamed dataset: only the (bounded) evaluation split is held in memory
+      self.streaming, self.synthetic = True, False
+      header = read_shard_header(self.train_shards[0])
+      self.shape = header["shape"]
+      self.train_count = sum(read_shard_header(p)["count"] for p in self.train_shards)
+      test_shards = find_shards(name, "test") or find_shards(name, "validation")
+      parts = [read_shard(p, limit=4096) for p in test_shards[:4]] or [read_shard(self.train_shards[-1], limit=1024)]
+      self.x_test, self.y_test = np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
+      self.x_train, self.y_train = None, None
+      meta = self.train_shards[0].parent / "meta.json"
+      if meta.is_file():
+        self.classes = int(json.loads(meta.read_text())["classes"])
+      else:
+        self.classes = int(max(int(read_shard(p)[1].max()) for p in self.train_shards)) + 1
+      return
     path = _find_npz(name)
     if path is not None:
       with np.load(path) as blob:
@@ -63,6 +144,7 @@ class Dataset:
       self.synthetic = False
       self.classes = int(self.y_train.max()) + 1
       self.shape = tuple(self.x_train.shape[1:])
+      self.train_count = len(self.y_train)
       return
     if name not in _SHAPES or _SHAPES[name] is None:
       raise tools.UserException("Dataset " + repr(name) + " not found (expected " + repr(str(DATASETS_DIR / name / (name + ".npz"))) + ")")
@@ -79,6 +161,14 @@ class Dataset:
     self.y_test = rng.integers(0, classes, size=ntest, dtype=np.int64)
     self.x_train = self._render(self.y_train, rng)
     self.x_test = self._render(self.y_test, rng)
+    self.train_count = ntrain
+
+  def train_stream(self, batch_size, device, seed=0, transform=None, readers=1, part=0, parts=1):
+    """The training input pipeline of one worker: in-memory `BatchStream`, or the native shard reader when the dataset is streamed
+    (`readers` = reader threads, the reference's `nb-fetcher-threads`; `part`/`parts` give each worker a disjoint residue class)."""
+    if self.streaming:
+      return ShardStream(self.train_shards, batch_size, device, seed=seed, transform=transform, readers=readers, part=part, parts=parts)
+    return BatchStream(self.x_train, self.y_train, batch_size, device, seed=seed, transform=transform)
 
   def _render(self, labels, rng):
     h, w, c = self.shape
@@ -108,7 +198,9 @@ class BatchStream:
     self._queue = None
     self._thread = None
     self._stop = False
-    self.h2d_bytes = self.batch * int(np.prod(images.shape[1:])) * images.dtype.itemsize + self.batch * 8
+    self.sample_shape = tuple(images.shape[1:])
+    self.sample_dtype = torch.from_numpy(images[:1]).dtype
+    self.h2d_bytes = self.batch * int(np.prod(self.sample_shape)) * images.dtype.itemsize + self.batch * 8
 
   def _next_indices(self):
     if self._cursor + self.batch > len(self._order):
@@ -132,8 +224,8 @@ class BatchStream:
   def _producer(self):
     torch.cuda.set_device(self.device)
     stream = torch.cuda.Stream(self.device)
-    shape = (self.batch,) + tuple(self.images.shape[1:])
-    slots = [(torch.empty(shape, dtype=torch.from_numpy(self.images[:1]).dtype).pin_memory(), torch.empty(self.batch, dtype=torch.int64).pin_memory()) for _ in range(self._depth + 2)]
+    shape = (self.batch,) + self.sample_shape
+    slots = [(torch.empty(shape, dtype=self.sample_dtype).pin_memory(), torch.empty(self.batch, dtype=torch.int64).pin_memory()) for _ in range(self._depth + 2)]
     i = 0
     events = [None] * len(slots)
     while not self._stop:
@@ -177,3 +269,49 @@ class BatchStream:
 
   def close(self):
     self._stop = True
+
+
+class ShardStream(BatchStream):
+  """`BatchStream` fed by the native streaming reader (`native/py_loader`): nothing but the pinned ring lives in host memory."""
+
+  def __init__(self, paths, batch_size, device, seed=0, shuffle=True, depth=2, transform=None, readers=1, part=0, parts=1, pool=0, min_after_dequeue=-1):
+    from .. import native
+    self._lib = native.library("py_loader")
+    lib = self._lib
+    lib.agb_loader_open.restype = ctypes.c_void_p
+    lib.agb_loader_last_error.restype = ctypes.c_char_p
+    lib.agb_loader_next.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    lib.agb_loader_info.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    lib.agb_loader_close.argtypes = [ctypes.c_void_p]
+    names = (ctypes.c_char_p * len(paths))(*[str(p).encode() for p in paths])
+    self._handle = lib.agb_loader_open(names, ctypes.c_int(len(paths)), ctypes.c_int(int(batch_size)), ctypes.c_int(max(1, int(readers))), ctypes.c_ulonglong(seed & (2 ** 64 - 1)),
+                                       ctypes.c_int(1 if shuffle else 0), ctypes.c_longlong(pool), ctypes.c_longlong(min_after_dequeue), ctypes.c_int(part), ctypes.c_int(parts))
+    if not self._handle:
+      raise tools.UserException("Cannot open the dataset shards: " + lib.agb_loader_last_error().decode())
+    info = (ctypes.c_ulonglong * 6)()
+    lib.agb_loader_info(self._handle, info)
+    self.total = int(info[0])
+    self.batch = int(batch_size)
+    self.device = torch.device(device)
+    self.shuffle, self.transform = shuffle, transform
+    self._cuda = self.device.type == "cuda"
+    self._depth = depth
+    self._queue, self._thread, self._stop = None, None, False
+    self.sample_shape, self.sample_dtype = (int(info[2]), int(info[3]), int(info[4])), torch.uint8
+    self.h2d_bytes = self.batch * int(info[5]) + self.batch * 8
+
+  def _host_batch(self, slot=None):
+    if slot is None:
+      slot = (torch.empty((self.batch,) + self.sample_shape, dtype=torch.uint8), torch.empty(self.batch, dtype=torch.int64))
+    if self._lib.agb_loader_next(self._handle, ctypes.c_void_p(slot[0].data_ptr()), ctypes.c_void_p(slot[1].data_ptr())) != 0:
+      raise tools.UserException("Dataset reader failed: " + self._lib.agb_loader_last_error().decode())
+    return slot
+
+  def close(self):
+    super().close()
+    thread = self._thread
+    if thread is not None and thread.is_alive():
+      thread.join(timeout=2.0)
+    if self._handle and (thread is None or not thread.is_alive()):
+      self._lib.agb_loader_close(self._handle)
+      self._handle = None

@@ -1,8 +1,10 @@
 """`cnnet`: small CNN on CIFAR-10 (reference: `experiments/cnnet.py:54-196`).
 
-Args: `batch-size:32`, `eval-batch-size:1024`, `nb-fetcher-threads`, `nb-batcher-threads` (accepted; the input
-pipeline here is one prefetch thread per stream), `preprocessing:cifarnet`. Each worker dequeues its own batches.
-`cifarnet` preprocessing = per-image standardisation (train: + random horizontal flip), done on the device.
+Args: `batch-size:32`, `eval-batch-size:1024`, `nb-fetcher-threads` (reader threads when CIFAR-10 is streamed from shards),
+`nb-batcher-threads` (accepted), `preprocessing:cifarnet`. Each worker dequeues its own batches.
+slim's `cifarnet` preprocessing runs on the device in one kernel (`ops/preprocess.py`): training = zero-pad 4 + random 32x32 crop +
+mirror + random brightness (63) + random contrast [0.2, 1.8] + per-image standardisation, evaluation = standardisation; its random
+draws come from a device-resident counter, so the training step stays CUDA-graph replayable.
 """
 
 import torch
@@ -35,14 +37,17 @@ class CNNetExperiment(_Experiment):
     if self.data.synthetic:
       tools.warning("CIFAR-10 files not found: using the synthetic CIFAR-10-shaped dataset", context="cnnet")
     self._streams = {}
-    self.stochastic_preprocess = True   # the random flip of `cifarnet` preprocessing: no CUDA-graph replay of the step
+    from ..ops.preprocess import Preprocessor
+    self.preprocessor = Preprocessor("cifarnet", 32, pad=4, seed=self.args["seed"])
+    self.stochastic_preprocess = False   # counter-based augmentation kernel: replayable
 
   def model(self):
     return simple.cnnet(10)
 
   def train_stream(self, worker, nbworkers, device):
     if worker not in self._streams:
-      self._streams[worker] = BatchStream(self.data.x_train, self.data.y_train, self.args["batch-size"], device, seed=self.args["seed"] + worker)
+      self._streams[worker] = self.data.train_stream(self.args["batch-size"], device, seed=self.args["seed"] + worker, readers=self.args["nb-fetcher-threads"],
+                                                     part=worker, parts=nbworkers)
     return self._streams[worker]
 
   def eval_batch(self, device):
@@ -51,7 +56,7 @@ class CNNetExperiment(_Experiment):
     return next(self._eval_stream)
 
   def preprocess(self, inputs, ctx, training):
-    return cifarnet_preprocess(inputs, ctx.dtype, training, ctx.generator)
+    return self.preprocessor(inputs, ctx.dtype, training, backend=ctx.backend, stream_id=getattr(ctx, "worker_id", 0) or 0).contiguous(memory_format=torch.channels_last)
 
 
 register("cnnet", CNNetExperiment)

@@ -27,7 +27,17 @@ def _native():
   return nn_native
 
 
+fallbacks = {}   # op name -> number of times the torch provider served a call made with backend == "native" (diagnostics, tests)
+
+
+def set_strict(flag):
+  """Raise instead of falling back to the torch provider when a native op cannot take its arguments."""
+  global _STRICT
+  _STRICT = bool(flag)
+
+
 def _fallback(op):
+  fallbacks[op] = fallbacks.get(op, 0) + 1
   if _STRICT:
     raise tools.UserException("Native op " + repr(op) + " unavailable for these arguments and AGB_NATIVE_STRICT is set")
 
@@ -112,6 +122,7 @@ def depthwise_forward(backend, x, weight, stride, pads):
     out = _native().depthwise_forward(x, weight, stride, pads)
     if out is not None:
       return out
+    _fallback("depthwise_forward")
   t, b, l, r = pads
   xp = F.pad(x, (l, r, t, b))
   return F.conv2d(xp, weight.permute(0, 3, 1, 2), None, stride, 0, 1, x.shape[1]).contiguous(memory_format=_CL)
@@ -123,6 +134,7 @@ def depthwise_backward(backend, dy, x, weight, stride, pads, grad_w, groups=1, g
     out = _native().depthwise_backward(dy, x, weight, stride, pads, grad_w, groups, group_stride)
     if out is not None:
       return out
+    _fallback("depthwise_backward")
   t, b, l, r = pads
   n, c, h, w = x.shape
   xp = F.pad(x, (l, r, t, b))
@@ -194,6 +206,7 @@ def batchnorm_add_relu_forward(backend, x, gamma, beta, moving_mean, moving_var,
     out = _native().batchnorm_forward(x, gamma, beta, moving_mean, moving_var, decay, eps, True, groups, residual)
     if out is not None:
       return out
+    _fallback("batchnorm_add_relu_forward")
   y, mean, rstd = batchnorm_forward(backend, x, gamma, beta, moving_mean, moving_var, decay, eps, False, groups)
   return add_relu_forward(backend, y, residual, True), mean, rstd
 
@@ -204,6 +217,7 @@ def batchnorm_add_relu_backward(backend, dy, x, y, gamma, mean, rstd, grad_gamma
     out = _native().batchnorm_backward(dy, x, y, gamma, mean, rstd, True, grad_gamma, grad_beta, groups, group_stride, True)
     if out is not None:
       return out
+    _fallback("batchnorm_add_relu_backward")
   g = relu_backward(backend, dy, y)
   return batchnorm_backward(backend, g, x, None, gamma, mean, rstd, False, grad_gamma, grad_beta, groups, group_stride), g
 
@@ -284,6 +298,7 @@ def relu_backward(backend, dy, y):
     out = _native().relu_backward(dy, y)
     if out is not None:
       return out
+    _fallback("relu_backward")
   return _relu_mask(dy, y)
 
 
@@ -292,6 +307,7 @@ def add_relu_forward(backend, a, b, relu):
     out = _native().add_relu_forward(a, b, relu)
     if out is not None:
       return out
+    _fallback("add_relu_forward")
   y = a + b
   return torch.relu_(y) if relu else y
 
@@ -305,6 +321,7 @@ def add_forward(backend, a, b):
     out = _native().add_relu_forward(a, b, False)
     if out is not None:
       return out
+    _fallback("add_forward")
   return a + b
 
 
@@ -334,13 +351,19 @@ def maxpool_backward(backend, dy, shape, index, k, stride, pads, x, y):
 def avgpool2d_forward(backend, x, k, stride, pads):
   """Native k x k average pool with the TF "SAME" divisor, or None (the caller keeps its aten implementation)."""
   if backend == "native" and x.is_cuda:
-    return _native().avgpool2d_forward(x, k, stride, pads)
+    out = _native().avgpool2d_forward(x, k, stride, pads)
+    if out is None:
+      _fallback("avgpool2d_forward")
+    return out
   return None
 
 
 def avgpool2d_backward(backend, dy, shape, k, stride, pads):
   if backend == "native" and dy.is_cuda:
-    return _native().avgpool2d_backward(dy, shape, k, stride, pads)
+    out = _native().avgpool2d_backward(dy, shape, k, stride, pads)
+    if out is None:
+      _fallback("avgpool2d_backward")
+    return out
   return None
 
 
@@ -349,6 +372,7 @@ def relu6_forward(backend, x):
     out = _native().relu6(x)
     if out is not None:
       return out
+    _fallback("relu6_forward")
   return torch.clamp(x, 0.0, 6.0)
 
 
@@ -357,6 +381,7 @@ def relu6_backward(backend, dy, x):
     out = _native().relu6(x, dy)
     if out is not None:
       return out
+    _fallback("relu6_backward")
   return dy * ((x > 0) & (x < 6)).to(dy.dtype)
 
 
@@ -365,6 +390,7 @@ def global_avgpool_forward(backend, x):
     out = _native().global_avgpool_forward(x)
     if out is not None:
       return out
+    _fallback("global_avgpool_forward")
   return (x if x.dtype == torch.float64 else x.float()).mean(dim=(2, 3), keepdim=True).to(x.dtype)
 
 
@@ -374,6 +400,7 @@ def global_avgpool_backward(backend, dy, shape):
     out = _native().global_avgpool_backward(dy, shape)
     if out is not None:
       return out
+    _fallback("global_avgpool_backward")
   return (dy / (h * w)).expand(n, c, h, w).contiguous(memory_format=_CL)
 
 
@@ -382,6 +409,7 @@ def subsample_forward(backend, x, stride):
     out = _native().subsample_forward(x, stride)
     if out is not None:
       return out
+    _fallback("subsample_forward")
   return x[:, :, ::stride, ::stride].contiguous(memory_format=_CL)
 
 
@@ -390,6 +418,7 @@ def subsample_backward(backend, dy, shape, stride):
     out = _native().subsample_backward(dy, shape, stride)
     if out is not None:
       return out
+    _fallback("subsample_backward")
   n, c, h, w = shape
   dx = torch.zeros((n, h, w, c), dtype=dy.dtype, device=dy.device).permute(0, 3, 1, 2)  # zeros allocated directly in NHWC memory
   dx[:, :, ::stride, ::stride] = dy
@@ -406,6 +435,7 @@ def softmax_xent(backend, logits, labels, label_smoothing=0.0, groups=1):
     out = _native().softmax_xent(logits, labels, label_smoothing, groups)
     if out is not None:
       return out
+    _fallback("softmax_xent")
   if groups > 1:
     outs = [softmax_xent(backend, lg, lb, label_smoothing) for lg, lb in zip(_chunks(logits, groups), _chunks(labels, groups))]
     return torch.stack([o[0] for o in outs]), torch.cat([o[1] for o in outs], dim=0)
@@ -432,6 +462,7 @@ def image_normalize(backend, images, mode, dtype):
     out = _native().image_normalize(images, mode, dtype)
     if out is not None:
       return out
+    _fallback("image_normalize")
   x = images.to(torch.float32)
   if mode == "vgg" and x.shape[-1] == 3:
     x = x - torch.tensor(_VGG_MEANS, device=x.device)

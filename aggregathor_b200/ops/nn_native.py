@@ -529,11 +529,10 @@ def layernorm_backward(dy, x, gamma, mean, rstd, grad_gamma, grad_beta):
 
 
 # ---------------------------------------------------------------------------- #
-# Depthwise convolution, SAME average pooling, ReLU6 (native/op_nn/depthwise.cu). Written after this round's GPU budget was spent:
-# compiled, index arithmetic checked against torch by a CPU emulation, covered by gated tests (`AGB_NATIVE_PREVIEW=1`), off by
-# default until validated on a B200 — the aten provider is used otherwise.
+# Depthwise convolution, SAME average pooling, ReLU6 (native/op_nn/depthwise.cu): validated on a B200 in round 2
+# (`profiles/r2_call01_preview_pytest.log`), on by default; `AGB_NATIVE_DEPTHWISE=0` routes these layers to the aten provider.
 
-_DEPTHWISE = os.environ.get("AGB_NATIVE_PREVIEW", os.environ.get("AGB_NATIVE_DEPTHWISE", "0")) not in ("", "0")
+_DEPTHWISE = os.environ.get("AGB_NATIVE_DEPTHWISE", os.environ.get("AGB_NATIVE_PREVIEW", "1")) not in ("", "0")
 
 
 def _depthwise_ok(x, weight):

@@ -14,6 +14,14 @@ by Pillow.
     python -m aggregathor_b200.tools.datasets folder <dir with train/<class>/*.jpg and val|test/<class>/*.jpg> flowers --image-size 224
 
 The result goes to `experiments/datasets/<name>/<name>.npz` (or `--output`); keras' own `mnist.npz` is picked up as it is.
+
+Datasets larger than host memory are written as *shards* for the streaming reader (`native/py_loader`, `experiments/_data.py`):
+
+    python -m aggregathor_b200.tools.datasets slim <dir with train-00000-of-01024 ...> imagenet --shards 0 --store-size 256 --labels-offset 1
+
+`--shards 0` = one shard per source TFRecord file, converted one file at a time (nothing but the current file is held in memory);
+`--shards N` (> 0) splits an in-memory import into N training shards. Images are stored at `--store-size` (short side resized, centre
+crop to a square): slim's aspect-preserving resize / distorted-box crops are then taken from the stored image on the device.
 """
 
 import argparse
@@ -100,12 +108,20 @@ def parse_example(payload):
   return features
 
 
-def _decode_image(encoded, image_size=None):
+def _decode_image(encoded, image_size=None, keep_aspect=False):
   from PIL import Image
   image = Image.open(io.BytesIO(encoded))
   image = image.convert("L" if image.mode in ("L", "1") else "RGB")
   if image_size is not None and image.size != (image_size, image_size):
-    image = image.resize((image_size, image_size), Image.BILINEAR)
+    if keep_aspect:   # short side -> image_size, then the central square
+      w, h = image.size
+      scale = image_size / min(w, h)
+      nw, nh = max(image_size, round(w * scale)), max(image_size, round(h * scale))
+      image = image.resize((nw, nh), Image.BILINEAR)
+      left, top = (nw - image_size) // 2, (nh - image_size) // 2
+      image = image.crop((left, top, left + image_size, top + image_size))
+    else:
+      image = image.resize((image_size, image_size), Image.BILINEAR)
   array = np.asarray(image, dtype=np.uint8)
   return array[..., None] if array.ndim == 2 else array
 
@@ -232,6 +248,70 @@ def from_image_folder(directory, image_size, limit=None):
 
 
 # ---------------------------------------------------------------------------- #
+# Shards for the streaming reader
+
+def _shard_dir(name, output=None):
+  from ..experiments._data import DATASETS_DIR
+  target = pathlib.Path(output) if output else DATASETS_DIR / name
+  target.mkdir(parents=True, exist_ok=True)
+  return target
+
+
+def write_shards(name, x_train, y_train, x_test, y_test, shards, output=None):
+  """Split an in-memory import into `shards` training shards (+ 1 test shard per 8) under `experiments/datasets/<name>/`."""
+  import json
+  from ..experiments._data import SHARD_SUFFIX, write_shard
+  target = _shard_dir(name, output)
+  written = []
+  for split, x, y, count in (("train", x_train, y_train, max(1, shards)), ("test", x_test, y_test, max(1, shards // 8))):
+    bounds = np.linspace(0, len(y), count + 1).astype(np.int64)
+    for i in range(count):
+      if bounds[i + 1] > bounds[i]:
+        written.append(write_shard(target / ("%s-%05d-of-%05d%s" % (split, i, count, SHARD_SUFFIX)), x[bounds[i]:bounds[i + 1]], y[bounds[i]:bounds[i + 1]]))
+  classes = int(max(np.max(y_train), np.max(y_test) if len(y_test) else 0)) + 1
+  (target / "meta.json").write_text(json.dumps({"name": name, "classes": classes, "train": int(len(y_train)), "test": int(len(y_test)), "shape": list(np.asarray(x_train).shape[1:])}))
+  info("Dataset %r: %d training and %d test images in %d shard(s) -> %s" % (name, len(y_train), len(y_test), len(written), target))
+  return written
+
+
+def slim_to_shards(directory, name, store_size, labels_offset=0, limit=None, output=None):
+  """One shard per slim TFRecord file, one file in memory at a time (ImageNet: 1024 training + 128 validation files)."""
+  import json
+  from ..experiments._data import SHARD_SUFFIX, write_shard
+  directory = pathlib.Path(directory)
+  files = sorted(p for p in directory.iterdir() if p.is_file() and ("tfrecord" in p.name or "-of-" in p.name))
+  splits = {"train": [p for p in files if "train" in p.name], "test": [p for p in files if "validation" in p.name or "test" in p.name]}
+  if not splits["train"]:
+    raise UserException("No '*train*' TFRecord file found in " + repr(str(directory)))
+  target = _shard_dir(name, output)
+  counts, top_label, shape = {}, 0, None
+  for split, paths in splits.items():
+    counts[split] = 0
+    for index, path in enumerate(paths):
+      images, labels = [], []
+      for payload in read_tfrecords(path):
+        example = parse_example(payload)
+        if "image/encoded" not in example or "image/class/label" not in example:
+          raise UserException("Record without 'image/encoded' / 'image/class/label' in " + repr(str(path)))
+        images.append(_decode_image(example["image/encoded"][0], store_size, keep_aspect=True))
+        labels.append(int(example["image/class/label"][0]) - labels_offset)
+        if limit is not None and counts[split] + len(images) >= limit:
+          break
+      if not images:
+        continue
+      if len({image.shape for image in images}) > 1:
+        raise UserException("Images of different sizes in %r: pass --store-size" % str(path))
+      write_shard(target / ("%s-%05d-of-%05d%s" % (split, index, len(paths), SHARD_SUFFIX)), np.stack(images), np.asarray(labels, dtype=np.int64))
+      counts[split] += len(images)
+      top_label = max(top_label, max(labels))
+      shape = images[0].shape
+      if limit is not None and counts[split] >= limit:
+        break
+  (target / "meta.json").write_text(json.dumps({"name": name, "classes": top_label + 1, "train": counts["train"], "test": counts.get("test", 0), "shape": list(shape)}))
+  info("Dataset %r: %d training and %d test images streamed into shards -> %s" % (name, counts["train"], counts.get("test", 0), target))
+  return target
+
+
 def write_npz(name, x_train, y_train, x_test, y_test, output=None):
   from ..experiments._data import DATASETS_DIR
   target = pathlib.Path(output) if output else DATASETS_DIR / name / (name + ".npz")
@@ -251,8 +331,13 @@ def main(argv=None):
   parser.add_argument("--image-size", type=int, default=None, help="resize every image to this square size (needed for ImageNet-like sources)")
   parser.add_argument("--limit", type=int, default=None, help="keep at most this many images per split (everything is held in memory)")
   parser.add_argument("--labels-offset", type=int, default=0, help="subtracted from the stored labels (slim's ImageNet labels start at 1)")
-  parser.add_argument("--output", type=str, default=None, help="target .npz (default: experiments/datasets/<name>/<name>.npz)")
+  parser.add_argument("--output", type=str, default=None, help="target .npz (default: experiments/datasets/<name>/<name>.npz) or shard directory")
+  parser.add_argument("--shards", type=int, default=None, help="write shards for the streaming reader instead of one .npz: N training shards, 0 = one per source file (slim)")
+  parser.add_argument("--store-size", type=int, default=None, help="storage resolution of sharded images (short side resized + central square crop); default --image-size")
   args = parser.parse_args(sys.argv[1:] if argv is None else argv)
+  if args.shards is not None and args.format == "slim" and args.shards == 0:
+    slim_to_shards(args.source, args.name, args.store_size or args.image_size, args.labels_offset, args.limit, args.output)
+    return 0
   if args.format == "slim":
     arrays = from_slim_tfrecords(args.source, args.name, args.image_size, args.limit, args.labels_offset)
   elif args.format == "mnist":
@@ -263,7 +348,10 @@ def main(argv=None):
     if args.image_size is None:
       raise UserException("'folder' sources need --image-size")
     arrays = from_image_folder(args.source, args.image_size, args.limit)
-  write_npz(args.name, *arrays, output=args.output)
+  if args.shards is not None:
+    write_shards(args.name, *arrays, shards=args.shards, output=args.output)
+  else:
+    write_npz(args.name, *arrays, output=args.output)
   return 0
 
 

@@ -244,6 +244,23 @@ def test_deploy_local_cluster_with_lossy_workers(tmp_path):
   assert "drop-chunks" in out
 
 
+def test_deploy_ships_its_source_through_the_pipe(tmp_path):
+  """NFS-free deployment (`--ship always`): every rank unpacks the tarball it receives on stdin into a private directory and runs from
+  there (what a remote `ssh host` does; here through `sh -c`), no file of this checkout is read by the ranks."""
+  port = 7700 + os.getpid() % 250
+  cluster = '{"ps": ["127.0.0.1:%d"], "workers": ["127.0.0.1:%d", "127.0.0.1:%d"]}' % (port, port + 1, port + 2)
+  runner = ("--experiment mnist --aggregator median --nb-workers 2 --max-step 3 --learning-rate-args initial-rate:0.05 "
+            "--evaluation-file - --checkpoint-dir %s --checkpoint-delta -1 --checkpoint-period -1 --summary-dir -" % (tmp_path / "c"))
+  env = dict(os.environ, AGB_NUM_THREADS="2", OMP_NUM_THREADS="2", AGB_PRINT_ROOT="1")
+  proc = subprocess.run([sys.executable, str(ROOT / "deploy.py"), "--cluster", cluster, "--deploy", "--ship", "always", "--runner", runner],
+                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600, env=env, cwd=str(tmp_path))
+  out = proc.stdout.decode(errors="replace")
+  assert proc.returncode == 0, out[-3000:]
+  assert len(re.findall(r"Step \d+: total loss = ([0-9.eE+-]+)", out)) == 3
+  roots = set(re.findall(r"package root: (\S+)", out))
+  assert roots and all("agb-rank-" in root for root in roots), roots
+
+
 def test_slim_augmentation_options():
   """`augment:flip` / `augment:crop-flip`: every output image is a (possibly mirrored) window of the replicate-padded input, evaluation is untouched."""
   exp = experiments.instantiate("slim-resnet_v1_18-cifar10", ["batch-size:4", "synthetic-samples:64", "augment:crop-flip", "image-size:16"])

@@ -365,8 +365,8 @@ def test_subsample(shape, stride):
   assert dx.shape == x.shape and torch.equal(dx.contiguous(), ops.subsample_backward("torch", dy, shape, stride).contiguous())
 
 
-_PREVIEW = __import__("os").environ.get("AGB_NATIVE_PREVIEW", __import__("os").environ.get("AGB_NATIVE_DEPTHWISE", "0")) not in ("", "0")
-_preview = pytest.mark.skipif(not _PREVIEW, reason="depthwise / SAME average pool / ReLU6 kernels are opt-in (AGB_NATIVE_PREVIEW=1) until validated on a B200")
+_PREVIEW = __import__("os").environ.get("AGB_NATIVE_DEPTHWISE", __import__("os").environ.get("AGB_NATIVE_PREVIEW", "1")) not in ("", "0")
+_preview = pytest.mark.skipif(not _PREVIEW, reason="depthwise / SAME average pool / ReLU6 kernels switched off (AGB_NATIVE_DEPTHWISE=0)")
 
 
 @_preview
@@ -409,3 +409,44 @@ def test_avgpool2d_and_relu6_native(shape, k, stride, padding):
     outs[backend] = (y, dx, a, da)
   for got, want, tol in zip(outs["native"], outs["torch"], (1e-2, 1e-2, 1e-2, 1e-2)):
     _close(got, want, tol)
+
+
+def _factory_names():
+  from aggregathor_b200.models import nets_factory
+  return sorted(nets_factory.networks_map)
+
+
+@pytest.mark.parametrize("name", _factory_names())
+def test_every_factory_net_trains_one_step_on_native_kernels(name):
+  """All 33 names of the slim factory (reference: `external/slim/nets/nets_factory.py:39-72`): one training step at a reduced
+  resolution with the native provider; reports which ops (if any) were served by the aten provider instead."""
+  from aggregathor_b200.engine.flat import FlatLayout
+  from aggregathor_b200.models import Context, nets_factory
+  from aggregathor_b200.ops import nn as ops
+  model = nets_factory.get_network(name, 11)
+  size = model.input_shape[-1]   # full resolution: the VGG / AlexNet / OverFeat heads are sized for it
+  layout, states = FlatLayout(), {}
+  model.declare(layout, states)
+  layout.freeze()
+  params = torch.zeros(layout.padded_size, device="cuda")
+  host = torch.zeros(layout.padded_size)
+  host_states = {k: torch.zeros(v) for k, v in states.items()}
+  model.initialize(layout.views(host), host_states, torch.Generator().manual_seed(1))
+  params.copy_(host)
+  ctx = Context("native", True, torch.bfloat16, "cuda")
+  ctx.master = layout.views(params)
+  ctx.weights = layout.views(params.to(torch.bfloat16))
+  ctx.state = {k: v.cuda() for k, v in host_states.items()}
+  grads = torch.zeros_like(params)
+  ctx.grads = layout.views(grads)
+  ctx.generator = torch.Generator(device="cuda").manual_seed(2)
+  channels = model.input_shape[0]
+  x = torch.randn((2, channels, size, size), device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+  labels = torch.randint(0, 11, (2,), device="cuda")
+  before = dict(ops.fallbacks)
+  loss = float(model.loss_and_backward(x, labels, ctx))
+  torch.cuda.synchronize()
+  served_by_aten = {k: v - before.get(k, 0) for k, v in ops.fallbacks.items() if v - before.get(k, 0) > 0}
+  assert loss == loss and float(grads.abs().sum()) > 0
+  print("%s: aten fallbacks %r" % (name, served_by_aten))
+  assert not served_by_aten, served_by_aten
