@@ -1,4 +1,4 @@
-// Implicit-GEMM k x k convolution (stride 1, "same" zero padding) on tcgen05: no im2col buffer.
+// Implicit-GEMM k x k convolution (stride 1 or 2, zero padding) on tcgen05: no im2col buffer.
 //
 // Activations are NHWC, so the A operand of the forward GEMM for filter tap (kh, kw) and a 64-channel slice is simply the
 // activation tensor shifted by (kh - pad, kw - pad). A 4-D TMA tensor map (C, W, H, N) lets one `cp.async.bulk.tensor.4d`
@@ -11,6 +11,13 @@
 //   dgrad    dx[p, ci]     = sum_{kh,kw,co} dy[p + (pad-kh, pad-kw), co] * W[co, kh, kw, ci]      A: 4-D box of dy, B: MN-major W tap
 //   wgrad    dW[co,kh,kw,ci] = sum_p dy[p, co] * x[p + (kh-pad, kw-pad), ci]                       A, B: 4-D MN-major boxes (K = pixels)
 //
+// Stride 2 (ResNet's down-sampling 3x3 convolutions, `external/slim/nets/resnet_v1.py:123-128`): the forward and weight-gradient
+// products read x through a tensor map whose TMA *element strides* are (1, 2, 2, 1) — the box of bw x bh output pixels fetches every
+// second input pixel, still one bulk-tensor copy per tap. The data gradient splits dx into its four pixel parities: the pixels
+// (2i + ph, 2j + pw) only receive the taps with kh = ph + pad_t (mod 2), kw = pw + pad_l (mod 2), each a stride-1 shifted box of dy,
+// so every parity class is a small stride-1 problem (1, 2, 2 and 4 taps for a 3x3 filter) whose epilogue scatters its rows to the
+// strided dx addresses.
+//
 // Pipeline, TMEM double buffering and epilogue are those of the persistent GEMM (gemm_kernels.cuh); only the producer's
 // coordinates and the epilogue's row -> address mapping differ.
 
@@ -19,8 +26,10 @@
 namespace {
 
 struct ConvParams {
-    int N, H, W;            // pixel grid (stride 1 => input and output share it)
-    int Cin, Cout, k, pad;
+    int N, H, W;            // input (x / dx) pixel grid
+    int OH, OW;             // output (y / dy) pixel grid (= H, W for stride 1 "same" convolutions)
+    int Cin, Cout, k, stride, pad_t, pad_l;
+    int GH, GW;             // grid the M tiles (fwd, dgrad) or K blocks (wgrad) walk over: fwd/wgrad OH x OW; dgrad H/stride x W/stride per parity
     int bw, bh, bn;         // pixel box of one M tile (fwd/dgrad: product <= 128) or one K block (wgrad: product <= 64)
     int tiles_w, tiles_h, tiles_n;
     int groups, images_per_group;   // wgrad of several logical workers: K ranges = image ranges, one output per group
@@ -28,14 +37,15 @@ struct ConvParams {
 
 enum ConvMode { kFwd = 0, kDgrad = 1, kWgrad = 2 };
 
-inline int make_tmap_4d_bf16(CUtensorMap* map, void const* base, int C, int W, int H, int N, int bw, int bh, int bn) {
+// `estride` > 1: the box covers bw * estride x bh * estride source pixels and TMA keeps every estride-th one (bw x bh land in smem).
+inline int make_tmap_4d_bf16(CUtensorMap* map, void const* base, int C, int W, int H, int N, int bw, int bh, int bn, int estride = 1) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn)
         return 201;
     cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(N)};
     cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(W) * C * 2, static_cast<cuuint64_t>(H) * W * C * 2};
-    cuuint32_t box[4] = {64, static_cast<cuuint32_t>(bw), static_cast<cuuint32_t>(bh), static_cast<cuuint32_t>(bn)};
-    cuuint32_t elem[4] = {1, 1, 1, 1};
+    cuuint32_t box[4] = {64, static_cast<cuuint32_t>(bw * estride), static_cast<cuuint32_t>(bh * estride), static_cast<cuuint32_t>(bn)};
+    cuuint32_t elem[4] = {1, static_cast<cuuint32_t>(estride), static_cast<cuuint32_t>(estride), 1};
     CUresult res = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (res != CUDA_SUCCESS) {
@@ -70,7 +80,8 @@ __global__ void __launch_bounds__(kPersistentThreads, 1) conv_tcgen05_kernel(con
     // number of K blocks of one work item before splitting
     int const cchunks = (MODE == kFwd ? cp.Cin : cp.Cout) / 64;
     int const groups = (MODE == kWgrad && cp.groups > 1) ? cp.groups : 1;
-    int const total_kblocks = MODE == kWgrad ? pixel_tiles / groups : taps * cchunks;
+    int const parities = (MODE == kDgrad && cp.stride > 1) ? cp.stride * cp.stride : 1;   // dgrad of a strided convolution: one sub-problem per pixel parity
+    int const total_kblocks = MODE == kWgrad ? pixel_tiles / groups : taps * cchunks;     // upper bound per item for dgrad parities (their tap subsets are smaller)
     int const total_items = items_mn * splits * groups;
 
     // Pixel boxes smaller than the MMA tile (7x7 maps) leave rows that TMA never writes: zero the ring once.
@@ -107,15 +118,32 @@ __global__ void __launch_bounds__(kPersistentThreads, 1) conv_tcgen05_kernel(con
     uint32_t const b_bytes = MODE == kWgrad ? (BN / 64) * box_rows * 128u : Cfg::kBBytes;
 
     // item -> (m index, n tile, tap for wgrad, k split)
-    struct Item { int pw, ph, pn, n0, tap, kb_begin, nkb, m0, group; };
+    // par_h / par_w: pixel parity of a strided dgrad item; first_kh / nkh (and _kw): the taps that reach that parity (kh = first_kh + stride * i)
+    struct Item { int pw, ph, pn, n0, tap, kb_begin, nkb, m0, group, par_h, par_w, first_kh, first_kw, nkw; };
     auto decode = [&](int item) {
         Item it;
         it.group = item / (items_mn * splits);
         item -= it.group * items_mn * splits;
-        int const mn = item % items_mn, split = item / items_mn;
+        int mn = item % items_mn;
+        int const split = item / items_mn;
+        it.par_h = it.par_w = it.first_kh = it.first_kw = 0;
+        it.nkw = cp.k;
+        int item_kblocks = total_kblocks;
+        if (parities > 1) {
+            int const per_parity = items_mn / parities;
+            int const parity = mn / per_parity;
+            mn -= parity * per_parity;
+            it.par_h = parity / cp.stride;
+            it.par_w = parity % cp.stride;
+            it.first_kh = (it.par_h + cp.pad_t) % cp.stride;
+            it.first_kw = (it.par_w + cp.pad_l) % cp.stride;
+            int const nkh = it.first_kh < cp.k ? (cp.k - it.first_kh + cp.stride - 1) / cp.stride : 0;
+            it.nkw = it.first_kw < cp.k ? (cp.k - it.first_kw + cp.stride - 1) / cp.stride : 0;
+            item_kblocks = nkh * it.nkw * cchunks;
+        }
         it.kb_begin = split * p.kblocks_per_split;
-        int const kb_end = min(total_kblocks, it.kb_begin + p.kblocks_per_split);
-        it.nkb = kb_end - it.kb_begin;
+        int const kb_end = min(item_kblocks, it.kb_begin + p.kblocks_per_split);
+        it.nkb = max(kb_end - it.kb_begin, 0);
         if (MODE == kWgrad) {
             int const m_tiles = (cp.Cout + kBM - 1) / kBM, n_tiles = (cp.Cin + BN - 1) / BN;
             it.tap = mn / (m_tiles * n_tiles);
@@ -148,7 +176,7 @@ __global__ void __launch_bounds__(kPersistentThreads, 1) conv_tcgen05_kernel(con
                     int const kb = it.kb_begin + i;
                     mbar_expect_tx(full + s, a_bytes + b_bytes);
                     if (MODE == kWgrad) {
-                        // K block = pixel box `kb`; A = dy[box, co chunk], B = x[box shifted by the tap, ci chunk]
+                        // K block = pixel box `kb` of the dy grid; A = dy[box, co chunk], B = x[box * stride shifted by the tap, ci chunk]
                         int const w0 = (kb % cp.tiles_w) * cp.bw, h0 = ((kb / cp.tiles_w) % cp.tiles_h) * cp.bh;
                         int const n0p = (kb / (cp.tiles_w * cp.tiles_h)) * cp.bn + it.group * cp.images_per_group;
                         int const kh = it.tap / cp.k, kw = it.tap % cp.k;
@@ -156,11 +184,23 @@ __global__ void __launch_bounds__(kPersistentThreads, 1) conv_tcgen05_kernel(con
                         tma_load_4d(a_dst + kBK * 128, &tmap_a, full + s, it.m0 + 64, w0, h0, n0p);
 #pragma unroll
                         for (int c = 0; c < BN / 64; ++c)
-                            tma_load_4d(b_dst + c * kBK * 128, &tmap_b, full + s, it.n0 + c * 64, w0 + kw - cp.pad, h0 + kh - cp.pad, n0p);
+                            tma_load_4d(b_dst + c * kBK * 128, &tmap_b, full + s, it.n0 + c * 64, w0 * cp.stride + kw - cp.pad_l, h0 * cp.stride + kh - cp.pad_t, n0p);
                     } else {
-                        int const tap = kb / cchunks, c0 = (kb % cchunks) * 64;
-                        int const kh = tap / cp.k, kw = tap % cp.k;
-                        int const dw = MODE == kFwd ? kw - cp.pad : cp.pad - kw, dh = MODE == kFwd ? kh - cp.pad : cp.pad - kh;
+                        int const tap_index = kb / cchunks, c0 = (kb % cchunks) * 64;
+                        int kh, kw, dw, dh;
+                        if (MODE == kFwd) {         // x[oh * s + kh - pad_t, ow * s + kw - pad_l]: the map's element strides do the "* s"
+                            kh = tap_index / cp.k; kw = tap_index % cp.k;
+                            dw = it.pw * (cp.stride - 1) + kw - cp.pad_l;
+                            dh = it.ph * (cp.stride - 1) + kh - cp.pad_t;
+                        } else if (parities == 1) { // dy[h + pad_t - kh, w + pad_l - kw]
+                            kh = tap_index / cp.k; kw = tap_index % cp.k;
+                            dw = cp.pad_l - kw; dh = cp.pad_t - kh;
+                        } else {                    // pixel (s*i + par_h, s*j + par_w) <- dy[i + (par_h + pad_t - kh) / s, j + (par_w + pad_l - kw) / s], kh = par_h + pad_t (mod s)
+                            kh = it.first_kh + cp.stride * (tap_index / it.nkw); kw = it.first_kw + cp.stride * (tap_index % it.nkw);
+                            dh = (it.par_h + cp.pad_t - kh) / cp.stride;   // exact: the numerator is a multiple of the stride (may be negative)
+                            dw = (it.par_w + cp.pad_l - kw) / cp.stride;
+                        }
+                        int const tap = kh * cp.k + kw;
                         tma_load_4d(a_dst, &tmap_a, full + s, c0, it.pw + dw, it.ph + dh, it.pn);
                         if (MODE == kFwd) {
                             tma_load_2d(b_dst, &tmap_b, full + s, tap * cp.Cin + c0, it.n0);
@@ -208,9 +248,12 @@ __global__ void __launch_bounds__(kPersistentThreads, 1) conv_tcgen05_kernel(con
                 offset = static_cast<long long>(co) * p.ldc + it.tap * cp.Cin + it.group * p.c_group_stride;
             } else {                // row = pixel of the box, (w fastest, then h, then n)
                 int const bi_w = r % cp.bw, bi_h = (r / cp.bw) % cp.bh, bi_n = r / (cp.bw * cp.bh);
-                int const w = it.pw + bi_w, h = it.ph + bi_h, n = it.pn + bi_n;
-                valid = r < box_rows && w < cp.W && h < cp.H && n < cp.N;
-                offset = ((static_cast<long long>(n) * cp.H + h) * cp.W + w) * p.ldc;
+                int const gw = it.pw + bi_w, gh = it.ph + bi_h, n = it.pn + bi_n;
+                valid = r < box_rows && gw < cp.GW && gh < cp.GH && n < cp.N;
+                if (MODE == kFwd)      // y[n, gh, gw]
+                    offset = ((static_cast<long long>(n) * cp.OH + gh) * cp.OW + gw) * p.ldc;
+                else                   // dx[n, gh * s + parity_h, gw * s + parity_w] (s = 1: the pixel itself)
+                    offset = ((static_cast<long long>(n) * cp.H + gh * cp.stride + it.par_h) * cp.W + gw * cp.stride + it.par_w) * p.ldc;
             }
             epilogue_rows_staged<BN>(p, tmem_base + buf * Cfg::kTmemCols, (warp & 3) | (((warp - 2) >> 2) << 2), lane, valid, offset, it.n0, epi_stage);
             tc_fence_before();
@@ -274,10 +317,18 @@ bool choose_box(int W, int H, int N, int rows, int& bw, int& bh, int& bn) {
 extern "C" {
 
 // mode 0: y = conv(x, W) (+bias, ReLU) ; mode 1: dx = conv_transpose(dy, W) ; mode 2: dW (+)= dy^T * x (fp32, atomics; caller zeroes).
-// x / dy / y / dx are NHWC bf16 with N x H x W pixels (stride-1, same padding: pad = (k - 1) / 2, odd k);
-// W is [Cout][k][k][Cin] bf16; dW is [Cout][k][k][Cin] fp32. Cin % 64 == 0 and Cout % 64 == 0.
+// x / dx are NHWC bf16 with N x H x W pixels, y / dy with N x OH x OW pixels, OH = (H + pad_t + pad_b - k) / stride + 1 (the bottom / right
+// padding is implied: whatever the boxes read beyond the image is zero). stride 1 or 2; W is [Cout][k][k][Cin] bf16; dW is
+// [Cout][k][k][Cin] fp32. Cin % 64 == 0 and Cout % 64 == 0. For stride 2: H, W even, OH = H / 2, OW = W / 2.
+int agb_conv_implicit_strided(int mode, void const* act, void const* other, void* out, int N, int H, int W, int OH, int OW, int Cin, int Cout, int k, int stride, int pad_t, int pad_l,
+                              void const* bias, int relu, int out_fp32, int splits, int bn, int groups, long long c_group_stride, void* stream);
+
 int agb_conv_implicit_grouped(int mode, void const* act, void const* other, void* out, int N, int H, int W, int Cin, int Cout, int k, void const* bias, int relu,
-                              int out_fp32, int splits, int bn, int groups, long long c_group_stride, void* stream);
+                              int out_fp32, int splits, int bn, int groups, long long c_group_stride, void* stream) {
+    if ((k & 1) == 0)
+        return 401;
+    return agb_conv_implicit_strided(mode, act, other, out, N, H, W, H, W, Cin, Cout, k, 1, (k - 1) / 2, (k - 1) / 2, bias, relu, out_fp32, splits, bn, groups, c_group_stride, stream);
+}
 
 int agb_conv_implicit(int mode, void const* act, void const* other, void* out, int N, int H, int W, int Cin, int Cout, int k, void const* bias, int relu,
                       int out_fp32, int splits, int bn, void* stream) {
@@ -286,20 +337,27 @@ int agb_conv_implicit(int mode, void const* act, void const* other, void* out, i
 
 // `groups` > 1 (mode 2 only): the N images are `groups` consecutive batches of N / groups images; group g accumulates its weight gradient
 // into out + g * c_group_stride.
-int agb_conv_implicit_grouped(int mode, void const* act, void const* other, void* out, int N, int H, int W, int Cin, int Cout, int k, void const* bias, int relu,
-                              int out_fp32, int splits, int bn, int groups, long long c_group_stride, void* stream) {
-    if ((k & 1) == 0 || Cin % 64 || Cout % 64 || N < 1)
+int agb_conv_implicit_strided(int mode, void const* act, void const* other, void* out, int N, int H, int W, int OH, int OW, int Cin, int Cout, int k, int stride, int pad_t, int pad_l,
+                              void const* bias, int relu, int out_fp32, int splits, int bn, int groups, long long c_group_stride, void* stream) {
+    if (k < 1 || Cin % 64 || Cout % 64 || N < 1 || (stride != 1 && stride != 2) || pad_t < 0 || pad_l < 0 || pad_t >= k || pad_l >= k)
         return 401;
+    if (stride == 2 && ((H & 1) || (W & 1) || OH != H / 2 || OW != W / 2 || k < 2))
+        return 405;
+    if (stride == 1 && (OH != H || OW != W))
+        return 405;
     if (groups < 1)
         groups = 1;
     if (groups > 1 && (mode != 2 || N % groups))
         return 404;
     ConvParams cp{};
-    cp.N = N; cp.H = H; cp.W = W; cp.Cin = Cin; cp.Cout = Cout; cp.k = k; cp.pad = (k - 1) / 2;
+    cp.N = N; cp.H = H; cp.W = W; cp.OH = OH; cp.OW = OW; cp.Cin = Cin; cp.Cout = Cout; cp.k = k; cp.stride = stride; cp.pad_t = pad_t; cp.pad_l = pad_l;
     cp.groups = groups; cp.images_per_group = N / groups;
-    if (!choose_box(W, H, mode == 2 ? N / groups : N, mode == 2 ? 64 : 128, cp.bw, cp.bh, cp.bn))   // boxes never straddle two workers
+    // the grid the boxes tile: output pixels (fwd, wgrad) or, for the data gradient, the pixels of one parity class of dx
+    cp.GH = mode == 1 ? H / stride : OH;
+    cp.GW = mode == 1 ? W / stride : OW;
+    if (!choose_box(cp.GW, cp.GH, mode == 2 ? N / groups : N, mode == 2 ? 64 : 128, cp.bw, cp.bh, cp.bn))   // boxes never straddle two workers
         return 402;
-    cp.tiles_w = W / cp.bw; cp.tiles_h = H / cp.bh; cp.tiles_n = N / cp.bn;
+    cp.tiles_w = cp.GW / cp.bw; cp.tiles_h = cp.GH / cp.bh; cp.tiles_n = N / cp.bn;
     int const pixel_tiles = cp.tiles_w * cp.tiles_h * cp.tiles_n;
     GemmParams p{};
     p.C = out;
@@ -310,10 +368,10 @@ int agb_conv_implicit_grouped(int mode, void const* act, void const* other, void
     int status, items_mn, total_kblocks;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (mode == 0) {
-        p.M = N * H * W; p.N = Cout; p.K = k * k * Cin; p.ldc = Cout;
+        p.M = N * OH * OW; p.N = Cout; p.K = k * k * Cin; p.ldc = Cout;
         if (bn == 0)
             bn = Cout <= 64 ? 64 : 128;
-        if ((status = make_tmap_4d_bf16(&ta, act, Cin, W, H, N, cp.bw, cp.bh, cp.bn)))
+        if ((status = make_tmap_4d_bf16(&ta, act, Cin, W, H, N, cp.bw, cp.bh, cp.bn, stride)))
             return status;
         if ((status = make_tmap_2d_bf16(&tb, other, static_cast<uint64_t>(k) * k * Cin, Cout, static_cast<uint64_t>(k) * k * Cin, kBK, bn)))
             return status;
@@ -323,21 +381,23 @@ int agb_conv_implicit_grouped(int mode, void const* act, void const* other, void
         p.M = N * H * W; p.N = Cin; p.K = k * k * Cout; p.ldc = Cin;
         if (bn == 0)
             bn = Cin <= 64 ? 64 : 128;
-        if ((status = make_tmap_4d_bf16(&ta, act, Cout, W, H, N, cp.bw, cp.bh, cp.bn)))
+        if ((status = make_tmap_4d_bf16(&ta, act, Cout, OW, OH, N, cp.bw, cp.bh, cp.bn)))
             return status;
         if ((status = make_tmap_2d_bf16(&tb, other, static_cast<uint64_t>(k) * k * Cin, Cout, static_cast<uint64_t>(k) * k * Cin, 64, kBK)))
             return status;
-        items_mn = pixel_tiles * ((Cin + bn - 1) / bn);
+        items_mn = pixel_tiles * ((Cin + bn - 1) / bn) * stride * stride;   // one sub-problem per pixel parity
         total_kblocks = k * k * (Cout / 64);
+        if (stride > 1 && splits > 1)
+            return 406;
     } else if (mode == 2) {
-        p.M = Cout; p.N = Cin; p.K = N * H * W; p.ldc = static_cast<long long>(k) * k * Cin;
+        p.M = Cout; p.N = Cin; p.K = N * OH * OW; p.ldc = static_cast<long long>(k) * k * Cin;
         if (!out_fp32)
             return 205;
         if (bn == 0)
             bn = Cin <= 64 ? 64 : 128;
-        if ((status = make_tmap_4d_bf16(&ta, act, Cout, W, H, N, cp.bw, cp.bh, cp.bn)))
+        if ((status = make_tmap_4d_bf16(&ta, act, Cout, OW, OH, N, cp.bw, cp.bh, cp.bn)))
             return status;
-        if ((status = make_tmap_4d_bf16(&tb, other, Cin, W, H, N, cp.bw, cp.bh, cp.bn)))
+        if ((status = make_tmap_4d_bf16(&tb, other, Cin, W, H, N, cp.bw, cp.bh, cp.bn, stride)))
             return status;
         items_mn = k * k * ((Cout + kBM - 1) / kBM) * ((Cin + bn - 1) / bn);
         total_kblocks = pixel_tiles / groups;

@@ -629,21 +629,21 @@ __global__ void image_normalize_kernel(unsigned char const* __restrict__ x, bf16
 // ---------------------------------------------------------------------------- //
 // im2col: x NHWC [N,H,W,C] -> col [N*OH*OW, ldcol] with column order (kh, kw, c); zero padding, zero tail columns.
 // One thread per (output pixel, kh, kw, channel octet) when C % 8 == 0, scalar path otherwise (the 3-channel stem).
-__global__ void im2col_kernel(bf16 const* __restrict__ x, bf16* __restrict__ col, int N, int H, int W, int C, int OH, int OW, int k, int s, int pad_t, int pad_l, long long ldcol) {
+__global__ void im2col_kernel(bf16 const* __restrict__ x, bf16* __restrict__ col, int N, int H, int W, int C, int OH, int OW, int KH, int KW, int s, int pad_t, int pad_l, long long ldcol) {
     pdl_trigger();
     pdl_wait();
     if ((C & 7) == 0) {
         int const octets = C >> 3;
-        long long const total = static_cast<long long>(N) * OH * OW * k * k * octets;
+        long long const total = static_cast<long long>(N) * OH * OW * KH * KW * octets;
         long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
         long long const stride = static_cast<long long>(gridDim.x) * blockDim.x;
         for (; i < total; i += stride) {
             int const o = static_cast<int>(i % octets);
             long long rest = i / octets;
-            int const kw = static_cast<int>(rest % k);
-            rest /= k;
-            int const kh = static_cast<int>(rest % k);
-            rest /= k;
+            int const kw = static_cast<int>(rest % KW);
+            rest /= KW;
+            int const kh = static_cast<int>(rest % KH);
+            rest /= KH;
             long long const pixel = rest;
             int const ow = static_cast<int>(rest % OW);
             rest /= OW;
@@ -653,7 +653,7 @@ __global__ void im2col_kernel(bf16 const* __restrict__ x, bf16* __restrict__ col
             uint4 v = make_uint4(0, 0, 0, 0);
             if (h >= 0 && h < H && w >= 0 && w < W)
                 v = *reinterpret_cast<uint4 const*>(x + ((static_cast<long long>(n) * H + h) * W + w) * C + o * 8);
-            *reinterpret_cast<uint4*>(col + pixel * ldcol + (kh * k + kw) * C + o * 8) = v;
+            *reinterpret_cast<uint4*>(col + pixel * ldcol + (kh * KW + kw) * C + o * 8) = v;
         }
     } else {
         // Few-channel stem (C = 1 or 3): one thread per (output pixel, group of 8 columns) gathers 8 scalars (L1 hits) and
@@ -662,7 +662,7 @@ __global__ void im2col_kernel(bf16 const* __restrict__ x, bf16* __restrict__ col
         long long const total = static_cast<long long>(N) * OH * OW * groups8;
         long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
         long long const stride = static_cast<long long>(gridDim.x) * blockDim.x;
-        int const kcol = k * k * C;
+        int const kcol = KH * KW * C;
         for (; i < total; i += stride) {
             int const g8 = static_cast<int>(i % groups8);
             long long rest = i / groups8;
@@ -671,7 +671,7 @@ __global__ void im2col_kernel(bf16 const* __restrict__ x, bf16* __restrict__ col
             int const oh = static_cast<int>(rest % OH);
             int const n = static_cast<int>(rest / OH);
             int j = g8 * 8;
-            int c = j % C, kw = (j / C) % k, kh = j / (C * k);
+            int c = j % C, kw = (j / C) % KW, kh = j / (C * KW);
             float v[8];
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj, ++j) {
@@ -683,7 +683,7 @@ __global__ void im2col_kernel(bf16 const* __restrict__ x, bf16* __restrict__ col
                 }
                 if (++c == C) {
                     c = 0;
-                    if (++kw == k) {
+                    if (++kw == KW) {
                         kw = 0;
                         ++kh;
                     }
@@ -695,7 +695,7 @@ __global__ void im2col_kernel(bf16 const* __restrict__ x, bf16* __restrict__ col
 }
 
 // col2im (gather form): dx[n,h,w,c] = sum over (kh,kw) of dcol[n, oh, ow, (kh,kw,c)] for the windows covering (h,w). C % 8 == 0.
-__global__ void col2im_kernel(bf16 const* __restrict__ dcol, bf16* __restrict__ dx, int N, int H, int W, int C, int OH, int OW, int k, int s, int pad_t, int pad_l, long long ldcol) {
+__global__ void col2im_kernel(bf16 const* __restrict__ dcol, bf16* __restrict__ dx, int N, int H, int W, int C, int OH, int OW, int KH, int KW, int s, int pad_t, int pad_l, long long ldcol) {
     pdl_trigger();
     pdl_wait();
     int const octets = C >> 3;
@@ -713,14 +713,14 @@ __global__ void col2im_kernel(bf16 const* __restrict__ dcol, bf16* __restrict__ 
 #pragma unroll
         for (int j = 0; j < 8; ++j)
             acc[j] = 0.f;
-        for (int kh = 0; kh < k; ++kh) {
+        for (int kh = 0; kh < KH; ++kh) {
             int const th = h + pad_t - kh;
             if (th < 0 || th % s)
                 continue;
             int const oh = th / s;
             if (oh >= OH)
                 continue;
-            for (int kw = 0; kw < k; ++kw) {
+            for (int kw = 0; kw < KW; ++kw) {
                 int const tw = w + pad_l - kw;
                 if (tw < 0 || tw % s)
                     continue;
@@ -728,7 +728,7 @@ __global__ void col2im_kernel(bf16 const* __restrict__ dcol, bf16* __restrict__ 
                 if (ow >= OW)
                     continue;
                 float v[8];
-                unpack8(*reinterpret_cast<uint4 const*>(dcol + ((static_cast<long long>(n) * OH + oh) * OW + ow) * ldcol + (kh * k + kw) * C + o * 8), v);
+                unpack8(*reinterpret_cast<uint4 const*>(dcol + ((static_cast<long long>(n) * OH + oh) * OW + ow) * ldcol + (kh * KW + kw) * C + o * 8), v);
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                     acc[j] += v[j];
@@ -1341,20 +1341,20 @@ int agb_image_normalize(void const* x, void* y, long long pixels, int C, int Cpa
     return 0;
 }
 
-int agb_im2col(void const* x, void* col, int N, int H, int W, int C, int OH, int OW, int k, int s, int pad_t, int pad_l, long long ldcol, void* stream) {
+int agb_im2col(void const* x, void* col, int N, int H, int W, int C, int OH, int OW, int kh, int kw, int s, int pad_t, int pad_l, long long ldcol, void* stream) {
     if (ldcol & 7)
         return 301;
-    long long const work = (C & 7) == 0 ? static_cast<long long>(N) * OH * OW * k * k * (C >> 3) : static_cast<long long>(N) * OH * OW * (ldcol >> 3);
-    AGB_CUDA_OK(launch_pdl(im2col_kernel, dim3(grid_for(work, kThreads, 148 * 16)), dim3(kThreads), 0, static_cast<cudaStream_t>(stream), static_cast<bf16 const*>(x), static_cast<bf16*>(col), N, H, W, C, OH, OW, k, s, pad_t, pad_l, ldcol));
+    long long const work = (C & 7) == 0 ? static_cast<long long>(N) * OH * OW * kh * kw * (C >> 3) : static_cast<long long>(N) * OH * OW * (ldcol >> 3);
+    AGB_CUDA_OK(launch_pdl(im2col_kernel, dim3(grid_for(work, kThreads, 148 * 16)), dim3(kThreads), 0, static_cast<cudaStream_t>(stream), static_cast<bf16 const*>(x), static_cast<bf16*>(col), N, H, W, C, OH, OW, kh, kw, s, pad_t, pad_l, ldcol));
     AGB_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
-int agb_col2im(void const* dcol, void* dx, int N, int H, int W, int C, int OH, int OW, int k, int s, int pad_t, int pad_l, long long ldcol, void* stream) {
+int agb_col2im(void const* dcol, void* dx, int N, int H, int W, int C, int OH, int OW, int kh, int kw, int s, int pad_t, int pad_l, long long ldcol, void* stream) {
     if ((C & 7) || (ldcol & 7))
         return 301;
     long long const work = static_cast<long long>(N) * H * W * (C >> 3);
-    AGB_CUDA_OK(launch_pdl(col2im_kernel, dim3(grid_for(work, kThreads, 148 * 16)), dim3(kThreads), 0, static_cast<cudaStream_t>(stream), static_cast<bf16 const*>(dcol), static_cast<bf16*>(dx), N, H, W, C, OH, OW, k, s, pad_t, pad_l, ldcol));
+    AGB_CUDA_OK(launch_pdl(col2im_kernel, dim3(grid_for(work, kThreads, 148 * 16)), dim3(kThreads), 0, static_cast<cudaStream_t>(stream), static_cast<bf16 const*>(dcol), static_cast<bf16*>(dx), N, H, W, C, OH, OW, kh, kw, s, pad_t, pad_l, ldcol));
     AGB_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -255,7 +255,7 @@ def conv2d_forward(x, weight, bias, stride, pads, relu, aux=None):
     y = mm_nt(_as_rows(x), weight.reshape(weight.shape[0], -1), bias, relu)
     return _from_rows(y if y.stride(0) == y.shape[1] else y.contiguous(), n, h, w)
   if _implicit_ok(x, weight, stride, pads):
-    return conv2d_forward_implicit(x, weight, bias, relu)
+    return conv2d_forward_implicit(x, weight, bias, relu, stride, pads)
   if enabled("convk") and _general_ok(x, weight):
     return conv2d_forward_general(x, weight, bias, stride, pads, relu, aux)
   return None
@@ -278,7 +278,7 @@ def conv2d_backward(dy, x, weight, y, stride, pads, relu, has_bias, need_dx, gra
     fork.join()
     return dx
   if _implicit_ok(x, weight, stride, pads) and dy.dtype == torch.bfloat16:
-    return conv2d_backward_implicit(dy, x, weight, y, relu, has_bias, need_dx, grad_w, grad_b, groups, group_stride)
+    return conv2d_backward_implicit(dy, x, weight, y, relu, has_bias, need_dx, grad_w, grad_b, groups, group_stride, stride, pads)
   if enabled("convk") and _general_ok(x, weight) and dy.dtype == torch.bfloat16:
     return conv2d_backward_general(dy, x, weight, y, stride, pads, relu, has_bias, need_dx, grad_w, grad_b, groups, group_stride, aux)
   return NotImplemented
@@ -287,13 +287,13 @@ def conv2d_backward(dy, x, weight, y, stride, pads, relu, has_bias, need_dx, gra
 # ---------------------------------------------------------------------------- #
 # General k x k convolution: im2col (bf16, column order kh, kw, c) + the same three GEMMs
 
-def _im2col(x, k, stride, pads, oh, ow):
+def _im2col(x, kh, kw, stride, pads, oh, ow):
   n, c, h, w = x.shape
-  kcol = k * k * c
+  kcol = kh * kw * c
   ld = (kcol + 7) // 8 * 8
   col = torch.empty((n * oh * ow, ld), dtype=torch.bfloat16, device=x.device)
   func = _lib().agb_im2col
-  _check(func(_ptr(x), _ptr(col), ctypes.c_int(n), ctypes.c_int(h), ctypes.c_int(w), ctypes.c_int(c), ctypes.c_int(oh), ctypes.c_int(ow), ctypes.c_int(k),
+  _check(func(_ptr(x), _ptr(col), ctypes.c_int(n), ctypes.c_int(h), ctypes.c_int(w), ctypes.c_int(c), ctypes.c_int(oh), ctypes.c_int(ow), ctypes.c_int(kh), ctypes.c_int(kw),
               ctypes.c_int(stride), ctypes.c_int(pads[0]), ctypes.c_int(pads[2]), ctypes.c_longlong(ld), _stream()), "im2col")
   return col[:, :kcol]
 
@@ -308,14 +308,14 @@ def _weight_rows(weight):
 
 
 def _general_ok(x, weight):
-  return x.is_contiguous(memory_format=torch.channels_last) and x.dtype == torch.bfloat16 and weight.shape[0] % 8 == 0 and weight.shape[1] == weight.shape[2]
+  return x.is_contiguous(memory_format=torch.channels_last) and x.dtype == torch.bfloat16 and weight.shape[0] % 8 == 0
 
 
 def conv2d_forward_general(x, weight, bias, stride, pads, relu, aux=None):
   n, c, h, w = x.shape
-  k = weight.shape[1]
-  oh, ow = _out_size(h, k, stride, pads[0], pads[1]), _out_size(w, k, stride, pads[2], pads[3])
-  col = _im2col(x, k, stride, pads, oh, ow)
+  kh, kw = weight.shape[1], weight.shape[2]   # rectangular filters too (the 1x7 / 7x1 / 1x3 / 3x1 factorised kernels of the Inception families)
+  oh, ow = _out_size(h, kh, stride, pads[0], pads[1]), _out_size(w, kw, stride, pads[2], pads[3])
+  col = _im2col(x, kh, kw, stride, pads, oh, ow)
   if aux is not None:
     aux["col"] = col  # the weight gradient multiplies by the same matrix: keep it instead of rebuilding it
   y = mm_nt(col, _weight_rows(weight), bias, relu)
@@ -324,7 +324,7 @@ def conv2d_forward_general(x, weight, bias, stride, pads, relu, aux=None):
 
 def conv2d_backward_general(dy, x, weight, y, stride, pads, relu, has_bias, need_dx, grad_w, grad_b, groups=1, group_stride=0, aux=None):
   n, c, h, w = x.shape
-  k = weight.shape[1]
+  kh, kw = weight.shape[1], weight.shape[2]
   oh, ow = dy.shape[2], dy.shape[3]
   dy = _masked(dy, y, relu)
   if not dy.is_contiguous(memory_format=torch.channels_last):
@@ -334,7 +334,7 @@ def conv2d_backward_general(dy, x, weight, y, stride, pads, relu, has_bias, need
     return NotImplemented
   col = aux.pop("col", None) if aux is not None else None
   if col is None or col.shape[0] != n * oh * ow:
-    col = _im2col(x, k, stride, pads, oh, ow)
+    col = _im2col(x, kh, kw, stride, pads, oh, ow)
   with _Fork() as fork:
     mm_tn(dy2d, col, out=grad_w.view(grad_w.shape[0], -1), groups=groups, group_stride=group_stride)
     if has_bias:
@@ -345,59 +345,78 @@ def conv2d_backward_general(dy, x, weight, y, stride, pads, relu, has_bias, need
   dcol = mm_nn(dy2d, _weight_rows(weight))
   dx = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=x.device)
   func = _lib().agb_col2im
-  _check(func(_ptr(dcol), _ptr(dx), ctypes.c_int(n), ctypes.c_int(h), ctypes.c_int(w), ctypes.c_int(c), ctypes.c_int(oh), ctypes.c_int(ow), ctypes.c_int(k),
+  _check(func(_ptr(dcol), _ptr(dx), ctypes.c_int(n), ctypes.c_int(h), ctypes.c_int(w), ctypes.c_int(c), ctypes.c_int(oh), ctypes.c_int(ow), ctypes.c_int(kh), ctypes.c_int(kw),
               ctypes.c_int(stride), ctypes.c_int(pads[0]), ctypes.c_int(pads[2]), ctypes.c_longlong(dcol.stride(0)), _stream()), "col2im")
   fork.join()
   return dx.permute(0, 3, 1, 2)
 
 
 # ---------------------------------------------------------------------------- #
-# Implicit-GEMM convolution (native/op_nn/conv.cu): stride 1, odd k, "same" padding, Cin % 64 == 0, Cout % 64 == 0
+# Implicit-GEMM convolution (native/op_nn/conv.cu): Cin % 64 == 0, Cout % 64 == 0, square k x k filters;
+#   stride 1: odd k, "same" padding (output grid = input grid);
+#   stride 2: even H and W, output H/2 x W/2 (slim `conv2d_same`'s explicit (k-1)//2 padding, or TF "SAME"), k >= 2.
+
+def _implicit_geometry(x, weight, stride, pads):
+  """(OH, OW) when the implicit-GEMM kernels take this convolution, else None."""
+  k = weight.shape[1]
+  if not (enabled("implicit") and k > 1 and weight.shape[2] == k and x.shape[1] % 64 == 0 and weight.shape[0] % 64 == 0 and x.dtype == torch.bfloat16
+          and x.is_contiguous(memory_format=torch.channels_last) and weight.is_contiguous()):
+    return None
+  h, w = x.shape[2], x.shape[3]
+  oh, ow = _out_size(h, k, stride, pads[0], pads[1]), _out_size(w, k, stride, pads[2], pads[3])
+  if stride == 1:
+    pad = (k - 1) // 2
+    return (oh, ow) if (k % 2 == 1 and tuple(pads) == (pad, pad, pad, pad)) else None
+  if stride == 2 and enabled("implicit2") and h % 2 == 0 and w % 2 == 0 and (oh, ow) == (h // 2, w // 2) and pads[0] < k and pads[2] < k:
+    return oh, ow
+  return None
+
 
 def _implicit_ok(x, weight, stride, pads):
-  k = weight.shape[1]
-  pad = (k - 1) // 2
-  return (enabled("implicit") and k > 1 and k % 2 == 1 and weight.shape[2] == k and stride == 1 and tuple(pads) == (pad, pad, pad, pad)
-          and x.shape[1] % 64 == 0 and weight.shape[0] % 64 == 0 and x.dtype == torch.bfloat16 and x.is_contiguous(memory_format=torch.channels_last)
-          and weight.is_contiguous())
+  return _implicit_geometry(x, weight, stride, pads) is not None
 
 
-def _conv_implicit(mode, act, other, out, n, h, w, cin, cout, k, bias=None, relu=False, splits=1, bn=0, groups=1, group_stride=0):
-  _check(_lib().agb_conv_implicit_grouped(ctypes.c_int(mode), _ptr(act), _ptr(other), _ptr(out), ctypes.c_int(n), ctypes.c_int(h), ctypes.c_int(w), ctypes.c_int(cin),
-                                          ctypes.c_int(cout), ctypes.c_int(k), _ptr(bias), ctypes.c_int(1 if relu else 0), ctypes.c_int(1 if out.dtype == torch.float32 else 0),
-                                          ctypes.c_int(splits), ctypes.c_int(bn), ctypes.c_int(groups), ctypes.c_longlong(group_stride), _stream()), "conv_implicit")
+def _conv_implicit(mode, act, other, out, n, h, w, oh, ow, cin, cout, k, stride, pads, bias=None, relu=False, splits=1, bn=0, groups=1, group_stride=0):
+  _check(_lib().agb_conv_implicit_strided(ctypes.c_int(mode), _ptr(act), _ptr(other), _ptr(out), ctypes.c_int(n), ctypes.c_int(h), ctypes.c_int(w), ctypes.c_int(oh), ctypes.c_int(ow),
+                                          ctypes.c_int(cin), ctypes.c_int(cout), ctypes.c_int(k), ctypes.c_int(stride), ctypes.c_int(pads[0]), ctypes.c_int(pads[2]), _ptr(bias),
+                                          ctypes.c_int(1 if relu else 0), ctypes.c_int(1 if out.dtype == torch.float32 else 0), ctypes.c_int(splits), ctypes.c_int(bn), ctypes.c_int(groups),
+                                          ctypes.c_longlong(group_stride), _stream()), "conv_implicit")
   return out
 
 
-def conv2d_forward_implicit(x, weight, bias, relu):
+def conv2d_forward_implicit(x, weight, bias, relu, stride=1, pads=None):
   n, cin, h, w = x.shape
   cout, k = weight.shape[0], weight.shape[1]
-  y = torch.empty((n, h, w, cout), dtype=torch.bfloat16, device=x.device)
+  pads = pads if pads is not None else ((k - 1) // 2,) * 4
+  oh, ow = _implicit_geometry(x, weight, stride, pads)
+  y = torch.empty((n, oh, ow, cout), dtype=torch.bfloat16, device=x.device)
   if bias is not None and bias.dtype != torch.float32:
     bias = bias.float()
-  _conv_implicit(0, x, weight, y, n, h, w, cin, cout, k, bias, relu)
+  _conv_implicit(0, x, weight, y, n, h, w, oh, ow, cin, cout, k, stride, pads, bias, relu)
   return y.permute(0, 3, 1, 2)
 
 
-def conv2d_backward_implicit(dy, x, weight, y, relu, has_bias, need_dx, grad_w, grad_b, groups=1, group_stride=0):
+def conv2d_backward_implicit(dy, x, weight, y, relu, has_bias, need_dx, grad_w, grad_b, groups=1, group_stride=0, stride=1, pads=None):
   n, cin, h, w = x.shape
   cout, k = weight.shape[0], weight.shape[1]
+  pads = pads if pads is not None else ((k - 1) // 2,) * 4
+  oh, ow = dy.shape[2], dy.shape[3]
   dy = _masked(dy, y, relu)
   if not dy.is_contiguous(memory_format=torch.channels_last):
     dy = dy.contiguous(memory_format=torch.channels_last)
   tiles = k * k * ((cout + 127) // 128) * ((cin + 127) // 128)
-  kblocks = max(1, n * h * w // 64 // groups)
+  kblocks = max(1, n * oh * ow // 64 // groups)
   splits = max(1, min(kblocks, (2 * SM_COUNT + tiles * groups - 1) // (tiles * groups), 64))
   with _Fork() as fork:
     if not _prezeroed:
       _all_groups(grad_w, groups, group_stride).zero_()
-    _conv_implicit(2, dy, x, grad_w, n, h, w, cin, cout, k, splits=splits, groups=groups, group_stride=group_stride)
+    _conv_implicit(2, dy, x, grad_w, n, h, w, oh, ow, cin, cout, k, stride, pads, splits=splits, groups=groups, group_stride=group_stride)
     if has_bias:
       colsum(_as_rows(dy), out=grad_b, groups=groups, group_stride=group_stride)
   dx = None
   if need_dx:
     dx = torch.empty((n, h, w, cin), dtype=torch.bfloat16, device=x.device)
-    _conv_implicit(1, dy, weight, dx, n, h, w, cin, cout, k)
+    _conv_implicit(1, dy, weight, dx, n, h, w, oh, ow, cin, cout, k, stride, pads)
     dx = dx.permute(0, 3, 1, 2)
   fork.join()
   return dx

@@ -58,6 +58,8 @@ class Preprocessor:
 
   def counter(self, device):
     device = torch.device(device)
+    if device.type == "cuda" and device.index is None:
+      device = torch.device("cuda", torch.cuda.current_device())
     if device not in self._counters:
       self._counters[device] = torch.zeros(1, dtype=torch.int64, device=device)
     return self._counters[device]
