@@ -67,7 +67,22 @@ class Manager:
     self.model.declare(self.layout, state_shapes)
     self.layout.freeze()
     # -- aggregation engine (owns params + gradient rows) -------------------------- #
-    self.aggregation = make_aggregation(engine, aggregator, self.layout, nbworkers, self.optimizer, group, self.device, **(engine_args or {}))
+    engine_args = dict(engine_args or {})
+    self._bucket_layers = {}
+    plain_step = attack is None and not authenticate and not ((self.l1 or -1.) > 0. or (self.l2 or -1.) > 0.)
+    if cuda and engine in ("auto", "fused") and aggregator.fused_spec() is not None:
+      engine_args.setdefault("device_state", True)
+      if plain_step and aggregator.fused_spec().rule in ("krum", "bulyan") and os.environ.get("AGB_OVERLAP", "1") not in ("", "0") and "buckets" not in engine_args:
+        buckets, self._bucket_layers = self._plan_buckets()
+        if len(buckets) > 1:
+          engine_args["buckets"] = buckets
+    try:
+      self.aggregation = make_aggregation(engine, aggregator, self.layout, nbworkers, self.optimizer, group, self.device, **engine_args)
+    except TypeError:   # engines without these options (host, baseline)
+      self.aggregation = make_aggregation(engine, aggregator, self.layout, nbworkers, self.optimizer, group, self.device)
+    if not getattr(self.aggregation, "overlappable", False):
+      self._bucket_layers = {}
+    self._side_stream = None
     self.w = self.aggregation.w
     self.params = self.aggregation.params
     self.grads = self.aggregation.grads
@@ -143,6 +158,8 @@ class Manager:
                     and type(experiment).losses is type(experiment).__mro__[-2].losses)
     self.use_graphs = bool(use_graphs) and cuda
     self._graph = None
+    self._graph_whole = False
+    self._overlap_armed = False  # set for the duration of a step once `aggregation.prepare()` has run (phase A needs the step's scalars)
     self._graph_warmup = 2       # eager steps before capture (lazy kernel attributes, workspaces, autotuning)
     self._graph_launches = 0
     tools.info("Model %r: %d variables, d = %d (padded %d); %d worker(s) on this rank%s; compute dtype %s; nn backend %r; engine %r" % (
@@ -167,16 +184,29 @@ class Manager:
       return True
     return any(Manager._has_dropout(child) for child in module.children())
 
+  @property
+  def _whole_step_graph(self):
+    """The captured graph holds the aggregation too (fused engine with device-resident step state, nothing host-driven in between)."""
+    return (getattr(self.aggregation, "device_state", False) and self.attack is None and self.authenticator is None
+            and not ((self.l1 or -1.) > 0. or (self.l2 or -1.) > 0.) and os.environ.get("AGB_GRAPH_AGGREGATION", "1") not in ("", "0"))
+
   def _capture(self, batches):
-    """Record every local worker's forward + backward into one CUDA graph (static shapes, static buffers)."""
+    """Record every local worker's forward + backward — and, with the fused engine, the aggregation kernels and the refresh of the
+    compute copy of the parameters — into one CUDA graph (static shapes, static buffers)."""
     from ..ops import counters
     self._static_batches = [(x.clone(), y.clone()) for x, y in batches]
     torch.cuda.synchronize(self.device)
+    if self.world > 1:
+      dist.barrier(group=self.group)   # capture is slow and its kernels do not run: keep the ranks aligned around it
     graph = torch.cuda.CUDAGraph()
     before = counters.launches
+    whole = self._whole_step_graph
     try:
       with torch.cuda.graph(graph):
         self._static_losses = self._run_workers(self._static_batches, None)
+        if whole:
+          self.aggregation.step(stream=None, loss_in=self._static_losses, prepared=True)
+          self._refresh_weights()
     except Exception as err:
       tools.warning("CUDA graph capture failed (" + str(err).splitlines()[0] + "): staying in eager mode", context="graph")
       self.use_graphs = False
@@ -184,7 +214,9 @@ class Manager:
       return False
     self._graph_launches = counters.launches - before
     self._graph = graph
-    tools.info("Captured the workers' forward/backward into a CUDA graph (%d native kernel launches per replay)" % self._graph_launches, context="graph")
+    self._graph_whole = whole
+    tools.info("Captured the workers' forward/backward%s into a CUDA graph (%d native kernel launches per replay)" % (
+      " + aggregation" if whole else "", self._graph_launches), context="graph")
     return True
 
   def _run_workers(self, batches, trace):
@@ -198,10 +230,66 @@ class Manager:
     return self._run_workers_inner(batches, trace)
 
   def _run_workers_inner(self, batches, trace):
-    if self.batched and trace is None:
-      return self.experiment.losses_batched(self.model, batches, self.batched_ctx).float()
-    losses = self.experiment.losses(self.model, batches, self.contexts, trace)
-    return torch.stack([l.float().reshape(()) for l in losses])
+    hooked = self.batched_ctx if (self.batched and trace is None) else (self.contexts[-1] if self.contexts else None)
+    overlap = bool(self._bucket_layers) and hooked is not None and self._overlap_armed
+    if overlap:   # the bucket of a layer is complete once the LAST local worker has differentiated it
+      main = torch.cuda.current_stream(self.device)
+      if self._side_stream is None:
+        self._side_stream = torch.cuda.Stream(device=self.device, priority=-1)
+      side = self._side_stream
+
+      def publish(layer):
+        seg = self._bucket_layers.get(id(layer))
+        if seg is not None:
+          side.wait_stream(main)
+          self.aggregation.phase_a(seg, stream=side)
+      hooked.backward_hook = publish
+    try:
+      if self.batched and trace is None:
+        losses = self.experiment.losses_batched(self.model, batches, self.batched_ctx).float()
+      else:
+        per_worker = self.experiment.losses(self.model, batches, self.contexts, trace)
+        losses = torch.stack([l.float().reshape(()) for l in per_worker])
+    finally:
+      if hooked is not None:
+        hooked.backward_hook = None
+    if overlap:
+      main.wait_stream(side)
+    return losses
+
+  def _plan_buckets(self):
+    """Gradient buckets for the overlapped distance pass: top-level layers in backward order, cut where the accumulated share of the
+    parameters passes 50 %, 80 % and 94 % (ResNet-50: logits + block4, block3, block2; the remaining 6 % — the layers whose backward
+    finishes last — are handled by the finish kernel itself). Returns ([(lo, hi)] in completion order, {id(layer): bucket})."""
+    from ..models.core import Sequential
+    root = self.model.root
+    if not isinstance(root, Sequential) or len(root.layers) < 4:
+      return [], {}
+    spans = []
+    for layer in root.layers:
+      scratch = FlatLayout()
+      layer.declare(scratch, {})
+      names = scratch.names
+      if names:
+        lo = min(self.layout.offset(name) for name in names)
+        spans.append((layer, lo))
+      else:
+        spans.append((layer, None))
+    total = self.layout.padded_size
+    cuts, thresholds, upper, pending = [], [0.5, 0.8, 0.94], total, None
+    for layer, lo in reversed(spans):
+      if lo is None:
+        continue
+      share = (total - lo) / total
+      if thresholds and share >= thresholds[0] and lo % 4 == 0 and lo < upper and lo > 0:
+        cuts.append((layer, lo, upper))
+        upper = lo
+        while thresholds and share >= thresholds[0]:
+          thresholds.pop(0)
+    if not cuts:
+      return [], {}
+    buckets = [(lo, hi) for _, lo, hi in cuts] + [(0, upper)]
+    return buckets, {id(layer): index for index, (layer, _, _) in enumerate(cuts)}
 
   def _replay(self, batches):
     from ..ops import counters
@@ -218,7 +306,8 @@ class Manager:
     trace = self.tracer if self.tracer.enabled else None
     if self.use_graphs and trace is None and self._graph is None and self.step >= self._graph_warmup:
       self._capture(batches)
-    if self._graph is not None and trace is None:
+    self._last_step_replayed = self._graph is not None and trace is None
+    if self._last_step_replayed:
       losses = self._replay(batches)
     else:
       losses = list(self._run_workers(batches, trace).unbind(0))
@@ -252,20 +341,34 @@ class Manager:
   def train(self):
     """One synchronous training step (the reference's `sess.run(train_tn)`); returns the total loss as a 0-d device tensor."""
     rate = self.rate(self.step)
+    fused = hasattr(self.aggregation, "prepare")
+    if fused:
+      self.aggregation.prepare(rate)   # host scalars of the step (stream-ordered, outside any graph)
+    self._overlap_armed = fused
     with self.tracer.span("Workers: loss and gradient computation"):
       losses = self.compute_gradients()
-    if self.authenticator is not None:
-      with self.tracer.span("Authentication: sign, exchange, verify"):
-        self.authenticate_gradients()
-    with self.tracer.span("Master: aggregated gradient computation and application"):
-      self.aggregation.step(rate)
-    self._refresh_weights()
+    self._overlap_armed = False
+    replayed_whole = self._graph is not None and self._graph_whole and self._last_step_replayed
+    if not replayed_whole:
+      if self.authenticator is not None:
+        with self.tracer.span("Authentication: sign, exchange, verify"):
+          self.authenticate_gradients()
+      with self.tracer.span("Master: aggregated gradient computation and application"):
+        if fused:
+          loss_in = torch.stack([l.float().reshape(()) for l in losses]) if losses else None
+          self.aggregation.step(loss_in=loss_in, prepared=True)
+        else:
+          self.aggregation.step(rate)
+      self._refresh_weights()
     self.step += 1
-    total = torch.stack([l.float().reshape(()) for l in losses]).sum() if losses else self._loss_buf.new_zeros(())
-    if self.world > 1:
-      self._loss_buf[0] = total
-      dist.all_reduce(self._loss_buf, group=self.group)
-      total = self._loss_buf[0]
+    if fused:
+      total = self.aggregation.loss_out[0]   # summed over workers and ranks (rank order) by the aggregation kernel: no collective here
+    else:
+      total = torch.stack([l.float().reshape(()) for l in losses]).sum() if losses else self._loss_buf.new_zeros(())
+      if self.world > 1:
+        self._loss_buf[0] = total
+        dist.all_reduce(self._loss_buf, group=self.group)
+        total = self._loss_buf[0]
     self.total_loss = total
     if self.debug_checksum:
       self.check_replicas()

@@ -42,6 +42,7 @@ class Context:
     self.generator = None       # torch.Generator for dropout
     self.aux_heads = []         # `AuxHead`s that produced side logits during the current training forward
     self.need_input_grad = False
+    self.backward_hook = None   # callable(layer) run by `Sequential.backward` after each child: gradient-bucket publication
     self.groups = 1             # logical workers batched in one pass (their batches are consecutive along dim 0)
     self.group_stride = 0       # elements between two workers' gradient rows (`grads` are worker 0's views)
 
@@ -436,8 +437,11 @@ class Sequential(Module):
     return x
 
   def backward(self, dy, ctx):
+    hook = ctx.backward_hook
     for layer in reversed(self.layers):
       dy = layer.backward(dy, ctx)
+      if hook is not None:
+        hook(layer)   # every gradient of `layer` (and of everything after it) has been written: see `Manager._plan_buckets`
     return dy
 
 

@@ -15,16 +15,20 @@ from .. import tools
 from ..aggregators import FusedSpec
 from . import counters
 
-MAX_WORKERS = 16
+MAX_WORKERS = 32
 MAX_RANKS = 16
 MAX_PAIRS = MAX_WORKERS * (MAX_WORKERS - 1) // 2
+MAX_SEGMENTS = 8
+FLAG_SLOTS = MAX_SEGMENTS + 2
+SIGNAL_BYTES = FLAG_SLOTS * MAX_RANKS * 4
+MAILBOX_BYTES = MAX_RANKS * (MAX_PAIRS + 1) * 4
 OPTIMIZERS = {"none": 0, "sgd": 1, "adam": 2, "rmsprop": 3, "adagrad": 4, "adadelta": 5}
 
 _ERRORS = {
-  100: "unsupported number of workers/ranks (n <= 16, R <= 16)", 101: "slice bounds must be multiples of 4 elements",
+  100: "unsupported number of workers/ranks (n <= 32, R <= 16)", 101: "segment bounds must be multiples of 4 elements (at most 8 segments)",
   102: "unknown rule", 103: "invalid Krum parameters", 104: "invalid Bulyan parameters", 105: "invalid beta",
   106: "optimizer requested without parameter buffers", 107: "optimizer slots missing", 108: "scratch buffers missing",
-  109: "signal pads missing"}
+  109: "signal pads missing", 110: "more than 8 workers over several ranks need the staging buffer", 111: "invalid phase A launch"}
 
 
 def _lib():
@@ -48,65 +52,79 @@ def max_ctas():
 
 
 class FusedLauncher:
-  """Holds the scratch buffers and argument arrays of one rank's fused aggregation kernel."""
+  """Holds the scratch buffers and argument arrays of one rank's fused aggregation kernels (phase A kernels + finish kernel)."""
 
-  def __init__(self, device, n):
+  def __init__(self, device, n, phase_a_ctas=48):
     if n > MAX_WORKERS:
-      raise tools.UserException("The sm_100a aggregation kernels hold one value per worker in registers and support n <= %d workers (got %d)" % (MAX_WORKERS, n))
+      raise tools.UserException("The sm_100a aggregation kernels support n <= %d workers (got %d)" % (MAX_WORKERS, n))
     self.device = torch.device(device)
     self.n = n
     with torch.cuda.device(self.device):
       ctas = max(1, max_ctas())
+    self.phase_a_ctas = max(1, min(int(os.environ.get("AGB_PHASE_A_CTAS", phase_a_ctas)), ctas))
     self.cta_partials = torch.zeros(ctas * MAX_PAIRS, dtype=torch.float32, device=self.device)
-    self.local_mailbox = torch.zeros(MAX_RANKS * MAX_PAIRS, dtype=torch.float32, device=self.device)
+    self.seg_partials = torch.zeros(MAX_SEGMENTS * self.phase_a_ctas * MAX_PAIRS, dtype=torch.float32, device=self.device)
+    self.local_mailbox = torch.zeros(MAILBOX_BYTES // 4, dtype=torch.float32, device=self.device)
     self.dist_out = torch.zeros(n * n, dtype=torch.float32, device=self.device)
     self.info = torch.zeros(64, dtype=torch.int32, device=self.device)
-    self._ptrs = (ctypes.c_ulonglong * 96)()
-    self._ints = (ctypes.c_int * 11)()
-    self._longs = (ctypes.c_longlong * 3)()
+    self._ptrs = (ctypes.c_ulonglong * 112)()
+    self._ints = (ctypes.c_int * 24)()
+    self._longs = (ctypes.c_longlong * (1 + 2 * MAX_SEGMENTS))()
     self._floats = (ctypes.c_float * 4)()
     self._func = _lib().agb_gar_fused
     self._func.restype = ctypes.c_int
+    self._phase_a = _lib().agb_gar_phase_a
+    self._phase_a.restype = ctypes.c_int
     timeout = os.environ.get("AGB_FLAG_TIMEOUT_S")
     if timeout is not None:   # bound of the cross-GPU flag waits (default 120 s, 0 = wait forever)
       with torch.cuda.device(self.device):
         _check(_lib().agb_gar_set_flag_timeout(ctypes.c_double(float(timeout))), "gar_set_flag_timeout")
 
-  def launch(self, spec, rows, lo, hi, *, agg_out=None, opt="none", lr=0.0, hyper=(0.0, 0.0, 0.0), param=None,
-             slot0=None, slot1=None, param_dst=None, param_mc=0, param_bf16_dst=None, rank=0, R=1, signals=None, mailboxes=None,
-             epoch=1, staging=None, max_ctas_limit=0, stream=None, grad_mc=0, workers_per_rank=1, row_stride=0):
-    """`rows`: n device addresses of the workers' gradient rows; pointers are raw ints (local or peer-mapped)."""
+  def _fill(self, spec, rows, segments, *, agg_out=None, opt="none", lr=0.0, hyper=(0.0, 0.0, 0.0), param=None, slot0=None, slot1=None, param_dst=None, param_mc=0,
+            param_bf16_dst=None, rank=0, R=1, signals=None, mailboxes=None, epoch=1, staging=None, max_ctas_limit=0, grad_mc=0, workers_per_rank=1, row_stride=0,
+            first_seg=0, epoch_ptr=None, hyper_ptr=None, loss_in=None, loss_out=None):
     ptrs = self._ptrs
-    for i in range(96):
+    for i in range(112):
       ptrs[i] = 0
     if len(rows) != spec.n:
       raise tools.UserException("Expected %d gradient rows, got %d" % (spec.n, len(rows)))
+    if not 1 <= len(segments) <= MAX_SEGMENTS:
+      raise tools.UserException("Between 1 and %d coordinate segments per rank (got %d)" % (MAX_SEGMENTS, len(segments)))
     for i, row in enumerate(rows):
       ptrs[i] = row
     addr = lambda t: 0 if t is None else (t if isinstance(t, int) else t.data_ptr())
-    ptrs[16] = addr(agg_out)
-    ptrs[17] = addr(param)
-    ptrs[18] = addr(slot0)
-    ptrs[19] = addr(slot1)
-    ptrs[20] = int(param_mc or 0)
-    ptrs[21] = self.cta_partials.data_ptr()
-    ptrs[22] = addr(staging)
-    ptrs[23] = self.dist_out.data_ptr()
-    ptrs[24] = self.info.data_ptr()
-    ptrs[25] = int(grad_mc or 0)
+    ptrs[32], ptrs[33], ptrs[34], ptrs[35], ptrs[36] = addr(agg_out), addr(param), addr(slot0), addr(slot1), int(param_mc or 0)
+    ptrs[37], ptrs[38], ptrs[39], ptrs[40], ptrs[41] = self.cta_partials.data_ptr(), addr(staging), self.dist_out.data_ptr(), self.info.data_ptr(), int(grad_mc or 0)
+    ptrs[42], ptrs[43], ptrs[44], ptrs[45], ptrs[46] = addr(epoch_ptr), addr(hyper_ptr), self.seg_partials.data_ptr(), addr(loss_in), addr(loss_out)
     for q in range(R):
-      ptrs[32 + q] = addr(param_dst[q]) if param_dst is not None else (addr(param) if q == 0 else 0)
-      ptrs[48 + q] = addr(signals[q]) if signals is not None else 0
-      ptrs[64 + q] = addr(mailboxes[q]) if mailboxes is not None else (self.local_mailbox.data_ptr() if q == 0 else 0)
-      ptrs[80 + q] = addr(param_bf16_dst[q]) if param_bf16_dst is not None else 0
+      ptrs[48 + q] = addr(param_dst[q]) if param_dst is not None else (addr(param) if q == 0 else 0)
+      ptrs[64 + q] = addr(signals[q]) if signals is not None else 0
+      ptrs[80 + q] = addr(mailboxes[q]) if mailboxes is not None else (self.local_mailbox.data_ptr() if q == 0 else 0)
+      ptrs[96 + q] = addr(param_bf16_dst[q]) if param_bf16_dst is not None else 0
     ints = self._ints
     ints[0], ints[1], ints[2], ints[3], ints[4] = spec.n, spec.f, spec.m, spec.beta, spec.rule_id
     ints[5], ints[6], ints[7], ints[8], ints[9] = R, rank, OPTIMIZERS[opt], epoch & 0x7fffffff, max_ctas_limit
-    self._longs[0], self._longs[1], self._longs[2] = lo, hi, row_stride
-    ints[10] = workers_per_rank
+    ints[10], ints[11], ints[12], ints[13] = workers_per_rank, len(segments), first_seg, (loss_in.numel() if loss_in is not None else 0)
+    ints[14], ints[15] = self.phase_a_ctas, self.phase_a_ctas
+    self._longs[0] = row_stride
+    for s in range(MAX_SEGMENTS):
+      lo, hi = segments[s] if s < len(segments) else (0, 0)
+      self._longs[1 + s], self._longs[1 + MAX_SEGMENTS + s] = lo, hi
+      ints[16 + s] = self.phase_a_ctas if s < first_seg else 0
     self._floats[0], self._floats[1], self._floats[2], self._floats[3] = lr, hyper[0], hyper[1], hyper[2]
+
+  def launch(self, spec, rows, lo=None, hi=None, *, segments=None, stream=None, **kwargs):
+    """The finish kernel (the whole aggregation unless `first_seg` segments were pre-accumulated by `phase_a`).
+    `rows`: n device addresses of the workers' gradient rows (raw ints, local or peer-mapped); owned coordinates `[lo, hi)` or `segments`."""
+    self._fill(spec, rows, segments if segments is not None else [(lo, hi)], **kwargs)
     with torch.cuda.device(self.device):
-      _check(self._func(ptrs, ints, self._longs, self._floats, _stream_ptr(stream)), "gar_fused")
+      _check(self._func(self._ptrs, self._ints, self._longs, self._floats, _stream_ptr(stream)), "gar_fused")
+
+  def phase_a(self, spec, rows, segments, seg, *, stream=None, **kwargs):
+    """Pre-accumulate the partial distances of owned segment `seg` (and stage its tile) on a few CTAs, e.g. under the backward pass."""
+    self._fill(spec, rows, segments, **kwargs)
+    with torch.cuda.device(self.device):
+      _check(self._phase_a(self._ptrs, self._ints, self._longs, self._floats, ctypes.c_int(seg), _stream_ptr(stream)), "gar_phase_a")
 
 
 _launchers = {}

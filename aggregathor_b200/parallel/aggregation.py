@@ -143,11 +143,19 @@ class BaselineAggregation(_AggregationBase):
 
 
 class FusedAggregation(_AggregationBase):
-  """Fused P2P gather + rule + optimizer + broadcast kernel over symmetric memory."""
+  """Fused P2P gather + rule + optimizer + broadcast kernels over symmetric memory.
+
+  `buckets`: coordinate ranges `[(lo, hi), ...]` covering the flat vector, in the order the backward pass completes them (last
+  layers first). Every rank owns 1/R of EVERY bucket (its *segments*), so the distance pass of a bucket can start on all ranks as
+  soon as the backward pass has produced it (`phase_a(k)`, side stream) while earlier layers are still being differentiated;
+  `step()` launches the finish kernel. Without buckets a rank owns one contiguous slice (`layout.slice_bounds`).
+  `device_state=True` keeps the flag epoch and the step-varying optimizer scalars in device memory (`prepare(rate)` refreshes
+  them) so that the launches can be captured once in a CUDA graph; the total loss of the step comes out of the kernel
+  (`loss_out`, summed over ranks in rank order): no NCCL call on the step path."""
 
   name = "fused"
 
-  def __init__(self, gar, layout, nbworkers, optimizer, group=None, device="cuda", keep_aggregate=False, bf16_copy=False, max_ctas=0):
+  def __init__(self, gar, layout, nbworkers, optimizer, group=None, device="cuda", keep_aggregate=False, bf16_copy=False, max_ctas=0, buckets=None, device_state=False):
     super().__init__(gar, layout, nbworkers, optimizer, group)
     self.device = torch.device(device)
     self.spec = gar.fused_spec()
@@ -156,9 +164,13 @@ class FusedAggregation(_AggregationBase):
     if self.spec.n != nbworkers:
       raise tools.UserException("GAR built for %d workers used with %d" % (self.spec.n, nbworkers))
     d, w, R = self.d, self.w, self.world
-    self.lo, self.hi = layout.slice_bounds(self.rank, R)
-    distance_rule = self.spec.rule in ("krum", "bulyan")
-    sizes = {"grads": w * d * 4, "params": d * 4, "signals": 3 * gar_ops.MAX_RANKS * 4, "mailbox": gar_ops.MAX_RANKS * gar_ops.MAX_PAIRS * 4}
+    self.distance_rule = self.spec.rule in ("krum", "bulyan")
+    self.buckets = self._check_buckets(buckets, d)
+    self.segments_of = [[self._share(lo, hi, q, R) for lo, hi in self.buckets] for q in range(R)]
+    self.segments = self.segments_of[self.rank]
+    self.lo, self.hi = self.segments[0][0], self.segments[-1][1]   # meaningful for a single bucket (contiguous slice)
+    owned = sum(hi - lo for lo, hi in self.segments)
+    sizes = {"grads": w * d * 4, "params": d * 4, "signals": gar_ops.SIGNAL_BYTES, "mailbox": gar_ops.MAILBOX_BYTES}
     if bf16_copy:
       sizes["params_bf16"] = d * 2
     self.heap = SymmetricHeap(SymmetricHeap.required(*sizes.values()), self.device, group)
@@ -169,11 +181,19 @@ class FusedAggregation(_AggregationBase):
     self.params_bf16 = self.heap.local("params_bf16", torch.bfloat16) if bf16_copy else None
     self.slots = optimizer.make_slots(self.params)
     self.aggregate_out = torch.zeros(d, dtype=torch.float32, device=self.device) if keep_aggregate else None
-    # staging keeps the P2P-loaded slice local so that phase D does not cross NVLink again
-    self.staging = torch.empty((self.n, self.hi - self.lo), dtype=torch.float32, device=self.device) if (distance_rule and R > 1) else None
+    # staging keeps the P2P-loaded tiles local so that later passes never cross NVLink again (and rows beyond the 8 held in registers
+    # can be re-read); needed whenever the distance pass and the aggregation pass are different launches too
+    need_staging = self.distance_rule and (R > 1 or len(self.buckets) > 1 or self.n > 8)
+    self.staging = torch.empty((self.n, owned), dtype=torch.float32, device=self.device) if need_staging else None
     self.launcher = gar_ops.FusedLauncher(self.device, self.n)
     self.max_ctas = max_ctas
     self.epoch = 0
+    self.device_state = bool(device_state)
+    self.epoch_dev = torch.zeros(1, dtype=torch.int32, device=self.device) if device_state else None
+    self.hyper_dev = torch.zeros(4, dtype=torch.float32, device=self.device) if device_state else None
+    self._hyper_host = torch.zeros(4, dtype=torch.float32).pin_memory() if device_state else None
+    self.loss_out = torch.zeros(1, dtype=torch.float32, device=self.device)
+    self._pre_accumulated = 0
     self._row_views = None
     heap = self.heap
     self._rows = [heap.peer(i // w, "grads") + (i % w) * d * 4 for i in range(self.n)]
@@ -184,12 +204,34 @@ class FusedAggregation(_AggregationBase):
     self._param_mc = heap.multicast("params") if R > 1 else 0
     # in-switch (NVLS) reduction of the gradients for the `average` rule instead of 7 P2P loads (0.241 vs 0.312 ms at 8 GPUs); AGB_NVLS_REDUCE=0 disables
     self._grad_mc = heap.multicast("grads") if (R > 1 and self.spec.rule == "average" and os.environ.get("AGB_NVLS_REDUCE", "1") not in ("", "0")) else 0
-    tools.info("Fused aggregation: rule %r, n = %d (%d per rank), d = %d, slice [%d, %d), provider %s, NVLS multicast %s" % (
-      self.spec.rule, self.n, w, d, self.lo, self.hi, heap.provider, "on" if self._param_mc else "off"), context="fused")
+    tools.info("Fused aggregation: rule %r, n = %d (%d per rank), d = %d, %d bucket(s), %d owned coordinates, provider %s, NVLS multicast %s" % (
+      self.spec.rule, self.n, w, d, len(self.buckets), owned, heap.provider, "on" if self._param_mc else "off"), context="fused")
+
+  @staticmethod
+  def _check_buckets(buckets, d):
+    if not buckets:
+      return [(0, d)]
+    buckets = [(int(lo), int(hi)) for lo, hi in buckets]
+    if len(buckets) > gar_ops.MAX_SEGMENTS:
+      raise tools.UserException("At most %d gradient buckets" % gar_ops.MAX_SEGMENTS)
+    covered = sorted(buckets)
+    if covered[0][0] != 0 or covered[-1][1] != d or any(a[1] != b[0] for a, b in zip(covered, covered[1:])) or any(lo % 4 or hi % 4 or hi <= lo for lo, hi in covered):
+      raise tools.UserException("Gradient buckets must tile [0, d) with bounds that are multiples of 4: " + repr(buckets))
+    return buckets
+
+  @staticmethod
+  def _share(lo, hi, rank, world):
+    quads = (hi - lo) // 4
+    return lo + (quads * rank // world) * 4, lo + (quads * (rank + 1) // world) * 4
 
   @property
   def last_aggregate(self):
     return self.aggregate_out
+
+  @property
+  def overlappable(self):
+    """Whether `phase_a` exists for this rule (the distance pass of Krum / Bulyan is additive over coordinates)."""
+    return self.distance_rule and len(self.buckets) > 1
 
   def visible_rows(self):
     """Every worker's row through the peer mapping — the very addresses the fused kernel dereferences."""
@@ -206,29 +248,53 @@ class FusedAggregation(_AggregationBase):
   def consumed_slices(self):
     return [self.rank]
 
-  def step(self, rate, stream=None):
+  def _common(self, rate_args):
+    lr, hyper = rate_args
+    return dict(opt=self.optimizer.name, lr=lr, hyper=hyper, param=self.params, slot0=self.slots[0] if len(self.slots) > 0 else None,
+                slot1=self.slots[1] if len(self.slots) > 1 else None, param_dst=self._param_dst, param_mc=self._param_mc, param_bf16_dst=self._param_bf16_dst,
+                rank=self.rank, R=self.world, signals=self._signals, mailboxes=self._mailboxes, staging=self.staging, max_ctas_limit=self.max_ctas,
+                grad_mc=self._grad_mc, workers_per_rank=self.w, row_stride=self.d, epoch_ptr=self.epoch_dev, hyper_ptr=self.hyper_dev)
+
+  def prepare(self, rate):
+    """Host side of one step: advance the update counter and (device-state mode) refresh the device copy of the optimizer scalars.
+    Stream-ordered before the kernels of the step; never part of a captured graph."""
     self.updates += 1
     self.epoch += 1
-    lr, hyper = self.optimizer.kernel_args(rate, self.updates)
-    self.launcher.launch(
-      self.spec, self._rows, self.lo, self.hi, agg_out=self.aggregate_out, opt=self.optimizer.name, lr=lr, hyper=hyper,
-      param=self.params, slot0=self.slots[0] if len(self.slots) > 0 else None, slot1=self.slots[1] if len(self.slots) > 1 else None,
-      param_dst=self._param_dst, param_mc=self._param_mc, param_bf16_dst=self._param_bf16_dst, rank=self.rank, R=self.world,
-      signals=self._signals, mailboxes=self._mailboxes, epoch=self.epoch, staging=self.staging, max_ctas_limit=self.max_ctas, stream=stream,
-      grad_mc=self._grad_mc, workers_per_rank=self.w, row_stride=self.d)
+    self._rate_args = self.optimizer.kernel_args(rate, self.updates)
+    if self.device_state:
+      lr, hyper = self._rate_args
+      self._hyper_host[0], self._hyper_host[1], self._hyper_host[2], self._hyper_host[3] = lr, hyper[0], hyper[1], hyper[2]
+      self.hyper_dev.copy_(self._hyper_host, non_blocking=True)
+
+  def phase_a(self, seg, stream=None):
+    """Distance pass + staging of bucket `seg` (buckets must be pre-accumulated in order 0, 1, ...). Call between `prepare` and `step`."""
+    if seg != self._pre_accumulated:
+      raise AssertionError("buckets are pre-accumulated in order")
+    self.launcher.phase_a(self.spec, self._rows, self.segments, seg, stream=stream, epoch=self.epoch, first_seg=seg + 1, **self._common(self._rate_args))
+    self._pre_accumulated = seg + 1
+
+  def step(self, rate=None, stream=None, loss_in=None, prepared=False):
+    """The finish kernel. `rate` is ignored when `prepare(rate)` was already called for this step (`prepared=True`)."""
+    if not prepared:
+      self.prepare(rate)
+    first_seg, self._pre_accumulated = self._pre_accumulated, 0
+    self.launcher.launch(self.spec, self._rows, segments=self.segments, agg_out=self.aggregate_out, epoch=self.epoch, stream=stream, first_seg=first_seg,
+                         loss_in=loss_in, loss_out=self.loss_out, **self._common(self._rate_args))
 
   def full_slots(self):
-    """Optimizer slots are only maintained on the owned slice: assemble the full vectors (checkpoints)."""
+    """Optimizer slots are only maintained on the owned segments: assemble the full vectors (checkpoints)."""
     if self.world == 1 or not self.slots:
       return self.slots
     full = []
     for slot in self.slots:
       merged = slot.clone()
       for q in range(self.world):
-        lo, hi = self.layout.slice_bounds(q, self.world)
-        piece = merged[lo:hi].contiguous() if q == self.rank else torch.empty(hi - lo, dtype=slot.dtype, device=slot.device)
-        dist.broadcast(piece, src=dist.get_global_rank(self.group, q) if self.group is not None else q, group=self.group)
-        merged[lo:hi] = piece
+        for lo, hi in self.segments_of[q]:
+          if hi == lo:
+            continue
+          piece = merged[lo:hi].contiguous() if q == self.rank else torch.empty(hi - lo, dtype=slot.dtype, device=slot.device)
+          dist.broadcast(piece, src=dist.get_global_rank(self.group, q) if self.group is not None else q, group=self.group)
+          merged[lo:hi] = piece
       full.append(merged)
     return full
 

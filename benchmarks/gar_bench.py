@@ -45,6 +45,37 @@ def main():
   if rank != 0:
     tools.set_rank_tag("r" + str(rank))
   n = args.nb_workers
+  # measured peer bandwidth of this box: every rank pulls 256 MiB from its right neighbour at the same time (kernel P2P loads), the
+  # denominator of the link-roofline fractions below (B200_PROFILING.md quotes 770 GB/s for this pool)
+  peer_gbs = None
+  if world > 1:
+    import ctypes
+    from aggregathor_b200 import native
+    from aggregathor_b200.parallel.symm import SymmetricHeap
+    nbytes = 256 << 20
+    heap = SymmetricHeap(SymmetricHeap.required(nbytes), device)
+    heap.region("buf", nbytes)
+    dst = torch.empty(nbytes // 4, dtype=torch.float32, device=device)
+    comm = native.library("op_comm")
+    src = heap.peer((rank + 1) % world, "buf")
+    times = []
+    for it in range(6):
+      torch.cuda.synchronize()
+      dist.barrier()
+      torch.cuda.synchronize()
+      begin, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      begin.record()
+      comm.agb_comm_p2p_copy(ctypes.c_ulonglong(src), ctypes.c_ulonglong(dst.data_ptr()), ctypes.c_longlong(nbytes // 4), ctypes.c_int(0), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+      end.record()
+      torch.cuda.synchronize()
+      ms = torch.tensor([begin.elapsed_time(end)], device=device, dtype=torch.float64)
+      dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+      if it >= 2:
+        times.append(float(ms.item()))
+    peer_gbs = nbytes / min(times) / 1e6
+    if rank == 0:
+      print("measured peer pull bandwidth: %.1f GB/s per GPU (all ranks pulling at once)" % peer_gbs)
+    del heap, dst
   layout = FlatLayout()
   layout.add("theta", (args.d,))
   layout.freeze()
@@ -106,6 +137,49 @@ def main():
         engine.step(0.1)
     fused_ms = time_engine(fused)
     base_ms = time_engine(base)
+    # overlapped variant (Krum / Bulyan): the distance pass of the first three buckets runs as separate small launches (in training:
+    # on a side stream under the backward pass); what stays exposed at the end of the step is the finish kernel alone
+    exposed_ms = bucketed_ms = None
+    if rule in ("krum", "bulyan"):
+      c1, c2, c3 = (d // 2) // 8 * 8, (d // 5) // 8 * 8, (d // 16) // 8 * 8
+      over = FusedAggregation(gar, layout, n, build(optimizers, "optimizer", "sgd", []), device=device, keep_aggregate=True,
+                              buckets=[(c1, d), (c2, c1), (c3, c2), (0, c3)], device_state=True)
+      over.params.copy_(init)
+      over.grads.copy_(grads)
+      side = torch.cuda.Stream(device=device, priority=-1)
+
+      def over_step(time_finish=None):
+        over.prepare(0.1)
+        side.wait_stream(torch.cuda.current_stream())
+        for k in range(3):
+          over.phase_a(k, stream=side)
+        torch.cuda.current_stream().wait_stream(side)
+        if time_finish is not None:
+          time_finish[0].record()
+        over.step(prepared=True)
+        if time_finish is not None:
+          time_finish[1].record()
+      over_step()
+      torch.cuda.synchronize()
+      over_diff = float((over.params - base.params).abs().max()) if False else None
+      for _ in range(3):
+        over_step()
+      torch.cuda.synchronize()
+      if world > 1:
+        dist.barrier()
+      torch.cuda.synchronize()
+      total_b, total_e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.iters)]
+      total_b.record()
+      for it in range(args.iters):
+        over_step(pairs[it])
+      total_e.record()
+      torch.cuda.synchronize()
+      ms = torch.tensor([total_b.elapsed_time(total_e) / args.iters, sum(b.elapsed_time(e) for b, e in pairs) / args.iters], device=device, dtype=torch.float64)
+      if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+      bucketed_ms, exposed_ms = float(ms[0]), float(ms[1])
+      del over
     slice_bytes = (fused.hi - fused.lo) * 4
     # bytes entering each GPU over NVLink: slices of the (n - w) remote workers + the (R-1)/R of the parameters pushed by peers
     nvlink_in = (n - w) * slice_bytes + (d * 4 - slice_bytes) if world > 1 else 0
@@ -114,6 +188,8 @@ def main():
                      "replicas_identical": identical, "nvlink_bytes_in_per_gpu": nvlink_in, "gather_gbs_per_gpu": (n * slice_bytes) / fused_ms / 1e6,
                      "nvlink_gbs_per_gpu": nvlink_in / fused_ms / 1e6 if world > 1 else None,
                      "frac_of_770_gbs": (nvlink_in / fused_ms / 1e6) / 770.0 if world > 1 else None,
+                     "measured_peer_gbs": peer_gbs, "frac_of_measured_peer": (nvlink_in / fused_ms / 1e6) / peer_gbs if peer_gbs else None,
+                     "bucketed_total_ms": bucketed_ms, "finish_kernel_exposed_ms": exposed_ms,
                      "local_hbm_bytes": hbm, "hbm_gbs": hbm / fused_ms / 1e6 if world == 1 else None}
     if rank == 0:
       print(rule, json.dumps(results[rule]))

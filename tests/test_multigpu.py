@@ -28,7 +28,7 @@ def _torchrun(nproc, script_args, timeout=600):
 
 @pytest.mark.skipif(_gpus() < 2, reason="needs at least 2 GPUs")
 def test_fused_matches_baseline_on_all_ranks(tmp_path):
-  nproc = 2 if _gpus() < 4 else 4
+  nproc = _ranks_for(8)
   code, out = _torchrun(nproc, [str(ROOT / "benchmarks" / "gar_bench.py"), "--gar-dim", "1000003", "--gar-iters", "3", "--gar-out", str(tmp_path)])
   assert code == 0, out[-4000:]
   results = json.loads((tmp_path / ("gar_bench_%d.json" % nproc)).read_text())["results"]
@@ -38,13 +38,39 @@ def test_fused_matches_baseline_on_all_ranks(tmp_path):
     assert entry["max_abs_diff_vs_baseline"] < 1e-4, (rule, entry)
 
 
+def _ranks_for(nb_workers):
+  """Largest rank count <= visible GPUs that divides the number of logical workers (every visible GPU when possible)."""
+  return max(r for r in range(1, min(_gpus(), nb_workers) + 1) if nb_workers % r == 0)
+
+
+@pytest.mark.skipif(_gpus() < 2, reason="needs at least 2 GPUs")
+def test_overlapped_whole_step_graph_keeps_replicas_identical(tmp_path):
+  """No attack, Krum on cnnet: the step is ONE CUDA graph (forward/backward + bucketed distance pass on a side stream + finish kernel,
+  loss through the kernel's mailbox, no NCCL on the step path) on every visible GPU; replicas stay bit-identical and the loss falls."""
+  nproc = _ranks_for(8)
+  workers = ", ".join('"127.0.0.1:%d"' % (7001 + i) for i in range(nproc))
+  args = [str(ROOT / "runner.py"), "--server", '{"ps": ["127.0.0.1:7000"], "workers": [%s], "eval": ["127.0.0.1:7000"]}' % workers, "--no-wait",
+          "--experiment", "cnnet", "--experiment-args", "batch-size:16", "--aggregator", "krum", "--nb-workers", "8", "--nb-decl-byz-workers", "2",
+          "--max-step", "14", "--use-gpu", "--reuse-gpu", "--debug-checksum", "--learning-rate-args", "initial-rate:0.02",
+          "--evaluation-delta", "7", "--evaluation-period", "-1", "--checkpoint-dir", str(tmp_path / "c"), "--checkpoint-delta", "14", "--checkpoint-period", "-1", "--summary-dir", "-"]
+  code, out = _torchrun(nproc, args)
+  assert code == 0, out[-4000:]
+  assert "Replica divergence" not in out and "Step 13: total loss" in out
+  assert "forward/backward + aggregation into a CUDA graph" in out and "bucket(s)" in out
+  import re
+  losses = [float(x) for x in re.findall(r"Step \d+: total loss = ([0-9.eE+-]+)", out)]
+  assert len(losses) == 14 and all(l == l for l in losses) and min(losses[-4:]) < losses[0]
+
+
 @pytest.mark.skipif(_gpus() < 2, reason="needs at least 2 GPUs")
 def test_training_keeps_replicas_identical(tmp_path):
-  args = [str(ROOT / "runner.py"), "--server", '{"ps": ["127.0.0.1:7000"], "workers": ["127.0.0.1:7001", "127.0.0.1:7002"], "eval": ["127.0.0.1:7000"]}', "--no-wait",
+  nproc = _ranks_for(8)
+  workers = ", ".join('"127.0.0.1:%d"' % (7001 + i) for i in range(nproc))
+  args = [str(ROOT / "runner.py"), "--server", '{"ps": ["127.0.0.1:7000"], "workers": [%s], "eval": ["127.0.0.1:7000"]}' % workers, "--no-wait",
           "--experiment", "cnnet", "--experiment-args", "batch-size:16", "--aggregator", "krum", "--nb-workers", "8", "--nb-decl-byz-workers", "2",
           "--nb-real-byz-workers", "2", "--attack", "flip", "--attack-args", "factor:-20", "--max-step", "12", "--use-gpu", "--reuse-gpu", "--debug-checksum",
           "--evaluation-delta", "6", "--evaluation-period", "-1", "--checkpoint-dir", str(tmp_path / "c"), "--checkpoint-delta", "12", "--checkpoint-period", "-1", "--summary-dir", "-"]
-  code, out = _torchrun(2, args)
+  code, out = _torchrun(nproc, args)
   assert code == 0, out[-4000:]
   assert "Replica divergence" not in out and "Step 11: total loss" in out
   assert (tmp_path / "c" / "model-12.index").exists()
