@@ -8,6 +8,9 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
 
 namespace agb {
 namespace sm100 {
@@ -95,6 +98,11 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(static_cast<uint32_t>(accumulate)) : "memory");
 }
+// Same with fp32 operands read as TF32 (10-bit mantissa), fp32 accumulation.
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(static_cast<uint32_t>(accumulate)) : "memory");
+}
 // Arrive on `bar` once every previously issued tcgen05.mma of this thread has completed (implies fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
@@ -138,7 +146,16 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t 
     desc |= static_cast<uint64_t>(2) << 61;                               // layout type: SWIZZLE_128B
     return desc;
 }
-// Instruction descriptor for kind::f16 with bf16 A/B and fp32 accumulators.
+// Instruction descriptor for kind::f16 / kind::tf32 with fp32 accumulators; `format`: 0 = F16, 1 = BF16, 2 = TF32 (both operands).
+__host__ __device__ constexpr uint32_t umma_idesc(int m, int n, bool a_mn_major, bool b_mn_major, uint32_t format) {
+    return (1u << 4)                                   // D format: F32
+         | (format << 7)                               // A format
+         | (format << 10)                              // B format
+         | (static_cast<uint32_t>(a_mn_major) << 15)
+         | (static_cast<uint32_t>(b_mn_major) << 16)
+         | (static_cast<uint32_t>(n >> 3) << 17)
+         | (static_cast<uint32_t>(m >> 4) << 24);
+}
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n, bool a_mn_major, bool b_mn_major) {
     return (1u << 4)                                   // D format: F32
          | (1u << 7)                                   // A format: BF16
@@ -167,43 +184,85 @@ inline EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 
-// 2-D bf16 tensor map: `inner` contiguous elements per row, `rows` rows of `row_stride` elements, box = box_inner x box_rows, 128B swizzle.
-inline int make_tmap_2d_bf16(CUtensorMap* map, void const* base, uint64_t inner, uint64_t rows, uint64_t row_stride, uint32_t box_inner, uint32_t box_rows) {
+// Tensor maps are pure functions of (base, dims, strides, box, element strides): the same layer is launched with the same arguments every
+// step, so encoded descriptors are memoised (cuTensorMapEncodeTiled is a driver call of a few microseconds; an eager step — evaluation,
+// tracing, experiments that opt out of CUDA graphs — made ~300 of them).
+struct TmapKey {
+    void const* base;
+    uint64_t dims[4], strides[3];
+    uint32_t box[4], elem[4], rank, dtype;
+    bool operator==(TmapKey const& o) const { return std::memcmp(this, &o, sizeof(TmapKey)) == 0; }
+};
+struct TmapKeyHash {
+    size_t operator()(TmapKey const& k) const {
+        uint64_t h = 1469598103934665603ull;
+        unsigned char const* p = reinterpret_cast<unsigned char const*>(&k);
+        for (size_t i = 0; i < sizeof(TmapKey); ++i)
+            h = (h ^ p[i]) * 1099511628211ull;
+        return static_cast<size_t>(h);
+    }
+};
+inline int encode_cached(CUtensorMap* map, CUtensorMapDataType dtype, uint32_t rank, void const* base, cuuint64_t const* dims, cuuint64_t const* strides, cuuint32_t const* box,
+                         cuuint32_t const* elem) {
+    static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+    static std::mutex mutex;
+    TmapKey key;
+    std::memset(&key, 0, sizeof(key));
+    key.base = base; key.rank = rank; key.dtype = static_cast<uint32_t>(dtype);
+    for (uint32_t i = 0; i < rank; ++i) {
+        key.dims[i] = dims[i]; key.box[i] = box[i]; key.elem[i] = elem[i];
+        if (i + 1 < rank)
+            key.strides[i] = strides[i];
+    }
+    {
+        std::lock_guard<std::mutex> guard(mutex);
+        auto it = cache.find(key);
+        if (it != cache.end()) {
+            *map = it->second;
+            return 0;
+        }
+    }
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn)
         return 201;
-    cuuint64_t dims[2] = {inner, rows};
-    cuuint64_t strides[1] = {row_stride * 2};
-    cuuint32_t box[2] = {box_inner, box_rows};
-    cuuint32_t elem[2] = {1, 1};
-    CUresult res = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult res = fn(map, dtype, rank, const_cast<void*>(base), dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (res != CUDA_SUCCESS) {
-        std::fprintf(stderr, "[agb] cuTensorMapEncodeTiled failed (%d): base %p inner %llu rows %llu stride %llu box %ux%u\n", (int) res, base,
-                     (unsigned long long) inner, (unsigned long long) rows, (unsigned long long) row_stride, box_inner, box_rows);
+        std::fprintf(stderr, "[agb] cuTensorMapEncodeTiled(rank %u) failed (%d): base %p dims %llu %llu %llu %llu box %u %u %u %u\n", rank, (int) res, base, (unsigned long long) dims[0],
+                     (unsigned long long) (rank > 1 ? dims[1] : 0), (unsigned long long) (rank > 2 ? dims[2] : 0), (unsigned long long) (rank > 3 ? dims[3] : 0), box[0],
+                     rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
         return 202;
     }
+    std::lock_guard<std::mutex> guard(mutex);
+    if (cache.size() > 16384)   // addresses change when buffers are re-allocated: keep the table bounded
+        cache.clear();
+    cache.emplace(key, *map);
     return 0;
+}
+
+// 2-D bf16 tensor map: `inner` contiguous elements per row, `rows` rows of `row_stride` elements, box = box_inner x box_rows, 128B swizzle.
+inline int make_tmap_2d(CUtensorMap* map, void const* base, uint64_t inner, uint64_t rows, uint64_t row_stride, uint32_t box_inner, uint32_t box_rows, int elem_bytes) {
+    cuuint64_t dims[2] = {inner, rows};
+    cuuint64_t strides[1] = {row_stride * elem_bytes};
+    cuuint32_t box[2] = {box_inner, box_rows};
+    cuuint32_t elem[2] = {1, 1};
+    return encode_cached(map, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, elem);
+}
+inline int make_tmap_2d_bf16(CUtensorMap* map, void const* base, uint64_t inner, uint64_t rows, uint64_t row_stride, uint32_t box_inner, uint32_t box_rows) {
+    return make_tmap_2d(map, base, inner, rows, row_stride, box_inner, box_rows, 2);
 }
 
 // 3-D bf16 tensor map over a row-major [groups][rows][inner] view (row stride `row_stride`, group stride `rows * row_stride`):
 // boxes never straddle a group, rows past the end of a group are zero-filled (grouped weight-gradient GEMMs).
-inline int make_tmap_3d_bf16(CUtensorMap* map, void const* base, uint64_t inner, uint64_t rows, uint64_t groups, uint64_t row_stride, uint32_t box_inner, uint32_t box_rows) {
-    EncodeTiledFn fn = encode_tiled_fn();
-    if (!fn)
-        return 201;
+inline int make_tmap_3d(CUtensorMap* map, void const* base, uint64_t inner, uint64_t rows, uint64_t groups, uint64_t row_stride, uint32_t box_inner, uint32_t box_rows, int elem_bytes) {
     cuuint64_t dims[3] = {inner, rows, groups};
-    cuuint64_t strides[2] = {row_stride * 2, rows * row_stride * 2};
+    cuuint64_t strides[2] = {row_stride * elem_bytes, rows * row_stride * elem_bytes};
     cuuint32_t box[3] = {box_inner, box_rows, 1};
     cuuint32_t elem[3] = {1, 1, 1};
-    CUresult res = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (res != CUDA_SUCCESS) {
-        std::fprintf(stderr, "[agb] cuTensorMapEncodeTiled(3d) failed (%d): inner %llu rows %llu groups %llu stride %llu\n", (int) res, (unsigned long long) inner,
-                     (unsigned long long) rows, (unsigned long long) groups, (unsigned long long) row_stride);
-        return 202;
-    }
-    return 0;
+    return encode_cached(map, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, elem);
+}
+inline int make_tmap_3d_bf16(CUtensorMap* map, void const* base, uint64_t inner, uint64_t rows, uint64_t groups, uint64_t row_stride, uint32_t box_inner, uint32_t box_rows) {
+    return make_tmap_3d(map, base, inner, rows, groups, row_stride, box_inner, box_rows, 2);
 }
 
 } // namespace agb

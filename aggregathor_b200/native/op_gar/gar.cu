@@ -654,13 +654,28 @@ __global__ void __launch_bounds__(N <= 8 ? 512 : 256, 1) gar_fused_kernel(GarArg
 #pragma unroll
                     for (int c = 0; c < VEC; ++c)
                         sum[c] = 0.f;
-                    for (int i = 0; i < n; ++i) {   // ascending worker index: fixed summation order
-                        if ((mask >> i) & 1u) {
-                            float g[VEC];
-                            load_row(i, g);
+                    if (N <= 16) {   // all selected rows in flight at once, summed in ascending worker order
+                        float g[N][VEC];
 #pragma unroll
-                            for (int c = 0; c < VEC; ++c)
-                                sum[c] += g[c];
+                        for (int i = 0; i < N; ++i)
+                            if ((mask >> i) & 1u)
+                                load_row(i, g[i]);
+#pragma unroll
+                        for (int i = 0; i < N; ++i)
+                            if ((mask >> i) & 1u) {
+#pragma unroll
+                                for (int c = 0; c < VEC; ++c)
+                                    sum[c] += g[i][c];
+                            }
+                    } else {
+                        for (int i = 0; i < n; ++i) {
+                            if ((mask >> i) & 1u) {
+                                float g[VEC];
+                                load_row(i, g);
+#pragma unroll
+                                for (int c = 0; c < VEC; ++c)
+                                    sum[c] += g[c];
+                            }
                         }
                     }
                     float const count = static_cast<float>(a.m);
@@ -723,12 +738,27 @@ __global__ void __launch_bounds__(N <= 8 ? 512 : 256, 1) gar_fused_kernel(GarArg
                             sum[0] += t.x; sum[1 % VEC] += t.y; sum[2 % VEC] += t.z; sum[3 % VEC] += t.w;
                         }
                     } else {
-                        for (int i = 0; i < n; ++i) {
-                            float g[VEC];
-                            V<VEC>::load_stream(a.grad[i] + x, g);
+                        if (N <= 16) {
+                            float g[N][VEC];
 #pragma unroll
-                            for (int c = 0; c < VEC; ++c)
-                                sum[c] += g[c];
+                            for (int i = 0; i < N; ++i)
+                                if (i < n)
+                                    V<VEC>::load_stream(a.grad[i] + x, g[i]);
+#pragma unroll
+                            for (int i = 0; i < N; ++i)
+                                if (i < n) {
+#pragma unroll
+                                    for (int c = 0; c < VEC; ++c)
+                                        sum[c] += g[i][c];
+                                }
+                        } else {
+                            for (int i = 0; i < n; ++i) {
+                                float g[VEC];
+                                V<VEC>::load_stream(a.grad[i] + x, g);
+#pragma unroll
+                                for (int c = 0; c < VEC; ++c)
+                                    sum[c] += g[c];
+                            }
                         }
                     }
                     float const count = static_cast<float>(n);

@@ -38,27 +38,20 @@ struct ConvParams {
 enum ConvMode { kFwd = 0, kDgrad = 1, kWgrad = 2 };
 
 // `estride` > 1: the box covers bw * estride x bh * estride source pixels and TMA keeps every estride-th one (bw x bh land in smem).
-inline int make_tmap_4d_bf16(CUtensorMap* map, void const* base, int C, int W, int H, int N, int bw, int bh, int bn, int estride = 1) {
-    EncodeTiledFn fn = encode_tiled_fn();
-    if (!fn)
-        return 201;
+template<typename E>
+inline int make_tmap_4d(CUtensorMap* map, void const* base, int C, int W, int H, int N, int bw, int bh, int bn, int estride = 1) {
+    constexpr cuuint64_t kB = E::kBytes;
     cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(N)};
-    cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(W) * C * 2, static_cast<cuuint64_t>(H) * W * C * 2};
-    cuuint32_t box[4] = {64, static_cast<cuuint32_t>(bw * estride), static_cast<cuuint32_t>(bh * estride), static_cast<cuuint32_t>(bn)};
+    cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * kB, static_cast<cuuint64_t>(W) * C * kB, static_cast<cuuint64_t>(H) * W * C * kB};
+    cuuint32_t box[4] = {static_cast<cuuint32_t>(E::kChunk), static_cast<cuuint32_t>(bw * estride), static_cast<cuuint32_t>(bh * estride), static_cast<cuuint32_t>(bn)};
     cuuint32_t elem[4] = {1, static_cast<cuuint32_t>(estride), static_cast<cuuint32_t>(estride), 1};
-    CUresult res = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (res != CUDA_SUCCESS) {
-        std::fprintf(stderr, "[agb] cuTensorMapEncodeTiled(4d) failed (%d): C %d W %d H %d N %d box %d %d %d\n", (int) res, C, W, H, N, bw, bh, bn);
-        return 202;
-    }
-    return 0;
+    return encode_cached(map, E::kTf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, elem);
 }
 
 // One persistent kernel for the three products. `tmap_a`: 4-D map of the activation that plays A (x for fwd, dy for dgrad and
 // wgrad); `tmap_b`: 2-D weight map (fwd: K-major rows [Cout][k*k*Cin]; dgrad: the same matrix read as MN-major boxes) or
 // the 4-D map of x (wgrad).
-template<int BN, int MODE>
+template<int BN, int MODE, typename E = ElemBF16>
 __global__ void __launch_bounds__(kPersistentThreads, 1) conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                                                                     GemmParams const p, ConvParams const cp, int items_mn, int splits) {
     constexpr bool A_MN = MODE == kWgrad, B_MN = MODE != kFwd;
@@ -78,14 +71,15 @@ __global__ void __launch_bounds__(kPersistentThreads, 1) conv_tcgen05_kernel(con
     int const pixel_tiles = cp.tiles_w * cp.tiles_h * cp.tiles_n;
     int const box_rows = cp.bw * cp.bh * cp.bn;
     // number of K blocks of one work item before splitting
-    int const cchunks = (MODE == kFwd ? cp.Cin : cp.Cout) / 64;
+    int const cchunks = (MODE == kFwd ? cp.Cin : cp.Cout) / E::kChunk;
+    constexpr int kChunkBytes = E::kBK * 128;   // one MN-major chunk of a stage
     int const groups = (MODE == kWgrad && cp.groups > 1) ? cp.groups : 1;
     int const parities = (MODE == kDgrad && cp.stride > 1) ? cp.stride * cp.stride : 1;   // dgrad of a strided convolution: one sub-problem per pixel parity
     int const total_kblocks = MODE == kWgrad ? pixel_tiles / groups : taps * cchunks;     // upper bound per item for dgrad parities (their tap subsets are smaller)
     int const total_items = items_mn * splits * groups;
 
     // Pixel boxes smaller than the MMA tile (7x7 maps) leave rows that TMA never writes: zero the ring once.
-    if (box_rows < (MODE == kWgrad ? 64 : 128)) {
+    if (box_rows < (MODE == kWgrad ? E::kBK : 128)) {
         uint4* ring = reinterpret_cast<uint4*>(smem);
         for (uint32_t i = threadIdx.x; i < PCfg::kStages * Cfg::kStageBytes / 16; i += blockDim.x)
             ring[i] = make_uint4(0, 0, 0, 0);
@@ -114,8 +108,8 @@ __global__ void __launch_bounds__(kPersistentThreads, 1) conv_tcgen05_kernel(con
     pdl_wait();      // ... our inputs are complete only once the previous kernel has finished
 
     // Bytes that one stage really receives (boxes may be smaller than the tile): A box rows * 128 B per 64-wide chunk.
-    uint32_t const a_bytes = MODE == kWgrad ? 2u * box_rows * 128u : static_cast<uint32_t>(box_rows) * 128u;
-    uint32_t const b_bytes = MODE == kWgrad ? (BN / 64) * box_rows * 128u : Cfg::kBBytes;
+    uint32_t const a_bytes = MODE == kWgrad ? static_cast<uint32_t>(kBM / E::kChunk) * box_rows * 128u : static_cast<uint32_t>(box_rows) * 128u;
+    uint32_t const b_bytes = MODE == kWgrad ? (BN / E::kChunk) * box_rows * 128u : Cfg::kBBytes;
 
     // item -> (m index, n tile, tap for wgrad, k split)
     // par_h / par_w: pixel parity of a strided dgrad item; first_kh / nkh (and _kw): the taps that reach that parity (kh = first_kh + stride * i)
@@ -180,13 +174,14 @@ __global__ void __launch_bounds__(kPersistentThreads, 1) conv_tcgen05_kernel(con
                         int const w0 = (kb % cp.tiles_w) * cp.bw, h0 = ((kb / cp.tiles_w) % cp.tiles_h) * cp.bh;
                         int const n0p = (kb / (cp.tiles_w * cp.tiles_h)) * cp.bn + it.group * cp.images_per_group;
                         int const kh = it.tap / cp.k, kw = it.tap % cp.k;
-                        tma_load_4d(a_dst, &tmap_a, full + s, it.m0, w0, h0, n0p);
-                        tma_load_4d(a_dst + kBK * 128, &tmap_a, full + s, it.m0 + 64, w0, h0, n0p);
 #pragma unroll
-                        for (int c = 0; c < BN / 64; ++c)
-                            tma_load_4d(b_dst + c * kBK * 128, &tmap_b, full + s, it.n0 + c * 64, w0 * cp.stride + kw - cp.pad_l, h0 * cp.stride + kh - cp.pad_t, n0p);
+                        for (int c = 0; c < kBM / E::kChunk; ++c)
+                            tma_load_4d(a_dst + c * kChunkBytes, &tmap_a, full + s, it.m0 + c * E::kChunk, w0, h0, n0p);
+#pragma unroll
+                        for (int c = 0; c < BN / E::kChunk; ++c)
+                            tma_load_4d(b_dst + c * kChunkBytes, &tmap_b, full + s, it.n0 + c * E::kChunk, w0 * cp.stride + kw - cp.pad_l, h0 * cp.stride + kh - cp.pad_t, n0p);
                     } else {
-                        int const tap_index = kb / cchunks, c0 = (kb % cchunks) * 64;
+                        int const tap_index = kb / cchunks, c0 = (kb % cchunks) * E::kChunk;
                         int kh, kw, dw, dh;
                         if (MODE == kFwd) {         // x[oh * s + kh - pad_t, ow * s + kw - pad_l]: the map's element strides do the "* s"
                             kh = tap_index / cp.k; kw = tap_index % cp.k;
@@ -206,8 +201,8 @@ __global__ void __launch_bounds__(kPersistentThreads, 1) conv_tcgen05_kernel(con
                             tma_load_2d(b_dst, &tmap_b, full + s, tap * cp.Cin + c0, it.n0);
                         } else { // dgrad: B[k = co, n = ci] = W[co][tap][ci]: MN-major boxes of 64 ci x 64 co
 #pragma unroll
-                            for (int c = 0; c < BN / 64; ++c)
-                                tma_load_2d(b_dst + c * kBK * 128, &tmap_b, full + s, tap * cp.Cin + it.n0 + c * 64, c0);
+                            for (int c = 0; c < BN / E::kChunk; ++c)
+                                tma_load_2d(b_dst + c * kChunkBytes, &tmap_b, full + s, tap * cp.Cin + it.n0 + c * E::kChunk, c0);
                         }
                     }
                 }
@@ -226,7 +221,7 @@ __global__ void __launch_bounds__(kPersistentThreads, 1) conv_tcgen05_kernel(con
                     int const s = ring % PCfg::kStages;
                     mbar_wait(full + s, (ring / PCfg::kStages) & 1, 23);
                     tc_fence_after();
-                    consume_stage<BN, A_MN, B_MN>(smem_u32(smem + s * Cfg::kStageBytes), acc, i == 0);
+                    consume_stage<BN, A_MN, B_MN, E>(smem_u32(smem + s * Cfg::kStageBytes), acc, i == 0);
                     umma_commit(empty + s);
                 }
                 umma_commit(tmem_full + buf);
@@ -268,10 +263,10 @@ __global__ void __launch_bounds__(kPersistentThreads, 1) conv_tcgen05_kernel(con
         tmem_dealloc<PCfg::kTmemCols>(tmem_base);
 }
 
-template<int BN, int MODE>
+template<int BN, int MODE, typename E = ElemBF16>
 int launch_conv(CUtensorMap const& ta, CUtensorMap const& tb, GemmParams const& p, ConvParams const& cp, int items_mn, int splits, cudaStream_t stream) {
     using PCfg = PersistentConfig<BN>;
-    auto kernel = conv_tcgen05_kernel<BN, MODE>;
+    auto kernel = conv_tcgen05_kernel<BN, MODE, E>;
     static bool configured = false;
     static int sms = 0;
     if (!configured) {
@@ -312,6 +307,96 @@ bool choose_box(int W, int H, int N, int rows, int& bw, int& bh, int& bn) {
     return best >= 0;
 }
 
+template<typename E>
+int conv_implicit_impl(int mode, void const* act, void const* other, void* out, int N, int H, int W, int OH, int OW, int Cin, int Cout, int k, int stride, int pad_t, int pad_l,
+                              void const* bias, int relu, int out_fp32, int splits, int bn, int groups, long long c_group_stride, void* stream) {
+    if (k < 1 || Cin % E::kChunk || Cout % E::kChunk || N < 1 || (stride != 1 && stride != 2) || pad_t < 0 || pad_l < 0 || pad_t >= k || pad_l >= k)
+        return 401;
+    if (stride == 2 && ((H & 1) || (W & 1) || OH != H / 2 || OW != W / 2 || k < 2))
+        return 405;
+    if (stride == 1 && (OH != H || OW != W))
+        return 405;
+    if (groups < 1)
+        groups = 1;
+    if (groups > 1 && (mode != 2 || N % groups))
+        return 404;
+    ConvParams cp{};
+    cp.N = N; cp.H = H; cp.W = W; cp.OH = OH; cp.OW = OW; cp.Cin = Cin; cp.Cout = Cout; cp.k = k; cp.stride = stride; cp.pad_t = pad_t; cp.pad_l = pad_l;
+    cp.groups = groups; cp.images_per_group = N / groups;
+    // the grid the boxes tile: output pixels (fwd, wgrad) or, for the data gradient, the pixels of one parity class of dx
+    cp.GH = mode == 1 ? H / stride : OH;
+    cp.GW = mode == 1 ? W / stride : OW;
+    if (!choose_box(cp.GW, cp.GH, mode == 2 ? N / groups : N, mode == 2 ? E::kBK : 128, cp.bw, cp.bh, cp.bn))   // boxes never straddle two workers
+        return 402;
+    cp.tiles_w = cp.GW / cp.bw; cp.tiles_h = cp.GH / cp.bh; cp.tiles_n = N / cp.bn;
+    int const pixel_tiles = cp.tiles_w * cp.tiles_h * cp.tiles_n;
+    GemmParams p{};
+    p.C = out;
+    p.bias = static_cast<float const*>(bias);
+    p.relu = relu;
+    p.out_fp32 = out_fp32;
+    CUtensorMap ta, tb;
+    int status, items_mn, total_kblocks;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (mode == 0) {
+        p.M = N * OH * OW; p.N = Cout; p.K = k * k * Cin; p.ldc = Cout;
+        if (bn == 0)
+            bn = Cout <= 64 ? 64 : 128;
+        if ((status = make_tmap_4d<E>(&ta, act, Cin, W, H, N, cp.bw, cp.bh, cp.bn, stride)))
+            return status;
+        if ((status = make_tmap_2d(&tb, other, static_cast<uint64_t>(k) * k * Cin, Cout, static_cast<uint64_t>(k) * k * Cin, E::kBK, bn, E::kBytes)))
+            return status;
+        items_mn = pixel_tiles * ((Cout + bn - 1) / bn);
+        total_kblocks = k * k * (Cin / E::kChunk);
+    } else if (mode == 1) {
+        p.M = N * H * W; p.N = Cin; p.K = k * k * Cout; p.ldc = Cin;
+        if (bn == 0)
+            bn = Cin <= 64 ? 64 : 128;
+        if ((status = make_tmap_4d<E>(&ta, act, Cout, OW, OH, N, cp.bw, cp.bh, cp.bn)))
+            return status;
+        if ((status = make_tmap_2d(&tb, other, static_cast<uint64_t>(k) * k * Cin, Cout, static_cast<uint64_t>(k) * k * Cin, E::kChunk, E::kBK, E::kBytes)))
+            return status;
+        items_mn = pixel_tiles * ((Cin + bn - 1) / bn) * stride * stride;   // one sub-problem per pixel parity
+        total_kblocks = k * k * (Cout / E::kChunk);
+        if (stride > 1 && splits > 1)
+            return 406;
+    } else if (mode == 2) {
+        p.M = Cout; p.N = Cin; p.K = N * OH * OW; p.ldc = static_cast<long long>(k) * k * Cin;
+        if (!out_fp32)
+            return 205;
+        if (bn == 0)
+            bn = Cin <= 64 ? 64 : 128;
+        if ((status = make_tmap_4d<E>(&ta, act, Cout, OW, OH, N, cp.bw, cp.bh, cp.bn)))
+            return status;
+        if ((status = make_tmap_4d<E>(&tb, other, Cin, W, H, N, cp.bw, cp.bh, cp.bn, stride)))
+            return status;
+        items_mn = k * k * ((Cout + kBM - 1) / kBM) * ((Cin + bn - 1) / bn);
+        total_kblocks = pixel_tiles / groups;
+    } else {
+        return 403;
+    }
+    if (splits < 1)
+        splits = 1;
+    if (splits > total_kblocks)
+        splits = total_kblocks;
+    if (splits > 1 && !out_fp32)
+        return 205;
+    p.atomic = splits > 1;
+    p.groups = groups; p.c_group_stride = c_group_stride;
+    p.kblocks_per_split = (total_kblocks + splits - 1) / splits;
+    splits = (total_kblocks + p.kblocks_per_split - 1) / p.kblocks_per_split;
+#define AGB_CONV_DISPATCH(MODE) \
+    switch (bn) { \
+        case 64: return launch_conv<64, MODE, E>(ta, tb, p, cp, items_mn, splits, s); \
+        case 128: return launch_conv<128, MODE, E>(ta, tb, p, cp, items_mn, splits, s); \
+    } \
+    return 203;
+    if (mode == 0) { AGB_CONV_DISPATCH(kFwd) }
+    if (mode == 1) { AGB_CONV_DISPATCH(kDgrad) }
+    AGB_CONV_DISPATCH(kWgrad)
+#undef AGB_CONV_DISPATCH
+}
+
 } // namespace
 
 extern "C" {
@@ -339,91 +424,13 @@ int agb_conv_implicit(int mode, void const* act, void const* other, void* out, i
 // into out + g * c_group_stride.
 int agb_conv_implicit_strided(int mode, void const* act, void const* other, void* out, int N, int H, int W, int OH, int OW, int Cin, int Cout, int k, int stride, int pad_t, int pad_l,
                               void const* bias, int relu, int out_fp32, int splits, int bn, int groups, long long c_group_stride, void* stream) {
-    if (k < 1 || Cin % 64 || Cout % 64 || N < 1 || (stride != 1 && stride != 2) || pad_t < 0 || pad_l < 0 || pad_t >= k || pad_l >= k)
-        return 401;
-    if (stride == 2 && ((H & 1) || (W & 1) || OH != H / 2 || OW != W / 2 || k < 2))
-        return 405;
-    if (stride == 1 && (OH != H || OW != W))
-        return 405;
-    if (groups < 1)
-        groups = 1;
-    if (groups > 1 && (mode != 2 || N % groups))
-        return 404;
-    ConvParams cp{};
-    cp.N = N; cp.H = H; cp.W = W; cp.OH = OH; cp.OW = OW; cp.Cin = Cin; cp.Cout = Cout; cp.k = k; cp.stride = stride; cp.pad_t = pad_t; cp.pad_l = pad_l;
-    cp.groups = groups; cp.images_per_group = N / groups;
-    // the grid the boxes tile: output pixels (fwd, wgrad) or, for the data gradient, the pixels of one parity class of dx
-    cp.GH = mode == 1 ? H / stride : OH;
-    cp.GW = mode == 1 ? W / stride : OW;
-    if (!choose_box(cp.GW, cp.GH, mode == 2 ? N / groups : N, mode == 2 ? 64 : 128, cp.bw, cp.bh, cp.bn))   // boxes never straddle two workers
-        return 402;
-    cp.tiles_w = cp.GW / cp.bw; cp.tiles_h = cp.GH / cp.bh; cp.tiles_n = N / cp.bn;
-    int const pixel_tiles = cp.tiles_w * cp.tiles_h * cp.tiles_n;
-    GemmParams p{};
-    p.C = out;
-    p.bias = static_cast<float const*>(bias);
-    p.relu = relu;
-    p.out_fp32 = out_fp32;
-    CUtensorMap ta, tb;
-    int status, items_mn, total_kblocks;
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (mode == 0) {
-        p.M = N * OH * OW; p.N = Cout; p.K = k * k * Cin; p.ldc = Cout;
-        if (bn == 0)
-            bn = Cout <= 64 ? 64 : 128;
-        if ((status = make_tmap_4d_bf16(&ta, act, Cin, W, H, N, cp.bw, cp.bh, cp.bn, stride)))
-            return status;
-        if ((status = make_tmap_2d_bf16(&tb, other, static_cast<uint64_t>(k) * k * Cin, Cout, static_cast<uint64_t>(k) * k * Cin, kBK, bn)))
-            return status;
-        items_mn = pixel_tiles * ((Cout + bn - 1) / bn);
-        total_kblocks = k * k * (Cin / 64);
-    } else if (mode == 1) {
-        p.M = N * H * W; p.N = Cin; p.K = k * k * Cout; p.ldc = Cin;
-        if (bn == 0)
-            bn = Cin <= 64 ? 64 : 128;
-        if ((status = make_tmap_4d_bf16(&ta, act, Cout, OW, OH, N, cp.bw, cp.bh, cp.bn)))
-            return status;
-        if ((status = make_tmap_2d_bf16(&tb, other, static_cast<uint64_t>(k) * k * Cin, Cout, static_cast<uint64_t>(k) * k * Cin, 64, kBK)))
-            return status;
-        items_mn = pixel_tiles * ((Cin + bn - 1) / bn) * stride * stride;   // one sub-problem per pixel parity
-        total_kblocks = k * k * (Cout / 64);
-        if (stride > 1 && splits > 1)
-            return 406;
-    } else if (mode == 2) {
-        p.M = Cout; p.N = Cin; p.K = N * OH * OW; p.ldc = static_cast<long long>(k) * k * Cin;
-        if (!out_fp32)
-            return 205;
-        if (bn == 0)
-            bn = Cin <= 64 ? 64 : 128;
-        if ((status = make_tmap_4d_bf16(&ta, act, Cout, OW, OH, N, cp.bw, cp.bh, cp.bn)))
-            return status;
-        if ((status = make_tmap_4d_bf16(&tb, other, Cin, W, H, N, cp.bw, cp.bh, cp.bn, stride)))
-            return status;
-        items_mn = k * k * ((Cout + kBM - 1) / kBM) * ((Cin + bn - 1) / bn);
-        total_kblocks = pixel_tiles / groups;
-    } else {
-        return 403;
-    }
-    if (splits < 1)
-        splits = 1;
-    if (splits > total_kblocks)
-        splits = total_kblocks;
-    if (splits > 1 && !out_fp32)
-        return 205;
-    p.atomic = splits > 1;
-    p.groups = groups; p.c_group_stride = c_group_stride;
-    p.kblocks_per_split = (total_kblocks + splits - 1) / splits;
-    splits = (total_kblocks + p.kblocks_per_split - 1) / p.kblocks_per_split;
-#define AGB_CONV_DISPATCH(MODE) \
-    switch (bn) { \
-        case 64: return launch_conv<64, MODE>(ta, tb, p, cp, items_mn, splits, s); \
-        case 128: return launch_conv<128, MODE>(ta, tb, p, cp, items_mn, splits, s); \
-    } \
-    return 203;
-    if (mode == 0) { AGB_CONV_DISPATCH(kFwd) }
-    if (mode == 1) { AGB_CONV_DISPATCH(kDgrad) }
-    AGB_CONV_DISPATCH(kWgrad)
-#undef AGB_CONV_DISPATCH
+    return conv_implicit_impl<ElemBF16>(mode, act, other, out, N, H, W, OH, OW, Cin, Cout, k, stride, pad_t, pad_l, bias, relu, out_fp32, splits, bn, groups, c_group_stride, stream);
+}
+
+// fp32 activations / weights multiplied as TF32 (kind::tf32); channel counts multiples of 32; outputs are fp32.
+int agb_conv_implicit_strided_tf32(int mode, void const* act, void const* other, void* out, int N, int H, int W, int OH, int OW, int Cin, int Cout, int k, int stride, int pad_t, int pad_l,
+                                   void const* bias, int relu, int splits, int bn, int groups, long long c_group_stride, void* stream) {
+    return conv_implicit_impl<ElemTF32>(mode, act, other, out, N, H, W, OH, OW, Cin, Cout, k, stride, pad_t, pad_l, bias, relu, 1, splits, bn, groups, c_group_stride, stream);
 }
 
 } // extern "C"

@@ -74,4 +74,56 @@ int agb_gemm_bf16_grouped(void const* A, void const* B, void* C, int M, int N, i
     return b_mn ? dispatch_bn<false, true>(bn, ta, tb, p, splits, s) : dispatch_bn<false, false>(bn, ta, tb, p, splits, s);
 }
 
+// fp32 operands multiplied as TF32 (kind::tf32), fp32 accumulation and output: same layouts and options as agb_gemm_bf16_grouped;
+// lda / ldb multiples of 4 elements, bases 16-byte aligned, bn in {64, 128} (0 = automatic), C is fp32.
+int agb_gemm_tf32_grouped(void const* A, void const* B, void* C, int M, int N, int K, long long lda, long long ldb, long long ldc,
+                          int a_mn, int b_mn, void const* bias, int relu, int splits, int bn, int groups, long long c_group_stride, void* stream) {
+    using E = ElemTF32;
+    if (M <= 0 || N <= 0 || K <= 0)
+        return 0;
+    if ((lda & 3) || (ldb & 3) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15))
+        return 204;
+    if (groups < 1)
+        groups = 1;
+    if (groups > 1 && !(a_mn && b_mn))
+        return 206;
+    if (splits < 1)
+        splits = 1;
+    if (bn == 0)
+        bn = N <= 64 ? 64 : 128;
+    int const total_kblocks = (K + E::kBK - 1) / E::kBK;
+    if (splits > total_kblocks)
+        splits = total_kblocks;
+    GemmParams p{};
+    p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.C = C;
+    p.bias = static_cast<float const*>(bias);
+    p.relu = relu; p.out_fp32 = 1; p.atomic = splits > 1;
+    p.groups = groups; p.c_group_stride = c_group_stride;
+    p.kblocks_per_split = (total_kblocks + splits - 1) / splits;
+    splits = (total_kblocks + p.kblocks_per_split - 1) / p.kblocks_per_split;
+    CUtensorMap ta, tb;
+    int status;
+    uint64_t const m = static_cast<uint64_t>(M), n = static_cast<uint64_t>(N), k = static_cast<uint64_t>(K), g = static_cast<uint64_t>(groups);
+    if (a_mn && b_mn)
+        status = make_tmap_3d(&ta, A, m, k, g, static_cast<uint64_t>(lda), E::kChunk, E::kBK, 4);
+    else if (a_mn)
+        status = make_tmap_2d(&ta, A, m, k, static_cast<uint64_t>(lda), E::kChunk, E::kBK, 4);
+    else
+        status = make_tmap_2d(&ta, A, k, m, static_cast<uint64_t>(lda), E::kBK, kBM, 4);
+    if (status)
+        return status;
+    if (a_mn && b_mn)
+        status = make_tmap_3d(&tb, B, n, k, g, static_cast<uint64_t>(ldb), E::kChunk, E::kBK, 4);
+    else if (b_mn)
+        status = make_tmap_2d(&tb, B, n, k, static_cast<uint64_t>(ldb), E::kChunk, E::kBK, 4);
+    else
+        status = make_tmap_2d(&tb, B, k, n, static_cast<uint64_t>(ldb), E::kBK, static_cast<uint32_t>(bn), 4);
+    if (status)
+        return status;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (a_mn)
+        return b_mn ? dispatch_bn_tf32<true, true>(bn, ta, tb, p, splits, s) : dispatch_bn_tf32<true, false>(bn, ta, tb, p, splits, s);
+    return b_mn ? dispatch_bn_tf32<false, true>(bn, ta, tb, p, splits, s) : dispatch_bn_tf32<false, false>(bn, ta, tb, p, splits, s);
+}
+
 } // extern "C"

@@ -30,14 +30,31 @@ using namespace agb::sm100;
 namespace {
 
 constexpr int kBM = 128;       // UMMA M
-constexpr int kBK = 64;        // K elements per stage = one 128-byte swizzle row
+constexpr int kBK = 64;        // bf16: K elements per stage = one 128-byte swizzle row
 constexpr int kUmmaK = 16;
 constexpr int kThreads = 192;
 
+// Operand element types. A pipeline stage is always 128 bytes of K per row (one swizzle row) and one tcgen05.mma consumes 32 bytes of it:
+//   bf16  kind::f16   64 K-elements per stage, 16 per instruction, MN-major chunks of 64 elements
+//   tf32  kind::tf32  32 K-elements per stage,  8 per instruction, MN-major chunks of 32 elements - fp32 operands straight from memory
+//         (the tensor core reads the top 19 bits): the parity-precision path for the fp32 reference (`graph.py:267-273`)
+struct ElemBF16 {
+    using type = __nv_bfloat16;
+    static constexpr int kBytes = 2, kBK = 64, kUmmaK = 16, kChunk = 64;
+    static constexpr uint32_t kFormat = 1;   // instruction-descriptor A/B format: BF16
+    static constexpr bool kTf32 = false;
+};
+struct ElemTF32 {
+    using type = float;
+    static constexpr int kBytes = 4, kBK = 32, kUmmaK = 8, kChunk = 32;
+    static constexpr uint32_t kFormat = 2;   // TF32
+    static constexpr bool kTf32 = true;
+};
+
 template<int BN> struct Config {
     static constexpr int kStages = BN <= 64 ? 4 : 3;   // <= 97 KB of smem for BN <= 128: two CTAs per SM
-    static constexpr uint32_t kABytes = kBM * kBK * 2;
-    static constexpr uint32_t kBBytes = BN * kBK * 2;
+    static constexpr uint32_t kABytes = kBM * 128;   // 128 rows x 128 bytes of K (either element type)
+    static constexpr uint32_t kBBytes = BN * 128;
     static constexpr uint32_t kStageBytes = kABytes + kBBytes;
     static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /* alignment slack */ + 256 /* barriers */;
     static constexpr uint32_t kTmemCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
@@ -270,46 +287,53 @@ __device__ __forceinline__ void epilogue_tile(GemmParams const& p, uint32_t tmem
     epilogue_rows<BN>(p, tmem_acc, warp, row < p.M, static_cast<long long>(row) * p.ldc, n0);
 }
 
-// Loads of one pipeline stage (A and B tiles of k-block `k`).
-template<int BN, bool A_MN, bool B_MN>
+// Loads of one pipeline stage (A and B tiles of the k-block starting at element `k`).
+template<int BN, bool A_MN, bool B_MN, typename E = ElemBF16>
 __device__ __forceinline__ void produce_stage(CUtensorMap const* tmap_a, CUtensorMap const* tmap_b, uint8_t* a_dst, uint64_t* bar, int m0, int n0, int k, int group = -1) {
     uint8_t* b_dst = a_dst + Config<BN>::kABytes;
+    constexpr int kChunkBytes = E::kBK * 128;   // one MN-major chunk: kBK k-rows of 128 bytes
     mbar_expect_tx(bar, Config<BN>::kStageBytes);
     if (A_MN && B_MN && group >= 0) {   // grouped weight gradient: 3-D maps (inner, row in group, group)
-        tma_load_3d(a_dst, tmap_a, bar, m0, k, group);
-        tma_load_3d(a_dst + kBK * 128, tmap_a, bar, m0 + 64, k, group);
 #pragma unroll
-        for (int c = 0; c < BN / 64; ++c)
-            tma_load_3d(b_dst + c * kBK * 128, tmap_b, bar, n0 + c * 64, k, group);
+        for (int c = 0; c < kBM / E::kChunk; ++c)
+            tma_load_3d(a_dst + c * kChunkBytes, tmap_a, bar, m0 + c * E::kChunk, k, group);
+#pragma unroll
+        for (int c = 0; c < BN / E::kChunk; ++c)
+            tma_load_3d(b_dst + c * kChunkBytes, tmap_b, bar, n0 + c * E::kChunk, k, group);
         return;
     }
-    if (A_MN) { // rows = K index, 64 M-elements per row; one box per 64-wide M chunk
-        tma_load_2d(a_dst, tmap_a, bar, m0, k);
-        tma_load_2d(a_dst + kBK * 128, tmap_a, bar, m0 + 64, k);
+    if (A_MN) { // rows = K index, kChunk M-elements per row; one box per chunk
+#pragma unroll
+        for (int c = 0; c < kBM / E::kChunk; ++c)
+            tma_load_2d(a_dst + c * kChunkBytes, tmap_a, bar, m0 + c * E::kChunk, k);
     } else {
         tma_load_2d(a_dst, tmap_a, bar, k, m0);
     }
     if (B_MN) {
 #pragma unroll
-        for (int c = 0; c < BN / 64; ++c)
-            tma_load_2d(b_dst + c * kBK * 128, tmap_b, bar, n0 + c * 64, k);
+        for (int c = 0; c < BN / E::kChunk; ++c)
+            tma_load_2d(b_dst + c * kChunkBytes, tmap_b, bar, n0 + c * E::kChunk, k);
     } else {
         tma_load_2d(b_dst, tmap_b, bar, k, n0);
     }
 }
 
-// tcgen05.mma over one staged k-block (4 instructions of K = 16).
-template<int BN, bool A_MN, bool B_MN>
+// tcgen05.mma over one staged k-block (4 instructions of 32 bytes of K each).
+template<int BN, bool A_MN, bool B_MN, typename E = ElemBF16>
 __device__ __forceinline__ void consume_stage(uint32_t a_addr, uint32_t tmem_acc, bool first) {
-    constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, A_MN, B_MN);
+    constexpr uint32_t idesc = umma_idesc(kBM, BN, A_MN, B_MN, E::kFormat);
     uint32_t const b_addr = a_addr + Config<BN>::kABytes;
+    constexpr int kChunkBytes = E::kBK * 128;
 #pragma unroll
-    for (int kk = 0; kk < kBK / kUmmaK; ++kk) {
-        // K-major: 16 K-elements = 32 B further inside the 128B swizzled row.
-        // MN-major: 16 K-rows = 16 * 128 B further; chunks of 64 MN-elements are kBK * 128 B apart.
-        uint64_t const da = A_MN ? umma_smem_desc(a_addr + kk * kUmmaK * 128, kBK * 128, 1024) : umma_smem_desc(a_addr + kk * kUmmaK * 2, 16, 1024);
-        uint64_t const db = B_MN ? umma_smem_desc(b_addr + kk * kUmmaK * 128, kBK * 128, 1024) : umma_smem_desc(b_addr + kk * kUmmaK * 2, 16, 1024);
-        umma_f16(tmem_acc, da, db, idesc, !(first && kk == 0));
+    for (int kk = 0; kk < E::kBK / E::kUmmaK; ++kk) {
+        // K-major: one instruction's K = 32 B further inside the 128B swizzled row.
+        // MN-major: kUmmaK k-rows = kUmmaK * 128 B further; chunks of kChunk MN-elements are kChunkBytes apart.
+        uint64_t const da = A_MN ? umma_smem_desc(a_addr + kk * E::kUmmaK * 128, kChunkBytes, 1024) : umma_smem_desc(a_addr + kk * 32, 16, 1024);
+        uint64_t const db = B_MN ? umma_smem_desc(b_addr + kk * E::kUmmaK * 128, kChunkBytes, 1024) : umma_smem_desc(b_addr + kk * 32, 16, 1024);
+        if (E::kTf32)
+            umma_tf32(tmem_acc, da, db, idesc, !(first && kk == 0));
+        else
+            umma_f16(tmem_acc, da, db, idesc, !(first && kk == 0));
     }
 }
 
@@ -323,7 +347,7 @@ template<int BN> struct PersistentConfig {
     static constexpr uint32_t kTmemCols = 2 * Config<BN>::kTmemCols;   // <= 512
 };
 
-template<int BN, bool A_MN, bool B_MN>
+template<int BN, bool A_MN, bool B_MN, typename E = ElemBF16>
 __global__ void __launch_bounds__(kPersistentThreads, 1) gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, GemmParams const p, int m_tiles, int n_tiles, int splits) {
     using Cfg = Config<BN>;
     using PCfg = PersistentConfig<BN>;
@@ -337,7 +361,7 @@ __global__ void __launch_bounds__(kPersistentThreads, 1) gemm_tcgen05_persistent
     uint8_t* epi_stage = smem + PCfg::kStages * Cfg::kStageBytes + 256;
 
     int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int const total_kblocks = (p.K + kBK - 1) / kBK;
+    int const total_kblocks = (p.K + E::kBK - 1) / E::kBK;
     int const total_items = m_tiles * n_tiles * splits * (p.groups > 1 ? p.groups : 1);
 
     if (warp == 0 && lane == 0) {
@@ -391,7 +415,7 @@ __global__ void __launch_bounds__(kPersistentThreads, 1) gemm_tcgen05_persistent
                 for (int i = 0; i < nkb; ++i, ++it) {
                     int const s = it % PCfg::kStages;
                     mbar_wait(empty + s, ((it / PCfg::kStages) & 1) ^ 1, 11);
-                    produce_stage<BN, A_MN, B_MN>(&tmap_a, &tmap_b, smem + s * Cfg::kStageBytes, full + s, m0, n0, (kb_begin + i) * kBK, grouped ? group : -1);
+                    produce_stage<BN, A_MN, B_MN, E>(&tmap_a, &tmap_b, smem + s * Cfg::kStageBytes, full + s, m0, n0, (kb_begin + i) * E::kBK, grouped ? group : -1);
                 }
             }
         }
@@ -409,7 +433,7 @@ __global__ void __launch_bounds__(kPersistentThreads, 1) gemm_tcgen05_persistent
                     int const s = it % PCfg::kStages;
                     mbar_wait(full + s, (it / PCfg::kStages) & 1, 13);
                     tc_fence_after();
-                    consume_stage<BN, A_MN, B_MN>(smem_u32(smem + s * Cfg::kStageBytes), acc, i == 0);
+                    consume_stage<BN, A_MN, B_MN, E>(smem_u32(smem + s * Cfg::kStageBytes), acc, i == 0);
                     umma_commit(empty + s);
                 }
                 umma_commit(tmem_full + buf);
@@ -515,7 +539,7 @@ __global__ void __launch_bounds__(kThreads, BN <= 128 ? 2 : 1) gemm_tcgen05_kern
 
 static int g_persistent = -1;   // -1: read AGB_GEMM_PERSISTENT at first use
 
-template<int BN, bool A_MN, bool B_MN>
+template<int BN, bool A_MN, bool B_MN, typename E = ElemBF16>
 int launch_gemm(CUtensorMap const& ta, CUtensorMap const& tb, GemmParams const& p, int splits, cudaStream_t stream) {
     using Cfg = Config<BN>;
     if (g_persistent < 0) {
@@ -523,9 +547,9 @@ int launch_gemm(CUtensorMap const& ta, CUtensorMap const& tb, GemmParams const& 
         g_persistent = env ? std::atoi(env) : 1;
     }
     int const m_tiles = (p.M + kBM - 1) / kBM, n_tiles = (p.N + BN - 1) / BN;
-    if (g_persistent) {
+    if (g_persistent || E::kTf32) {   // the TF32 path only exists as the persistent kernel
         using PCfg = PersistentConfig<BN>;
-        auto kernel = gemm_tcgen05_persistent_kernel<BN, A_MN, B_MN>;
+        auto kernel = gemm_tcgen05_persistent_kernel<BN, A_MN, B_MN, E>;
         static bool configured = false;
         static int sms = 0;
         if (!configured) {
@@ -540,8 +564,8 @@ int launch_gemm(CUtensorMap const& ta, CUtensorMap const& tb, GemmParams const& 
         AGB_CUDA_OK(launch_pdl(kernel, dim3(grid), dim3(kPersistentThreads), PCfg::kSmemBytes, stream, ta, tb, p, m_tiles, n_tiles, splits));
         return 0;
     }
-    if (p.groups > 1)
-        return 207;   // grouped products need the persistent kernel
+    if (p.groups > 1 || E::kTf32)
+        return 207;   // grouped / TF32 products need the persistent kernel
     auto kernel = gemm_tcgen05_kernel<BN, A_MN, B_MN>;
     static bool configured = false;
     if (!configured) {
@@ -560,6 +584,15 @@ int dispatch_bn(int bn, CUtensorMap const& ta, CUtensorMap const& tb, GemmParams
         case 64: return launch_gemm<64, A_MN, B_MN>(ta, tb, p, splits, stream);
         case 128: return launch_gemm<128, A_MN, B_MN>(ta, tb, p, splits, stream);
         case 256: return launch_gemm<256, A_MN, B_MN>(ta, tb, p, splits, stream);
+    }
+    return 203;
+}
+
+template<bool A_MN, bool B_MN>
+int dispatch_bn_tf32(int bn, CUtensorMap const& ta, CUtensorMap const& tb, GemmParams const& p, int splits, cudaStream_t stream) {
+    switch (bn) {
+        case 64: return launch_gemm<64, A_MN, B_MN, ElemTF32>(ta, tb, p, splits, stream);
+        case 128: return launch_gemm<128, A_MN, B_MN, ElemTF32>(ta, tb, p, splits, stream);
     }
     return 203;
 }

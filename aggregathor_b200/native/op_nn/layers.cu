@@ -19,6 +19,12 @@ namespace {
 
 using bf16 = __nv_bfloat16;
 
+// Activations are bf16 (default) or fp32 (the TF32 parity path: fp32 storage, `kind::tf32` products). Every kernel handles 8
+// consecutive channels per thread: one 16-byte vector of bf16, two of fp32.
+template<typename T> struct Oct;
+template<> struct alignas(16) Oct<bf16> { uint4 raw; };
+template<> struct alignas(16) Oct<float> { float4 lo, hi; };
+
 __device__ __forceinline__ void unpack8(uint4 const& raw, float (&v)[8]) {
     __nv_bfloat162 const* h = reinterpret_cast<__nv_bfloat162 const*>(&raw);
 #pragma unroll
@@ -36,6 +42,26 @@ __device__ __forceinline__ uint4 pack8(float const (&v)[8]) {
         h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
     return raw;
 }
+__device__ __forceinline__ void unpack8(Oct<bf16> const& o, float (&v)[8]) { unpack8(o.raw, v); }
+__device__ __forceinline__ void unpack8(Oct<float> const& o, float (&v)[8]) {
+    v[0] = o.lo.x; v[1] = o.lo.y; v[2] = o.lo.z; v[3] = o.lo.w; v[4] = o.hi.x; v[5] = o.hi.y; v[6] = o.hi.z; v[7] = o.hi.w;
+}
+template<typename T> __device__ __forceinline__ Oct<T> pack_oct(float const (&v)[8]);
+template<> __device__ __forceinline__ Oct<bf16> pack_oct<bf16>(float const (&v)[8]) { return Oct<bf16>{pack8(v)}; }
+template<> __device__ __forceinline__ Oct<float> pack_oct<float>(float const (&v)[8]) {
+    return Oct<float>{make_float4(v[0], v[1], v[2], v[3]), make_float4(v[4], v[5], v[6], v[7])};
+}
+template<typename T> __device__ __forceinline__ Oct<T> zero_oct() {
+    float const z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    return pack_oct<T>(z);
+}
+template<typename T> __device__ __forceinline__ Oct<T> load_oct(T const* p) { return *reinterpret_cast<Oct<T> const*>(p); }
+template<typename T> __device__ __forceinline__ void store_oct(T* p, Oct<T> const& o) { *reinterpret_cast<Oct<T>*>(p) = o; }
+__device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float to_f(float v) { return v; }
+template<typename T> __device__ __forceinline__ T from_f(float v);
+template<> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16(v); }
+template<> __device__ __forceinline__ float from_f<float>(float v) { return v; }
 
 constexpr int kThreads = 256;
 
@@ -108,8 +134,8 @@ __device__ void finalize_sums(double* sums, SumsFinalize const& f, int C, long l
     }
 }
 
-template<int MODE, int STRIP>
-__global__ void __launch_bounds__(kThreads) channel_sums_kernel(bf16 const* __restrict__ a, bf16 const* __restrict__ b, bf16 const* __restrict__ y, float const* __restrict__ mean,
+template<typename T, int MODE, int STRIP>
+__global__ void __launch_bounds__(kThreads) channel_sums_kernel(T const* __restrict__ a, T const* __restrict__ b, T const* __restrict__ y, float const* __restrict__ mean,
                                     float const* __restrict__ rstd, double* __restrict__ out, long long rows_per_group, int C, int rows_per_cta, SumsFinalize const fin) {
     pdl_trigger();
     pdl_wait();
@@ -139,17 +165,17 @@ __global__ void __launch_bounds__(kThreads) channel_sums_kernel(bf16 const* __re
     if (active) {
         constexpr int U = MODE == 1 ? 2 : kRowUnroll;
         for (long long r0 = row_begin + tr; r0 < row_end; r0 += kRowLanes * U) {
-            uint4 ra[U], rb[U], ry[U];
+            Oct<T> ra[U], rb[U], ry[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {   // issue every load of the batch before using any of them
                 long long const r = r0 + u * kRowLanes;
                 if (r < row_end) {
                     long long const idx = (base + r) * C + o * 8;
-                    ra[u] = *reinterpret_cast<uint4 const*>(a + idx);
+                    ra[u] = load_oct(a + idx);
                     if (MODE == 1)
-                        rb[u] = *reinterpret_cast<uint4 const*>(b + idx);
+                        rb[u] = load_oct(b + idx);
                     if (MODE != 0 && y)
-                        ry[u] = *reinterpret_cast<uint4 const*>(y + idx);
+                        ry[u] = load_oct(y + idx);
                 }
             }
 #pragma unroll
@@ -228,7 +254,8 @@ __global__ void __launch_bounds__(kThreads) channel_sums_kernel(bf16 const* __re
 
 // y = relu?(x * scale[g][c] + shift[g][c]). Each thread keeps a fixed channel octet (stride is a multiple of `octets`
 // whenever possible) so the coefficients stay in registers and no division happens in the loop.
-__global__ void __launch_bounds__(kThreads) bn_apply_kernel(bf16 const* __restrict__ x, bf16 const* __restrict__ residual, bf16* __restrict__ y, float const* __restrict__ scale,
+template<typename T>
+__global__ void __launch_bounds__(kThreads) bn_apply_kernel(T const* __restrict__ x, T const* __restrict__ residual, T* __restrict__ y, float const* __restrict__ scale,
                                 float const* __restrict__ shift, long long total_octets, int C, long long rows_per_group, int relu) {
     pdl_trigger();
     pdl_wait();
@@ -251,42 +278,43 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(bf16 const* __restri
             sh[j] = shift[g * C + o * 8 + j];
         }
     };
-    auto transform = [&](uint4 raw, long long index) {   // y = relu?(x * scale + shift (+ residual))
+    auto transform = [&](Oct<T> raw, long long index) {   // y = relu?(x * scale + shift (+ residual))
         float v[8], r[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         unpack8(raw, v);
         if (residual)
-            unpack8(*reinterpret_cast<uint4 const*>(residual + index * 8), r);
+            unpack8(load_oct(residual + index * 8), r);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             v[j] = v[j] * sc[j] + sh[j] + r[j];
             if (relu)
                 v[j] = fmaxf(v[j], 0.f);
         }
-        return pack8(v);
+        return pack_oct<T>(v);
     };
     if (single_group) {
         load_coefficients(0);
         constexpr int U = 4;   // four independent 16-byte loads in flight per thread
         for (; i + (U - 1) * stride < total_octets; i += U * stride) {
-            uint4 raw[U];
+            Oct<T> raw[U];
 #pragma unroll
             for (int u = 0; u < U; ++u)
-                raw[u] = *reinterpret_cast<uint4 const*>(x + (i + u * stride) * 8);
+                raw[u] = load_oct(x + (i + u * stride) * 8);
 #pragma unroll
             for (int u = 0; u < U; ++u)
-                *reinterpret_cast<uint4*>(y + (i + u * stride) * 8) = transform(raw[u], i + u * stride);
+                store_oct(y + (i + u * stride) * 8, transform(raw[u], i + u * stride));
         }
     }
     for (; i < total_octets; i += stride) {
         int const g = single_group ? 0 : static_cast<int>(i / octets_per_group);
         if (g != cached_group)
             load_coefficients(g);
-        *reinterpret_cast<uint4*>(y + i * 8) = transform(*reinterpret_cast<uint4 const*>(x + i * 8), i);
+        store_oct(y + i * 8, transform(load_oct(x + i * 8), i));
     }
 }
 
 // dx = a * dy' + b * x + c0 with per-(group, channel) coefficients prepared by the statistics kernel's last CTA.
-__global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(bf16 const* __restrict__ dy, bf16 const* __restrict__ x, bf16 const* __restrict__ y, bf16* __restrict__ dx, bf16* __restrict__ dmasked,
+template<typename T>
+__global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(T const* __restrict__ dy, T const* __restrict__ x, T const* __restrict__ y, T* __restrict__ dx, T* __restrict__ dmasked,
                                     float const* __restrict__ coef, long long total_octets, int C, long long rows_per_group) {
     pdl_trigger();
     pdl_wait();
@@ -311,7 +339,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(bf16 const* __re
             cc[j] = cf[3 * j + 2];
         }
     };
-    auto transform = [&](uint4 rd, uint4 rx, uint4 ry, bool masked, long long index) {
+    auto transform = [&](Oct<T> rd, Oct<T> rx, Oct<T> ry, bool masked, long long index) {
         float vd[8], vx[8];
         unpack8(rd, vd);
         unpack8(rx, vx);
@@ -322,80 +350,83 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(bf16 const* __re
             for (int j = 0; j < 8; ++j)
                 vd[j] = vy[j] > 0.f ? vd[j] : 0.f;
             if (dmasked)   // the gradient of the residual input of a fused add + ReLU
-                *reinterpret_cast<uint4*>(dmasked + index * 8) = pack8(vd);
+                store_oct(dmasked + index * 8, pack_oct<T>(vd));
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j)
             vd[j] = ca[j] * vd[j] + cb[j] * vx[j] + cc[j];
-        return pack8(vd);
+        return pack_oct<T>(vd);
     };
     bool const masked = y != nullptr;
     if (single_group) {
         load_coefficients(0);
         constexpr int U = 2;   // 2 x 3 independent 16-byte loads in flight per thread
         for (; i + (U - 1) * stride < total_octets; i += U * stride) {
-            uint4 rd[U], rx[U], ry[U];
+            Oct<T> rd[U], rx[U], ry[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 long long const e = (i + u * stride) * 8;
-                rd[u] = *reinterpret_cast<uint4 const*>(dy + e);
-                rx[u] = *reinterpret_cast<uint4 const*>(x + e);
-                ry[u] = masked ? *reinterpret_cast<uint4 const*>(y + e) : make_uint4(0, 0, 0, 0);
+                rd[u] = load_oct(dy + e);
+                rx[u] = load_oct(x + e);
+                ry[u] = masked ? load_oct(y + e) : zero_oct<T>();
             }
 #pragma unroll
             for (int u = 0; u < U; ++u)
-                *reinterpret_cast<uint4*>(dx + (i + u * stride) * 8) = transform(rd[u], rx[u], ry[u], masked, i + u * stride);
+                store_oct(dx + (i + u * stride) * 8, transform(rd[u], rx[u], ry[u], masked, i + u * stride));
         }
     }
     for (; i < total_octets; i += stride) {
         int const g = single_group ? 0 : static_cast<int>(i / octets_per_group);
         if (g != cached_group)
             load_coefficients(g);
-        uint4 const ry = masked ? *reinterpret_cast<uint4 const*>(y + i * 8) : make_uint4(0, 0, 0, 0);
-        *reinterpret_cast<uint4*>(dx + i * 8) = transform(*reinterpret_cast<uint4 const*>(dy + i * 8), *reinterpret_cast<uint4 const*>(x + i * 8), ry, masked, i);
+        Oct<T> const ry = masked ? load_oct(y + i * 8) : zero_oct<T>();
+        store_oct(dx + i * 8, transform(load_oct(dy + i * 8), load_oct(x + i * 8), ry, masked, i));
     }
 }
 
 // Strided pixel sub-sampling (the 1x1 stride-s "max-pool" of slim's identity shortcuts): y[n, oh, ow, :] = x[n, oh*s, ow*s, :].
 // grid.y = n * OH + oh, threads along (ow, channel octet): no per-element division.
-__global__ void subsample_fwd_kernel(bf16 const* __restrict__ x, bf16* __restrict__ y, int H, int W, int OH, int OW, int octets, int s) {
+template<typename T>
+__global__ void subsample_fwd_kernel(T const* __restrict__ x, T* __restrict__ y, int H, int W, int OH, int OW, int octets, int s) {
     pdl_trigger();
     pdl_wait();
     int const n = blockIdx.y / OH, oh = blockIdx.y % OH;
-    uint4 const* src = reinterpret_cast<uint4 const*>(x) + (static_cast<long long>(n) * H + static_cast<long long>(oh) * s) * W * octets;
-    uint4* dst = reinterpret_cast<uint4*>(y) + static_cast<long long>(blockIdx.y) * OW * octets;
+    Oct<T> const* src = reinterpret_cast<Oct<T> const*>(x) + (static_cast<long long>(n) * H + static_cast<long long>(oh) * s) * W * octets;
+    Oct<T>* dst = reinterpret_cast<Oct<T>*>(y) + static_cast<long long>(blockIdx.y) * OW * octets;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < OW * octets; i += gridDim.x * blockDim.x) {
         int const ow = i / octets, o = i - ow * octets;
         dst[i] = src[static_cast<long long>(ow) * s * octets + o];
     }
 }
 // Its backward writes the whole dx in one pass: dy at the sampled pixels, zero elsewhere (replaces a fill + a strided copy).
-__global__ void subsample_bwd_kernel(bf16 const* __restrict__ dy, bf16* __restrict__ dx, int H, int W, int OH, int OW, int octets, int s) {
+template<typename T>
+__global__ void subsample_bwd_kernel(T const* __restrict__ dy, T* __restrict__ dx, int H, int W, int OH, int OW, int octets, int s) {
     pdl_trigger();
     pdl_wait();
     int const n = blockIdx.y / H, h = blockIdx.y % H;
     bool const row_hit = h % s == 0 && h / s < OH;
-    uint4 const* src = reinterpret_cast<uint4 const*>(dy) + (static_cast<long long>(n) * OH + h / s) * OW * octets;
-    uint4* dst = reinterpret_cast<uint4*>(dx) + static_cast<long long>(blockIdx.y) * W * octets;
+    Oct<T> const* src = reinterpret_cast<Oct<T> const*>(dy) + (static_cast<long long>(n) * OH + h / s) * OW * octets;
+    Oct<T>* dst = reinterpret_cast<Oct<T>*>(dx) + static_cast<long long>(blockIdx.y) * W * octets;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < W * octets; i += gridDim.x * blockDim.x) {
         int const w = i / octets, o = i - w * octets;
         bool const hit = row_hit && w % s == 0 && w / s < OW;
-        dst[i] = hit ? src[static_cast<long long>(w / s) * octets + o] : make_uint4(0, 0, 0, 0);
+        dst[i] = hit ? src[static_cast<long long>(w / s) * octets + o] : zero_oct<T>();
     }
 }
 
 // out = relu?(a + b) ; b may be null (plain ReLU)
-__global__ void add_relu_kernel(bf16 const* __restrict__ a, bf16 const* __restrict__ b, bf16* __restrict__ out, long long octets, int relu) {
+template<typename T>
+__global__ void add_relu_kernel(T const* __restrict__ a, T const* __restrict__ b, T* __restrict__ out, long long octets, int relu) {
     pdl_trigger();
     pdl_wait();
     long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     long long const stride = static_cast<long long>(gridDim.x) * blockDim.x;
     for (; i < octets; i += stride) {
         float va[8];
-        unpack8(*reinterpret_cast<uint4 const*>(a + i * 8), va);
+        unpack8(load_oct(a + i * 8), va);
         if (b) {
             float vb[8];
-            unpack8(*reinterpret_cast<uint4 const*>(b + i * 8), vb);
+            unpack8(load_oct(b + i * 8), vb);
 #pragma unroll
             for (int j = 0; j < 8; ++j)
                 va[j] += vb[j];
@@ -405,30 +436,32 @@ __global__ void add_relu_kernel(bf16 const* __restrict__ a, bf16 const* __restri
             for (int j = 0; j < 8; ++j)
                 va[j] = fmaxf(va[j], 0.f);
         }
-        *reinterpret_cast<uint4*>(out + i * 8) = pack8(va);
+        store_oct(out + i * 8, pack_oct<T>(va));
     }
 }
 
 // dx = dy * (y > 0)
-__global__ void relu_bwd_kernel(bf16 const* __restrict__ dy, bf16 const* __restrict__ y, bf16* __restrict__ dx, long long octets) {
+template<typename T>
+__global__ void relu_bwd_kernel(T const* __restrict__ dy, T const* __restrict__ y, T* __restrict__ dx, long long octets) {
     pdl_trigger();
     pdl_wait();
     long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     long long const stride = static_cast<long long>(gridDim.x) * blockDim.x;
     for (; i < octets; i += stride) {
         float vd[8], vy[8];
-        unpack8(*reinterpret_cast<uint4 const*>(dy + i * 8), vd);
-        unpack8(*reinterpret_cast<uint4 const*>(y + i * 8), vy);
+        unpack8(load_oct(dy + i * 8), vd);
+        unpack8(load_oct(y + i * 8), vy);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
             vd[j] = vy[j] > 0.f ? vd[j] : 0.f;
-        *reinterpret_cast<uint4*>(dx + i * 8) = pack8(vd);
+        store_oct(dx + i * 8, pack_oct<T>(vd));
     }
 }
 
 // ---------------------------------------------------------------------------- //
 // Max pooling (k x k, stride s, explicit pads, -inf padding), NHWC. Forward also records the argmax (window-relative index).
-__global__ void maxpool_fwd_kernel(bf16 const* __restrict__ x, bf16* __restrict__ y, unsigned char* __restrict__ arg, int N, int H, int W, int C, int OH, int OW,
+template<typename T>
+__global__ void maxpool_fwd_kernel(T const* __restrict__ x, T* __restrict__ y, unsigned char* __restrict__ arg, int N, int H, int W, int C, int OH, int OW,
                                    int k, int s, int pad_t, int pad_l) {
     pdl_trigger();
     pdl_wait();
@@ -459,7 +492,7 @@ __global__ void maxpool_fwd_kernel(bf16 const* __restrict__ x, bf16* __restrict_
                 if (w < 0 || w >= W)
                     continue;
                 float v[8];
-                unpack8(*reinterpret_cast<uint4 const*>(x + ((static_cast<long long>(n) * H + h) * W + w) * C + o * 8), v);
+                unpack8(load_oct(x + ((static_cast<long long>(n) * H + h) * W + w) * C + o * 8), v);
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                     if (v[j] > best[j]) {
@@ -468,7 +501,7 @@ __global__ void maxpool_fwd_kernel(bf16 const* __restrict__ x, bf16* __restrict_
                     }
             }
         }
-        *reinterpret_cast<uint4*>(y + i * 8) = pack8(best);
+        store_oct(y + i * 8, pack_oct<T>(best));
         uint2 packed;
         unsigned char* pw = reinterpret_cast<unsigned char*>(&packed);
 #pragma unroll
@@ -481,13 +514,14 @@ __global__ void maxpool_fwd_kernel(bf16 const* __restrict__ x, bf16* __restrict_
 // Gather form: every input element sums the gradients of the windows whose argmax it is (no atomics).
 // grid.y = n * H + h (one input row per CTA row), threads along (w, channel octet): no per-element division by H or W, and the
 // candidate window rows are resolved once per CTA.
-__global__ void maxpool_bwd_kernel(bf16 const* __restrict__ dy, unsigned char const* __restrict__ arg, bf16* __restrict__ dx, int N, int H, int W, int C, int OH, int OW,
+template<typename T>
+__global__ void maxpool_bwd_kernel(T const* __restrict__ dy, unsigned char const* __restrict__ arg, T* __restrict__ dx, int N, int H, int W, int C, int OH, int OW,
                                    int k, int s, int pad_t, int pad_l) {
     pdl_trigger();
     pdl_wait();
     int const octets = C >> 3;
     int const n = blockIdx.y / H, h = blockIdx.y % H;
-    bf16* const out_row = dx + static_cast<long long>(blockIdx.y) * W * C;
+    T* const out_row = dx + static_cast<long long>(blockIdx.y) * W * C;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < W * octets; i += gridDim.x * blockDim.x) {
         int const w = i / octets, o = i - w * octets;
         float acc[8];
@@ -510,7 +544,7 @@ __global__ void maxpool_bwd_kernel(bf16 const* __restrict__ dy, unsigned char co
                     continue;
                 long long const oidx = (((static_cast<long long>(n) * OH + oh) * OW + ow) * octets + o) * 8;
                 float v[8];
-                unpack8(*reinterpret_cast<uint4 const*>(dy + oidx), v);
+                unpack8(load_oct(dy + oidx), v);
                 uint2 const packed = *reinterpret_cast<uint2 const*>(arg + oidx);
                 unsigned char const* pw = reinterpret_cast<unsigned char const*>(&packed);
                 unsigned char const me = static_cast<unsigned char>(kh * k + kw);
@@ -519,12 +553,13 @@ __global__ void maxpool_bwd_kernel(bf16 const* __restrict__ dy, unsigned char co
                     acc[j] += pw[j] == me ? v[j] : 0.f;
             }
         }
-        *reinterpret_cast<uint4*>(out_row + static_cast<long long>(i) * 8) = pack8(acc);
+        store_oct(out_row + static_cast<long long>(i) * 8, pack_oct<T>(acc));
     }
 }
 
 // Global average pool: x [N, HW, C] -> y [N, C]; backward broadcasts dy / HW.
-__global__ void avgpool_fwd_kernel(bf16 const* __restrict__ x, bf16* __restrict__ y, int N, int HW, int C) {
+template<typename T>
+__global__ void avgpool_fwd_kernel(T const* __restrict__ x, T* __restrict__ y, int N, int HW, int C) {
     pdl_trigger();
     pdl_wait();
     int const octets = C >> 3;
@@ -538,7 +573,7 @@ __global__ void avgpool_fwd_kernel(bf16 const* __restrict__ x, bf16* __restrict_
         acc[j] = 0.f;
     for (int p = 0; p < HW; ++p) {
         float v[8];
-        unpack8(*reinterpret_cast<uint4 const*>(x + (static_cast<long long>(n) * HW + p) * C + o * 8), v);
+        unpack8(load_oct(x + (static_cast<long long>(n) * HW + p) * C + o * 8), v);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
             acc[j] += v[j];
@@ -547,10 +582,11 @@ __global__ void avgpool_fwd_kernel(bf16 const* __restrict__ x, bf16* __restrict_
 #pragma unroll
     for (int j = 0; j < 8; ++j)
         acc[j] *= inv;
-    *reinterpret_cast<uint4*>(y + static_cast<long long>(i) * 8) = pack8(acc);
+    store_oct(y + static_cast<long long>(i) * 8, pack_oct<T>(acc));
 }
 
-__global__ void avgpool_bwd_kernel(bf16 const* __restrict__ dy, bf16* __restrict__ dx, int N, int HW, int C) {
+template<typename T>
+__global__ void avgpool_bwd_kernel(T const* __restrict__ dy, T* __restrict__ dx, int N, int HW, int C) {
     pdl_trigger();
     pdl_wait();
     int const octets = C >> 3;
@@ -562,46 +598,47 @@ __global__ void avgpool_bwd_kernel(bf16 const* __restrict__ dy, bf16* __restrict
         int const o = static_cast<int>(i % octets);
         int const n = static_cast<int>(i / (static_cast<long long>(HW) * octets));
         float v[8];
-        unpack8(*reinterpret_cast<uint4 const*>(dy + (static_cast<long long>(n) * octets + o) * 8), v);
+        unpack8(load_oct(dy + (static_cast<long long>(n) * octets + o) * 8), v);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
             v[j] *= inv;
-        *reinterpret_cast<uint4*>(dx + i * 8) = pack8(v);
+        store_oct(dx + i * 8, pack_oct<T>(v));
     }
 }
 
 // ---------------------------------------------------------------------------- //
 // Softmax cross-entropy, one warp per row. logits bf16 [B, ld] (K valid columns), labels int64.
 // loss += mean_b(-sum_k t_k log p_k) ; dlogits = (p - t) / B  (bf16, same leading dimension).
-__global__ void softmax_xent_kernel(bf16 const* __restrict__ logits, long long const* __restrict__ labels, bf16* __restrict__ dlogits, float* __restrict__ loss,
+template<typename T>
+__global__ void softmax_xent_kernel(T const* __restrict__ logits, long long const* __restrict__ labels, T* __restrict__ dlogits, float* __restrict__ loss,
                                     int B, int K, long long ld, float smoothing, int rows_per_group) {
     pdl_trigger();
     pdl_wait();
     int const warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= B)
         return;
-    bf16 const* row = logits + static_cast<long long>(warp) * ld;
+    T const* row = logits + static_cast<long long>(warp) * ld;
     float mx = -INFINITY;
     for (int k = lane; k < K; k += 32)
-        mx = fmaxf(mx, __bfloat162float(row[k]));
+        mx = fmaxf(mx, to_f(row[k]));
     for (int off = 16; off > 0; off >>= 1)
         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
     float sum = 0.f;
     for (int k = lane; k < K; k += 32)
-        sum += __expf(__bfloat162float(row[k]) - mx);
+        sum += __expf(to_f(row[k]) - mx);
     sum = warp_sum(sum);
     float const lse = mx + __logf(sum);
     int const label = static_cast<int>(labels[warp]);
     float const off_t = smoothing / static_cast<float>(K), on_t = 1.f - smoothing + off_t;
     float const inv_b = 1.f / static_cast<float>(rows_per_group);   // each group (logical worker) averages over its own batch
     float local = 0.f;
-    bf16* drow = dlogits + static_cast<long long>(warp) * ld;
+    T* drow = dlogits + static_cast<long long>(warp) * ld;
     for (int k = lane; k < K; k += 32) {
-        float const z = __bfloat162float(row[k]);
+        float const z = to_f(row[k]);
         float const logp = z - lse;
         float const t = k == label ? on_t : off_t;
         local -= t * logp;
-        drow[k] = __float2bfloat16((__expf(logp) - t) * inv_b);
+        drow[k] = from_f<T>((__expf(logp) - t) * inv_b);
     }
     local = warp_sum(local);
     if (lane == 0)
@@ -609,7 +646,8 @@ __global__ void softmax_xent_kernel(bf16 const* __restrict__ logits, long long c
 }
 
 // uint8 NHWC image -> bf16 NHWC activations with C padded to `Cpad`: y = (x - mean[c]) * scale
-__global__ void image_normalize_kernel(unsigned char const* __restrict__ x, bf16* __restrict__ y, long long pixels, int C, int Cpad, float m0, float m1, float m2, float scale) {
+template<typename T>
+__global__ void image_normalize_kernel(unsigned char const* __restrict__ x, T* __restrict__ y, long long pixels, int C, int Cpad, float m0, float m1, float m2, float scale) {
     pdl_trigger();
     pdl_wait();
     long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -621,7 +659,7 @@ __global__ void image_normalize_kernel(unsigned char const* __restrict__ x, bf16
                 float const m = c == 0 ? m0 : c == 1 ? m1 : m2;
                 v = (static_cast<float>(x[i * C + c]) - m) * scale;
             }
-            y[i * Cpad + c] = __float2bfloat16(v);
+            y[i * Cpad + c] = from_f<T>(v);
         }
     }
 }
@@ -629,7 +667,8 @@ __global__ void image_normalize_kernel(unsigned char const* __restrict__ x, bf16
 // ---------------------------------------------------------------------------- //
 // im2col: x NHWC [N,H,W,C] -> col [N*OH*OW, ldcol] with column order (kh, kw, c); zero padding, zero tail columns.
 // One thread per (output pixel, kh, kw, channel octet) when C % 8 == 0, scalar path otherwise (the 3-channel stem).
-__global__ void im2col_kernel(bf16 const* __restrict__ x, bf16* __restrict__ col, int N, int H, int W, int C, int OH, int OW, int KH, int KW, int s, int pad_t, int pad_l, long long ldcol) {
+template<typename T>
+__global__ void im2col_kernel(T const* __restrict__ x, T* __restrict__ col, int N, int H, int W, int C, int OH, int OW, int KH, int KW, int s, int pad_t, int pad_l, long long ldcol) {
     pdl_trigger();
     pdl_wait();
     if ((C & 7) == 0) {
@@ -650,10 +689,10 @@ __global__ void im2col_kernel(bf16 const* __restrict__ x, bf16* __restrict__ col
             int const oh = static_cast<int>(rest % OH);
             int const n = static_cast<int>(rest / OH);
             int const h = oh * s - pad_t + kh, w = ow * s - pad_l + kw;
-            uint4 v = make_uint4(0, 0, 0, 0);
+            Oct<T> v = zero_oct<T>();
             if (h >= 0 && h < H && w >= 0 && w < W)
-                v = *reinterpret_cast<uint4 const*>(x + ((static_cast<long long>(n) * H + h) * W + w) * C + o * 8);
-            *reinterpret_cast<uint4*>(col + pixel * ldcol + (kh * KW + kw) * C + o * 8) = v;
+                v = load_oct(x + ((static_cast<long long>(n) * H + h) * W + w) * C + o * 8);
+            store_oct(col + pixel * ldcol + (kh * KW + kw) * C + o * 8, v);
         }
     } else {
         // Few-channel stem (C = 1 or 3): one thread per (output pixel, group of 8 columns) gathers 8 scalars (L1 hits) and
@@ -679,7 +718,7 @@ __global__ void im2col_kernel(bf16 const* __restrict__ x, bf16* __restrict__ col
                 if (j < kcol) {
                     int const h = oh * s - pad_t + kh, w = ow * s - pad_l + kw;
                     if (h >= 0 && h < H && w >= 0 && w < W)
-                        v[jj] = __bfloat162float(x[((static_cast<long long>(n) * H + h) * W + w) * C + c]);
+                        v[jj] = to_f(x[((static_cast<long long>(n) * H + h) * W + w) * C + c]);
                 }
                 if (++c == C) {
                     c = 0;
@@ -689,13 +728,14 @@ __global__ void im2col_kernel(bf16 const* __restrict__ x, bf16* __restrict__ col
                     }
                 }
             }
-            *reinterpret_cast<uint4*>(col + (i / groups8) * ldcol + g8 * 8) = pack8(v);
+            store_oct(col + (i / groups8) * ldcol + g8 * 8, pack_oct<T>(v));
         }
     }
 }
 
 // col2im (gather form): dx[n,h,w,c] = sum over (kh,kw) of dcol[n, oh, ow, (kh,kw,c)] for the windows covering (h,w). C % 8 == 0.
-__global__ void col2im_kernel(bf16 const* __restrict__ dcol, bf16* __restrict__ dx, int N, int H, int W, int C, int OH, int OW, int KH, int KW, int s, int pad_t, int pad_l, long long ldcol) {
+template<typename T>
+__global__ void col2im_kernel(T const* __restrict__ dcol, T* __restrict__ dx, int N, int H, int W, int C, int OH, int OW, int KH, int KW, int s, int pad_t, int pad_l, long long ldcol) {
     pdl_trigger();
     pdl_wait();
     int const octets = C >> 3;
@@ -728,13 +768,13 @@ __global__ void col2im_kernel(bf16 const* __restrict__ dcol, bf16* __restrict__ 
                 if (ow >= OW)
                     continue;
                 float v[8];
-                unpack8(*reinterpret_cast<uint4 const*>(dcol + ((static_cast<long long>(n) * OH + oh) * OW + ow) * ldcol + (kh * KW + kw) * C + o * 8), v);
+                unpack8(load_oct(dcol + ((static_cast<long long>(n) * OH + oh) * OW + ow) * ldcol + (kh * KW + kw) * C + o * 8), v);
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                     acc[j] += v[j];
             }
         }
-        *reinterpret_cast<uint4*>(dx + i * 8) = pack8(acc);
+        store_oct(dx + i * 8, pack_oct<T>(acc));
     }
 }
 
@@ -1116,26 +1156,20 @@ int launch_bn_fused(BnFused p, long long rows, cudaStream_t s) {
     return 0;
 }
 
-template<int MODE>
-int launch_sums(SumsPlan const& plan, cudaStream_t s, bf16 const* a, bf16 const* b, bf16 const* y, float const* mean, float const* rstd, double* out,
+template<int MODE, typename T>
+int launch_sums(SumsPlan const& plan, cudaStream_t s, T const* a, T const* b, T const* y, float const* mean, float const* rstd, double* out,
                  long long rows_per_group, int C, SumsFinalize const& fin) {
     if (plan.strip == 32)
-        AGB_CUDA_OK(launch_pdl(channel_sums_kernel<MODE, 32>, dim3(plan.grid), dim3(kThreads), 0, s, a, b, y, mean, rstd, out, rows_per_group, C, plan.rows_per_cta, fin));
+        AGB_CUDA_OK(launch_pdl(channel_sums_kernel<T, MODE, 32>, dim3(plan.grid), dim3(kThreads), 0, s, a, b, y, mean, rstd, out, rows_per_group, C, plan.rows_per_cta, fin));
     else if (plan.strip == 16)
-        AGB_CUDA_OK(launch_pdl(channel_sums_kernel<MODE, 16>, dim3(plan.grid), dim3(kThreads), 0, s, a, b, y, mean, rstd, out, rows_per_group, C, plan.rows_per_cta, fin));
+        AGB_CUDA_OK(launch_pdl(channel_sums_kernel<T, MODE, 16>, dim3(plan.grid), dim3(kThreads), 0, s, a, b, y, mean, rstd, out, rows_per_group, C, plan.rows_per_cta, fin));
     else
-        AGB_CUDA_OK(launch_pdl(channel_sums_kernel<MODE, 8>, dim3(plan.grid), dim3(kThreads), 0, s, a, b, y, mean, rstd, out, rows_per_group, C, plan.rows_per_cta, fin));
+        AGB_CUDA_OK(launch_pdl(channel_sums_kernel<T, MODE, 8>, dim3(plan.grid), dim3(kThreads), 0, s, a, b, y, mean, rstd, out, rows_per_group, C, plan.rows_per_cta, fin));
     return 0;
 }
 
-} // namespace
-
-extern "C" {
-
-// Workspace layout for BN (caller provides, zeroed `sums` not required: it is cleared here):
-//   sums  double [groups*C*2] | save_mean, save_rstd, scale, shift float [groups*C] each (forward)
-//   sums  double [groups*C*2] | coef float [groups*C*3]                              (backward)
-int agb_bn_forward(void const* x, void const* residual, void* y, void const* gamma, void const* beta, void* moving_mean, void* moving_var, void* save_mean, void* save_rstd,
+template<typename T>
+int bn_forward_impl(void const* x, void const* residual, void* y, void const* gamma, void const* beta, void* moving_mean, void* moving_var, void* save_mean, void* save_rstd,
                    void* sums, void* scale, void* shift, long long rows, int C, int groups, float eps, float decay, int relu, void* stream) {
     if ((C & 7) || groups < 1 || rows % groups)
         return 301;
@@ -1150,15 +1184,16 @@ int agb_bn_forward(void const* x, void const* residual, void* y, void const* gam
     fin.moving_mean = static_cast<float*>(moving_mean); fin.moving_var = static_cast<float*>(moving_var);
     fin.groups = groups; fin.eps = eps; fin.decay = decay;
     SumsPlan plan = plan_sums(rpg, C, groups);
-    if (int status = launch_sums<0>(plan, s, static_cast<bf16 const*>(x), nullptr, nullptr, nullptr, nullptr, static_cast<double*>(sums), rpg, C, fin))
+    if (int status = launch_sums<0, T>(plan, s, static_cast<T const*>(x), nullptr, nullptr, nullptr, nullptr, static_cast<double*>(sums), rpg, C, fin))
         return status;
     long long const octets = rows * (C >> 3);
-    AGB_CUDA_OK(launch_pdl(bn_apply_kernel, dim3(grid_for(octets)), dim3(kThreads), 0, s, static_cast<bf16 const*>(x), static_cast<bf16 const*>(residual), static_cast<bf16*>(y), static_cast<float const*>(scale), static_cast<float const*>(shift), octets, C, rpg, relu));
+    AGB_CUDA_OK(launch_pdl(bn_apply_kernel<T>, dim3(grid_for(octets)), dim3(kThreads), 0, s, static_cast<T const*>(x), static_cast<T const*>(residual), static_cast<T*>(y), static_cast<float const*>(scale), static_cast<float const*>(shift), octets, C, rpg, relu));
     AGB_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
-int agb_bn_backward(void const* dy, void const* x, void const* y, void const* gamma, void const* save_mean, void const* save_rstd, void* dx, void* dmasked, void* dgamma, void* dbeta,
+template<typename T>
+int bn_backward_impl(void const* dy, void const* x, void const* y, void const* gamma, void const* save_mean, void const* save_rstd, void* dx, void* dmasked, void* dgamma, void* dbeta,
                     void* sums, void* coef, long long rows, int C, int groups, long long group_stride, void* stream) {
     if ((C & 7) || groups < 1 || rows % groups)
         return 301;
@@ -1172,15 +1207,189 @@ int agb_bn_backward(void const* dy, void const* x, void const* y, void const* ga
     fin.dgamma = static_cast<float*>(dgamma); fin.dbeta = static_cast<float*>(dbeta);
     fin.groups = groups; fin.group_stride = group_stride;
     SumsPlan plan = plan_sums(rpg, C, groups);
-    if (int status = launch_sums<1>(plan, s, static_cast<bf16 const*>(dy), static_cast<bf16 const*>(x), static_cast<bf16 const*>(y), static_cast<float const*>(save_mean),
+    if (int status = launch_sums<1, T>(plan, s, static_cast<T const*>(dy), static_cast<T const*>(x), static_cast<T const*>(y), static_cast<float const*>(save_mean),
                    static_cast<float const*>(save_rstd), static_cast<double*>(sums), rpg, C, fin))
         return status;
     long long const octets = rows * (C >> 3);
-    AGB_CUDA_OK(launch_pdl(bn_bwd_apply_kernel, dim3(grid_for(octets)), dim3(kThreads), 0, s, static_cast<bf16 const*>(dy), static_cast<bf16 const*>(x), static_cast<bf16 const*>(y), static_cast<bf16*>(dx),
-        static_cast<bf16*>(dmasked), static_cast<float const*>(coef), octets, C, rpg));
+    AGB_CUDA_OK(launch_pdl(bn_bwd_apply_kernel<T>, dim3(grid_for(octets)), dim3(kThreads), 0, s, static_cast<T const*>(dy), static_cast<T const*>(x), static_cast<T const*>(y), static_cast<T*>(dx),
+        static_cast<T*>(dmasked), static_cast<float const*>(coef), octets, C, rpg));
     AGB_CUDA_OK(cudaGetLastError());
     return 0;
 }
+
+template<typename T>
+int colsum_impl(void const* dy, void const* y, void* out, void* sums, long long rows, int C, int groups, long long group_stride, void* stream) {
+    if ((C & 7) || groups < 1 || rows % groups)
+        return 301;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    SumsFinalize fin{};
+    fin.ticket = reinterpret_cast<unsigned*>(static_cast<double*>(sums) + 2 * C * groups);
+    fin.dbeta = static_cast<float*>(out);
+    fin.groups = groups; fin.group_stride = group_stride;
+    SumsPlan plan = plan_sums(rows / groups, C, groups);
+    if (int status = launch_sums<2, T>(plan, s, static_cast<T const*>(dy), nullptr, static_cast<T const*>(y), nullptr, nullptr, static_cast<double*>(sums), rows / groups, C, fin))
+        return status;
+    AGB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+template<typename T>
+int add_relu_impl(void const* a, void const* b, void* out, long long n, int relu, void* stream) {
+    if (n & 7)
+        return 301;
+    AGB_CUDA_OK(launch_pdl(add_relu_kernel<T>, dim3(grid_for(n / 8)), dim3(kThreads), 0, static_cast<cudaStream_t>(stream), static_cast<T const*>(a), static_cast<T const*>(b), static_cast<T*>(out), n / 8, relu));
+    AGB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+template<typename T>
+int subsample_forward_impl(void const* x, void* y, int N, int H, int W, int C, int s, void* stream) {
+    if ((C & 7) || s < 1)
+        return 301;
+    int const OH = (H + s - 1) / s, OW = (W + s - 1) / s, octets = C >> 3;
+    if (static_cast<long long>(N) * OH > 65535)
+        return 399;
+    int const per_row = OW * octets;
+    AGB_CUDA_OK(launch_pdl(subsample_fwd_kernel<T>, dim3((per_row + kThreads - 1) / kThreads, N * OH), dim3(kThreads), 0, static_cast<cudaStream_t>(stream), static_cast<T const*>(x), static_cast<T*>(y), H, W, OH, OW, octets, s));
+    AGB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+template<typename T>
+int subsample_backward_impl(void const* dy, void* dx, int N, int H, int W, int C, int s, void* stream) {
+    if ((C & 7) || s < 1)
+        return 301;
+    int const OH = (H + s - 1) / s, OW = (W + s - 1) / s, octets = C >> 3;
+    if (static_cast<long long>(N) * H > 65535)
+        return 399;
+    int const per_row = W * octets;
+    AGB_CUDA_OK(launch_pdl(subsample_bwd_kernel<T>, dim3((per_row + kThreads - 1) / kThreads, N * H), dim3(kThreads), 0, static_cast<cudaStream_t>(stream), static_cast<T const*>(dy), static_cast<T*>(dx), H, W, OH, OW, octets, s));
+    AGB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+template<typename T>
+int relu_backward_impl(void const* dy, void const* y, void* dx, long long n, void* stream) {
+    if (n & 7)
+        return 301;
+    AGB_CUDA_OK(launch_pdl(relu_bwd_kernel<T>, dim3(grid_for(n / 8)), dim3(kThreads), 0, static_cast<cudaStream_t>(stream), static_cast<T const*>(dy), static_cast<T const*>(y), static_cast<T*>(dx), n / 8));
+    AGB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+template<typename T>
+int maxpool_forward_impl(void const* x, void* y, void* arg, int N, int H, int W, int C, int OH, int OW, int k, int s, int pad_t, int pad_l, void* stream) {
+    if ((C & 7) || k * k > 255)
+        return 301;
+    long long const work = static_cast<long long>(N) * OH * OW * (C >> 3);
+    AGB_CUDA_OK(launch_pdl(maxpool_fwd_kernel<T>, dim3(grid_for(work)), dim3(kThreads), 0, static_cast<cudaStream_t>(stream), static_cast<T const*>(x), static_cast<T*>(y), static_cast<unsigned char*>(arg), N, H, W, C, OH, OW, k, s, pad_t, pad_l));
+    AGB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+template<typename T>
+int maxpool_backward_impl(void const* dy, void const* arg, void* dx, int N, int H, int W, int C, int OH, int OW, int k, int s, int pad_t, int pad_l, void* stream) {
+    if (C & 7)
+        return 301;
+    if (H > 65535)
+        return 301;
+    // grid.y = images x rows is limited to 65535: very large batches go in slices of whole images
+    int const per_launch = 65535 / H;
+    for (int n0 = 0; n0 < N; n0 += per_launch) {
+        int const count = N - n0 < per_launch ? N - n0 : per_launch;
+        AGB_CUDA_OK(launch_pdl(maxpool_bwd_kernel<T>, dim3((W * (C >> 3) + kThreads - 1) / kThreads, count * H), dim3(kThreads), 0, static_cast<cudaStream_t>(stream),
+            static_cast<T const*>(dy) + static_cast<long long>(n0) * OH * OW * C, static_cast<unsigned char const*>(arg) + static_cast<long long>(n0) * OH * OW * C,
+            static_cast<T*>(dx) + static_cast<long long>(n0) * H * W * C, count, H, W, C, OH, OW, k, s, pad_t, pad_l));
+    }
+    AGB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+template<typename T>
+int avgpool_forward_impl(void const* x, void* y, int N, int HW, int C, void* stream) {
+    if (C & 7)
+        return 301;
+    AGB_CUDA_OK(launch_pdl(avgpool_fwd_kernel<T>, dim3((N * (C >> 3) + 127) / 128), dim3(128), 0, static_cast<cudaStream_t>(stream), static_cast<T const*>(x), static_cast<T*>(y), N, HW, C));
+    AGB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+template<typename T>
+int avgpool_backward_impl(void const* dy, void* dx, int N, int HW, int C, void* stream) {
+    if (C & 7)
+        return 301;
+    long long const work = static_cast<long long>(N) * HW * (C >> 3);
+    AGB_CUDA_OK(launch_pdl(avgpool_bwd_kernel<T>, dim3(grid_for(work)), dim3(kThreads), 0, static_cast<cudaStream_t>(stream), static_cast<T const*>(dy), static_cast<T*>(dx), N, HW, C));
+    AGB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+template<typename T>
+int softmax_xent_impl(void const* logits, void const* labels, void* dlogits, void* loss, int B, int K, long long ld, float smoothing, int groups, void* stream) {
+    if (groups < 1 || B % groups)
+        return 301;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    AGB_CUDA_OK(cudaMemsetAsync(loss, 0, sizeof(float) * groups, s));
+    int const warps_per_cta = 4;
+    AGB_CUDA_OK(launch_pdl(softmax_xent_kernel<T>, dim3((B + warps_per_cta - 1) / warps_per_cta), dim3(warps_per_cta * 32), 0, s, static_cast<T const*>(logits), static_cast<long long const*>(labels),
+        static_cast<T*>(dlogits), static_cast<float*>(loss), B, K, ld, smoothing, B / groups));
+    AGB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+template<typename T>
+int image_normalize_impl(void const* x, void* y, long long pixels, int C, int Cpad, float m0, float m1, float m2, float scale, void* stream) {
+    AGB_CUDA_OK(launch_pdl(image_normalize_kernel<T>, dim3(grid_for(pixels)), dim3(kThreads), 0, static_cast<cudaStream_t>(stream), static_cast<unsigned char const*>(x), static_cast<T*>(y), pixels, C, Cpad, m0, m1, m2, scale));
+    AGB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+template<typename T>
+int im2col_impl(void const* x, void* col, int N, int H, int W, int C, int OH, int OW, int kh, int kw, int s, int pad_t, int pad_l, long long ldcol, void* stream) {
+    if (ldcol & 7)
+        return 301;
+    long long const work = (C & 7) == 0 ? static_cast<long long>(N) * OH * OW * kh * kw * (C >> 3) : static_cast<long long>(N) * OH * OW * (ldcol >> 3);
+    AGB_CUDA_OK(launch_pdl(im2col_kernel<T>, dim3(grid_for(work, kThreads, 148 * 16)), dim3(kThreads), 0, static_cast<cudaStream_t>(stream), static_cast<T const*>(x), static_cast<T*>(col), N, H, W, C, OH, OW, kh, kw, s, pad_t, pad_l, ldcol));
+    AGB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+template<typename T>
+int col2im_impl(void const* dcol, void* dx, int N, int H, int W, int C, int OH, int OW, int kh, int kw, int s, int pad_t, int pad_l, long long ldcol, void* stream) {
+    if ((C & 7) || (ldcol & 7))
+        return 301;
+    long long const work = static_cast<long long>(N) * H * W * (C >> 3);
+    AGB_CUDA_OK(launch_pdl(col2im_kernel<T>, dim3(grid_for(work, kThreads, 148 * 16)), dim3(kThreads), 0, static_cast<cudaStream_t>(stream), static_cast<T const*>(dcol), static_cast<T*>(dx), N, H, W, C, OH, OW, kh, kw, s, pad_t, pad_l, ldcol));
+    AGB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+// Workspace layout for BN (caller provides, zeroed `sums` not required: it is cleared here):
+//   sums  double [groups*C*2] | save_mean, save_rstd, scale, shift float [groups*C] each (forward)
+//   sums  double [groups*C*2] | coef float [groups*C*3]                              (backward)
+int agb_bn_forward(void const* x, void const* residual, void* y, void const* gamma, void const* beta, void* moving_mean, void* moving_var, void* save_mean, void* save_rstd,
+                   void* sums, void* scale, void* shift, long long rows, int C, int groups, float eps, float decay, int relu, void* stream) {
+    return bn_forward_impl<bf16>(x, residual, y, gamma, beta, moving_mean, moving_var, save_mean, save_rstd, sums, scale, shift, rows, C, groups, eps, decay, relu, stream);
+}
+int agb_bn_forward_f32(void const* x, void const* residual, void* y, void const* gamma, void const* beta, void* moving_mean, void* moving_var, void* save_mean, void* save_rstd,
+                   void* sums, void* scale, void* shift, long long rows, int C, int groups, float eps, float decay, int relu, void* stream) {
+    return bn_forward_impl<float>(x, residual, y, gamma, beta, moving_mean, moving_var, save_mean, save_rstd, sums, scale, shift, rows, C, groups, eps, decay, relu, stream);
+}
+
+
+int agb_bn_backward(void const* dy, void const* x, void const* y, void const* gamma, void const* save_mean, void const* save_rstd, void* dx, void* dmasked, void* dgamma, void* dbeta,
+                    void* sums, void* coef, long long rows, int C, int groups, long long group_stride, void* stream) {
+    return bn_backward_impl<bf16>(dy, x, y, gamma, save_mean, save_rstd, dx, dmasked, dgamma, dbeta, sums, coef, rows, C, groups, group_stride, stream);
+}
+int agb_bn_backward_f32(void const* dy, void const* x, void const* y, void const* gamma, void const* save_mean, void const* save_rstd, void* dx, void* dmasked, void* dgamma, void* dbeta,
+                    void* sums, void* coef, long long rows, int C, int groups, long long group_stride, void* stream) {
+    return bn_backward_impl<float>(dy, x, y, gamma, save_mean, save_rstd, dx, dmasked, dgamma, dbeta, sums, coef, rows, C, groups, group_stride, stream);
+}
+
 
 // Single-launch variants; `ws` = zero-initialised workspace of agb_bn_fused_workspace_bytes() bytes, private to each direction.
 int agb_bn_fused_set_limits(long long forward_mb, long long backward_mb, long long min_rows) {
@@ -1226,137 +1435,107 @@ int agb_bn_backward_fused(void const* dy, void const* x, void const* y, void con
 // out[g * group_stride + c] = sum over the rows of group g of dy[r][c] (masked by y > 0 when y != null);
 // `sums` is a double [2*C*groups + 1] workspace.
 int agb_colsum(void const* dy, void const* y, void* out, void* sums, long long rows, int C, int groups, long long group_stride, void* stream) {
-    if ((C & 7) || groups < 1 || rows % groups)
-        return 301;
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    SumsFinalize fin{};
-    fin.ticket = reinterpret_cast<unsigned*>(static_cast<double*>(sums) + 2 * C * groups);
-    fin.dbeta = static_cast<float*>(out);
-    fin.groups = groups; fin.group_stride = group_stride;
-    SumsPlan plan = plan_sums(rows / groups, C, groups);
-    if (int status = launch_sums<2>(plan, s, static_cast<bf16 const*>(dy), nullptr, static_cast<bf16 const*>(y), nullptr, nullptr, static_cast<double*>(sums), rows / groups, C, fin))
-        return status;
-    AGB_CUDA_OK(cudaGetLastError());
-    return 0;
+    return colsum_impl<bf16>(dy, y, out, sums, rows, C, groups, group_stride, stream);
 }
+int agb_colsum_f32(void const* dy, void const* y, void* out, void* sums, long long rows, int C, int groups, long long group_stride, void* stream) {
+    return colsum_impl<float>(dy, y, out, sums, rows, C, groups, group_stride, stream);
+}
+
 
 int agb_add_relu(void const* a, void const* b, void* out, long long n, int relu, void* stream) {
-    if (n & 7)
-        return 301;
-    AGB_CUDA_OK(launch_pdl(add_relu_kernel, dim3(grid_for(n / 8)), dim3(kThreads), 0, static_cast<cudaStream_t>(stream), static_cast<bf16 const*>(a), static_cast<bf16 const*>(b), static_cast<bf16*>(out), n / 8, relu));
-    AGB_CUDA_OK(cudaGetLastError());
-    return 0;
+    return add_relu_impl<bf16>(a, b, out, n, relu, stream);
 }
+int agb_add_relu_f32(void const* a, void const* b, void* out, long long n, int relu, void* stream) {
+    return add_relu_impl<float>(a, b, out, n, relu, stream);
+}
+
 
 int agb_subsample_forward(void const* x, void* y, int N, int H, int W, int C, int s, void* stream) {
-    if ((C & 7) || s < 1)
-        return 301;
-    int const OH = (H + s - 1) / s, OW = (W + s - 1) / s, octets = C >> 3;
-    if (static_cast<long long>(N) * OH > 65535)
-        return 399;
-    int const per_row = OW * octets;
-    AGB_CUDA_OK(launch_pdl(subsample_fwd_kernel, dim3((per_row + kThreads - 1) / kThreads, N * OH), dim3(kThreads), 0, static_cast<cudaStream_t>(stream), static_cast<bf16 const*>(x), static_cast<bf16*>(y), H, W, OH, OW, octets, s));
-    AGB_CUDA_OK(cudaGetLastError());
-    return 0;
+    return subsample_forward_impl<bf16>(x, y, N, H, W, C, s, stream);
 }
+int agb_subsample_forward_f32(void const* x, void* y, int N, int H, int W, int C, int s, void* stream) {
+    return subsample_forward_impl<float>(x, y, N, H, W, C, s, stream);
+}
+
 
 int agb_subsample_backward(void const* dy, void* dx, int N, int H, int W, int C, int s, void* stream) {
-    if ((C & 7) || s < 1)
-        return 301;
-    int const OH = (H + s - 1) / s, OW = (W + s - 1) / s, octets = C >> 3;
-    if (static_cast<long long>(N) * H > 65535)
-        return 399;
-    int const per_row = W * octets;
-    AGB_CUDA_OK(launch_pdl(subsample_bwd_kernel, dim3((per_row + kThreads - 1) / kThreads, N * H), dim3(kThreads), 0, static_cast<cudaStream_t>(stream), static_cast<bf16 const*>(dy), static_cast<bf16*>(dx), H, W, OH, OW, octets, s));
-    AGB_CUDA_OK(cudaGetLastError());
-    return 0;
+    return subsample_backward_impl<bf16>(dy, dx, N, H, W, C, s, stream);
 }
+int agb_subsample_backward_f32(void const* dy, void* dx, int N, int H, int W, int C, int s, void* stream) {
+    return subsample_backward_impl<float>(dy, dx, N, H, W, C, s, stream);
+}
+
 
 int agb_relu_backward(void const* dy, void const* y, void* dx, long long n, void* stream) {
-    if (n & 7)
-        return 301;
-    AGB_CUDA_OK(launch_pdl(relu_bwd_kernel, dim3(grid_for(n / 8)), dim3(kThreads), 0, static_cast<cudaStream_t>(stream), static_cast<bf16 const*>(dy), static_cast<bf16 const*>(y), static_cast<bf16*>(dx), n / 8));
-    AGB_CUDA_OK(cudaGetLastError());
-    return 0;
+    return relu_backward_impl<bf16>(dy, y, dx, n, stream);
 }
+int agb_relu_backward_f32(void const* dy, void const* y, void* dx, long long n, void* stream) {
+    return relu_backward_impl<float>(dy, y, dx, n, stream);
+}
+
 
 int agb_maxpool_forward(void const* x, void* y, void* arg, int N, int H, int W, int C, int OH, int OW, int k, int s, int pad_t, int pad_l, void* stream) {
-    if ((C & 7) || k * k > 255)
-        return 301;
-    long long const work = static_cast<long long>(N) * OH * OW * (C >> 3);
-    AGB_CUDA_OK(launch_pdl(maxpool_fwd_kernel, dim3(grid_for(work)), dim3(kThreads), 0, static_cast<cudaStream_t>(stream), static_cast<bf16 const*>(x), static_cast<bf16*>(y), static_cast<unsigned char*>(arg), N, H, W, C, OH, OW, k, s, pad_t, pad_l));
-    AGB_CUDA_OK(cudaGetLastError());
-    return 0;
+    return maxpool_forward_impl<bf16>(x, y, arg, N, H, W, C, OH, OW, k, s, pad_t, pad_l, stream);
 }
+int agb_maxpool_forward_f32(void const* x, void* y, void* arg, int N, int H, int W, int C, int OH, int OW, int k, int s, int pad_t, int pad_l, void* stream) {
+    return maxpool_forward_impl<float>(x, y, arg, N, H, W, C, OH, OW, k, s, pad_t, pad_l, stream);
+}
+
 
 int agb_maxpool_backward(void const* dy, void const* arg, void* dx, int N, int H, int W, int C, int OH, int OW, int k, int s, int pad_t, int pad_l, void* stream) {
-    if (C & 7)
-        return 301;
-    if (H > 65535)
-        return 301;
-    // grid.y = images x rows is limited to 65535: very large batches go in slices of whole images
-    int const per_launch = 65535 / H;
-    for (int n0 = 0; n0 < N; n0 += per_launch) {
-        int const count = N - n0 < per_launch ? N - n0 : per_launch;
-        AGB_CUDA_OK(launch_pdl(maxpool_bwd_kernel, dim3((W * (C >> 3) + kThreads - 1) / kThreads, count * H), dim3(kThreads), 0, static_cast<cudaStream_t>(stream),
-            static_cast<bf16 const*>(dy) + static_cast<long long>(n0) * OH * OW * C, static_cast<unsigned char const*>(arg) + static_cast<long long>(n0) * OH * OW * C,
-            static_cast<bf16*>(dx) + static_cast<long long>(n0) * H * W * C, count, H, W, C, OH, OW, k, s, pad_t, pad_l));
-    }
-    AGB_CUDA_OK(cudaGetLastError());
-    return 0;
+    return maxpool_backward_impl<bf16>(dy, arg, dx, N, H, W, C, OH, OW, k, s, pad_t, pad_l, stream);
 }
+int agb_maxpool_backward_f32(void const* dy, void const* arg, void* dx, int N, int H, int W, int C, int OH, int OW, int k, int s, int pad_t, int pad_l, void* stream) {
+    return maxpool_backward_impl<float>(dy, arg, dx, N, H, W, C, OH, OW, k, s, pad_t, pad_l, stream);
+}
+
 
 int agb_avgpool_forward(void const* x, void* y, int N, int HW, int C, void* stream) {
-    if (C & 7)
-        return 301;
-    AGB_CUDA_OK(launch_pdl(avgpool_fwd_kernel, dim3((N * (C >> 3) + 127) / 128), dim3(128), 0, static_cast<cudaStream_t>(stream), static_cast<bf16 const*>(x), static_cast<bf16*>(y), N, HW, C));
-    AGB_CUDA_OK(cudaGetLastError());
-    return 0;
+    return avgpool_forward_impl<bf16>(x, y, N, HW, C, stream);
 }
+int agb_avgpool_forward_f32(void const* x, void* y, int N, int HW, int C, void* stream) {
+    return avgpool_forward_impl<float>(x, y, N, HW, C, stream);
+}
+
 
 int agb_avgpool_backward(void const* dy, void* dx, int N, int HW, int C, void* stream) {
-    if (C & 7)
-        return 301;
-    long long const work = static_cast<long long>(N) * HW * (C >> 3);
-    AGB_CUDA_OK(launch_pdl(avgpool_bwd_kernel, dim3(grid_for(work)), dim3(kThreads), 0, static_cast<cudaStream_t>(stream), static_cast<bf16 const*>(dy), static_cast<bf16*>(dx), N, HW, C));
-    AGB_CUDA_OK(cudaGetLastError());
-    return 0;
+    return avgpool_backward_impl<bf16>(dy, dx, N, HW, C, stream);
 }
+int agb_avgpool_backward_f32(void const* dy, void* dx, int N, int HW, int C, void* stream) {
+    return avgpool_backward_impl<float>(dy, dx, N, HW, C, stream);
+}
+
 
 int agb_softmax_xent(void const* logits, void const* labels, void* dlogits, void* loss, int B, int K, long long ld, float smoothing, int groups, void* stream) {
-    if (groups < 1 || B % groups)
-        return 301;
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    AGB_CUDA_OK(cudaMemsetAsync(loss, 0, sizeof(float) * groups, s));
-    int const warps_per_cta = 4;
-    AGB_CUDA_OK(launch_pdl(softmax_xent_kernel, dim3((B + warps_per_cta - 1) / warps_per_cta), dim3(warps_per_cta * 32), 0, s, static_cast<bf16 const*>(logits), static_cast<long long const*>(labels),
-        static_cast<bf16*>(dlogits), static_cast<float*>(loss), B, K, ld, smoothing, B / groups));
-    AGB_CUDA_OK(cudaGetLastError());
-    return 0;
+    return softmax_xent_impl<bf16>(logits, labels, dlogits, loss, B, K, ld, smoothing, groups, stream);
 }
+int agb_softmax_xent_f32(void const* logits, void const* labels, void* dlogits, void* loss, int B, int K, long long ld, float smoothing, int groups, void* stream) {
+    return softmax_xent_impl<float>(logits, labels, dlogits, loss, B, K, ld, smoothing, groups, stream);
+}
+
 
 int agb_image_normalize(void const* x, void* y, long long pixels, int C, int Cpad, float m0, float m1, float m2, float scale, void* stream) {
-    AGB_CUDA_OK(launch_pdl(image_normalize_kernel, dim3(grid_for(pixels)), dim3(kThreads), 0, static_cast<cudaStream_t>(stream), static_cast<unsigned char const*>(x), static_cast<bf16*>(y), pixels, C, Cpad, m0, m1, m2, scale));
-    AGB_CUDA_OK(cudaGetLastError());
-    return 0;
+    return image_normalize_impl<bf16>(x, y, pixels, C, Cpad, m0, m1, m2, scale, stream);
 }
+int agb_image_normalize_f32(void const* x, void* y, long long pixels, int C, int Cpad, float m0, float m1, float m2, float scale, void* stream) {
+    return image_normalize_impl<float>(x, y, pixels, C, Cpad, m0, m1, m2, scale, stream);
+}
+
 
 int agb_im2col(void const* x, void* col, int N, int H, int W, int C, int OH, int OW, int kh, int kw, int s, int pad_t, int pad_l, long long ldcol, void* stream) {
-    if (ldcol & 7)
-        return 301;
-    long long const work = (C & 7) == 0 ? static_cast<long long>(N) * OH * OW * kh * kw * (C >> 3) : static_cast<long long>(N) * OH * OW * (ldcol >> 3);
-    AGB_CUDA_OK(launch_pdl(im2col_kernel, dim3(grid_for(work, kThreads, 148 * 16)), dim3(kThreads), 0, static_cast<cudaStream_t>(stream), static_cast<bf16 const*>(x), static_cast<bf16*>(col), N, H, W, C, OH, OW, kh, kw, s, pad_t, pad_l, ldcol));
-    AGB_CUDA_OK(cudaGetLastError());
-    return 0;
+    return im2col_impl<bf16>(x, col, N, H, W, C, OH, OW, kh, kw, s, pad_t, pad_l, ldcol, stream);
+}
+int agb_im2col_f32(void const* x, void* col, int N, int H, int W, int C, int OH, int OW, int kh, int kw, int s, int pad_t, int pad_l, long long ldcol, void* stream) {
+    return im2col_impl<float>(x, col, N, H, W, C, OH, OW, kh, kw, s, pad_t, pad_l, ldcol, stream);
 }
 
+
 int agb_col2im(void const* dcol, void* dx, int N, int H, int W, int C, int OH, int OW, int kh, int kw, int s, int pad_t, int pad_l, long long ldcol, void* stream) {
-    if ((C & 7) || (ldcol & 7))
-        return 301;
-    long long const work = static_cast<long long>(N) * H * W * (C >> 3);
-    AGB_CUDA_OK(launch_pdl(col2im_kernel, dim3(grid_for(work, kThreads, 148 * 16)), dim3(kThreads), 0, static_cast<cudaStream_t>(stream), static_cast<bf16 const*>(dcol), static_cast<bf16*>(dx), N, H, W, C, OH, OW, kh, kw, s, pad_t, pad_l, ldcol));
-    AGB_CUDA_OK(cudaGetLastError());
-    return 0;
+    return col2im_impl<bf16>(dcol, dx, N, H, W, C, OH, OW, kh, kw, s, pad_t, pad_l, ldcol, stream);
 }
+int agb_col2im_f32(void const* dcol, void* dx, int N, int H, int W, int C, int OH, int OW, int kh, int kw, int s, int pad_t, int pad_l, long long ldcol, void* stream) {
+    return col2im_impl<float>(dcol, dx, N, H, W, C, OH, OW, kh, kw, s, pad_t, pad_l, ldcol, stream);
+}
+
 
 } // extern "C"

@@ -48,6 +48,15 @@ def enabled(op):
   return op not in _DISABLED and "all" not in _DISABLED
 
 
+# Activation dtypes: bf16 (kind::f16 products) or fp32 (kind::tf32 products, fp32 storage: the parity precision of the fp32 reference).
+_DTYPES = (torch.bfloat16, torch.float32)
+
+
+def _fn(name, tensor):
+  """C entry point of a layer kernel for the element type of `tensor` (`agb_<name>` / `agb_<name>_f32`)."""
+  return getattr(_lib(), name + ("_f32" if tensor.dtype == torch.float32 else ""))
+
+
 # ---------------------------------------------------------------------------- #
 # Pre-zeroed gradient rows: split-K weight gradients accumulate with fp32 atomics and need a zeroed destination. The trainer
 # clears the whole [workers, d] gradient matrix with ONE fill before the backward pass and declares it here, which replaces
@@ -108,17 +117,18 @@ class _Fork:
 # ---------------------------------------------------------------------------- #
 # GEMM
 
-def _rows(t):
-  """2-D bf16 operand with unit inner stride, row stride % 8 == 0 and a 16-byte aligned base (copy if needed)."""
-  if t.dtype != torch.bfloat16:
-    t = t.to(torch.bfloat16)
+def _rows(t, dtype=None):
+  """2-D bf16 / fp32 operand with unit inner stride, row stride % 8 == 0 and a 16-byte aligned base (copy if needed)."""
+  dtype = dtype if dtype is not None else (t.dtype if t.dtype in _DTYPES else torch.bfloat16)
+  if t.dtype != dtype:
+    t = t.to(dtype)
   if t.dim() != 2:
     t = t.reshape(t.shape[0], -1)
   if t.stride(1) == 1 and t.stride(0) % 8 == 0 and t.stride(0) >= t.shape[1] and t.data_ptr() % 16 == 0:
     return t
   rows, cols = t.shape
   ld = (cols + 7) // 8 * 8
-  buf = torch.zeros((rows, ld), dtype=torch.bfloat16, device=t.device)
+  buf = torch.zeros((rows, ld), dtype=dtype, device=t.device)
   buf[:, :cols] = t
   return buf[:, :cols]
 
@@ -135,10 +145,18 @@ def alloc_out(m, n, dtype, device):
 
 
 def _gemm(a, b, out, M, N, K, a_mn, b_mn, bias, relu, splits, bn, groups=1, group_stride=0):
-  func = _lib().agb_gemm_bf16_grouped
-  out_fp32 = 1 if out.dtype == torch.float32 else 0
   if out.stride(1) != 1:
     raise RuntimeError("GEMM output must have unit inner stride")
+  if a.dtype == torch.float32:   # TF32 products, fp32 output
+    if b.dtype != torch.float32 or out.dtype != torch.float32:
+      raise RuntimeError("TF32 GEMM needs fp32 operands and output")
+    status = _lib().agb_gemm_tf32_grouped(_ptr(a), _ptr(b), _ptr(out), ctypes.c_int(M), ctypes.c_int(N), ctypes.c_int(K), ctypes.c_longlong(a.stride(0)), ctypes.c_longlong(b.stride(0)),
+                                          ctypes.c_longlong(out.stride(0)), ctypes.c_int(1 if a_mn else 0), ctypes.c_int(1 if b_mn else 0), _ptr(bias), ctypes.c_int(1 if relu else 0),
+                                          ctypes.c_int(splits), ctypes.c_int(128 if bn == 256 else bn), ctypes.c_int(groups), ctypes.c_longlong(group_stride), _stream())
+    _check(status, "gemm_tf32")
+    return out
+  func = _lib().agb_gemm_bf16_grouped
+  out_fp32 = 1 if out.dtype == torch.float32 else 0
   status = func(_ptr(a), _ptr(b), _ptr(out), ctypes.c_int(M), ctypes.c_int(N), ctypes.c_int(K), ctypes.c_longlong(a.stride(0)), ctypes.c_longlong(b.stride(0)),
                 ctypes.c_longlong(out.stride(0)), ctypes.c_int(1 if a_mn else 0), ctypes.c_int(1 if b_mn else 0), _ptr(bias), ctypes.c_int(1 if relu else 0),
                 ctypes.c_int(out_fp32), ctypes.c_int(splits), ctypes.c_int(bn), ctypes.c_int(groups), ctypes.c_longlong(group_stride), _stream())
@@ -146,29 +164,45 @@ def _gemm(a, b, out, M, N, K, a_mn, b_mn, bias, relu, splits, bn, groups=1, grou
   return out
 
 
-def mm_nt(x, w, bias=None, relu=False, out=None, out_dtype=torch.bfloat16, bn=0):
-  """x[M,K] @ w[N,K]^T (+ fp32 bias[N], ReLU)."""
-  x, w = _rows(x), _rows(w)
+def mm_nt(x, w, bias=None, relu=False, out=None, out_dtype=None, bn=0):
+  """x[M,K] @ w[N,K]^T (+ fp32 bias[N], ReLU). fp32 operands are multiplied as TF32."""
+  x = _rows(x)
+  w = _rows(w, x.dtype)
   M, K = x.shape
   N = w.shape[0]
   if out is None:
-    out = alloc_out(M, N, out_dtype, x.device)
+    out = alloc_out(M, N, (out_dtype or x.dtype) if x.dtype == torch.bfloat16 else torch.float32, x.device)
   if bias is not None and bias.dtype != torch.float32:
     bias = bias.float()
   return _gemm(x, w, out, M, N, K, False, False, bias, relu, 1, bn)
 
 
-def mm_nn(x, w, out=None, out_dtype=torch.bfloat16, bn=0):
+def mm_nn(x, w, out=None, out_dtype=None, bn=0):
   """x[M,K] @ w[K,N]."""
-  x, w = _rows(x), _rows(w)
+  x = _rows(x)
+  w = _rows(w, x.dtype)
   M, K = x.shape
   N = w.shape[1]
   if out is None:
-    out = alloc_out(M, N, out_dtype, x.device)
+    out = alloc_out(M, N, (out_dtype or x.dtype) if x.dtype == torch.bfloat16 else torch.float32, x.device)
   return _gemm(x, w, out, M, N, K, False, True, None, False, 1, bn)
 
 
+# Split-K weight gradients accumulate their partial products with fp32 reductions (red.global.add.v4.f32) whose arrival order varies
+# from run to run: the last bits of a gradient can differ between two executions of the same step. `AGB_DETERMINISTIC=1` /
+# `set_deterministic(True)` gives bit-reproducible gradients by keeping every weight-gradient product in ONE accumulation chain per
+# output tile (no split-K): each tile is then summed in TMEM in a fixed k order. Slower on layers with few output tiles.
+_DETERMINISTIC = os.environ.get("AGB_DETERMINISTIC", "0") not in ("", "0")
+
+
+def set_deterministic(flag):
+  global _DETERMINISTIC
+  _DETERMINISTIC = bool(flag)
+
+
 def pick_splits(m_out, n_out, k, bn=128):
+  if _DETERMINISTIC:
+    return 1
   tiles = ((m_out + 127) // 128) * ((n_out + bn - 1) // bn)
   kblocks = (k + 63) // 64
   want = max(1, (2 * SM_COUNT + tiles - 1) // tiles)
@@ -186,7 +220,8 @@ def mm_tn(x, y, out=None, splits=None, bn=0, groups=1, group_stride=0):
   """x[K,M]^T @ y[K,N] -> fp32 [M,N]; split-K partial sums are accumulated with fp32 atomics (out is zeroed here).
   `groups` > 1: x and y hold `groups` consecutive blocks of K / groups rows, one product per block, written `group_stride`
   elements apart starting at `out` (the per-worker weight gradients, one launch)."""
-  x, y = _rows(x), _rows(y)
+  x = _rows(x)
+  y = _rows(y, x.dtype)
   K, M = x.shape
   K //= groups
   N = y.shape[1]
@@ -277,9 +312,9 @@ def conv2d_backward(dy, x, weight, y, stride, pads, relu, has_bias, need_dx, gra
     dx = _from_rows(mm_nn(dy2d, weight.reshape(weight.shape[0], -1)), n, h, w) if need_dx else None
     fork.join()
     return dx
-  if _implicit_ok(x, weight, stride, pads) and dy.dtype == torch.bfloat16:
+  if _implicit_ok(x, weight, stride, pads) and dy.dtype == x.dtype:
     return conv2d_backward_implicit(dy, x, weight, y, relu, has_bias, need_dx, grad_w, grad_b, groups, group_stride, stride, pads)
-  if enabled("convk") and _general_ok(x, weight) and dy.dtype == torch.bfloat16:
+  if enabled("convk") and _general_ok(x, weight) and dy.dtype == x.dtype:
     return conv2d_backward_general(dy, x, weight, y, stride, pads, relu, has_bias, need_dx, grad_w, grad_b, groups, group_stride, aux)
   return NotImplemented
 
@@ -291,8 +326,8 @@ def _im2col(x, kh, kw, stride, pads, oh, ow):
   n, c, h, w = x.shape
   kcol = kh * kw * c
   ld = (kcol + 7) // 8 * 8
-  col = torch.empty((n * oh * ow, ld), dtype=torch.bfloat16, device=x.device)
-  func = _lib().agb_im2col
+  col = torch.empty((n * oh * ow, ld), dtype=x.dtype, device=x.device)
+  func = _fn("agb_im2col", x)
   _check(func(_ptr(x), _ptr(col), ctypes.c_int(n), ctypes.c_int(h), ctypes.c_int(w), ctypes.c_int(c), ctypes.c_int(oh), ctypes.c_int(ow), ctypes.c_int(kh), ctypes.c_int(kw),
               ctypes.c_int(stride), ctypes.c_int(pads[0]), ctypes.c_int(pads[2]), ctypes.c_longlong(ld), _stream()), "im2col")
   return col[:, :kcol]
@@ -308,7 +343,7 @@ def _weight_rows(weight):
 
 
 def _general_ok(x, weight):
-  return x.is_contiguous(memory_format=torch.channels_last) and x.dtype == torch.bfloat16 and weight.shape[0] % 8 == 0
+  return x.is_contiguous(memory_format=torch.channels_last) and x.dtype in _DTYPES and weight.shape[0] % 8 == 0
 
 
 def conv2d_forward_general(x, weight, bias, stride, pads, relu, aux=None):
@@ -343,8 +378,8 @@ def conv2d_backward_general(dy, x, weight, y, stride, pads, relu, has_bias, need
     fork.join()
     return None
   dcol = mm_nn(dy2d, _weight_rows(weight))
-  dx = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=x.device)
-  func = _lib().agb_col2im
+  dx = torch.empty((n, h, w, c), dtype=x.dtype, device=x.device)
+  func = _fn("agb_col2im", x)
   _check(func(_ptr(dcol), _ptr(dx), ctypes.c_int(n), ctypes.c_int(h), ctypes.c_int(w), ctypes.c_int(c), ctypes.c_int(oh), ctypes.c_int(ow), ctypes.c_int(kh), ctypes.c_int(kw),
               ctypes.c_int(stride), ctypes.c_int(pads[0]), ctypes.c_int(pads[2]), ctypes.c_longlong(dcol.stride(0)), _stream()), "col2im")
   fork.join()
@@ -359,7 +394,8 @@ def conv2d_backward_general(dy, x, weight, y, stride, pads, relu, has_bias, need
 def _implicit_geometry(x, weight, stride, pads):
   """(OH, OW) when the implicit-GEMM kernels take this convolution, else None."""
   k = weight.shape[1]
-  if not (enabled("implicit") and k > 1 and weight.shape[2] == k and x.shape[1] % 64 == 0 and weight.shape[0] % 64 == 0 and x.dtype == torch.bfloat16
+  chunk = 64 if x.dtype == torch.bfloat16 else 32   # channels per 128-byte swizzle row
+  if not (enabled("implicit") and k > 1 and weight.shape[2] == k and x.shape[1] % chunk == 0 and weight.shape[0] % chunk == 0 and x.dtype in _DTYPES and weight.dtype == x.dtype
           and x.is_contiguous(memory_format=torch.channels_last) and weight.is_contiguous()):
     return None
   h, w = x.shape[2], x.shape[3]
@@ -377,6 +413,12 @@ def _implicit_ok(x, weight, stride, pads):
 
 
 def _conv_implicit(mode, act, other, out, n, h, w, oh, ow, cin, cout, k, stride, pads, bias=None, relu=False, splits=1, bn=0, groups=1, group_stride=0):
+  if act.dtype == torch.float32:   # TF32 products
+    _check(_lib().agb_conv_implicit_strided_tf32(ctypes.c_int(mode), _ptr(act), _ptr(other), _ptr(out), ctypes.c_int(n), ctypes.c_int(h), ctypes.c_int(w), ctypes.c_int(oh), ctypes.c_int(ow),
+                                                 ctypes.c_int(cin), ctypes.c_int(cout), ctypes.c_int(k), ctypes.c_int(stride), ctypes.c_int(pads[0]), ctypes.c_int(pads[2]), _ptr(bias),
+                                                 ctypes.c_int(1 if relu else 0), ctypes.c_int(splits), ctypes.c_int(bn), ctypes.c_int(groups), ctypes.c_longlong(group_stride), _stream()),
+           "conv_implicit_tf32")
+    return out
   _check(_lib().agb_conv_implicit_strided(ctypes.c_int(mode), _ptr(act), _ptr(other), _ptr(out), ctypes.c_int(n), ctypes.c_int(h), ctypes.c_int(w), ctypes.c_int(oh), ctypes.c_int(ow),
                                           ctypes.c_int(cin), ctypes.c_int(cout), ctypes.c_int(k), ctypes.c_int(stride), ctypes.c_int(pads[0]), ctypes.c_int(pads[2]), _ptr(bias),
                                           ctypes.c_int(1 if relu else 0), ctypes.c_int(1 if out.dtype == torch.float32 else 0), ctypes.c_int(splits), ctypes.c_int(bn), ctypes.c_int(groups),
@@ -389,7 +431,7 @@ def conv2d_forward_implicit(x, weight, bias, relu, stride=1, pads=None):
   cout, k = weight.shape[0], weight.shape[1]
   pads = pads if pads is not None else ((k - 1) // 2,) * 4
   oh, ow = _implicit_geometry(x, weight, stride, pads)
-  y = torch.empty((n, oh, ow, cout), dtype=torch.bfloat16, device=x.device)
+  y = torch.empty((n, oh, ow, cout), dtype=x.dtype, device=x.device)
   if bias is not None and bias.dtype != torch.float32:
     bias = bias.float()
   _conv_implicit(0, x, weight, y, n, h, w, oh, ow, cin, cout, k, stride, pads, bias, relu)
@@ -405,8 +447,8 @@ def conv2d_backward_implicit(dy, x, weight, y, relu, has_bias, need_dx, grad_w, 
   if not dy.is_contiguous(memory_format=torch.channels_last):
     dy = dy.contiguous(memory_format=torch.channels_last)
   tiles = k * k * ((cout + 127) // 128) * ((cin + 127) // 128)
-  kblocks = max(1, n * oh * ow // 64 // groups)
-  splits = max(1, min(kblocks, (2 * SM_COUNT + tiles * groups - 1) // (tiles * groups), 64))
+  kblocks = max(1, n * oh * ow // (64 if x.dtype == torch.bfloat16 else 32) // groups)
+  splits = 1 if _DETERMINISTIC else max(1, min(kblocks, (2 * SM_COUNT + tiles * groups - 1) // (tiles * groups), 64))
   with _Fork() as fork:
     if not _prezeroed:
       _all_groups(grad_w, groups, group_stride).zero_()
@@ -415,7 +457,7 @@ def conv2d_backward_implicit(dy, x, weight, y, relu, has_bias, need_dx, grad_w, 
       colsum(_as_rows(dy), out=grad_b, groups=groups, group_stride=group_stride)
   dx = None
   if need_dx:
-    dx = torch.empty((n, h, w, cin), dtype=torch.bfloat16, device=x.device)
+    dx = torch.empty((n, h, w, cin), dtype=x.dtype, device=x.device)
     _conv_implicit(1, dy, weight, dx, n, h, w, oh, ow, cin, cout, k, stride, pads)
     dx = dx.permute(0, 3, 1, 2)
   fork.join()
@@ -436,8 +478,12 @@ def _workspace(device, name, numel, dtype):
   return buf
 
 
-def _cl_ok(*tensors):
-  return all(t is None or (t.dtype == torch.bfloat16 and (t.dim() != 4 or t.is_contiguous(memory_format=torch.channels_last))) for t in tensors)
+def _cl_ok(*tensors, dtypes=_DTYPES):
+  """Every given tensor is channels_last (when 4-D) and they all share one supported activation dtype."""
+  present = [t for t in tensors if t is not None]
+  if not present or present[0].dtype not in dtypes or any(t.dtype != present[0].dtype for t in present):
+    return False
+  return all(t.dim() != 4 or t.is_contiguous(memory_format=torch.channels_last) for t in present)
 
 
 def colsum(dy2d, y2d=None, out=None, groups=1, group_stride=0):
@@ -451,7 +497,7 @@ def colsum(dy2d, y2d=None, out=None, groups=1, group_stride=0):
     _all_groups(out, groups, group_stride).copy_(src.reshape(groups, rows // groups, c).sum(dim=1) if groups > 1 else src.sum(dim=0))
     return out
   sums = _workspace(dy2d.device, "colsum", 2 * c * groups + 1, torch.float64)
-  _check(_lib().agb_colsum(_ptr(dy2d), _ptr(y2d), _ptr(out), _ptr(sums), ctypes.c_longlong(rows), ctypes.c_int(c), ctypes.c_int(groups), ctypes.c_longlong(group_stride), _stream()), "colsum")
+  _check(_fn("agb_colsum", dy2d)(_ptr(dy2d), _ptr(y2d), _ptr(out), _ptr(sums), ctypes.c_longlong(rows), ctypes.c_int(c), ctypes.c_int(groups), ctypes.c_longlong(group_stride), _stream()), "colsum")
   return out
 
 
@@ -486,7 +532,7 @@ def batchnorm_forward(x, gamma, beta, moving_mean, moving_var, decay, eps, relu,
     return None
   y = torch.empty_like(x, memory_format=torch.channels_last)
   stats = torch.empty((4, groups * c), dtype=torch.float32, device=x.device)  # save_mean, save_rstd, scale, shift
-  if _BN_FUSED:
+  if _BN_FUSED and x.dtype == torch.bfloat16:   # the resident-tile kernel is sized for 2-byte activations
     status = _lib().agb_bn_forward_fused(_ptr(x), _ptr(residual), _ptr(y), _ptr(gamma), _ptr(beta), _ptr(moving_mean), _ptr(moving_var), _ptr(stats[0]), _ptr(stats[1]),
                                          _ptr(_bn_fused_workspace(x.device, "bn_fused_fwd")), ctypes.c_longlong(rows), ctypes.c_int(c), ctypes.c_int(groups),
                                          ctypes.c_float(eps), ctypes.c_float(decay), ctypes.c_int(1 if relu else 0), _stream())
@@ -494,7 +540,7 @@ def batchnorm_forward(x, gamma, beta, moving_mean, moving_var, decay, eps, relu,
       _check(status, "bn_forward_fused")
       return y, stats[0], stats[1]
   sums = _workspace(x.device, "bn_sums", 2 * groups * c + 1, torch.float64)
-  _check(_lib().agb_bn_forward(_ptr(x), _ptr(residual), _ptr(y), _ptr(gamma), _ptr(beta), _ptr(moving_mean), _ptr(moving_var), _ptr(stats[0]), _ptr(stats[1]), _ptr(sums),
+  _check(_fn("agb_bn_forward", x)(_ptr(x), _ptr(residual), _ptr(y), _ptr(gamma), _ptr(beta), _ptr(moving_mean), _ptr(moving_var), _ptr(stats[0]), _ptr(stats[1]), _ptr(sums),
                                _ptr(stats[2]), _ptr(stats[3]), ctypes.c_longlong(rows), ctypes.c_int(c), ctypes.c_int(groups), ctypes.c_float(eps),
                                ctypes.c_float(decay), ctypes.c_int(1 if relu else 0), _stream()), "bn_forward")
   return y, stats[0], stats[1]
@@ -510,7 +556,7 @@ def batchnorm_backward(dy, x, y, gamma, mean, rstd, relu, grad_gamma, grad_beta,
   rows = n * h * w
   dx = torch.empty_like(x, memory_format=torch.channels_last)
   masked = torch.empty_like(dy, memory_format=torch.channels_last) if want_masked else None
-  if _BN_FUSED:
+  if _BN_FUSED and x.dtype == torch.bfloat16:
     status = _lib().agb_bn_backward_fused(_ptr(dy), _ptr(x), _ptr(y if relu else None), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dx), _ptr(masked), _ptr(grad_gamma),
                                           _ptr(grad_beta), _ptr(_bn_fused_workspace(x.device, "bn_fused_bwd")), ctypes.c_longlong(rows), ctypes.c_int(c), ctypes.c_int(groups),
                                           ctypes.c_longlong(group_stride), _stream())
@@ -519,7 +565,7 @@ def batchnorm_backward(dy, x, y, gamma, mean, rstd, relu, grad_gamma, grad_beta,
       return (dx, masked) if want_masked else dx
   sums = _workspace(x.device, "bn_sums", 2 * groups * c + 1, torch.float64)
   coef = _workspace(x.device, "bn_coef", 3 * groups * c, torch.float32)
-  _check(_lib().agb_bn_backward(_ptr(dy), _ptr(x), _ptr(y if relu else None), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dx), _ptr(masked), _ptr(grad_gamma), _ptr(grad_beta),
+  _check(_fn("agb_bn_backward", x)(_ptr(dy), _ptr(x), _ptr(y if relu else None), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dx), _ptr(masked), _ptr(grad_gamma), _ptr(grad_beta),
                                 _ptr(sums), _ptr(coef), ctypes.c_longlong(rows), ctypes.c_int(c), ctypes.c_int(groups), ctypes.c_longlong(group_stride), _stream()), "bn_backward")
   return (dx, masked) if want_masked else dx
 
@@ -555,7 +601,7 @@ _DEPTHWISE = os.environ.get("AGB_NATIVE_DEPTHWISE", os.environ.get("AGB_NATIVE_P
 
 
 def _depthwise_ok(x, weight):
-  return (_DEPTHWISE and enabled("depthwise") and _cl_ok(x) and x.dim() == 4 and x.shape[1] % 8 == 0 and weight.shape[0] == x.shape[1] and weight.shape[1] == weight.shape[2]
+  return (_DEPTHWISE and enabled("depthwise") and _cl_ok(x, dtypes=(torch.bfloat16,)) and x.dim() == 4 and x.shape[1] % 8 == 0 and weight.shape[0] == x.shape[1] and weight.shape[1] == weight.shape[2]
           and weight.dtype == torch.bfloat16)
 
 
@@ -597,7 +643,7 @@ def depthwise_backward(dy, x, weight, stride, pads, grad_w, groups=1, group_stri
 
 
 def avgpool2d_forward(x, k, stride, pads):
-  if not (_DEPTHWISE and enabled("pool") and _cl_ok(x) and x.dim() == 4 and x.shape[1] % 8 == 0):
+  if not (_DEPTHWISE and enabled("pool") and _cl_ok(x, dtypes=(torch.bfloat16,)) and x.dim() == 4 and x.shape[1] % 8 == 0):
     return None
   n, c, h, w = x.shape
   oh, ow = _out_size(h, k, stride, pads[0], pads[1]), _out_size(w, k, stride, pads[2], pads[3])
@@ -609,7 +655,7 @@ def avgpool2d_forward(x, k, stride, pads):
 
 def avgpool2d_backward(dy, shape, k, stride, pads):
   n, c, h, w = shape
-  if not (_DEPTHWISE and enabled("pool") and _cl_ok(dy) and dy.dim() == 4 and c % 8 == 0):
+  if not (_DEPTHWISE and enabled("pool") and _cl_ok(dy, dtypes=(torch.bfloat16,)) and dy.dim() == 4 and c % 8 == 0):
     return None
   if not dy.is_contiguous(memory_format=torch.channels_last):
     dy = dy.contiguous(memory_format=torch.channels_last)
@@ -637,8 +683,8 @@ def subsample_forward(x, stride):
   if not enabled("eltwise") or not _cl_ok(x) or x.dim() != 4 or x.shape[1] % 8:
     return None
   n, c, h, w = x.shape
-  y = torch.empty((n, -(-h // stride), -(-w // stride), c), dtype=torch.bfloat16, device=x.device)
-  status = _lib().agb_subsample_forward(_ptr(x), _ptr(y), ctypes.c_int(n), ctypes.c_int(h), ctypes.c_int(w), ctypes.c_int(c), ctypes.c_int(stride), _stream())
+  y = torch.empty((n, -(-h // stride), -(-w // stride), c), dtype=x.dtype, device=x.device)
+  status = _fn("agb_subsample_forward", x)(_ptr(x), _ptr(y), ctypes.c_int(n), ctypes.c_int(h), ctypes.c_int(w), ctypes.c_int(c), ctypes.c_int(stride), _stream())
   if status == _BN_UNSUPPORTED:
     return None
   _check(status, "subsample_forward")
@@ -651,8 +697,8 @@ def subsample_backward(dy, shape, stride):
     return None
   if not dy.is_contiguous(memory_format=torch.channels_last):
     dy = dy.contiguous(memory_format=torch.channels_last)
-  dx = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=dy.device)
-  status = _lib().agb_subsample_backward(_ptr(dy), _ptr(dx), ctypes.c_int(n), ctypes.c_int(h), ctypes.c_int(w), ctypes.c_int(c), ctypes.c_int(stride), _stream())
+  dx = torch.empty((n, h, w, c), dtype=dy.dtype, device=dy.device)
+  status = _fn("agb_subsample_backward", dy)(_ptr(dy), _ptr(dx), ctypes.c_int(n), ctypes.c_int(h), ctypes.c_int(w), ctypes.c_int(c), ctypes.c_int(stride), _stream())
   if status == _BN_UNSUPPORTED:
     return None
   _check(status, "subsample_backward")
@@ -660,18 +706,18 @@ def subsample_backward(dy, shape, stride):
 
 
 def relu_backward(dy, y):
-  if not enabled("eltwise") or dy.dtype != torch.bfloat16 or y.dtype != torch.bfloat16 or dy.numel() % 8 or dy.stride() != y.stride() or not (dy.is_contiguous() or dy.is_contiguous(memory_format=torch.channels_last)):
+  if not enabled("eltwise") or dy.dtype not in _DTYPES or y.dtype != dy.dtype or dy.numel() % 8 or dy.stride() != y.stride() or not (dy.is_contiguous() or dy.is_contiguous(memory_format=torch.channels_last)):
     return None
   dx = torch.empty_like(dy)
-  _check(_lib().agb_relu_backward(_ptr(dy), _ptr(y), _ptr(dx), ctypes.c_longlong(dy.numel()), _stream()), "relu_backward")
+  _check(_fn("agb_relu_backward", dy)(_ptr(dy), _ptr(y), _ptr(dx), ctypes.c_longlong(dy.numel()), _stream()), "relu_backward")
   return dx
 
 
 def add_relu_forward(a, b, relu):
-  if not enabled("eltwise") or a.dtype != torch.bfloat16 or b.dtype != torch.bfloat16 or a.numel() % 8 or a.stride() != b.stride() or not (a.is_contiguous() or a.is_contiguous(memory_format=torch.channels_last)):
+  if not enabled("eltwise") or a.dtype not in _DTYPES or b.dtype != a.dtype or a.numel() % 8 or a.stride() != b.stride() or not (a.is_contiguous() or a.is_contiguous(memory_format=torch.channels_last)):
     return None
   out = torch.empty_like(a)
-  _check(_lib().agb_add_relu(_ptr(a), _ptr(b), _ptr(out), ctypes.c_longlong(a.numel()), ctypes.c_int(1 if relu else 0), _stream()), "add_relu")
+  _check(_fn("agb_add_relu", a)(_ptr(a), _ptr(b), _ptr(out), ctypes.c_longlong(a.numel()), ctypes.c_int(1 if relu else 0), _stream()), "add_relu")
   return out
 
 
@@ -682,7 +728,7 @@ def maxpool_forward(x, k, stride, pads):
   oh, ow = _out_size(h, k, stride, pads[0], pads[1]), _out_size(w, k, stride, pads[2], pads[3])
   y = torch.empty((n, c, oh, ow), dtype=x.dtype, device=x.device).contiguous(memory_format=torch.channels_last)
   arg = torch.empty((n, oh, ow, c), dtype=torch.uint8, device=x.device)
-  _check(_lib().agb_maxpool_forward(_ptr(x), _ptr(y), _ptr(arg), ctypes.c_int(n), ctypes.c_int(h), ctypes.c_int(w), ctypes.c_int(c), ctypes.c_int(oh), ctypes.c_int(ow),
+  _check(_fn("agb_maxpool_forward", x)(_ptr(x), _ptr(y), _ptr(arg), ctypes.c_int(n), ctypes.c_int(h), ctypes.c_int(w), ctypes.c_int(c), ctypes.c_int(oh), ctypes.c_int(ow),
                                     ctypes.c_int(k), ctypes.c_int(stride), ctypes.c_int(pads[0]), ctypes.c_int(pads[2]), _stream()), "maxpool_forward")
   return y, arg
 
@@ -693,7 +739,7 @@ def maxpool_backward(dy, shape, arg, k, stride, pads):
     dy = dy.contiguous(memory_format=torch.channels_last)
   oh, ow = dy.shape[2], dy.shape[3]
   dx = torch.empty((n, c, h, w), dtype=dy.dtype, device=dy.device).contiguous(memory_format=torch.channels_last)
-  _check(_lib().agb_maxpool_backward(_ptr(dy), _ptr(arg), _ptr(dx), ctypes.c_int(n), ctypes.c_int(h), ctypes.c_int(w), ctypes.c_int(c), ctypes.c_int(oh), ctypes.c_int(ow),
+  _check(_fn("agb_maxpool_backward", dy)(_ptr(dy), _ptr(arg), _ptr(dx), ctypes.c_int(n), ctypes.c_int(h), ctypes.c_int(w), ctypes.c_int(c), ctypes.c_int(oh), ctypes.c_int(ow),
                                      ctypes.c_int(k), ctypes.c_int(stride), ctypes.c_int(pads[0]), ctypes.c_int(pads[2]), _stream()), "maxpool_backward")
   return dx
 
@@ -703,28 +749,28 @@ def global_avgpool_forward(x):
     return None
   n, c, h, w = x.shape
   y = torch.empty((n, c, 1, 1), dtype=x.dtype, device=x.device).contiguous(memory_format=torch.channels_last)
-  _check(_lib().agb_avgpool_forward(_ptr(x), _ptr(y), ctypes.c_int(n), ctypes.c_int(h * w), ctypes.c_int(c), _stream()), "avgpool_forward")
+  _check(_fn("agb_avgpool_forward", x)(_ptr(x), _ptr(y), ctypes.c_int(n), ctypes.c_int(h * w), ctypes.c_int(c), _stream()), "avgpool_forward")
   return y
 
 
 def global_avgpool_backward(dy, shape):
   n, c, h, w = shape
-  if not enabled("pool") or dy.dtype != torch.bfloat16 or c % 8:
+  if not enabled("pool") or dy.dtype not in _DTYPES or c % 8:
     return None
   dy = dy.reshape(n, c).contiguous()
   dx = torch.empty((n, c, h, w), dtype=dy.dtype, device=dy.device).contiguous(memory_format=torch.channels_last)
-  _check(_lib().agb_avgpool_backward(_ptr(dy), _ptr(dx), ctypes.c_int(n), ctypes.c_int(h * w), ctypes.c_int(c), _stream()), "avgpool_backward")
+  _check(_fn("agb_avgpool_backward", dy)(_ptr(dy), _ptr(dx), ctypes.c_int(n), ctypes.c_int(h * w), ctypes.c_int(c), _stream()), "avgpool_backward")
   return dx
 
 
 def softmax_xent(logits, labels, label_smoothing, groups=1):
-  if not enabled("xent") or logits.dtype != torch.bfloat16 or logits.stride(1) != 1:
+  if not enabled("xent") or logits.dtype not in _DTYPES or logits.stride(1) != 1:
     return None
   batch, classes = logits.shape
-  dlogits = torch.empty_strided(logits.shape, logits.stride(), dtype=torch.bfloat16, device=logits.device)
+  dlogits = torch.empty_strided(logits.shape, logits.stride(), dtype=logits.dtype, device=logits.device)
   loss = torch.empty((groups,) if groups > 1 else (), dtype=torch.float32, device=logits.device)
   labels = labels if labels.dtype == torch.int64 else labels.long()
-  _check(_lib().agb_softmax_xent(_ptr(logits), _ptr(labels), _ptr(dlogits), _ptr(loss), ctypes.c_int(batch), ctypes.c_int(classes), ctypes.c_longlong(logits.stride(0)),
+  _check(_fn("agb_softmax_xent", logits)(_ptr(logits), _ptr(labels), _ptr(dlogits), _ptr(loss), ctypes.c_int(batch), ctypes.c_int(classes), ctypes.c_longlong(logits.stride(0)),
                                  ctypes.c_float(label_smoothing), ctypes.c_int(groups), _stream()), "softmax_xent")
   return loss, dlogits
 
@@ -734,7 +780,7 @@ _MEANS = {"vgg": (123.68, 116.78, 103.94, 1.0), "inception": (127.5, 127.5, 127.
 
 def image_normalize(images, mode, dtype):
   """uint8 NHWC -> bf16 channels_last (N, Cpad, H, W) with the channel dimension zero-padded to 8 (TMA/im2col friendly)."""
-  if not enabled("image") or images.dtype != torch.uint8 or dtype != torch.bfloat16 or images.dim() != 4 or not images.is_contiguous():
+  if not enabled("image") or images.dtype != torch.uint8 or dtype not in _DTYPES or images.dim() != 4 or not images.is_contiguous():
     return None
   n, h, w, c = images.shape
   if c > 3:
@@ -742,7 +788,7 @@ def image_normalize(images, mode, dtype):
   m0, m1, m2, scale = _MEANS.get(mode, _MEANS["lenet"])
   if mode == "vgg" and c != 3:
     m0, m1, m2, scale = _MEANS["lenet"]
-  out = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=images.device)
-  _check(_lib().agb_image_normalize(_ptr(images), _ptr(out), ctypes.c_longlong(n * h * w), ctypes.c_int(c), ctypes.c_int(c), ctypes.c_float(m0), ctypes.c_float(m1),
+  out = torch.empty((n, h, w, c), dtype=dtype, device=images.device)
+  _check(_fn("agb_image_normalize", out)(_ptr(images), _ptr(out), ctypes.c_longlong(n * h * w), ctypes.c_int(c), ctypes.c_int(c), ctypes.c_float(m0), ctypes.c_float(m1),
                                     ctypes.c_float(m2), ctypes.c_float(scale), _stream()), "image_normalize")
   return out.permute(0, 3, 1, 2)

@@ -83,3 +83,54 @@ def test_linear_and_pointwise_conv_layers():
     results[backend] = (y.float(), dx.float(), gw)
   for a, b in zip(results["torch"], results["native"]):
     _check(b, a, tol=2e-2)
+
+
+# ---------------------------------------------------------------------------- #
+# TF32 path (kind::tf32): fp32 operands straight from memory, fp32 accumulation and output — the parity precision of the fp32 reference
+
+def _rand32(shape, seed):
+  gen = torch.Generator(device="cuda").manual_seed(seed)
+  return torch.randn(shape, device="cuda", generator=gen)
+
+
+def _tf32_tol(k):
+  return 2e-3 * max(1.0, (k / 64.0) ** 0.5)   # operands truncated to 10 mantissa bits: ~1e-3 relative per product, random-walk over k
+
+
+TF32_SHAPES = [(128, 128, 32), (256, 64, 128), (300, 200, 136), (32, 12, 104), (1000, 192, 4096), (25088, 256, 64), (77, 1000, 2048), (130, 72, 8)]
+
+
+@pytest.mark.parametrize("m,n,k", TF32_SHAPES)
+def test_tf32_mm_nt(m, n, k):
+  from aggregathor_b200.ops import nn_native as nat
+  x, w = _rand32((m, k), 11), _rand32((n, k), 12)
+  ref = x.double() @ w.double().t()
+  out = nat.mm_nt(x, w)
+  assert out.dtype == torch.float32
+  _check(out, ref.float(), tol=_tf32_tol(k))
+  bias = torch.randn(n, device="cuda")
+  _check(nat.mm_nt(x, w, bias=bias, relu=True), torch.relu(ref.float() + bias), tol=_tf32_tol(k))
+  _check(nat.mm_nt(x, w, bn=64), ref.float(), tol=_tf32_tol(k))
+
+
+@pytest.mark.parametrize("m,n,k", TF32_SHAPES)
+def test_tf32_mm_nn_and_tn(m, n, k):
+  from aggregathor_b200.ops import nn_native as nat
+  x, w = _rand32((m, k), 13), _rand32((k, n), 14)
+  _check(nat.mm_nn(x, w), (x.double() @ w.double()).float(), tol=_tf32_tol(k))
+  a, b = _rand32((k, m), 15), _rand32((k, n), 16)
+  ref = (a.double().t() @ b.double()).float()
+  _check(nat.mm_tn(a, b, splits=1), ref, tol=_tf32_tol(k))
+  _check(nat.mm_tn(a, b), ref, tol=_tf32_tol(k))
+
+
+def test_tf32_grouped_weight_gradient():
+  from aggregathor_b200.ops import nn_native as nat
+  groups, k, m, n = 4, 392, 96, 160
+  a, b = _rand32((groups * k, m), 17), _rand32((groups * k, n), 18)
+  rows = torch.zeros((groups, m * n + 64), device="cuda")
+  out = rows[0, :m * n].view(m, n)
+  nat.mm_tn(a, b, out=out, groups=groups, group_stride=rows.stride(0))
+  for g in range(groups):
+    ref = (a[g * k:(g + 1) * k].double().t() @ b[g * k:(g + 1) * k].double()).float()
+    _check(rows[g, :m * n].view(m, n), ref, tol=_tf32_tol(k))

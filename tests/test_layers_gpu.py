@@ -138,6 +138,95 @@ def test_rectangular_conv(kh, kw, stride, padding):
     _close(got, want, 2e-2)
 
 
+@pytest.mark.parametrize("cin,cout,k,stride,hw,pads", [(64, 64, 3, 1, 28, (1, 1, 1, 1)), (128, 96, 3, 2, 28, (1, 1, 1, 1)), (32, 64, 5, 1, 14, (2, 2, 2, 2)), (256, 128, 1, 1, 14, (0, 0, 0, 0)),
+                                                        (3, 64, 7, 2, 64, (3, 3, 3, 3)), (96, 32, 3, 1, 7, (1, 1, 1, 1))])
+def test_conv_tf32(cin, cout, k, stride, hw, pads):
+  """TF32 convolution path (fp32 activations and weights, kind::tf32 products) vs fp64 autograd: forward, wgrad, bias grad, dgrad."""
+  import torch.nn.functional as F
+  from aggregathor_b200.ops import nn as ops
+  n = 4
+  gen = torch.Generator(device="cuda").manual_seed(7)
+  x = torch.randn((n, cin, hw, hw), device="cuda", generator=gen).contiguous(memory_format=torch.channels_last)
+  w = (torch.randn((cout, k, k, cin), device="cuda", generator=gen) * (2.0 / (k * k * cin)) ** 0.5).contiguous()
+  bias = torch.randn(cout, device="cuda", generator=gen) * 0.1
+  xp = F.pad(x.double(), (pads[2], pads[3], pads[0], pads[1])).requires_grad_(True)
+  wf = w.double().permute(0, 3, 1, 2).clone().requires_grad_(True)
+  bf = bias.double().clone().requires_grad_(True)
+  pre = F.conv2d(xp, wf, bf, stride)
+  before = dict(ops.fallbacks)
+  y = ops.conv2d_forward("native", x, w, bias, stride, pads, True)
+  assert y.dtype == torch.float32
+  _close(y, torch.relu(pre).detach().float(), 4e-3)
+  dy = torch.randn(tuple(pre.shape), device="cuda", generator=gen).contiguous(memory_format=torch.channels_last)
+  pre.backward(dy.double() * (y > 0).double())
+  gw, gb = torch.zeros((cout, k, k, cin), device="cuda"), torch.zeros(cout, device="cuda")
+  dx, _, _ = ops.conv2d_backward("native", dy, x, w, y, stride, pads, True, True, cin % 8 == 0, gw, gb)
+  assert ops.fallbacks == before, "served by the aten provider"
+  _close(gw, wf.grad.permute(0, 2, 3, 1).float(), 4e-3)
+  _close(gb, bf.grad.float(), 4e-3)
+  if dx is not None:
+    _close(dx, xp.grad[:, :, pads[0]:pads[0] + hw, pads[2]:pads[2] + hw].float(), 4e-3)
+
+
+def test_resnet_step_tf32_matches_fp32_reference():
+  """One ResNet training step (slim resnet_v1_18, 64x64, per-worker groups) on the TF32 native path vs the aten provider in strict fp32:
+  loss to 1e-3, every gradient to 1 % of its scale."""
+  from aggregathor_b200.engine.flat import FlatLayout
+  from aggregathor_b200.models import Context, nets_factory
+  from aggregathor_b200.ops import nn as ops
+  torch.backends.cudnn.allow_tf32 = False
+  torch.backends.cuda.matmul.allow_tf32 = False
+  results = {}
+  for backend in ("native", "torch"):
+    model = nets_factory.get_network("resnet_v1_18", 16)
+    layout, states = FlatLayout(), {}
+    model.declare(layout, states)
+    layout.freeze()
+    host = torch.zeros(layout.padded_size)
+    host_states = {k: torch.zeros(v) for k, v in states.items()}
+    model.initialize(layout.views(host), host_states, torch.Generator().manual_seed(1))
+    params = host.cuda()
+    ctx = Context(backend, True, torch.float32, "cuda")
+    ctx.master = ctx.weights = layout.views(params)
+    ctx.state = {k: v.cuda() for k, v in host_states.items()}
+    grads = torch.zeros_like(params)
+    ctx.grads = layout.views(grads)
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn((8, 3, 64, 64), device="cuda", generator=gen).contiguous(memory_format=torch.channels_last)
+    labels = torch.randint(0, 16, (8,), device="cuda", generator=gen)
+    before = dict(ops.fallbacks)
+    loss = float(model.loss_and_backward(x, labels, ctx))
+    if backend == "native":
+      assert ops.fallbacks == before, {k: v - before.get(k, 0) for k, v in ops.fallbacks.items() if v != before.get(k, 0)}
+    results[backend] = (loss, grads, layout)
+  assert abs(results["native"][0] - results["torch"][0]) < 2e-3 * max(1.0, abs(results["torch"][0]))
+  layout = results["torch"][2]
+  for name in layout.names:
+    got, want = layout.view(results["native"][1], name), layout.view(results["torch"][1], name)
+    scale = float(want.abs().max())
+    assert float((got - want).abs().max()) <= 1e-2 * max(scale, 1e-3), (name, float((got - want).abs().max()), scale)
+
+
+def test_deterministic_weight_gradients():
+  """`set_deterministic(True)`: no split-K => the weight gradient of a GEMM-shaped and of an implicit-GEMM layer is bit-identical from run to run."""
+  from aggregathor_b200.ops import nn as ops
+  from aggregathor_b200.ops import nn_native
+  nn_native.set_deterministic(True)
+  try:
+    x, dy = _rand((8, 128, 28, 28), 41), _rand((8, 128, 28, 28), 42)
+    for k in (1, 3):
+      w = _rand((128, k, k, 128), 43, scale=0.05).contiguous()
+      pads = ((k - 1) // 2,) * 4
+      runs = []
+      for _ in range(3):
+        gw = torch.zeros((128, k, k, 128), device="cuda")
+        ops.conv2d_backward("native", dy, x, w, None, 1, pads, False, False, True, gw, None)
+        runs.append(gw.clone())
+      assert torch.equal(runs[0], runs[1]) and torch.equal(runs[0], runs[2])
+  finally:
+    nn_native.set_deterministic(False)
+
+
 def test_pools_and_eltwise():
   from aggregathor_b200.ops import nn as ops
   x = _rand((8, 64, 112, 112), 6)
