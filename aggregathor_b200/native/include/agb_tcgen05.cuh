@@ -132,18 +132,63 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
         v[i] = __uint_as_float(r[i]);
 }
 
+// ---- CTA pairs (cta_group::2): two CTAs of a cluster on the two SMs of a TPC issue ONE MMA over a 256-row tile ------------- //
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    return rank;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t smem_addr, uint32_t rank) {
+    uint32_t out;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(out) : "r"(smem_addr), "r"(rank));
+    return out;
+}
+__device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" :: "r"(cluster_addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
+}
+// TMA load whose completion bytes are credited to a barrier of the pair's leader CTA (`bar_cluster_addr` from mapa_shared(.., 0))
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, CUtensorMap const* map, uint32_t bar_cluster_addr, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1) : "memory");
+}
+template<uint32_t kCols> __device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem) {   // one warp of EACH CTA of the pair, same dst offset
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(dst_smem)), "n"(kCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template<uint32_t kCols> __device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(taddr), "n"(kCols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[256 rows: 128 from each CTA's smem] * B[N columns: N/2 from each CTA's smem]; issued by the leader CTA only.
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(static_cast<uint32_t>(accumulate)) : "memory");
+}
+// Arrive on the barrier at this shared-memory offset in every CTA of `cta_mask` once the MMAs issued so far have completed.
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" :: "r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+
 // ---- descriptors ---------------------------------------------------------------- //
 // Shared-memory matrix descriptor, 128-byte swizzle, bf16/fp16 operands.
 //   K-major  (rows = M/N index, 64 K-elements = 128 B per row): SBO = 1024 B (8 rows), LBO unused (1).
 //   MN-major (rows = K index, 64 MN-elements = 128 B per row): SBO = 1024 B (8 k-rows), LBO = byte distance
 //            between consecutive 64-element MN chunks.
-__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// `layout_type`: 2 = SWIZZLE_128B (16-byte chunks; every bf16 operand, K-major tf32 operands), 1 = SWIZZLE_128B_BASE32B (32-byte chunks
+// over 4-row atoms: the only layout of MN-major 32-bit operands; its k-groups are 4 rows = 512 B apart when rows are packed).
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type = 2) {
     uint64_t desc = 0;
     desc |= static_cast<uint64_t>((smem_addr & 0x3ffff) >> 4);            // start address, bits [0,14)
     desc |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3fff) << 16;       // leading byte offset, bits [16,30)
     desc |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3fff) << 32;       // stride byte offset, bits [32,46)
     desc |= static_cast<uint64_t>(1) << 46;                               // descriptor version (Blackwell)
-    desc |= static_cast<uint64_t>(2) << 61;                               // layout type: SWIZZLE_128B
+    desc |= static_cast<uint64_t>(layout_type) << 61;                     // layout type
     return desc;
 }
 // Instruction descriptor for kind::f16 / kind::tf32 with fp32 accumulators; `format`: 0 = F16, 1 = BF16, 2 = TF32 (both operands).
@@ -190,7 +235,7 @@ inline EncodeTiledFn encode_tiled_fn() {
 struct TmapKey {
     void const* base;
     uint64_t dims[4], strides[3];
-    uint32_t box[4], elem[4], rank, dtype;
+    uint32_t box[4], elem[4], rank, dtype, swizzle, pad;
     bool operator==(TmapKey const& o) const { return std::memcmp(this, &o, sizeof(TmapKey)) == 0; }
 };
 struct TmapKeyHash {
@@ -203,12 +248,12 @@ struct TmapKeyHash {
     }
 };
 inline int encode_cached(CUtensorMap* map, CUtensorMapDataType dtype, uint32_t rank, void const* base, cuuint64_t const* dims, cuuint64_t const* strides, cuuint32_t const* box,
-                         cuuint32_t const* elem) {
+                         cuuint32_t const* elem, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
     static std::mutex mutex;
     TmapKey key;
     std::memset(&key, 0, sizeof(key));
-    key.base = base; key.rank = rank; key.dtype = static_cast<uint32_t>(dtype);
+    key.base = base; key.rank = rank; key.dtype = static_cast<uint32_t>(dtype); key.swizzle = static_cast<uint32_t>(swizzle);
     for (uint32_t i = 0; i < rank; ++i) {
         key.dims[i] = dims[i]; key.box[i] = box[i]; key.elem[i] = elem[i];
         if (i + 1 < rank)
@@ -225,7 +270,7 @@ inline int encode_cached(CUtensorMap* map, CUtensorMapDataType dtype, uint32_t r
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn)
         return 201;
-    CUresult res = fn(map, dtype, rank, const_cast<void*>(base), dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+    CUresult res = fn(map, dtype, rank, const_cast<void*>(base), dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (res != CUDA_SUCCESS) {
         std::fprintf(stderr, "[agb] cuTensorMapEncodeTiled(rank %u) failed (%d): base %p dims %llu %llu %llu %llu box %u %u %u %u\n", rank, (int) res, base, (unsigned long long) dims[0],
@@ -241,12 +286,16 @@ inline int encode_cached(CUtensorMap* map, CUtensorMapDataType dtype, uint32_t r
 }
 
 // 2-D bf16 tensor map: `inner` contiguous elements per row, `rows` rows of `row_stride` elements, box = box_inner x box_rows, 128B swizzle.
-inline int make_tmap_2d(CUtensorMap* map, void const* base, uint64_t inner, uint64_t rows, uint64_t row_stride, uint32_t box_inner, uint32_t box_rows, int elem_bytes) {
+// MN-major 32-bit (tf32) operands must be laid out with 32-byte swizzle chunks (UMMA SWIZZLE_128B_BASE32B); everything else with 16-byte chunks.
+inline CUtensorMapSwizzle tmap_swizzle(int elem_bytes, bool mn_major) {
+    return (elem_bytes == 4 && mn_major) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
+}
+inline int make_tmap_2d(CUtensorMap* map, void const* base, uint64_t inner, uint64_t rows, uint64_t row_stride, uint32_t box_inner, uint32_t box_rows, int elem_bytes, bool mn_major = false) {
     cuuint64_t dims[2] = {inner, rows};
     cuuint64_t strides[1] = {row_stride * elem_bytes};
     cuuint32_t box[2] = {box_inner, box_rows};
     cuuint32_t elem[2] = {1, 1};
-    return encode_cached(map, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, elem);
+    return encode_cached(map, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, elem, tmap_swizzle(elem_bytes, mn_major));
 }
 inline int make_tmap_2d_bf16(CUtensorMap* map, void const* base, uint64_t inner, uint64_t rows, uint64_t row_stride, uint32_t box_inner, uint32_t box_rows) {
     return make_tmap_2d(map, base, inner, rows, row_stride, box_inner, box_rows, 2);
@@ -254,12 +303,12 @@ inline int make_tmap_2d_bf16(CUtensorMap* map, void const* base, uint64_t inner,
 
 // 3-D bf16 tensor map over a row-major [groups][rows][inner] view (row stride `row_stride`, group stride `rows * row_stride`):
 // boxes never straddle a group, rows past the end of a group are zero-filled (grouped weight-gradient GEMMs).
-inline int make_tmap_3d(CUtensorMap* map, void const* base, uint64_t inner, uint64_t rows, uint64_t groups, uint64_t row_stride, uint32_t box_inner, uint32_t box_rows, int elem_bytes) {
+inline int make_tmap_3d(CUtensorMap* map, void const* base, uint64_t inner, uint64_t rows, uint64_t groups, uint64_t row_stride, uint32_t box_inner, uint32_t box_rows, int elem_bytes, bool mn_major = false) {
     cuuint64_t dims[3] = {inner, rows, groups};
     cuuint64_t strides[2] = {row_stride * elem_bytes, rows * row_stride * elem_bytes};
     cuuint32_t box[3] = {box_inner, box_rows, 1};
     cuuint32_t elem[3] = {1, 1, 1};
-    return encode_cached(map, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, elem);
+    return encode_cached(map, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, elem, tmap_swizzle(elem_bytes, mn_major));
 }
 inline int make_tmap_3d_bf16(CUtensorMap* map, void const* base, uint64_t inner, uint64_t rows, uint64_t groups, uint64_t row_stride, uint32_t box_inner, uint32_t box_rows) {
     return make_tmap_3d(map, base, inner, rows, groups, row_stride, box_inner, box_rows, 2);

@@ -39,13 +39,13 @@ enum ConvMode { kFwd = 0, kDgrad = 1, kWgrad = 2 };
 
 // `estride` > 1: the box covers bw * estride x bh * estride source pixels and TMA keeps every estride-th one (bw x bh land in smem).
 template<typename E>
-inline int make_tmap_4d(CUtensorMap* map, void const* base, int C, int W, int H, int N, int bw, int bh, int bn, int estride = 1) {
+inline int make_tmap_4d(CUtensorMap* map, void const* base, int C, int W, int H, int N, int bw, int bh, int bn, int estride = 1, bool mn_major = false) {
     constexpr cuuint64_t kB = E::kBytes;
     cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(N)};
     cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * kB, static_cast<cuuint64_t>(W) * C * kB, static_cast<cuuint64_t>(H) * W * C * kB};
     cuuint32_t box[4] = {static_cast<cuuint32_t>(E::kChunk), static_cast<cuuint32_t>(bw * estride), static_cast<cuuint32_t>(bh * estride), static_cast<cuuint32_t>(bn)};
     cuuint32_t elem[4] = {1, static_cast<cuuint32_t>(estride), static_cast<cuuint32_t>(estride), 1};
-    return encode_cached(map, E::kTf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, elem);
+    return encode_cached(map, E::kTf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, elem, tmap_swizzle(E::kBytes, mn_major));
 }
 
 // One persistent kernel for the three products. `tmap_a`: 4-D map of the activation that plays A (x for fwd, dy for dgrad and
@@ -354,7 +354,7 @@ int conv_implicit_impl(int mode, void const* act, void const* other, void* out, 
             bn = Cin <= 64 ? 64 : 128;
         if ((status = make_tmap_4d<E>(&ta, act, Cout, OW, OH, N, cp.bw, cp.bh, cp.bn)))
             return status;
-        if ((status = make_tmap_2d(&tb, other, static_cast<uint64_t>(k) * k * Cin, Cout, static_cast<uint64_t>(k) * k * Cin, E::kChunk, E::kBK, E::kBytes)))
+        if ((status = make_tmap_2d(&tb, other, static_cast<uint64_t>(k) * k * Cin, Cout, static_cast<uint64_t>(k) * k * Cin, E::kChunk, E::kBK, E::kBytes, true)))
             return status;
         items_mn = pixel_tiles * ((Cin + bn - 1) / bn) * stride * stride;   // one sub-problem per pixel parity
         total_kblocks = k * k * (Cout / E::kChunk);
@@ -366,9 +366,9 @@ int conv_implicit_impl(int mode, void const* act, void const* other, void* out, 
             return 205;
         if (bn == 0)
             bn = Cin <= 64 ? 64 : 128;
-        if ((status = make_tmap_4d<E>(&ta, act, Cout, OW, OH, N, cp.bw, cp.bh, cp.bn)))
+        if ((status = make_tmap_4d<E>(&ta, act, Cout, OW, OH, N, cp.bw, cp.bh, cp.bn, 1, true)))
             return status;
-        if ((status = make_tmap_4d<E>(&tb, other, Cin, W, H, N, cp.bw, cp.bh, cp.bn, stride)))
+        if ((status = make_tmap_4d<E>(&tb, other, Cin, W, H, N, cp.bw, cp.bh, cp.bn, stride, true)))
             return status;
         items_mn = k * k * ((Cout + kBM - 1) / kBM) * ((Cin + bn - 1) / bn);
         total_kblocks = pixel_tiles / groups;

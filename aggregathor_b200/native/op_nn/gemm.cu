@@ -1,5 +1,6 @@
 // C entry points of the tcgen05 GEMM (kernels: gemm_kernels.cuh).
 #include "gemm_kernels.cuh"
+#include "gemm2_kernels.cuh"
 
 extern "C" {
 
@@ -74,6 +75,26 @@ int agb_gemm_bf16_grouped(void const* A, void const* B, void* C, int M, int N, i
     return b_mn ? dispatch_bn<false, true>(bn, ta, tb, p, splits, s) : dispatch_bn<false, false>(bn, ta, tb, p, splits, s);
 }
 
+// CTA-pair kernel (cta_group::2, 256 x 256 tiles): C[M,N] = A[M,K] * B[N,K]^T, both operands K-major bf16 (+bias, ReLU); for large
+// products (`ops/nn_native.py` picks it when the tile count fills the chip).
+int agb_gemm_bf16_pair(void const* A, void const* B, void* C, int M, int N, int K, long long lda, long long ldb, long long ldc, void const* bias, int relu, int out_fp32, void* stream) {
+    if (M <= 0 || N <= 0 || K <= 0)
+        return 0;
+    if ((lda & 7) || (ldb & 7) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15))
+        return 204;
+    GemmParams p{};
+    p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.C = C;
+    p.bias = static_cast<float const*>(bias);
+    p.relu = relu; p.out_fp32 = out_fp32; p.atomic = 0; p.groups = 1;
+    CUtensorMap ta, tb;
+    int status;
+    if ((status = make_tmap_2d_bf16(&ta, A, static_cast<uint64_t>(K), static_cast<uint64_t>(M), static_cast<uint64_t>(lda), kBK, kBM)))
+        return status;
+    if ((status = make_tmap_2d_bf16(&tb, B, static_cast<uint64_t>(K), static_cast<uint64_t>(N), static_cast<uint64_t>(ldb), kBK, 128)))
+        return status;
+    return launch_pair_gemm<256>(ta, tb, p, static_cast<cudaStream_t>(stream));
+}
+
 // fp32 operands multiplied as TF32 (kind::tf32), fp32 accumulation and output: same layouts and options as agb_gemm_bf16_grouped;
 // lda / ldb multiples of 4 elements, bases 16-byte aligned, bn in {64, 128} (0 = automatic), C is fp32.
 int agb_gemm_tf32_grouped(void const* A, void const* B, void* C, int M, int N, int K, long long lda, long long ldb, long long ldc,
@@ -105,17 +126,17 @@ int agb_gemm_tf32_grouped(void const* A, void const* B, void* C, int M, int N, i
     int status;
     uint64_t const m = static_cast<uint64_t>(M), n = static_cast<uint64_t>(N), k = static_cast<uint64_t>(K), g = static_cast<uint64_t>(groups);
     if (a_mn && b_mn)
-        status = make_tmap_3d(&ta, A, m, k, g, static_cast<uint64_t>(lda), E::kChunk, E::kBK, 4);
+        status = make_tmap_3d(&ta, A, m, k, g, static_cast<uint64_t>(lda), E::kChunk, E::kBK, 4, true);
     else if (a_mn)
-        status = make_tmap_2d(&ta, A, m, k, static_cast<uint64_t>(lda), E::kChunk, E::kBK, 4);
+        status = make_tmap_2d(&ta, A, m, k, static_cast<uint64_t>(lda), E::kChunk, E::kBK, 4, true);
     else
         status = make_tmap_2d(&ta, A, k, m, static_cast<uint64_t>(lda), E::kBK, kBM, 4);
     if (status)
         return status;
     if (a_mn && b_mn)
-        status = make_tmap_3d(&tb, B, n, k, g, static_cast<uint64_t>(ldb), E::kChunk, E::kBK, 4);
+        status = make_tmap_3d(&tb, B, n, k, g, static_cast<uint64_t>(ldb), E::kChunk, E::kBK, 4, true);
     else if (b_mn)
-        status = make_tmap_2d(&tb, B, n, k, static_cast<uint64_t>(ldb), E::kChunk, E::kBK, 4);
+        status = make_tmap_2d(&tb, B, n, k, static_cast<uint64_t>(ldb), E::kChunk, E::kBK, 4, true);
     else
         status = make_tmap_2d(&tb, B, k, n, static_cast<uint64_t>(ldb), E::kBK, static_cast<uint32_t>(bn), 4);
     if (status)

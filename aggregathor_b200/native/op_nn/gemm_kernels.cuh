@@ -328,8 +328,10 @@ __device__ __forceinline__ void consume_stage(uint32_t a_addr, uint32_t tmem_acc
     for (int kk = 0; kk < E::kBK / E::kUmmaK; ++kk) {
         // K-major: one instruction's K = 32 B further inside the 128B swizzled row.
         // MN-major: kUmmaK k-rows = kUmmaK * 128 B further; chunks of kChunk MN-elements are kChunkBytes apart.
-        uint64_t const da = A_MN ? umma_smem_desc(a_addr + kk * E::kUmmaK * 128, kChunkBytes, 1024) : umma_smem_desc(a_addr + kk * 32, 16, 1024);
-        uint64_t const db = B_MN ? umma_smem_desc(b_addr + kk * E::kUmmaK * 128, kChunkBytes, 1024) : umma_smem_desc(b_addr + kk * 32, 16, 1024);
+        // MN-major tf32: 32-byte-chunk swizzle over 4-row atoms (SWIZZLE_128B_BASE32B), k-groups of 4 rows 512 B apart.
+        constexpr uint32_t kMnSbo = E::kTf32 ? 512 : 1024, kMnLayout = E::kTf32 ? 1 : 2;
+        uint64_t const da = A_MN ? umma_smem_desc(a_addr + kk * E::kUmmaK * 128, kChunkBytes, kMnSbo, kMnLayout) : umma_smem_desc(a_addr + kk * 32, 16, 1024);
+        uint64_t const db = B_MN ? umma_smem_desc(b_addr + kk * E::kUmmaK * 128, kChunkBytes, kMnSbo, kMnLayout) : umma_smem_desc(b_addr + kk * 32, 16, 1024);
         if (E::kTf32)
             umma_tf32(tmem_acc, da, db, idesc, !(first && kk == 0));
         else

@@ -164,14 +164,42 @@ def _gemm(a, b, out, M, N, K, a_mn, b_mn, bias, relu, splits, bn, groups=1, grou
   return out
 
 
+# CTA-pair GEMM (`tcgen05.mma.cta_group::2`, 256 x 256 tiles, `native/op_nn/gemm2_kernels.cuh`): for products whose 256 x 256 tiles fill
+# the 74 SM pairs of the chip. AGB_GEMM_PAIR=0 disables, =2 forces it for every K-major bf16 product.
+_PAIR = os.environ.get("AGB_GEMM_PAIR", "1")
+
+
+def set_gemm_pair(mode):
+  """"0": never, "1": large products only (default), "2": every NT bf16 product."""
+  global _PAIR
+  _PAIR = str(mode)
+
+
+def _use_pair(M, N, K, bn):
+  if _PAIR == "0" or bn not in (0, 512):
+    return False
+  if _PAIR == "2" or bn == 512:
+    return True
+  tiles = ((M + 255) // 256) * ((N + 255) // 256)
+  return N >= 256 and K >= 256 and tiles >= 64
+
+
 def mm_nt(x, w, bias=None, relu=False, out=None, out_dtype=None, bn=0):
-  """x[M,K] @ w[N,K]^T (+ fp32 bias[N], ReLU). fp32 operands are multiplied as TF32."""
+  """x[M,K] @ w[N,K]^T (+ fp32 bias[N], ReLU). fp32 operands are multiplied as TF32. `bn=512` forces the CTA-pair kernel."""
   x = _rows(x)
   w = _rows(w, x.dtype)
   M, K = x.shape
   N = w.shape[0]
   if out is None:
     out = alloc_out(M, N, (out_dtype or x.dtype) if x.dtype == torch.bfloat16 else torch.float32, x.device)
+  if x.dtype == torch.bfloat16 and _use_pair(M, N, K, bn):
+    if bias is not None and bias.dtype != torch.float32:
+      bias = bias.float()
+    _check(_lib().agb_gemm_bf16_pair(_ptr(x), _ptr(w), _ptr(out), ctypes.c_int(M), ctypes.c_int(N), ctypes.c_int(K), ctypes.c_longlong(x.stride(0)), ctypes.c_longlong(w.stride(0)),
+                                     ctypes.c_longlong(out.stride(0)), _ptr(bias), ctypes.c_int(1 if relu else 0), ctypes.c_int(1 if out.dtype == torch.float32 else 0), _stream()), "gemm_bf16_pair")
+    return out
+  if bn == 512:
+    bn = 0
   if bias is not None and bias.dtype != torch.float32:
     bias = bias.float()
   return _gemm(x, w, out, M, N, K, False, False, bias, relu, 1, bn)

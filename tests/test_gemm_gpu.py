@@ -85,6 +85,18 @@ def test_linear_and_pointwise_conv_layers():
     _check(b, a, tol=2e-2)
 
 
+@pytest.mark.parametrize("m,n,k", [(256, 256, 64), (512, 256, 128), (300, 200, 136), (1000, 192, 4096), (25088, 256, 64), (77, 1000, 2048), (4096, 384, 4096), (130, 70, 8), (2048, 1024, 1024)])
+def test_pair_gemm(m, n, k):
+  """CTA-pair kernel (tcgen05.mma.cta_group::2, 256 x 256 tiles) vs fp32 matmul, ragged edges included."""
+  from aggregathor_b200.ops import nn_native as nat
+  x, w = _rand((m, k), 21), _rand((n, k), 22)
+  ref = x.float() @ w.float().t()
+  _check(nat.mm_nt(x, w, out_dtype=torch.float32, bn=512), ref)
+  _check(nat.mm_nt(x, w, bn=512), ref, tol=1e-2)
+  bias = torch.randn(n, device="cuda")
+  _check(nat.mm_nt(x, w, bias=bias, relu=True, out_dtype=torch.float32, bn=512), torch.relu(ref + bias))
+
+
 # ---------------------------------------------------------------------------- #
 # TF32 path (kind::tf32): fp32 operands straight from memory, fp32 accumulation and output — the parity precision of the fp32 reference
 
