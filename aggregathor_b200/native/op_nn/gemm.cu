@@ -4,6 +4,13 @@
 
 extern "C" {
 
+// 1 = 128 x 256 tiles for N >= 256 when the caller leaves the choice open (default), 0 = 128 x 128.
+static int g_wide_tiles = 1;
+int agb_gemm_set_wide_tiles(int enabled) {
+    g_wide_tiles = enabled ? 1 : 0;
+    return 0;
+}
+
 // 1 = persistent kernel (default), 0 = one tile per CTA.
 int agb_gemm_set_persistent(int enabled) {
     g_persistent = enabled ? 1 : 0;
@@ -39,8 +46,12 @@ int agb_gemm_bf16_grouped(void const* A, void const* B, void* C, int M, int N, i
         splits = 1;
     if (splits > 1 && !out_fp32)
         return 205;
-    if (bn == 0)
-        bn = N <= 64 ? 64 : 128;
+    if (bn == 0) {
+        // 128 x 256 tiles halve the B re-reads per flop and the MMA count per tile: measured 1.2-1.4x over 128 x 128 (`profiles/r2_gemm_tile_bench.txt`)
+        // whenever there are enough of them to occupy the chip
+        long long const wide_tiles = static_cast<long long>((M + kBM - 1) / kBM) * ((N + 255) / 256) * (groups > 1 ? groups : 1) * (splits > 1 ? splits : 1);
+        bn = N <= 64 ? 64 : (N >= 256 && g_wide_tiles && wide_tiles >= 96 ? 256 : 128);
+    }
     int const total_kblocks = (K + kBK - 1) / kBK;
     if (splits > total_kblocks)
         splits = total_kblocks;

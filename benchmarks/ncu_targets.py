@@ -27,6 +27,19 @@ if what in ("gemm", "all"):
   dy = rand(100352, 256)
   for _ in range(3):
     nat.mm_tn(dy, x)                                   # its weight gradient (split-K)
+if what == "gemm_wide":      # the shipped default for N >= 256: 128 x 256 tiles, persistent, double-buffered TMEM
+  a, b = rand(8192, 8192), rand(8192, 8192)
+  nat.set_gemm_pair("0")
+  for _ in range(3):
+    nat.mm_nt(a, b)
+if what == "gemm_pair":      # CTA-pair kernel (cta_group::2)
+  a, b = rand(8192, 8192), rand(8192, 8192)
+  for _ in range(3):
+    nat.mm_nt(a, b, bn=512)
+if what == "gemm_tf32":
+  a, b = torch.randn((8192, 8192), device="cuda"), torch.randn((8192, 8192), device="cuda")
+  for _ in range(3):
+    nat.mm_nt(a, b)
 if what in ("conv", "all"):
   x = rand(32, 64, 56, 56).contiguous(memory_format=CL)
   w = rand(64, 3, 3, 64)
