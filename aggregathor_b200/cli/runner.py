@@ -75,6 +75,7 @@ def make_parser():
   add("--engine", type=str, default="auto", choices=("auto", "fused", "baseline", "host"), help="Aggregation engine: fused sm_100a kernel over peer memory, NCCL all-gather baseline, or host C++")
   add("--nn-backend", type=str, default="auto", choices=("auto", "native", "torch"), help="Provider of the model kernels: hand-written sm_100a kernels or the torch/cuDNN library reference")
   add("--seed", type=int, default=0, help="Seed of the parameter initialisation and of the input streams")
+  add("--dtype", type=str, default="auto", choices=("auto", "bf16", "tf32", "fp32"), help="Compute precision on the GPU: bf16 tensor-core products (default), or fp32 storage with TF32 products (the precision class of the fp32 reference); fp32 on CPU")
   add("--debug-checksum", action="store_true", default=False, help="Check after every step that all ranks hold bit-identical parameters")
   add("--authenticate", action="store_true", default=False, help="Sign every published gradient (ed25519) and verify before aggregating; slices failing the check become NaN")
   return parser
@@ -247,7 +248,8 @@ def main(argv=None):
       engine = "baseline" if device.type == "cuda" else "host"  # absent workers: the GAR sees fewer rows than declared (reference behaviour)
     graph_mgr = Manager(experiment, aggregator, nb_instantiated, args.optimizer, args.optimizer_args, args.learning_rate, args.learning_rate_args,
                         (args.l1_regularize, args.l2_regularize), trace=args.trace, attack=attack, nb_real_byz=args.nb_real_byz_workers if attacked else 0,
-                        device=device, engine=engine, backend=args.nn_backend, seed=args.seed, placement=placement, debug_checksum=args.debug_checksum, authenticate=args.authenticate)
+                        device=device, engine=engine, backend=args.nn_backend, seed=args.seed, placement=placement, debug_checksum=args.debug_checksum, authenticate=args.authenticate,
+                        dtype={"bf16": torch.bfloat16, "tf32": torch.float32, "fp32": torch.float32}.get(args.dtype))
   if exit_pending:
     return 0
 

@@ -72,10 +72,13 @@ class Manager:
     plain_step = attack is None and not authenticate and not ((self.l1 or -1.) > 0. or (self.l2 or -1.) > 0.)
     if cuda and engine in ("auto", "fused") and aggregator.fused_spec() is not None:
       engine_args.setdefault("device_state", True)
-      # the bucketed distance pass hides NVLink latency under the backward pass; with a single rank there is none to hide and the extra
-      # staged copy only costs HBM bandwidth (measured: 29.3 -> 30.5 ms/step on 1 GPU): off unless forced with AGB_OVERLAP=2
+      # The bucketed distance pass moves the gather + distance work under the backward pass. It pays when the backward pass leaves the
+      # memory system idle — one batch-32 worker per rank, latency-bound kernels — and costs when the backward pass is itself
+      # bandwidth-bound (several batched workers per rank: measured 15.2 -> 15.7..16.1 ms/step at 2 ranks x 4 workers, 29.3 -> 30.5 on
+      # 1 rank, `profiles/README.md`). Default: on for single-worker ranks of multi-rank jobs; AGB_OVERLAP=0 off, =2 always.
       overlap = os.environ.get("AGB_OVERLAP", "1")
-      if plain_step and aggregator.fused_spec().rule in ("krum", "bulyan") and (overlap == "2" or (overlap not in ("", "0") and self.world > 1)) and "buckets" not in engine_args:
+      single_worker_ranks = self.world > 1 and nbworkers == self.world
+      if plain_step and aggregator.fused_spec().rule in ("krum", "bulyan") and (overlap == "2" or (overlap not in ("", "0") and single_worker_ranks)) and "buckets" not in engine_args:
         buckets, self._bucket_layers = self._plan_buckets()
         if len(buckets) > 1:
           engine_args["buckets"] = buckets
@@ -86,6 +89,9 @@ class Manager:
     if not getattr(self.aggregation, "overlappable", False):
       self._bucket_layers = {}
     self._side_stream = None
+    if cuda and backend == "native" and self.aggregation.w == 1 and "AGB_PDL" not in os.environ and "AGB_WGRAD_STREAM" not in os.environ and os.environ.get("AGB_LAUNCH_OVERLAP", "1") != "0":
+      from ..ops import nn_native
+      nn_native.set_launch_overlap(True)   # one batch-32 worker per rank: small kernels, overlap their launches and the weight gradients
     self.w = self.aggregation.w
     self.params = self.aggregation.params
     self.grads = self.aggregation.grads

@@ -26,13 +26,20 @@ __device__ __forceinline__ void pdl_wait() {
 __device__ __forceinline__ void pdl_trigger() {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
+inline int& pdl_state() {
+    static int state = -1;   // -1: read AGB_PDL at first use; 0 / 1: set (environment or `set_pdl`)
+    return state;
+}
 inline bool pdl_enabled() {
-    static int enabled = -1;
-    if (enabled < 0) {
+    int& state = pdl_state();
+    if (state < 0) {
         char const* env = std::getenv("AGB_PDL");
-        enabled = env ? (std::atoi(env) != 0) : 0;   // opt-in: measured neutral under CUDA-graph replay on B200 (profiles/README.md)
+        state = env ? (std::atoi(env) != 0) : 0;   // opt-in: neutral under CUDA-graph replay of batched workers, ~3 % on batch-32 passes (profiles/README.md)
     }
-    return enabled != 0;
+    return state != 0;
+}
+inline void set_pdl(int enabled) {
+    pdl_state() = enabled ? 1 : 0;
 }
 template<typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {

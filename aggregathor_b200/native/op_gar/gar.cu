@@ -903,7 +903,7 @@ template<int N, int VEC> int launch(GarArgs& a, int max_ctas, cudaStream_t strea
 //   [0..32) gradient rows | [32] agg_out | [33] param | [34] slot0 | [35] slot1 | [36] param_mc | [37] cta_partials | [38] staging
 //   [39] dist_out | [40] info | [41] grad_mc | [42] epoch_ptr | [43] hyper_ptr | [44] seg_partials | [45] loss_in | [46] loss_out
 //   [48..64) param_dst | [64..80) signal | [80..96) mailbox | [96..112) param_bf16_dst
-// ints: n f m beta rule R rank opt epoch max_ctas workers_per_rank nseg first_seg nloss seg_max_ctas phase_a_ctas | [16..24) seg_ctas
+// ints: n f m beta rule R rank opt epoch max_ctas workers_per_rank nseg first_seg nloss seg_max_ctas phase_a_ctas | [16..24) seg_ctas | [24] phase_a_threads
 // longs: row_stride | [1..9) seg_lo | [9..17) seg_hi ; floats: lr h0 h1 h2
 int fill_args(GarArgs& a, unsigned long long const* ptrs, int const* ints, long long const* longs, float const* floats) {
     a.n = ints[0]; a.f = ints[1]; a.m = ints[2]; a.beta = ints[3]; a.rule = ints[4];
@@ -1030,11 +1030,13 @@ int agb_gar_phase_a(unsigned long long const* ptrs, int const* ints, long long c
     if (seg < 0 || seg >= a.nseg || ctas < 1 || ctas > a.seg_max_ctas || !a.seg_partials || (a.rule != kKrum && a.rule != kBulyan))
         return 111;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    // 128-thread CTAs (16 K registers): small enough to share an SM with a persistent GEMM CTA of the backward pass
+    // small CTAs: a 64-thread CTA (8 K registers, 13 KB of static shared memory) fits beside a persistent GEMM CTA of the backward pass
+    // (320 threads x 168 registers, ~198 KB), so the distance pass shares SMs with it instead of taking them away
+    int threads = ints[24] >= 32 && ints[24] <= 256 ? (ints[24] / 32) * 32 : 64;
     if (a.n <= kBlockRows)
-        gar_phase_a_kernel<false><<<ctas, 128, 0, s>>>(a, seg);
+        gar_phase_a_kernel<false><<<ctas, threads, 0, s>>>(a, seg);
     else
-        gar_phase_a_kernel<true><<<ctas, 256, 0, s>>>(a, seg);
+        gar_phase_a_kernel<true><<<ctas, threads < 64 ? 64 : threads, 0, s>>>(a, seg);
     AGB_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -11,6 +11,12 @@ int agb_gemm_set_wide_tiles(int enabled) {
     return 0;
 }
 
+// Programmatic dependent launch between the kernels of this library (see agb_device.cuh).
+int agb_nn_set_pdl(int enabled) {
+    set_pdl(enabled);
+    return 0;
+}
+
 // 1 = persistent kernel (default), 0 = one tile per CTA.
 int agb_gemm_set_persistent(int enabled) {
     g_persistent = enabled ? 1 : 0;

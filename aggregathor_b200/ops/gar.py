@@ -54,7 +54,7 @@ def max_ctas():
 class FusedLauncher:
   """Holds the scratch buffers and argument arrays of one rank's fused aggregation kernels (phase A kernels + finish kernel)."""
 
-  def __init__(self, device, n, phase_a_ctas=48):
+  def __init__(self, device, n, phase_a_ctas=148, phase_a_threads=128):
     if n > MAX_WORKERS:
       raise tools.UserException("The sm_100a aggregation kernels support n <= %d workers (got %d)" % (MAX_WORKERS, n))
     self.device = torch.device(device)
@@ -62,13 +62,14 @@ class FusedLauncher:
     with torch.cuda.device(self.device):
       ctas = max(1, max_ctas())
     self.phase_a_ctas = max(1, min(int(os.environ.get("AGB_PHASE_A_CTAS", phase_a_ctas)), ctas))
+    self.phase_a_threads = int(os.environ.get("AGB_PHASE_A_THREADS", phase_a_threads))
     self.cta_partials = torch.zeros(ctas * MAX_PAIRS, dtype=torch.float32, device=self.device)
     self.seg_partials = torch.zeros(MAX_SEGMENTS * self.phase_a_ctas * MAX_PAIRS, dtype=torch.float32, device=self.device)
     self.local_mailbox = torch.zeros(MAILBOX_BYTES // 4, dtype=torch.float32, device=self.device)
     self.dist_out = torch.zeros(n * n, dtype=torch.float32, device=self.device)
     self.info = torch.zeros(64, dtype=torch.int32, device=self.device)
     self._ptrs = (ctypes.c_ulonglong * 112)()
-    self._ints = (ctypes.c_int * 24)()
+    self._ints = (ctypes.c_int * 32)()
     self._longs = (ctypes.c_longlong * (1 + 2 * MAX_SEGMENTS))()
     self._floats = (ctypes.c_float * 4)()
     self._func = _lib().agb_gar_fused
@@ -105,7 +106,7 @@ class FusedLauncher:
     ints[0], ints[1], ints[2], ints[3], ints[4] = spec.n, spec.f, spec.m, spec.beta, spec.rule_id
     ints[5], ints[6], ints[7], ints[8], ints[9] = R, rank, OPTIMIZERS[opt], epoch & 0x7fffffff, max_ctas_limit
     ints[10], ints[11], ints[12], ints[13] = workers_per_rank, len(segments), first_seg, (loss_in.numel() if loss_in is not None else 0)
-    ints[14], ints[15] = self.phase_a_ctas, self.phase_a_ctas
+    ints[14], ints[15], ints[24] = self.phase_a_ctas, self.phase_a_ctas, self.phase_a_threads
     self._longs[0] = row_stride
     for s in range(MAX_SEGMENTS):
       lo, hi = segments[s] if s < len(segments) else (0, 0)

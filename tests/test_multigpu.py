@@ -53,10 +53,14 @@ def test_overlapped_whole_step_graph_keeps_replicas_identical(tmp_path):
           "--experiment", "cnnet", "--experiment-args", "batch-size:16", "--aggregator", "krum", "--nb-workers", "8", "--nb-decl-byz-workers", "2",
           "--max-step", "14", "--use-gpu", "--reuse-gpu", "--debug-checksum", "--learning-rate-args", "initial-rate:0.02",
           "--evaluation-delta", "7", "--evaluation-period", "-1", "--checkpoint-dir", str(tmp_path / "c"), "--checkpoint-delta", "14", "--checkpoint-period", "-1", "--summary-dir", "-"]
-  code, out = _torchrun(nproc, args)
+  os.environ["AGB_OVERLAP"] = "2"   # the overlapped distance pass also when a rank hosts several workers
+  try:
+    code, out = _torchrun(nproc, args)
+  finally:
+    del os.environ["AGB_OVERLAP"]
   assert code == 0, out[-4000:]
   assert "Replica divergence" not in out and "Step 13: total loss" in out
-  assert "forward/backward + aggregation into a CUDA graph" in out and "bucket(s)" in out
+  assert "forward/backward + aggregation into a CUDA graph" in out and " 3 bucket(s)" in out
   import re
   losses = [float(x) for x in re.findall(r"Step \d+: total loss = ([0-9.eE+-]+)", out)]
   assert len(losses) == 14 and all(l == l for l in losses) and min(losses[-4:]) < losses[0]
