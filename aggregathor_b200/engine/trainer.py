@@ -72,11 +72,12 @@ class Manager:
     plain_step = attack is None and not authenticate and not ((self.l1 or -1.) > 0. or (self.l2 or -1.) > 0.)
     if cuda and engine in ("auto", "fused") and aggregator.fused_spec() is not None:
       engine_args.setdefault("device_state", True)
-      # The bucketed distance pass moves the gather + distance work under the backward pass. It pays when the backward pass leaves the
-      # memory system idle — one batch-32 worker per rank, latency-bound kernels — and costs when the backward pass is itself
-      # bandwidth-bound (several batched workers per rank: measured 15.2 -> 15.7..16.1 ms/step at 2 ranks x 4 workers, 29.3 -> 30.5 on
-      # 1 rank, `profiles/README.md`). Default: on for single-worker ranks of multi-rank jobs; AGB_OVERLAP=0 off, =2 always.
-      overlap = os.environ.get("AGB_OVERLAP", "1")
+      # The bucketed distance pass moves the gather + distance work of Krum / Bulyan under the backward pass (`gar_phase_a_kernel` on a side
+      # stream, bucket by bucket). Measured on B200s (`profiles/README.md`) it does not pay: the step is bandwidth- and launch-bound, not
+      # waiting on NVLink — 8 ranks x 1 worker 5.33 -> 5.48 ms/step, 2 ranks x 4 workers 15.2 -> 15.7, 1 rank 29.3 -> 30.5 — and the finish
+      # kernel alone is not shorter than the single-launch aggregation (0.37 vs 0.36 ms at 8 GPUs: flag barriers and the parameter
+      # broadcast dominate, not the gather). Hence opt-in: AGB_OVERLAP=1 for single-worker ranks of multi-rank jobs, =2 always.
+      overlap = os.environ.get("AGB_OVERLAP", "0")
       single_worker_ranks = self.world > 1 and nbworkers == self.world
       if plain_step and aggregator.fused_spec().rule in ("krum", "bulyan") and (overlap == "2" or (overlap not in ("", "0") and single_worker_ranks)) and "buckets" not in engine_args:
         buckets, self._bucket_layers = self._plan_buckets()

@@ -131,22 +131,29 @@ class FusedLauncher:
 _launchers = {}
 
 
+def _torch_rules(spec):
+  from ..aggregators import _ops
+  return {"average": _ops.torch_average, "average-nan": _ops.torch_average_nan, "median": _ops.torch_median,
+          "averaged-median": lambda M: _ops.torch_averaged_median(M, spec.beta), "krum": lambda M: _ops.torch_krum(M, spec.f, spec.m),
+          "bulyan": lambda M: _ops.torch_bulyan(M, spec.f, spec.m)}[spec.rule]
+
+
 def aggregate(spec, G, return_details=False):
   """Stand-alone aggregation of the CUDA matrix `G` ([n, d], fp32) with rule `spec` -> [d] tensor."""
   if not G.is_cuda:
     raise tools.UserException("ops.gar.aggregate expects a CUDA tensor")
-  if G.dtype != torch.float32:
-    out = aggregate(spec, G.float(), return_details)
-    return (out[0].to(G.dtype),) + out[1:] if return_details else out.to(G.dtype)
   n, d = G.shape
   if n != spec.n:
     spec = FusedSpec(spec.rule, n, spec.f, spec.m, spec.beta)
-  if n > MAX_WORKERS:  # beyond the register-resident kernels: torch ops on the same device
-    from ..aggregators import _ops
-    fallback = {"average": _ops.torch_average, "average-nan": _ops.torch_average_nan, "median": _ops.torch_median,
-                "averaged-median": lambda M: _ops.torch_averaged_median(M, spec.beta), "krum": lambda M: _ops.torch_krum(M, spec.f, spec.m),
-                "bulyan": lambda M: _ops.torch_bulyan(M, spec.f, spec.m)}[spec.rule]
-    return fallback(G)
+  if G.dtype == torch.float64 and not return_details:
+    # the reference's ops are registered for double too (`native/op_krum/op.cpp:47`): the sm_100a kernels are fp32, so double inputs are
+    # aggregated in double by the device-side torch implementations of the same rules (same ordering convention) instead of being rounded
+    return _torch_rules(spec)(G)
+  if G.dtype != torch.float32:
+    out = aggregate(spec, G.float(), return_details)
+    return (out[0].to(G.dtype),) + out[1:] if return_details else out.to(G.dtype)
+  if n > MAX_WORKERS:  # beyond the kernels' worker limit: torch ops on the same device
+    return _torch_rules(spec)(G)
   G = G.contiguous()
   pad = (-d) % 4
   if pad or G.data_ptr() % 16:

@@ -83,6 +83,22 @@ def test_bulyan(n, f, d):
   _close(out, ref)
 
 
+@pytest.mark.parametrize("rule,f", [("average", 0), ("median", 0), ("averaged-median", 2), ("krum", 2), ("bulyan", 1)])
+def test_double_precision_inputs_stay_double(rule, f):
+  """The reference's ops take float and double: double gradients on the device are aggregated in double (no silent rounding to fp32)."""
+  from aggregathor_b200.ops import gar as gar_ops
+  n = 9
+  G = _data(n, 3001, seed=4, outliers=f).double()
+  G += torch.randn(G.shape, generator=torch.Generator().manual_seed(1), dtype=torch.float64) * 1e-9   # structure below fp32 resolution
+  m = n - f - 2
+  spec = FusedSpec(rule, n, f=f, m=m, beta=(n - 4 * f - 2) if rule == "bulyan" else n - 2)
+  out = gar_ops.aggregate(spec, G.cuda())
+  ref = {"average": _ops.host_average, "median": _ops.host_median, "averaged-median": lambda M: _ops.host_averaged_median(M, n - 2),
+         "krum": lambda M: _ops.host_krum(M, f, m), "bulyan": lambda M: _ops.host_bulyan(M, f, m)}[rule](G)
+  assert out.dtype == torch.float64
+  assert float((out.cpu() - ref).abs().max()) <= 1e-12 * max(1.0, float(ref.abs().max()))
+
+
 def test_plugin_dispatch_on_cuda():
   G = _data(8, 3000, seed=11)
   for name, f in (("average", 0), ("median", 0), ("krum-co", 2), ("krum-tf", 2), ("krum-py", 2), ("averaged-median", 2), ("average-nan", 0)):
