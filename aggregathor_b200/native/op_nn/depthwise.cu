@@ -39,6 +39,8 @@ struct Geometry {
 
 // y[n, oh, ow, c] = sum_{kh, kw} x[n, oh*s + kh - pad_t, ow*s + kw - pad_l, c] * w[kh*k + kw][c]
 __global__ void __launch_bounds__(kThreads) depthwise_fwd_kernel(bf16 const* __restrict__ x, bf16 const* __restrict__ wt, bf16* __restrict__ y, Geometry const g, int first_image) {
+    pdl_trigger();
+    pdl_wait();
     int const octets = g.C >> 3;
     int const n = first_image + blockIdx.y / g.OH, oh = blockIdx.y % g.OH;
     uint4* const out_row = reinterpret_cast<uint4*>(y) + (static_cast<long long>(n) * g.OH + oh) * g.OW * octets;
@@ -67,6 +69,8 @@ __global__ void __launch_bounds__(kThreads) depthwise_fwd_kernel(bf16 const* __r
 
 // dx[n, h, w, c] = sum over the windows (oh, ow, kh, kw) that read pixel (h, w): dy[n, oh, ow, c] * w[kh*k + kw][c]
 __global__ void __launch_bounds__(kThreads) depthwise_dgrad_kernel(bf16 const* __restrict__ dy, bf16 const* __restrict__ wt, bf16* __restrict__ dx, Geometry const g, int first_image) {
+    pdl_trigger();
+    pdl_wait();
     int const octets = g.C >> 3;
     int const n = first_image + blockIdx.y / g.H, h = blockIdx.y % g.H;
     uint4* const out_row = reinterpret_cast<uint4*>(dx) + (static_cast<long long>(n) * g.H + h) * g.W * octets;
@@ -104,6 +108,8 @@ __global__ void __launch_bounds__(kThreads) depthwise_dgrad_kernel(bf16 const* _
 // grid.z = group; per-thread fp32 partial sums, then one fp32 atomic per (channel, tap) and CTA into the zero-initialised gradient.
 __global__ void __launch_bounds__(kThreads) depthwise_wgrad_kernel(bf16 const* __restrict__ dy, bf16 const* __restrict__ x, float* __restrict__ dw, Geometry const g,
                                                                    int images_per_group, long long group_stride, int positions_per_cta) {
+    pdl_trigger();
+    pdl_wait();
     int const octets = g.C >> 3, taps = g.k * g.k;
     int const t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= taps * octets)
@@ -212,6 +218,8 @@ namespace {
 
 // y[n, oh, ow, c] = mean over the in-image pixels of the k x k window at (oh*s - pad_t, ow*s - pad_l)
 __global__ void __launch_bounds__(kThreads) avgpool2d_fwd_kernel(bf16 const* __restrict__ x, bf16* __restrict__ y, Geometry const g, int first_image) {
+    pdl_trigger();
+    pdl_wait();
     int const octets = g.C >> 3;
     int const n = first_image + blockIdx.y / g.OH, oh = blockIdx.y % g.OH;
     int const h0 = max(0, oh * g.s - g.pad_t), h1 = min(g.H, oh * g.s - g.pad_t + g.k);
@@ -238,6 +246,8 @@ __global__ void __launch_bounds__(kThreads) avgpool2d_fwd_kernel(bf16 const* __r
 
 // dx[n, h, w, c] = sum over the windows containing (h, w) of dy[n, oh, ow, c] / (in-image size of that window)
 __global__ void __launch_bounds__(kThreads) avgpool2d_bwd_kernel(bf16 const* __restrict__ dy, bf16* __restrict__ dx, Geometry const g, int first_image) {
+    pdl_trigger();
+    pdl_wait();
     int const octets = g.C >> 3;
     int const n = first_image + blockIdx.y / g.H, h = blockIdx.y % g.H;
     uint4* const out_row = reinterpret_cast<uint4*>(dx) + (static_cast<long long>(n) * g.H + h) * g.W * octets;
@@ -274,6 +284,8 @@ __global__ void __launch_bounds__(kThreads) avgpool2d_bwd_kernel(bf16 const* __r
 
 // forward: y = min(max(x, 0), 6); backward: dx = dy where 0 < x < 6
 __global__ void __launch_bounds__(kThreads) relu6_kernel(bf16 const* __restrict__ x, bf16 const* __restrict__ dy, bf16* __restrict__ out, long long octets) {
+    pdl_trigger();
+    pdl_wait();
     long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     long long const stride = static_cast<long long>(gridDim.x) * blockDim.x;
     for (; i < octets; i += stride) {

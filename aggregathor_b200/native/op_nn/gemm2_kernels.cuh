@@ -8,7 +8,8 @@
 // the shared-memory bandwidth and half the L2 traffic per flop.
 //
 // Per CTA (both CTAs run the same program, `rank` = %cluster_ctarank):
-//   warp 0     TMA producer of its halves; completion bytes are credited to the LEADER's `full` barrier (cta_group::2 loads)
+//   warp 0     TMA producer of its halves; completion bytes are credited to the LEADER's `full` barrier (cta_group::2 loads), which
+//              the leader alone arms with the byte count of both CTAs
 //   warp 1     TMEM allocation (cta_group::2, both CTAs); in the leader only: one lane issues the MMAs, `tcgen05.commit` multicast
 //              releases the ring slot in both CTAs and finally arms both CTAs' `tmem_full`
 //   warps 2-9  epilogue of this CTA's 128 rows (TMEM lanes are per CTA), then a remote arrive on the leader's `tmem_empty`
@@ -51,7 +52,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
         for (int s = 0; s < Cfg::kStages; ++s) {
-            mbar_init(full + s, 2);      // one arrive.expect_tx from each CTA's producer (+ the bytes of both)
+            mbar_init(full + s, 1);      // the leader's arrive.expect_tx, armed with the bytes of BOTH CTAs' loads
             mbar_init(empty + s, 1);     // the leader's multicast commit
         }
         for (int b = 0; b < 2; ++b) {
@@ -90,7 +91,11 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     mbar_wait(empty + s, ((it / Cfg::kStages) & 1) ^ 1, 31);
                     uint32_t const leader_full = mapa_shared(smem_u32(full + s), 0);
                     uint8_t* a_dst = smem + s * Cfg::kStageBytes;
-                    mbar_expect_tx_cluster(leader_full, Cfg::kStageBytes);
+                    // Only the leader arms the barrier (a local arrive: a remote `arrive.release.cluster` per k-block costs the producer a
+                    // MEMBAR + ERRBAR each time, 60 % of its cycles in the first version of this kernel). The peer's bytes may land
+                    // before the leader's expect_tx: the transaction count goes negative, the phase still needs the leader's arrive.
+                    if (leader)
+                        mbar_expect_tx(full + s, 2 * Cfg::kStageBytes);
                     tma_load_2d_2sm(a_dst, &tmap_a, leader_full, i * kBK, m0 + static_cast<int>(rank) * kBM);
                     tma_load_2d_2sm(a_dst + Cfg::kABytes, &tmap_b, leader_full, i * kBK, n0 + static_cast<int>(rank) * (BN / 2));
                 }

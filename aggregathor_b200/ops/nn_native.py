@@ -189,8 +189,10 @@ def _use_pair(M, N, K, bn):
     return False
   if _PAIR == "2" or bn == 512:
     return True
+  # measured on B200 (`profiles/r2_call14_gemm_tile_bench.jsonl`): 8192^3 1559 vs 1297 TFLOP/s (128 x 256 tiles), 6272 x 2048 x 1024
+  # 835 vs 778; short reductions (K = 256: 382 vs 431) do not amortise the deeper pipeline fill of the pair
   tiles = ((M + 255) // 256) * ((N + 255) // 256)
-  return N >= 256 and K >= 256 and tiles >= 64
+  return N >= 512 and K >= 1024 and tiles >= 64
 
 
 def mm_nt(x, w, bias=None, relu=False, out=None, out_dtype=None, bn=0):

@@ -19,3 +19,4 @@ done
 ls -la gpurun_out/*.ncu-rep | awk '{print $5, $9}'
 du -sm gpurun_out | cut -f1
 head -n 20 gpurun_out/r2c12_ncu_gemm_pair_hotspots.txt | cut -c1-200
+timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/r2c12_bench_1gpu.log 2>&1; grep -a '^{"metric' gpurun_out/r2c12_bench_1gpu.log | cut -c1-900

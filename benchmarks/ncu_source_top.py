@@ -21,7 +21,15 @@ for block in blocks:
   reader = list(csv.reader(io.StringIO("\n".join(block))))
   if len(reader) < 3:
     continue
+  title = ""
+  while reader and "Source" not in reader[0] and "SASS" not in reader[0]:   # leading "Kernel Name", ... rows
+    title = reader[0][1] if len(reader[0]) > 1 else title
+    reader = reader[1:]
+  if len(reader) < 2:
+    continue
   header = reader[0]
+  if title:
+    print("#", title[:160])
   sample_cols = [i for i, h in enumerate(header) if "Sampling" in h and "All" in h] or [i for i, h in enumerate(header) if "Sampl" in h]
   if not sample_cols:
     print("columns:", header[:12])

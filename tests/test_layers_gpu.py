@@ -212,6 +212,73 @@ def test_resnet_step_tf32_matches_fp32_reference():
   assert native_loss <= 8.0 * lib_loss + 5e-3 * max(1.0, abs(ref_loss)), (native_loss, lib_loss)
 
 
+def test_launch_overlap_keeps_gradients():
+  """Programmatic dependent launch + weight gradients on a side stream (what single-worker ranks run) must not change the result:
+  one slim resnet_v1_50 step (batch 32, 224 x 224: the single-launch batch norm is on its envelope), weight gradients without split-K,
+  serial vs overlapped launches, eager and replayed from a CUDA graph, compared up to the run-to-run spread of the serial path; every
+  kernel started early has to wait for its producer."""
+  from aggregathor_b200.engine.flat import FlatLayout
+  from aggregathor_b200.models import Context, nets_factory
+  from aggregathor_b200.ops import nn_native
+  model = nets_factory.get_network("resnet_v1_50", 1000)
+  layout, states = FlatLayout(), {}
+  model.declare(layout, states)
+  layout.freeze()
+  host = torch.zeros(layout.padded_size)
+  host_states = {k: torch.zeros(v) for k, v in states.items()}
+  model.initialize(layout.views(host), host_states, torch.Generator().manual_seed(1))
+  params = host.cuda()
+  gen = torch.Generator(device="cuda").manual_seed(3)
+  x = torch.randn((32, 3, 224, 224), device="cuda", generator=gen).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+  labels = torch.randint(0, 1000, (32,), device="cuda", generator=gen)
+
+  def step(graph):
+    ctx = Context("native", True, torch.bfloat16, "cuda")
+    ctx.master = layout.views(params)
+    ctx.weights = layout.views(params.to(torch.bfloat16))
+    ctx.state = {k: v.cuda() for k, v in host_states.items()}
+    grads = torch.zeros_like(params)
+    ctx.grads = layout.views(grads)
+    if not graph:
+      loss = model.loss_and_backward(x, labels, ctx)
+      torch.cuda.synchronize()
+      return float(loss), grads
+    stream = torch.cuda.Stream()
+    stream.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(stream):
+      model.loss_and_backward(x, labels, ctx)           # warm-up (workspaces, tensor maps)
+      stream.synchronize()
+      captured = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(captured, stream=stream):
+        grads.zero_()
+        loss = model.loss_and_backward(x, labels, ctx)
+      for _ in range(3):
+        captured.replay()
+      stream.synchronize()
+    return float(loss), grads.clone()
+
+  nn_native.set_deterministic(True)
+  try:
+    for graph in (False, True):
+      # each mode against its own serial run: the warm-up and the replays of the graph mode move the moving mean the forward pass
+      # pivots its variance sums on, a rounding-level change that a randomly initialised 50-layer bf16 network amplifies
+      nn_native.set_launch_overlap(False)
+      loss_serial, grads_serial = step(graph)
+      _, again = step(graph)
+      assert loss_serial == loss_serial and float(grads_serial.abs().max()) > 0
+      norm = float(grads_serial.norm())
+      noise = float((again - grads_serial).norm()) / norm     # run-to-run spread of the serial path
+      nn_native.set_launch_overlap(True)
+      loss, grads = step(graph)
+      nn_native.set_launch_overlap(False)
+      error = float((grads - grads_serial).norm()) / norm
+      assert abs(loss - loss_serial) <= 1e-3 * abs(loss_serial), (graph, loss, loss_serial)
+      assert error <= max(5 * noise, 1e-3), (graph, error, noise)
+  finally:
+    nn_native.set_launch_overlap(False)
+    nn_native.set_deterministic(False)
+
+
 def test_deterministic_weight_gradients():
   """`set_deterministic(True)`: no split-K => the weight gradient of a GEMM-shaped and of an implicit-GEMM layer is bit-identical from run to run."""
   from aggregathor_b200.ops import nn as ops
