@@ -356,7 +356,7 @@ class AvgPool(Module):
       return nn_ops.avgpool2d_backward(ctx.backend, dy, shape, self.k, self.stride, pads)
     h, w = size
     dy = (dy * self._count(h, w, pads, dy)).contiguous(memory_format=torch.channels_last)
-    proto = torch.empty(shape, dtype=dy.dtype, device=dy.device).contiguous(memory_format=torch.channels_last)
+    proto = torch.empty(shape, dtype=dy.dtype, device=dy.device, memory_format=torch.channels_last)
     dxp = torch.ops.aten.avg_pool2d_backward(dy, proto, [self.k, self.k], [self.stride, self.stride], [0, 0], False, True, 1)
     return dxp[:, :, pads[0]:pads[0] + h, pads[2]:pads[2] + w].contiguous(memory_format=torch.channels_last)
 

@@ -765,7 +765,7 @@ def maxpool_forward(x, k, stride, pads):
     return None
   n, c, h, w = x.shape
   oh, ow = _out_size(h, k, stride, pads[0], pads[1]), _out_size(w, k, stride, pads[2], pads[3])
-  y = torch.empty((n, c, oh, ow), dtype=x.dtype, device=x.device).contiguous(memory_format=torch.channels_last)
+  y = torch.empty((n, c, oh, ow), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
   arg = torch.empty((n, oh, ow, c), dtype=torch.uint8, device=x.device)
   _check(_fn("agb_maxpool_forward", x)(_ptr(x), _ptr(y), _ptr(arg), ctypes.c_int(n), ctypes.c_int(h), ctypes.c_int(w), ctypes.c_int(c), ctypes.c_int(oh), ctypes.c_int(ow),
                                     ctypes.c_int(k), ctypes.c_int(stride), ctypes.c_int(pads[0]), ctypes.c_int(pads[2]), _stream()), "maxpool_forward")
@@ -777,7 +777,7 @@ def maxpool_backward(dy, shape, arg, k, stride, pads):
   if not dy.is_contiguous(memory_format=torch.channels_last):
     dy = dy.contiguous(memory_format=torch.channels_last)
   oh, ow = dy.shape[2], dy.shape[3]
-  dx = torch.empty((n, c, h, w), dtype=dy.dtype, device=dy.device).contiguous(memory_format=torch.channels_last)
+  dx = torch.empty((n, c, h, w), dtype=dy.dtype, device=dy.device, memory_format=torch.channels_last)
   _check(_fn("agb_maxpool_backward", dy)(_ptr(dy), _ptr(arg), _ptr(dx), ctypes.c_int(n), ctypes.c_int(h), ctypes.c_int(w), ctypes.c_int(c), ctypes.c_int(oh), ctypes.c_int(ow),
                                      ctypes.c_int(k), ctypes.c_int(stride), ctypes.c_int(pads[0]), ctypes.c_int(pads[2]), _stream()), "maxpool_backward")
   return dx
@@ -787,7 +787,7 @@ def global_avgpool_forward(x):
   if not enabled("pool") or not _cl_ok(x) or x.shape[1] % 8:
     return None
   n, c, h, w = x.shape
-  y = torch.empty((n, c, 1, 1), dtype=x.dtype, device=x.device).contiguous(memory_format=torch.channels_last)
+  y = torch.empty((n, c, 1, 1), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
   _check(_fn("agb_avgpool_forward", x)(_ptr(x), _ptr(y), ctypes.c_int(n), ctypes.c_int(h * w), ctypes.c_int(c), _stream()), "avgpool_forward")
   return y
 
@@ -797,7 +797,7 @@ def global_avgpool_backward(dy, shape):
   if not enabled("pool") or dy.dtype not in _DTYPES or c % 8:
     return None
   dy = dy.reshape(n, c).contiguous()
-  dx = torch.empty((n, c, h, w), dtype=dy.dtype, device=dy.device).contiguous(memory_format=torch.channels_last)
+  dx = torch.empty((n, c, h, w), dtype=dy.dtype, device=dy.device, memory_format=torch.channels_last)
   _check(_fn("agb_avgpool_backward", dy)(_ptr(dy), _ptr(dx), ctypes.c_int(n), ctypes.c_int(h * w), ctypes.c_int(c), _stream()), "avgpool_backward")
   return dx
 
