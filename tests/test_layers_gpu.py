@@ -110,6 +110,25 @@ def test_conv(cin, cout, k, stride, hw, pads, implicit, monkeypatch):
     _close(dx, xp.grad[:, :, pads[0]:pads[0] + hw, pads[2]:pads[2] + hw], 1e-2)
 
 
+@pytest.mark.parametrize("c,h,w,k,stride,pads,dtype", [(3, 224, 224, 7, 2, (3, 3, 3, 3), torch.bfloat16), (3, 35, 37, 3, 2, (0, 0, 0, 0), torch.bfloat16), (1, 28, 28, 5, 1, (2, 2, 2, 2), torch.bfloat16),
+                                                        (3, 33, 31, 7, 2, (2, 3, 2, 3), torch.float32), (3, 299, 299, 3, 2, (0, 0, 0, 0), torch.bfloat16)])
+def test_stem_im2col(c, h, w, k, stride, pads, dtype):
+  """The shared-memory staged im2col of few-channel inputs (column order kh, kw, c; zero padding, zero tail columns) vs `F.unfold`."""
+  import torch.nn.functional as F
+  from aggregathor_b200.ops import nn_native
+  n = 3
+  gen = torch.Generator(device="cuda").manual_seed(c * 100 + h)
+  x = torch.randn((n, c, h, w), device="cuda", generator=gen).to(dtype).contiguous(memory_format=torch.channels_last)
+  oh, ow = (h + pads[0] + pads[1] - k) // stride + 1, (w + pads[2] + pads[3] - k) // stride + 1
+  col = nn_native._im2col(x, k, k, stride, pads, oh, ow)
+  assert col.shape == (n * oh * ow, k * k * c)
+  padded = F.pad(x.float(), (pads[2], pads[3], pads[0], pads[1]))
+  want = F.unfold(padded, k, stride=stride).reshape(n, c, k, k, oh * ow).permute(0, 4, 2, 3, 1).reshape(n * oh * ow, k * k * c)   # (c, kh, kw) -> (kh, kw, c)
+  assert torch.equal(col.float(), want)
+  full = col.as_strided((col.shape[0], col.stride(0)), (col.stride(0), 1))
+  assert float(full[:, k * k * c:].abs().max()) == 0.0 if col.stride(0) > k * k * c else True
+
+
 @pytest.mark.parametrize("kh,kw,stride,padding", [(1, 7, 1, "SAME"), (7, 1, 1, "SAME"), (3, 1, 1, "SAME"), (1, 3, 2, "SAME"), (3, 1, 1, "VALID")])
 def test_rectangular_conv(kh, kw, stride, padding):
   """The factorised 1x7 / 7x1 / 1x3 / 3x1 convolutions of the Inception families on the native im2col + tcgen05 GEMM path."""
