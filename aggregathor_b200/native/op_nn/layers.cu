@@ -460,7 +460,8 @@ __global__ void relu_bwd_kernel(T const* __restrict__ dy, T const* __restrict__ 
 
 // ---------------------------------------------------------------------------- //
 // Max pooling (k x k, stride s, explicit pads, -inf padding), NHWC. Forward also records the argmax (window-relative index).
-template<typename T>
+// K > 0: window size known at compile time — the K * K taps are loaded first (all in flight), then compared; K = 0: any window.
+template<typename T, int K>
 __global__ void maxpool_fwd_kernel(T const* __restrict__ x, T* __restrict__ y, unsigned char* __restrict__ arg, int N, int H, int W, int C, int OH, int OW,
                                    int k, int s, int pad_t, int pad_l) {
     pdl_trigger();
@@ -483,22 +484,46 @@ __global__ void maxpool_fwd_kernel(T const* __restrict__ x, T* __restrict__ y, u
             best[j] = -INFINITY;
             where[j] = 0;
         }
-        for (int kh = 0; kh < k; ++kh) {
-            int const h = oh * s - pad_t + kh;
-            if (h < 0 || h >= H)
-                continue;
-            for (int kw = 0; kw < k; ++kw) {
-                int const w = ow * s - pad_l + kw;
-                if (w < 0 || w >= W)
-                    continue;
+        if (K > 0) {
+            Oct<T> taps[K > 0 ? K * K : 1];
+            bool valid[K > 0 ? K * K : 1];
+#pragma unroll
+            for (int t = 0; t < K * K; ++t) {
+                int const h = oh * s - pad_t + t / K, w = ow * s - pad_l + t % K;
+                valid[t] = h >= 0 && h < H && w >= 0 && w < W;
+                taps[t] = zero_oct<T>();
+                if (valid[t])
+                    taps[t] = load_oct(x + ((static_cast<long long>(n) * H + h) * W + w) * C + o * 8);
+            }
+#pragma unroll
+            for (int t = 0; t < K * K; ++t) {
                 float v[8];
-                unpack8(load_oct(x + ((static_cast<long long>(n) * H + h) * W + w) * C + o * 8), v);
+                unpack8(taps[t], v);
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                    if (v[j] > best[j]) {
+                    if (valid[t] && v[j] > best[j]) {
                         best[j] = v[j];
-                        where[j] = static_cast<unsigned char>(kh * k + kw);
+                        where[j] = static_cast<unsigned char>(t);
                     }
+            }
+        } else {
+            for (int kh = 0; kh < k; ++kh) {
+                int const h = oh * s - pad_t + kh;
+                if (h < 0 || h >= H)
+                    continue;
+                for (int kw = 0; kw < k; ++kw) {
+                    int const w = ow * s - pad_l + kw;
+                    if (w < 0 || w >= W)
+                        continue;
+                    float v[8];
+                    unpack8(load_oct(x + ((static_cast<long long>(n) * H + h) * W + w) * C + o * 8), v);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (v[j] > best[j]) {
+                            best[j] = v[j];
+                            where[j] = static_cast<unsigned char>(kh * k + kw);
+                        }
+                }
             }
         }
         store_oct(y + i * 8, pack_oct<T>(best));
@@ -514,7 +539,7 @@ __global__ void maxpool_fwd_kernel(T const* __restrict__ x, T* __restrict__ y, u
 // Gather form: every input element sums the gradients of the windows whose argmax it is (no atomics).
 // grid.y = n * H + h (one input row per CTA row), threads along (w, channel octet): no per-element division by H or W, and the
 // candidate window rows are resolved once per CTA.
-template<typename T>
+template<typename T, int K>
 __global__ void maxpool_bwd_kernel(T const* __restrict__ dy, unsigned char const* __restrict__ arg, T* __restrict__ dx, int N, int H, int W, int C, int OH, int OW,
                                    int k, int s, int pad_t, int pad_l) {
     pdl_trigger();
@@ -528,29 +553,57 @@ __global__ void maxpool_bwd_kernel(T const* __restrict__ dy, unsigned char const
 #pragma unroll
         for (int j = 0; j < 8; ++j)
             acc[j] = 0.f;
-        for (int kh = 0; kh < k; ++kh) {
-            int const th = h + pad_t - kh;
-            if (th < 0 || th % s)
-                continue;
-            int const oh = th / s;
-            if (oh >= OH)
-                continue;
-            for (int kw = 0; kw < k; ++kw) {
-                int const tw = w + pad_l - kw;
-                if (tw < 0 || tw % s)
-                    continue;
-                int const ow = tw / s;
-                if (ow >= OW)
-                    continue;
-                long long const oidx = (((static_cast<long long>(n) * OH + oh) * OW + ow) * octets + o) * 8;
+        if (K > 0) {   // every candidate window's (dy, argmax) pair in flight before the first use
+            Oct<T> grad[K > 0 ? K * K : 1];
+            uint2 who[K > 0 ? K * K : 1];
+            bool valid[K > 0 ? K * K : 1];
+#pragma unroll
+            for (int t = 0; t < K * K; ++t) {
+                int const th = h + pad_t - t / K, tw = w + pad_l - t % K;
+                int const oh = th / s, ow = tw / s;
+                valid[t] = th >= 0 && tw >= 0 && th % s == 0 && tw % s == 0 && oh < OH && ow < OW;
+                grad[t] = zero_oct<T>();
+                who[t] = make_uint2(0u, 0u);
+                if (valid[t]) {
+                    long long const oidx = (((static_cast<long long>(n) * OH + oh) * OW + ow) * octets + o) * 8;
+                    grad[t] = load_oct(dy + oidx);
+                    who[t] = *reinterpret_cast<uint2 const*>(arg + oidx);
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < K * K; ++t) {
                 float v[8];
-                unpack8(load_oct(dy + oidx), v);
-                uint2 const packed = *reinterpret_cast<uint2 const*>(arg + oidx);
-                unsigned char const* pw = reinterpret_cast<unsigned char const*>(&packed);
-                unsigned char const me = static_cast<unsigned char>(kh * k + kw);
+                unpack8(grad[t], v);
+                unsigned char const* pw = reinterpret_cast<unsigned char const*>(&who[t]);
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                    acc[j] += pw[j] == me ? v[j] : 0.f;
+                    acc[j] += (valid[t] && pw[j] == static_cast<unsigned char>(t)) ? v[j] : 0.f;
+            }
+        } else {
+            for (int kh = 0; kh < k; ++kh) {
+                int const th = h + pad_t - kh;
+                if (th < 0 || th % s)
+                    continue;
+                int const oh = th / s;
+                if (oh >= OH)
+                    continue;
+                for (int kw = 0; kw < k; ++kw) {
+                    int const tw = w + pad_l - kw;
+                    if (tw < 0 || tw % s)
+                        continue;
+                    int const ow = tw / s;
+                    if (ow >= OW)
+                        continue;
+                    long long const oidx = (((static_cast<long long>(n) * OH + oh) * OW + ow) * octets + o) * 8;
+                    float v[8];
+                    unpack8(load_oct(dy + oidx), v);
+                    uint2 const packed = *reinterpret_cast<uint2 const*>(arg + oidx);
+                    unsigned char const* pw = reinterpret_cast<unsigned char const*>(&packed);
+                    unsigned char const me = static_cast<unsigned char>(kh * k + kw);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        acc[j] += pw[j] == me ? v[j] : 0.f;
+                }
             }
         }
         store_oct(out_row + static_cast<long long>(i) * 8, pack_oct<T>(acc));
@@ -1000,6 +1053,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bn_fused_kernel(BnFused cons
                         rb[u] = gb[i];
                     if (BWD && gm)
                         rm[u] = gm[i];
+                    if (!BWD && gb && (i & 7) == 0)   // the residual is only needed after the barrier: have its lines in L2 by then
+                        asm volatile("prefetch.global.L2 [%0];" :: "l"(gb + i));
                 }
             }
 #pragma unroll
@@ -1157,14 +1212,36 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bn_fused_kernel(BnFused cons
     };
     long long const resident_end = nvec < p.stash_vecs ? nvec : static_cast<long long>(p.stash_vecs);
     long long i = threadIdx.x;
-    for (; i < resident_end; i += stride) {            // the tile kept on chip
-        float va[8], vx[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        unpack8(stash_a[i], va);
-        if (BWD)
-            unpack8(stash_b[i], vx);
-        else if (gb)
-            unpack8(gb[i], vx);
-        gout[i] = finish(va, vx);
+    if (!BWD && gb) {                                  // the tile kept on chip + the residual from memory, 4 loads in flight per thread
+        constexpr int R = 4;                           // (one dependent load per iteration cost 5-13 us per launch)
+        for (; i < resident_end; i += static_cast<long long>(stride) * R) {
+            uint4 rb[R];
+#pragma unroll
+            for (int u = 0; u < R; ++u) {
+                long long const k = i + static_cast<long long>(u) * stride;
+                if (k < resident_end)
+                    rb[u] = gb[k];
+            }
+#pragma unroll
+            for (int u = 0; u < R; ++u) {
+                long long const k = i + static_cast<long long>(u) * stride;
+                if (k >= resident_end)
+                    continue;
+                float va[8], vx[8];
+                unpack8(stash_a[k], va);
+                unpack8(rb[u], vx);
+                gout[k] = finish(va, vx);
+            }
+        }
+        i = static_cast<long long>(threadIdx.x) >= resident_end ? threadIdx.x : threadIdx.x + ((resident_end - 1 - threadIdx.x) / stride + 1) * stride;
+    } else {
+        for (; i < resident_end; i += stride) {        // the tile kept on chip
+            float va[8], vx[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            unpack8(stash_a[i], va);
+            if (BWD)
+                unpack8(stash_b[i], vx);
+            gout[i] = finish(va, vx);
+        }
     }
     constexpr int V = BWD ? 2 : 4;                     // the rest is streamed again (L2 / HBM), several loads in flight per thread
     for (; i < nvec; i += static_cast<long long>(stride) * V) {
@@ -1365,7 +1442,8 @@ int maxpool_forward_impl(void const* x, void* y, void* arg, int N, int H, int W,
     if ((C & 7) || k * k > 255)
         return 301;
     long long const work = static_cast<long long>(N) * OH * OW * (C >> 3);
-    AGB_CUDA_OK(launch_pdl(maxpool_fwd_kernel<T>, dim3(grid_for(work)), dim3(kThreads), 0, static_cast<cudaStream_t>(stream), static_cast<T const*>(x), static_cast<T*>(y), static_cast<unsigned char*>(arg), N, H, W, C, OH, OW, k, s, pad_t, pad_l));
+    auto kernel = k == 3 ? maxpool_fwd_kernel<T, 3> : (k == 2 ? maxpool_fwd_kernel<T, 2> : maxpool_fwd_kernel<T, 0>);
+    AGB_CUDA_OK(launch_pdl(kernel, dim3(grid_for(work)), dim3(kThreads), 0, static_cast<cudaStream_t>(stream), static_cast<T const*>(x), static_cast<T*>(y), static_cast<unsigned char*>(arg), N, H, W, C, OH, OW, k, s, pad_t, pad_l));
     AGB_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -1380,7 +1458,10 @@ int maxpool_backward_impl(void const* dy, void const* arg, void* dx, int N, int 
     int const per_launch = 65535 / H;
     for (int n0 = 0; n0 < N; n0 += per_launch) {
         int const count = N - n0 < per_launch ? N - n0 : per_launch;
-        AGB_CUDA_OK(launch_pdl(maxpool_bwd_kernel<T>, dim3((W * (C >> 3) + kThreads - 1) / kThreads, count * H), dim3(kThreads), 0, static_cast<cudaStream_t>(stream),
+        // the window-size-specialised variant (every candidate's loads in flight) measured SLOWER here: 150 vs 83 us for the ResNet
+        // stem pool at batch 32 — its 2 * K * K runtime divisions by the stride cost more than the few dependent loads they hide
+        auto kernel = maxpool_bwd_kernel<T, 0>;
+        AGB_CUDA_OK(launch_pdl(kernel, dim3((W * (C >> 3) + kThreads - 1) / kThreads, count * H), dim3(kThreads), 0, static_cast<cudaStream_t>(stream),
             static_cast<T const*>(dy) + static_cast<long long>(n0) * OH * OW * C, static_cast<unsigned char const*>(arg) + static_cast<long long>(n0) * OH * OW * C,
             static_cast<T*>(dx) + static_cast<long long>(n0) * H * W * C, count, H, W, C, OH, OW, k, s, pad_t, pad_l));
     }
