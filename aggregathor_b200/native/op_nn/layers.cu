@@ -539,7 +539,7 @@ __global__ void maxpool_fwd_kernel(T const* __restrict__ x, T* __restrict__ y, u
 // Gather form: every input element sums the gradients of the windows whose argmax it is (no atomics).
 // grid.y = n * H + h (one input row per CTA row), threads along (w, channel octet): no per-element division by H or W, and the
 // candidate window rows are resolved once per CTA.
-template<typename T, int K>
+template<typename T>
 __global__ void maxpool_bwd_kernel(T const* __restrict__ dy, unsigned char const* __restrict__ arg, T* __restrict__ dx, int N, int H, int W, int C, int OH, int OW,
                                    int k, int s, int pad_t, int pad_l) {
     pdl_trigger();
@@ -553,57 +553,29 @@ __global__ void maxpool_bwd_kernel(T const* __restrict__ dy, unsigned char const
 #pragma unroll
         for (int j = 0; j < 8; ++j)
             acc[j] = 0.f;
-        if (K > 0) {   // every candidate window's (dy, argmax) pair in flight before the first use
-            Oct<T> grad[K > 0 ? K * K : 1];
-            uint2 who[K > 0 ? K * K : 1];
-            bool valid[K > 0 ? K * K : 1];
-#pragma unroll
-            for (int t = 0; t < K * K; ++t) {
-                int const th = h + pad_t - t / K, tw = w + pad_l - t % K;
-                int const oh = th / s, ow = tw / s;
-                valid[t] = th >= 0 && tw >= 0 && th % s == 0 && tw % s == 0 && oh < OH && ow < OW;
-                grad[t] = zero_oct<T>();
-                who[t] = make_uint2(0u, 0u);
-                if (valid[t]) {
-                    long long const oidx = (((static_cast<long long>(n) * OH + oh) * OW + ow) * octets + o) * 8;
-                    grad[t] = load_oct(dy + oidx);
-                    who[t] = *reinterpret_cast<uint2 const*>(arg + oidx);
-                }
-            }
-#pragma unroll
-            for (int t = 0; t < K * K; ++t) {
+        for (int kh = 0; kh < k; ++kh) {
+            int const th = h + pad_t - kh;
+            if (th < 0 || th % s)
+                continue;
+            int const oh = th / s;
+            if (oh >= OH)
+                continue;
+            for (int kw = 0; kw < k; ++kw) {
+                int const tw = w + pad_l - kw;
+                if (tw < 0 || tw % s)
+                    continue;
+                int const ow = tw / s;
+                if (ow >= OW)
+                    continue;
+                long long const oidx = (((static_cast<long long>(n) * OH + oh) * OW + ow) * octets + o) * 8;
                 float v[8];
-                unpack8(grad[t], v);
-                unsigned char const* pw = reinterpret_cast<unsigned char const*>(&who[t]);
+                unpack8(load_oct(dy + oidx), v);
+                uint2 const packed = *reinterpret_cast<uint2 const*>(arg + oidx);
+                unsigned char const* pw = reinterpret_cast<unsigned char const*>(&packed);
+                unsigned char const me = static_cast<unsigned char>(kh * k + kw);
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                    acc[j] += (valid[t] && pw[j] == static_cast<unsigned char>(t)) ? v[j] : 0.f;
-            }
-        } else {
-            for (int kh = 0; kh < k; ++kh) {
-                int const th = h + pad_t - kh;
-                if (th < 0 || th % s)
-                    continue;
-                int const oh = th / s;
-                if (oh >= OH)
-                    continue;
-                for (int kw = 0; kw < k; ++kw) {
-                    int const tw = w + pad_l - kw;
-                    if (tw < 0 || tw % s)
-                        continue;
-                    int const ow = tw / s;
-                    if (ow >= OW)
-                        continue;
-                    long long const oidx = (((static_cast<long long>(n) * OH + oh) * OW + ow) * octets + o) * 8;
-                    float v[8];
-                    unpack8(load_oct(dy + oidx), v);
-                    uint2 const packed = *reinterpret_cast<uint2 const*>(arg + oidx);
-                    unsigned char const* pw = reinterpret_cast<unsigned char const*>(&packed);
-                    unsigned char const me = static_cast<unsigned char>(kh * k + kw);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        acc[j] += pw[j] == me ? v[j] : 0.f;
-                }
+                    acc[j] += pw[j] == me ? v[j] : 0.f;
             }
         }
         store_oct(out_row + static_cast<long long>(i) * 8, pack_oct<T>(acc));
@@ -1458,9 +1430,9 @@ int maxpool_backward_impl(void const* dy, void const* arg, void* dx, int N, int 
     int const per_launch = 65535 / H;
     for (int n0 = 0; n0 < N; n0 += per_launch) {
         int const count = N - n0 < per_launch ? N - n0 : per_launch;
-        // the window-size-specialised variant (every candidate's loads in flight) measured SLOWER here: 150 vs 83 us for the ResNet
-        // stem pool at batch 32 — its 2 * K * K runtime divisions by the stride cost more than the few dependent loads they hide
-        auto kernel = maxpool_bwd_kernel<T, 0>;
+        // (a variant with every candidate window's loads issued up front — window 3, stride 2 at compile time — measured slower:
+        // 103 vs 85 us for the ResNet stem pool at batch 32, 772 vs 617 us at batch 256; the loop skips 5 of the 9 candidates early)
+        auto kernel = maxpool_bwd_kernel<T>;
         AGB_CUDA_OK(launch_pdl(kernel, dim3((W * (C >> 3) + kThreads - 1) / kThreads, count * H), dim3(kThreads), 0, static_cast<cudaStream_t>(stream),
             static_cast<T const*>(dy) + static_cast<long long>(n0) * OH * OW * C, static_cast<unsigned char const*>(arg) + static_cast<long long>(n0) * OH * OW * C,
             static_cast<T*>(dx) + static_cast<long long>(n0) * H * W * C, count, H, W, C, OH, OW, k, s, pad_t, pad_l));

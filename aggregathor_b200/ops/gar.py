@@ -198,6 +198,40 @@ def checksum(tensor):
   return out
 
 
+def sha256_tree_host(data):
+  """The digest `sha256` computes, on host bytes: a SHA-256 tree over 1024-byte leaves, every node hashed with a (level, index) header
+  (`native/op_gar/digest.cu`)."""
+  import hashlib
+  import struct
+  level, buf = 0, bytes(data)
+  while True:
+    count = max(1, (len(buf) + 1023) // 1024)
+    nodes = [hashlib.sha256(struct.pack("<IIQ", level, 0, i) + buf[i * 1024:(i + 1) * 1024]).digest() for i in range(count)]
+    if count == 1:
+      return nodes[0]
+    level, buf = level + 1, b"".join(nodes)
+
+
+_sha_scratch = {}
+
+
+def sha256(tensor):
+  """SHA-256 tree digest (32 bytes, uint8 tensor on the same device) of a contiguous CUDA tensor whose size is a multiple of 4 bytes:
+  the cryptographic digest signed by gradient authentication."""
+  if not tensor.is_contiguous():
+    tensor = tensor.contiguous()
+  nbytes = tensor.numel() * tensor.element_size()
+  lib = _lib()
+  lib.agb_sha256_scratch_bytes.restype = ctypes.c_longlong
+  need = int(lib.agb_sha256_scratch_bytes(ctypes.c_longlong(nbytes)))
+  scratch = _sha_scratch.get(tensor.device)
+  if scratch is None or scratch.numel() < need:
+    scratch = _sha_scratch[tensor.device] = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=tensor.device)
+  out = torch.empty(32, dtype=torch.uint8, device=tensor.device)
+  _check(lib.agb_sha256_tree(ctypes.c_void_p(tensor.data_ptr()), ctypes.c_longlong(nbytes), ctypes.c_void_p(scratch.data_ptr()), ctypes.c_void_p(out.data_ptr()), _stream_ptr()), "sha256_tree")
+  return out
+
+
 def cast_bf16_(src, dst):
   """fp32 -> bf16 copy of a flat buffer (compute copy of the master parameters)."""
   func = _lib().agb_cast_bf16

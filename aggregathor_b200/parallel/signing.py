@@ -9,8 +9,9 @@ Here gradients are not sent, they are *published* in peer-mapped memory and read
 unit that is signed is the digest of a published row, split along the same coordinate slices the ranks consume:
 
 * start-up: one ed25519 key pair per rank; public keys exchanged through the process group (the control plane);
-* every step, for each local worker: digest of each of the R coordinate slices of its row (device checksum kernel on GPUs,
-  blake2b on CPU), one signature over (step, worker, digests); records are all-gathered;
+* every step, for each local worker: digest of each of the R coordinate slices of its row (a SHA-256 tree computed by a device
+  kernel on GPUs — `native/op_gar/digest.cu` — blake2b on CPU, 32 bytes either way), one signature over (step, worker, digests);
+  records are all-gathered;
 * every rank then checks each record's signature against the owner's public key and recomputes the digest of the slice(s) it
   is about to consume — through the peer mapping, i.e. over exactly the bytes its aggregation kernel will read — and fills a
   slice whose signature or digest does not match with NaN (the reference's "drop"): the forged part of that worker's gradient
@@ -19,11 +20,7 @@ unit that is signed is the digest of a published row, split along the same coord
 
 This costs a host round trip per step and is therefore opt-in (`runner.py --authenticate`), like the reference's transport.
 
-Limits, stated plainly (weaker than per-message signatures over a socket):
-* on GPUs the signed digest is the 64-bit position-dependent mixing sum of `native/op_gar` (`checksum_kernel`), not a
-  cryptographic hash: the ed25519 signature authenticates the digest, but an adversary that can search millions of free
-  coordinates could craft a second row with the same digest. The host path uses blake2b. A keyed / cryptographic device
-  digest is the obvious hardening; the protocol does not change.
+Limit, stated plainly (weaker than per-message signatures over a socket):
 * verify-then-use: the consumer verifies the peer-mapped row in place and its aggregation kernel re-reads the same memory
   afterwards. The owner of the row could rewrite it in between (it is its own memory). Ranks are separate processes of one
   job on one trusted box — the threat model the feature covers is a *corrupted* or *forged-in-flight* row (fault injection
@@ -79,7 +76,7 @@ except ImportError:  # pragma: no cover - same primitive through `cryptography`
 
 
 def _message(step, worker, digests):
-  return struct.pack("<qq%dq" % len(digests), int(step), int(worker), *[int(d) for d in digests])
+  return struct.pack("<qq", int(step), int(worker)) + b"".join(bytes(d) for d in digests)
 
 
 class Authenticator:
@@ -106,16 +103,17 @@ class Authenticator:
   # -- digests ---------------------------------------------------------------------- #
   @staticmethod
   def digest(piece):
-    """Signed 64-bit digest of a flat fp32 tensor slice (device checksum kernel on CUDA, blake2b on the host)."""
+    """32-byte cryptographic digest (uint8 tensor on the slice's device) of a flat fp32 slice: SHA-256 tree kernel on CUDA, blake2b
+    on the host."""
     if piece.is_cuda:
       from ..ops import gar as gar_ops
-      return gar_ops.checksum(piece)
-    raw = hashlib.blake2b(piece.contiguous().numpy().tobytes(), digest_size=8).digest()
-    return torch.tensor([int.from_bytes(raw, "little", signed=True)], dtype=torch.int64)
+      return gar_ops.sha256(piece)
+    raw = hashlib.blake2b(piece.contiguous().numpy().tobytes(), digest_size=32).digest()
+    return torch.frombuffer(bytearray(raw), dtype=torch.uint8)
 
   def _digests(self, row, slices):
-    values = torch.cat([self.digest(row[self.bounds[s][0]:self.bounds[s][1]]).reshape(1) for s in slices])
-    return [int(v) for v in values.cpu()]
+    values = torch.stack([self.digest(row[self.bounds[s][0]:self.bounds[s][1]]) for s in slices]).cpu()   # one device -> host copy
+    return [bytes(v.numpy().tobytes()) for v in values]
 
   # -- protocol ----------------------------------------------------------------------- #
   def publish(self, step, local_rows, after_sign=None):

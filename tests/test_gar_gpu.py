@@ -193,3 +193,35 @@ def test_drop_chunks_and_checksum():
   b = a.clone()
   b[17] += 1e-3
   assert int(gar_ops.checksum(a)) != int(gar_ops.checksum(b))
+
+
+@pytest.mark.parametrize("numel", [0, 1, 255, 256, 257, 8195, 262144, 1000003])
+def test_sha256_tree_digest_matches_hashlib(numel):
+  """The device digest signed by gradient authentication (`native/op_gar/digest.cu`: SHA-256 tree over 1024-byte leaves) vs the same
+  tree built with hashlib on the host; 16-byte aligned and merely 4-byte aligned buffers; one flipped bit changes the digest."""
+  from aggregathor_b200.ops import gar as gar_ops
+  gen = torch.Generator(device="cuda").manual_seed(numel + 1)
+  base = torch.randn(numel + 1, device="cuda", generator=gen)
+  for view in (base[:numel], base[1:numel + 1]):                 # the second view starts 4 bytes into the allocation
+    got = bytes(gar_ops.sha256(view).cpu().numpy().tobytes())
+    assert got == gar_ops.sha256_tree_host(view.cpu().numpy().tobytes()), (numel, view.data_ptr() % 16)
+  if numel:
+    before = bytes(gar_ops.sha256(base[:numel]).cpu().numpy().tobytes())
+    tampered = base[:numel].clone()
+    tampered.view(torch.int32)[numel // 2] ^= 1
+    assert bytes(gar_ops.sha256(tampered).cpu().numpy().tobytes()) != before
+
+
+def test_authenticator_digests_on_cuda():
+  """`Authenticator` on one rank with device rows: honest rows verify, a row modified after signing loses exactly its slice."""
+  from aggregathor_b200.parallel.signing import Authenticator
+  layout = FlatLayout()
+  layout.add("w", (1000, 37))
+  layout.freeze()
+  auth = Authenticator(layout, 3)
+  rows = {i: torch.randn(layout.padded_size, device="cuda") for i in range(3)}
+  records = auth.publish(5, list(rows.items()))
+  assert auth.verify(5, rows, records, [0]) == []
+  rows[1][123] += 1.0
+  assert auth.verify(5, rows, records, [0]) == [(1, 0)]
+  assert bool(torch.isnan(rows[1][:layout.size]).all()) and not bool(torch.isnan(rows[0]).any())
