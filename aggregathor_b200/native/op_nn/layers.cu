@@ -582,6 +582,64 @@ __global__ void maxpool_bwd_kernel(T const* __restrict__ dy, unsigned char const
     }
 }
 
+// Max-pool backward for window 3, stride 2 (the stem pools of ResNet / Inception): one thread per 2 x 2 block of input pixels and
+// channel octet. With H' = h + pad_t, the rows H' in {2a, 2a+1} are only covered by the windows oh in {a-1, a} (kh = H' - 2 oh), same
+// for the columns: FOUR (dy, argmax) pairs, loaded together, serve four outputs — the per-pixel gather above needs nine dependent
+// candidates for the same four pixels.
+template<typename T>
+__global__ void __launch_bounds__(kThreads) maxpool3s2_bwd_kernel(T const* __restrict__ dy, unsigned char const* __restrict__ arg, T* __restrict__ dx, int H, int W, int C, int OH, int OW,
+                                                                  int pad_t, int pad_l, int A, int B) {
+    pdl_trigger();
+    pdl_wait();
+    int const octets = C >> 3;
+    int const n = blockIdx.y / A, a = blockIdx.y % A;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B * octets; i += gridDim.x * blockDim.x) {
+        int const b = i / octets, o = i - b * octets;
+        Oct<T> grad[4];
+        uint2 who[4];
+        bool valid[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {              // t = 2 * di + dj: window (a - di, b - dj)
+            int const oh = a - (t >> 1), ow = b - (t & 1);
+            valid[t] = oh >= 0 && oh < OH && ow >= 0 && ow < OW;
+            grad[t] = zero_oct<T>();
+            who[t] = make_uint2(0u, 0u);
+            if (valid[t]) {
+                long long const oidx = (((static_cast<long long>(n) * OH + oh) * OW + ow) * octets + o) * 8;
+                grad[t] = load_oct(dy + oidx);
+                who[t] = *reinterpret_cast<uint2 const*>(arg + oidx);
+            }
+        }
+        float g[4][8];
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+            unpack8(grad[t], g[t]);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {              // p = 2 * pi + pj: input pixel (2a + pi - pad_t, 2b + pj - pad_l)
+            int const pi = p >> 1, pj = p & 1;
+            int const h = 2 * a + pi - pad_t, w = 2 * b + pj - pad_l;
+            if (h < 0 || h >= H || w < 0 || w >= W)
+                continue;
+            float acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                acc[j] = 0.f;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                int const di = t >> 1, dj = t & 1;
+                if ((pi == 1 && di == 1) || (pj == 1 && dj == 1))
+                    continue;                      // kh / kw would be 3: outside the window
+                unsigned char const me = static_cast<unsigned char>((pi + 2 * di) * 3 + (pj + 2 * dj));
+                unsigned char const* pw = reinterpret_cast<unsigned char const*>(&who[t]);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    acc[j] += (valid[t] && pw[j] == me) ? g[t][j] : 0.f;
+            }
+            store_oct(dx + (((static_cast<long long>(n) * H + h) * W + w) * octets + o) * 8, pack_oct<T>(acc));
+        }
+    }
+}
+
 // Global average pool: x [N, HW, C] -> y [N, C]; backward broadcasts dy / HW.
 template<typename T>
 __global__ void avgpool_fwd_kernel(T const* __restrict__ x, T* __restrict__ y, int N, int HW, int C) {
@@ -1426,6 +1484,18 @@ int maxpool_backward_impl(void const* dy, void const* arg, void* dx, int N, int 
         return 301;
     if (H > 65535)
         return 301;
+    if (k == 3 && s == 2 && pad_t >= 0 && pad_t <= 2 && pad_l >= 0 && pad_l <= 2) {
+        int const A = (H - 1 + pad_t) / 2 + 1, B = (W - 1 + pad_l) / 2 + 1;      // 2 x 2 blocks of (h + pad_t, w + pad_l)
+        int const per = 65535 / A;
+        for (int n0 = 0; n0 < N; n0 += per) {
+            int const count = N - n0 < per ? N - n0 : per;
+            AGB_CUDA_OK(launch_pdl(maxpool3s2_bwd_kernel<T>, dim3((B * (C >> 3) + kThreads - 1) / kThreads, count * A), dim3(kThreads), 0, static_cast<cudaStream_t>(stream),
+                static_cast<T const*>(dy) + static_cast<long long>(n0) * OH * OW * C, static_cast<unsigned char const*>(arg) + static_cast<long long>(n0) * OH * OW * C,
+                static_cast<T*>(dx) + static_cast<long long>(n0) * H * W * C, H, W, C, OH, OW, pad_t, pad_l, A, B));
+        }
+        AGB_CUDA_OK(cudaGetLastError());
+        return 0;
+    }
     // grid.y = images x rows is limited to 65535: very large batches go in slices of whole images
     int const per_launch = 65535 / H;
     for (int n0 = 0; n0 < N; n0 += per_launch) {

@@ -329,6 +329,15 @@ def test_pools_and_eltwise():
       res[backend] = (y, ops.maxpool_backward(backend, dy, x.shape, index, k, s, pads, x, y))
     _close(res["native"][0], res["torch"][0], 1e-6)
     _close(res["native"][1], res["torch"][1], 1e-2)
+  for shape, pads in (((3, 16, 15, 17), (1, 1, 1, 1)), ((3, 16, 15, 17), (0, 0, 0, 0)), ((2, 24, 35, 35), (0, 0, 0, 0)), ((2, 8, 6, 9), (0, 1, 1, 0)), ((2, 8, 5, 4), (1, 0, 0, 1))):
+    xs = _rand(shape, 12)        # odd maps, every parity of the padding: the 2 x 2-block backward of the 3x3/2 pools
+    res = {}
+    for backend in ("torch", "native"):
+      y, index = ops.maxpool_forward(backend, xs, 3, 2, pads)
+      dy = _rand(tuple(y.shape), 13)
+      res[backend] = (y, ops.maxpool_backward(backend, dy, xs.shape, index, 3, 2, pads, xs, y))
+    _close(res["native"][0], res["torch"][0], 1e-6)
+    _close(res["native"][1], res["torch"][1], 1e-2)
   z = _rand((8, 2048, 7, 7), 8)
   _close(ops.global_avgpool_forward("native", z), ops.global_avgpool_forward("torch", z), 1e-2)
   d = _rand((8, 2048, 1, 1), 9)
