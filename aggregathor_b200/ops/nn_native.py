@@ -81,15 +81,17 @@ class prezeroed_gradients:
 # ---------------------------------------------------------------------------- #
 # Weight-gradient side stream: the weight gradient of a layer is off the critical path of the backward chain, so it can run
 # next to the data gradient of the same layer (fork before, join after; under CUDA-graph capture this becomes two parallel
-# branches of the graph). Opt-in with AGB_WGRAD_STREAM=1.
+# branches of the graph). On for single-worker ranks (`set_launch_overlap`), AGB_WGRAD_STREAM=0|1 forces it.
 
 _WGRAD_STREAM = os.environ.get("AGB_WGRAD_STREAM", "0") not in ("", "0")
 
 
 def set_launch_overlap(flag):
-  """Weight gradients on a side stream + programmatic dependent launch between the nn kernels: worth ~5 % when a rank runs ONE
-  batch-32 worker (small kernels, many under-filled grids: 43.3 -> 41.2 ms for 8 sequential passes), neutral for batched workers.
-  The trainer switches it on for single-worker ranks unless AGB_PDL / AGB_WGRAD_STREAM are set explicitly."""
+  """Weight gradients on a side stream + programmatic dependent launch between the nn kernels: worth ~4 % when a rank runs ONE
+  batch-32 worker (small kernels, many under-filled grids: 41.2 -> 39.5 ms for 8 sequential passes on one GPU, 5.37 -> 5.16 ms per
+  step at 8 GPUs), neutral-to-negative for batched workers. The trainer switches it on for single-worker ranks unless AGB_PDL /
+  AGB_WGRAD_STREAM are set explicitly. Every kernel launched through `launch_pdl` must execute `griddepcontrol.wait` before touching
+  global memory (`tests/test_layers_gpu.py::test_launch_overlap_keeps_gradients`, `benchmarks/overlap_check.py`)."""
   global _WGRAD_STREAM
   _WGRAD_STREAM = bool(flag)
   _lib().agb_nn_set_pdl(ctypes.c_int(1 if flag else 0))
