@@ -147,6 +147,12 @@ class Manager:
     self.eval_ctx.weights, self.eval_ctx.master, self.eval_ctx.state = self.weight_views, self.master_views, self.states
     self.eval_ctx.generator = self._dropout_gen
     self.streams = [experiment.train_stream(i, nbworkers, self.device) for i in self.local_workers]
+    self._stream_group = None
+    if cuda and os.environ.get("AGB_GROUP_STREAMS", "1") not in ("", "0"):
+      from ..experiments._data import StreamGroup
+      if StreamGroup.eligible(self.streams):
+        self._stream_group = StreamGroup(self.streams)   # one pinned slab + one H2D copy per step for all the workers of this rank
+        self._grouped_source = self.streams              # (only while `self.streams` is still this very list: callers may swap it)
     # -- attack --------------------------------------------------------------------- #
     self.nb_real_byz = nb_real_byz
     self.attack = attack
@@ -204,7 +210,13 @@ class Manager:
     """Record every local worker's forward + backward — and, with the fused engine, the aggregation kernels and the refresh of the
     compute copy of the parameters — into one CUDA graph (static shapes, static buffers)."""
     from ..ops import counters
-    self._static_batches = [(x.clone(), y.clone()) for x, y in batches]
+    uniform = len(batches) > 1 and all(x.shape == batches[0][0].shape and x.dtype == batches[0][0].dtype and y.shape == batches[0][1].shape and y.dtype == batches[0][1].dtype
+                                       for x, y in batches)
+    if uniform:   # static inputs as two slabs (views per worker): a grouped input stream refreshes them with one copy each
+      slab_x, slab_y = torch.stack([x for x, _ in batches]), torch.stack([y for _, y in batches])
+      self._static_batches, self._static_slabs = [(slab_x[j], slab_y[j]) for j in range(len(batches))], (slab_x, slab_y)
+    else:
+      self._static_batches, self._static_slabs = [(x.clone(), y.clone()) for x, y in batches], (None, None)
     torch.cuda.synchronize(self.device)
     if self.world > 1:
       dist.barrier(group=self.group)   # capture is slow and its kernels do not run: keep the ranks aligned around it
@@ -303,16 +315,27 @@ class Manager:
 
   def _replay(self, batches):
     from ..ops import counters
-    for (sx, sy), (x, y) in zip(self._static_batches, batches):
-      sx.copy_(x, non_blocking=True)
-      sy.copy_(y, non_blocking=True)
+    slab_x, slab_y = self._static_slabs
+    grouped_x = slab_x is not None and getattr(batches, "x_all", None) is not None and batches.x_all.shape == slab_x.shape
+    grouped_y = slab_y is not None and getattr(batches, "y_all", None) is not None and batches.y_all.shape == slab_y.shape
+    if grouped_x:
+      slab_x.copy_(batches.x_all, non_blocking=True)    # every worker's images in one copy
+    if grouped_y:
+      slab_y.copy_(batches.y_all, non_blocking=True)
+    if not (grouped_x and grouped_y):
+      for (sx, sy), (x, y) in zip(self._static_batches, batches):
+        if not grouped_x:
+          sx.copy_(x, non_blocking=True)
+        if not grouped_y:
+          sy.copy_(y, non_blocking=True)
     self._graph.replay()
     counters.bump(self._graph_launches)
     return list(self._static_losses.unbind(0))
 
   def compute_gradients(self):
     """Phase 1-3 of a step: local workers' losses and gradients (+ regularisation, + attacks). Returns the list of losses."""
-    batches = [next(stream) for stream in self.streams]
+    group = self._stream_group
+    batches = next(group) if (group is not None and self.streams is self._grouped_source) else [next(stream) for stream in self.streams]
     trace = self.tracer if self.tracer.enabled else None
     if self.use_graphs and trace is None and self._graph is None and self.step >= self._graph_warmup:
       self._capture(batches)
@@ -436,6 +459,8 @@ class Manager:
       dist.barrier(group=self.group)
 
   def close(self):
+    if self._stream_group is not None:
+      self._stream_group.close()
     for stream in self.streams:
       close = getattr(stream, "close", None)
       if close is not None:

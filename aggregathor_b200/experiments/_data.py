@@ -183,12 +183,45 @@ class Dataset:
     return out
 
 
+def _indexed(device):
+  """`torch.device` with an explicit index for CUDA ("cuda" -> the current device): producer threads call `torch.cuda.set_device`."""
+  device = torch.device(device)
+  if device.type == "cuda" and device.index is None:
+    device = torch.device("cuda", torch.cuda.current_device())
+  return device
+
+
+def _guarded(producer):
+  """Producer-thread body that hands its exception to the consumer (a `None` in the queue) instead of dying silently and leaving
+  `next()` blocked forever."""
+  def run(self):
+    try:
+      producer(self)
+    except BaseException as err:   # noqa: B902 - re-raised in the consumer thread
+      self._error = err
+      while not self._stop:
+        try:
+          self._queue.put(None, timeout=0.1)
+          break
+        except queue.Full:
+          continue
+  return run
+
+
+def _take(self):
+  item = self._queue.get()
+  if item is None:
+    self._queue.put(None)          # every later call fails too
+    raise RuntimeError("the input pipeline's producer thread failed: %r" % (self._error,)) from self._error
+  return item
+
+
 class BatchStream:
   """Infinite shuffled batch iterator with pinned double buffering and asynchronous H2D copies."""
 
   def __init__(self, images, labels, batch_size, device, seed=0, shuffle=True, depth=2, transform=None):
     self.images, self.labels, self.batch = images, labels, int(batch_size)
-    self.device = torch.device(device)
+    self.device = _indexed(device)
     self.shuffle, self.transform = shuffle, transform
     self._rng = np.random.default_rng(seed)
     self._order = np.arange(len(labels))
@@ -198,17 +231,20 @@ class BatchStream:
     self._queue = None
     self._thread = None
     self._stop = False
+    self._error = None
+    self._lock = threading.Lock()
     self.sample_shape = tuple(images.shape[1:])
     self.sample_dtype = torch.from_numpy(images[:1]).dtype
     self.h2d_bytes = self.batch * int(np.prod(self.sample_shape)) * images.dtype.itemsize + self.batch * 8
 
   def _next_indices(self):
-    if self._cursor + self.batch > len(self._order):
-      if self.shuffle:
-        self._rng.shuffle(self._order)
-      self._cursor = 0
-    idx = self._order[self._cursor:self._cursor + self.batch]
-    self._cursor += self.batch
+    with self._lock:   # the stream's own producer thread and a `StreamGroup` may both draw from it
+      if self._cursor + self.batch > len(self._order):
+        if self.shuffle:
+          self._rng.shuffle(self._order)
+        self._cursor = 0
+      idx = self._order[self._cursor:self._cursor + self.batch].copy()
+      self._cursor += self.batch
     return np.sort(idx) if not self.shuffle else idx
 
   def _host_batch(self, slot=None):
@@ -221,6 +257,7 @@ class BatchStream:
       return slot
     return x, y
 
+  @_guarded
   def _producer(self):
     torch.cuda.set_device(self.device)
     stream = torch.cuda.Stream(self.device)
@@ -258,7 +295,7 @@ class BatchStream:
         self._queue = queue.Queue(maxsize=self._depth)
         self._thread = threading.Thread(target=self._producer, name="input", daemon=True)
         self._thread.start()
-      x, y, done = self._queue.get()
+      x, y, done = _take(self)
       consumer = torch.cuda.current_stream(self.device)
       consumer.wait_event(done)
       # allocated on the producer's side stream, consumed here: tell the caching allocator, or the block could be handed back to the
@@ -266,6 +303,91 @@ class BatchStream:
       x.record_stream(consumer)
       y.record_stream(consumer)
     return (x, y) if self.transform is None else self.transform(x, y)
+
+  def close(self):
+    self._stop = True
+
+
+class GroupedBatches(list):
+  """The per-worker batches of one step, `[(x, y), ...]`, when they are slices of ONE device tensor each (`x_all`, `y_all`): the
+  trainer then refreshes its static graph inputs with one copy instead of one per worker."""
+  x_all = None
+  y_all = None
+
+
+class StreamGroup:
+  """The in-memory batch streams of the logical workers hosted by one rank, served by ONE producer thread, ONE pinned slab and ONE
+  host -> device copy per step (the streams keep their own shuffled orders: every worker still draws its own batches). With `w`
+  workers per rank this replaces `w` queues, `2 w` copies and `w` events per step — host work that sits between two steps when the
+  caller reads the loss every step."""
+
+  def __init__(self, streams, depth=2):
+    self.streams = list(streams)
+    first = self.streams[0]
+    self.device, self.batch = first.device, first.batch
+    self._depth = depth
+    self._queue = None
+    self._thread = None
+    self._stop = False
+    self._error = None
+
+  @staticmethod
+  def eligible(streams):
+    """Plain `BatchStream`s (not the shard reader) of one CUDA device with identical batch geometry, none of them started yet."""
+    if len(streams) < 2 or any(type(s) is not BatchStream for s in streams) or len(set(id(s) for s in streams)) != len(streams):
+      return False   # (a stream shared by several workers — `shared-batch` — must keep handing out ONE sequence of batches)
+    first = streams[0]
+    return first._cuda and all(s.device == first.device and s.batch == first.batch and s.sample_shape == first.sample_shape and s.sample_dtype == first.sample_dtype
+                               and s._thread is None for s in streams)
+
+  @_guarded
+  def _producer(self):
+    torch.cuda.set_device(self.device)
+    stream = torch.cuda.Stream(self.device)
+    first, count = self.streams[0], len(self.streams)
+    shape = (count, self.batch) + first.sample_shape
+    slots = [(torch.empty(shape, dtype=first.sample_dtype).pin_memory(), torch.empty((count, self.batch), dtype=torch.int64).pin_memory()) for _ in range(self._depth + 2)]
+    events = [None] * len(slots)
+    i = 0
+    while not self._stop:
+      slot = slots[i % len(slots)]
+      if events[i % len(slots)] is not None:
+        events[i % len(slots)].synchronize()  # the previous copy out of this pinned slot has completed
+      for j, source in enumerate(self.streams):
+        source._host_batch((slot[0][j], slot[1][j]))
+      with torch.cuda.stream(stream):
+        x = slot[0].to(self.device, non_blocking=True)
+        y = slot[1].to(self.device, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(stream)
+      events[i % len(slots)] = done
+      while not self._stop:
+        try:
+          self._queue.put((x, y, done), timeout=0.1)
+          break
+        except queue.Full:
+          continue
+      i += 1
+
+  def __iter__(self):
+    return self
+
+  def __next__(self):
+    if self._thread is None:
+      self._queue = queue.Queue(maxsize=self._depth)
+      self._thread = threading.Thread(target=self._producer, name="input-group", daemon=True)
+      self._thread.start()
+    x, y, done = _take(self)
+    consumer = torch.cuda.current_stream(self.device)
+    consumer.wait_event(done)
+    x.record_stream(consumer)
+    y.record_stream(consumer)
+    batches = GroupedBatches()
+    for j, source in enumerate(self.streams):
+      batches.append((x[j], y[j]) if source.transform is None else source.transform(x[j], y[j]))
+    batches.x_all = x if all(b[0].data_ptr() == x[j].data_ptr() and b[0].shape == x[j].shape for j, b in enumerate(batches)) else None
+    batches.y_all = y if all(b[1].data_ptr() == y[j].data_ptr() and b[1].shape == y[j].shape for j, b in enumerate(batches)) else None
+    return batches
 
   def close(self):
     self._stop = True
@@ -292,11 +414,11 @@ class ShardStream(BatchStream):
     lib.agb_loader_info(self._handle, info)
     self.total = int(info[0])
     self.batch = int(batch_size)
-    self.device = torch.device(device)
+    self.device = _indexed(device)
     self.shuffle, self.transform = shuffle, transform
     self._cuda = self.device.type == "cuda"
     self._depth = depth
-    self._queue, self._thread, self._stop = None, None, False
+    self._queue, self._thread, self._stop, self._error = None, None, False, None
     self.sample_shape, self.sample_dtype = (int(info[2]), int(info[3]), int(info[4])), torch.uint8
     self.h2d_bytes = self.batch * int(info[5]) + self.batch * 8
 

@@ -164,3 +164,51 @@ def test_augmentation_replays_from_a_cuda_graph():
   first = out.clone()
   graph.replay()
   assert not torch.equal(first, out)   # the captured counter increment makes every replay draw new crops
+
+
+def test_producer_failures_reach_the_consumer():
+  """A producer thread that dies hands its exception to `next()` instead of leaving the consumer blocked on an empty queue."""
+  import queue
+  import threading
+
+  class Failing:
+    def __init__(self):
+      self._queue, self._stop, self._error = queue.Queue(maxsize=2), False, None
+
+    @_data._guarded
+    def _producer(self):
+      raise ValueError("no such device")
+
+  stream = Failing()
+  threading.Thread(target=stream._producer, daemon=True).start()
+  for _ in range(2):
+    with pytest.raises(RuntimeError, match="producer thread failed"):
+      _data._take(stream)
+  assert str(_data._indexed("cpu")) == "cpu"
+
+
+@pytest.mark.gpu
+def test_stream_group_serves_every_worker_its_own_sequence():
+  """`StreamGroup`: one producer / pinned slab / H2D copy per step for all the workers of a rank; every worker still receives exactly
+  the batches its own `BatchStream` (same seed) would have produced, as slices of one device tensor."""
+  rng = np.random.default_rng(0)
+  images = rng.integers(0, 255, size=(96, 6, 5, 3), dtype=np.uint8)
+  labels = np.arange(96, dtype=np.int64)
+  make = lambda seed, transform=None: _data.BatchStream(images, labels, 8, "cuda", seed=seed, transform=transform)
+  group = _data.StreamGroup([make(1), make(2), make(3)])
+  reference = [make(1), make(2), make(3)]
+  assert _data.StreamGroup.eligible(group.streams) and not _data.StreamGroup.eligible([reference[0], reference[0]])
+  for _ in range(15):                      # crosses an epoch boundary (96 / 8 = 12 batches)
+    batches = next(group)
+    assert isinstance(batches, _data.GroupedBatches) and batches.x_all.shape == (3, 8, 6, 5, 3) and batches.y_all.shape == (3, 8)
+    for (x, y), source in zip(batches, reference):
+      want_x, want_y = next(source)
+      assert torch.equal(x, want_x) and torch.equal(y, want_y)
+      assert torch.equal(x.cpu(), torch.from_numpy(images[y.cpu().numpy()]))
+  shifted = _data.StreamGroup([make(1, lambda x, y: (x, y - 1)), make(2, lambda x, y: (x, y - 1))])
+  batches = next(shifted)
+  assert batches.x_all is not None and batches.y_all is None and int(batches[0][1].min()) >= -1
+  for s in (group, shifted):
+    s.close()
+  for s in reference:
+    s.close()
