@@ -321,3 +321,21 @@ def test_single_host_detection_across_processes(tmp_path):
                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=300, cwd=str(ROOT))
   out = proc.stdout.decode(errors="replace")
   assert proc.returncode == 0 and out.count("True") == 2 and "False" not in out, out[-2000:]   # the two ranks' lines may interleave
+
+
+def test_sha256_tree_digest_specification():
+  """The digest signed on GPUs, on the host: a SHA-256 tree over 1024-byte leaves whose nodes carry (level, index) headers."""
+  import hashlib
+  import struct
+  from aggregathor_b200.ops.gar import sha256_tree_host
+  leaf = bytes(range(256)) * 4
+  assert sha256_tree_host(b"") == hashlib.sha256(struct.pack("<IIQ", 0, 0, 0)).digest()
+  assert sha256_tree_host(leaf[:1000]) == hashlib.sha256(struct.pack("<IIQ", 0, 0, 0) + leaf[:1000]).digest()
+  two = leaf + leaf[:4]
+  nodes = hashlib.sha256(struct.pack("<IIQ", 0, 0, 0) + leaf).digest() + hashlib.sha256(struct.pack("<IIQ", 0, 0, 1) + leaf[:4]).digest()
+  assert sha256_tree_host(two) == hashlib.sha256(struct.pack("<IIQ", 1, 0, 0) + nodes).digest()
+  assert sha256_tree_host(leaf + leaf) != sha256_tree_host(leaf)                     # length extension changes the root
+  swapped = leaf[4:8] + leaf[:4] + leaf[8:]
+  assert sha256_tree_host(swapped) != sha256_tree_host(leaf)                         # not a commutative sum
+  big = bytes(40000)
+  assert len(sha256_tree_host(big)) == 32 and sha256_tree_host(big) != sha256_tree_host(bytes(40004))
